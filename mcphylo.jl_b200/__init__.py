@@ -1,0 +1,15 @@
+"""mcphylo.jl_b200 — B200-native Felsenstein likelihood + branch-length gradient behind the
+PhyloDist logpdf / gradlogpdf interface of MCPhylo.jl.
+
+Import as `mcphylo_jl_b200` (see the shim package of that name).  Host-side modules mirror
+the reference's names; all device work goes through the C-ABI library built from csrc/
+(include/mcphylo_b200.h).  There is no CPU fallback: evaluating without the CUDA library or
+without a GPU raises.
+"""
+from .tree import (GeneralNode, Node, ParseNewick, newick, post_order, pre_order, get_leaves,  # noqa: F401
+                   get_mother, find_by_name, find_num, number_nodes, get_branchlength_vector,
+                   set_branchlength_vector, tree_length, NNI, flatten, FlatTree)
+from .substitution_models import Restriction, JC, GTR, freeK, setmatrix, freeK_equilibrium  # noqa: F401
+from .rates import discrete_gamma_rates, mean_boundaries, median_boundaries  # noqa: F401
+from .parser import (ParseNexus, ParseCSV, datafortree, codesfortree, dense_to_codes,  # noqa: F401
+                     get_alphabet, FileSyntaxError)

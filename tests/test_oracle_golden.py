@@ -1,0 +1,112 @@
+"""Pins the CPU oracle (oracle/felsenstein_oracle.c) against the reference's known answers
+(tests/golden/*.json, from /root/reference/test/likelihood/felsenstein.jl) and against
+independent mathematics (expm pruning without rescaling, central finite differences)."""
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+import mcphylo_jl_b200 as mcp
+from conftest import golden_case
+
+
+def _eval(orc, tree, x, model, pi, srates, rates, want_grad=True, nthreads=1):
+    ft = mcp.flatten(tree)
+    U, D, Uinv, mu = model(np.asarray(pi, float), np.asarray(srates, float))
+    return orc.felsenstein(x, ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu,
+                           np.asarray(rates, float), np.asarray(pi, float), want_grad, nthreads)
+
+
+def test_primates_logpdf(oracle):
+    tree, x, _, _, fx = golden_case("primates")
+    assert list(x.shape) == [4, 898, 22]
+    ll, _ = _eval(oracle, tree, x, mcp.JC, fx["base_freq"], [1.0], [1.0], want_grad=False)
+    assert abs(ll - fx["logpdf"]) <= 1e-12 * abs(fx["logpdf"])
+
+
+def test_simudata_gradient(oracle):
+    tree, x, _, _, fx = golden_case("simudata")
+    ll, grad = _eval(oracle, tree, x, mcp.JC, fx["base_freq"], [1.0], [1.0])
+    g = np.asarray(fx["grad"])
+    assert grad.shape == (17,)
+    assert np.max(np.abs(grad - g) / np.abs(g)) <= 1e-12
+    # the reference's logL golden is stale; it holds at the reference's own tolerance only
+    assert abs(ll - fx["logpdf_loose"]) <= fx["logpdf_rtol"] * abs(ll)
+    assert abs(ll - (-738.7363926174138)) <= 1e-12 * abs(ll)
+
+
+def test_threads_do_not_change_result(oracle):
+    tree, x, _, _, fx = golden_case("simudata")
+    a = _eval(oracle, tree, x, mcp.JC, fx["base_freq"], [1.0], [1.0], nthreads=1)
+    b = _eval(oracle, tree, x, mcp.JC, fx["base_freq"], [1.0], [1.0], nthreads=4)
+    assert abs(a[0] - b[0]) <= 1e-13 * abs(a[0])
+    assert np.allclose(a[1], b[1], rtol=1e-12, atol=0)
+
+
+def _plain_pruning(tree, x, Q, mu, rates, pi):
+    """Independent check: expm transition matrices, no rescaling, rate categories summed as
+    independent replicas (the reference's semantics)."""
+    ll = 0.0
+    K, S, _ = x.shape
+    for r in rates:
+        def partial(node):
+            if node.nchild == 0:
+                return np.asarray(x[:, :, node.num - 1])
+            out = np.ones((K, S))
+            for c in node.children:
+                out = out * (expm(Q * mu * c.inc_length * r) @ partial(c))
+            return out
+        ll += np.log(np.asarray(pi) @ partial(tree)).sum()
+    return ll
+
+
+@pytest.mark.parametrize("model,pi,srates,rates", [
+    ("JC", [0.25] * 4, [1.0], [1.0]),
+    ("GTR", [0.1, 0.2, 0.3, 0.4], [1.0, 2.0, 1.5, 0.8, 2.5, 1.2], [0.03338775337571049, 0.2519159175077897, 0.8202684796606095, 2.8944278494558904]),
+])
+def test_against_unscaled_expm(oracle, model, pi, srates, rates):
+    tree, x, _, _, _ = golden_case("simudata")
+    f = getattr(mcp, model)
+    U, D, Uinv, mu = f(np.asarray(pi), np.asarray(srates))
+    Q = U @ np.diag(D) @ Uinv
+    ll, _ = _eval(oracle, tree, x, f, pi, srates, rates, want_grad=False)
+    ref = _plain_pruning(tree, x, Q, mu, rates, pi)
+    assert abs(ll - ref) <= 1e-11 * abs(ref)
+
+
+def test_restriction_two_state(oracle):
+    rng = np.random.default_rng(5)
+    tree = mcp.ParseNewick("((a:0.1,b:0.2)x:0.05,(c:0.3,(d:0.07,e:0.11)y:0.2)z:0.15,f:0.4);")
+    codes = rng.integers(0, 3, size=(6, 40)).astype(np.uint8)
+    ft = mcp.flatten(tree)
+    x = oracle.codes_to_dense(codes, ft.leaf_nums, 2, ft.NN)
+    pi = [0.3, 0.7]
+    U, D, Uinv, mu = mcp.Restriction(pi, [])
+    Q = U @ np.diag(D) @ Uinv
+    ll, grad = _eval(oracle, tree, x, mcp.Restriction, pi, [], [1.0])
+    assert abs(ll - _plain_pruning(tree, x, Q, mu, [1.0], pi)) <= 1e-11 * abs(ll)
+    # central finite differences on every branch
+    blv = ft.blv.copy()
+    for b in range(ft.NN - 1):
+        h = 1e-6
+        vals = []
+        for sgn in (+1, -1):
+            t = blv.copy()
+            t[b] += sgn * h
+            vals.append(oracle.felsenstein(x, ft.postorder_num, ft.parent_num, t, U, D, Uinv, mu,
+                                           np.ones(1), np.asarray(pi), False, 1)[0])
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(fd - grad[b]) <= 1e-6 * max(1.0, abs(grad[b]))
+
+
+def test_transition_matches_expm(oracle):
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    U, D, Uinv, mu = mcp.GTR(pi, np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2]))
+    Q = U @ np.diag(D) @ Uinv
+    blv = np.array([0.0, 1e-4, 0.1, 1.0, 7.5])
+    rates = np.array([0.5, 2.0])
+    P, dP = oracle.transition(U, D, Uinv, mu, rates, blv, want_dP=True)
+    for b, t in enumerate(blv):
+        for r, rate in enumerate(rates):
+            E = expm(Q * mu * t * rate)
+            assert np.allclose(P[:, :, r, b], E, rtol=0, atol=1e-13)
+            assert np.allclose(dP[:, :, r, b], (Q * mu * rate) @ E, rtol=0, atol=1e-12)
