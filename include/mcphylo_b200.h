@@ -1,0 +1,163 @@
+/*
+ * mcphylo_b200.h — C ABI of libmcphylo_b200.so
+ *
+ * B200 (sm_100a) implementation of the one hot path of MCPhylo.jl: the Felsenstein-pruning
+ * log-likelihood of a PhyloDist and its analytic branch-length gradient.  These entry points
+ * are what a Julia `ccall` (or any FFI) binds to replace
+ *
+ *     logpdf(d::PhyloDist, x)        /root/reference/src/distributions/Phylodist.jl:107-122
+ *     gradlogpdf(d::PhyloDist, x)    /root/reference/src/distributions/Phylodist.jl:124-138
+ *     logpdf / __logpdf(d::MultiplePhyloDist, x)   Phylodist.jl:281-297
+ *
+ * i.e. everything from `my_repeat`/`parallel_transition_prob` down through
+ * `FelsensteinFunction` (src/Likelihood/LikelihoodCalculator_Node.jl:3-114).  The substitution
+ * model's eigendecomposition (U, D, Uinv, mu) and the tree traversal stay on the caller's side
+ * and arrive here as flat arrays.
+ *
+ * Conventions
+ *   - Plain C types only.  Every pointer is HOST memory owned by the caller and only read (or,
+ *     for outputs, written) during the call, unless a parameter is explicitly named d_* (device).
+ *   - Matrices are column-major (Julia layout).  Node numbers are 1-based `node.num`; the root
+ *     must carry the largest number NN; arrays "indexed by num" use position num-1.
+ *   - Every function returns 0 on success and a negative mcp_status on failure; the message is
+ *     available from mcp_last_error().  Nothing here calls abort()/exit() or throws across the
+ *     boundary.  There is no CPU fallback: without a usable CUDA device mcp_create fails.
+ *   - A context is thread-compatible, not thread-safe: one call at a time per context.
+ *   - Semantics follow the reference exactly: rate categories are NOT mixed
+ *     (logL = sum_r sum_s log L(s | r), VectorizedFunctions.jl:76-87), branch lengths are not
+ *     clamped, multifurcations and single-child nodes are allowed.
+ */
+#ifndef MCPHYLO_B200_H
+#define MCPHYLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCP_ABI_VERSION 1
+
+typedef struct mcp_ctx mcp_ctx;             /* one per (process, GPU) */
+typedef struct mcp_alignment mcp_alignment; /* leaf data resident on the GPU */
+
+typedef enum mcp_status {
+    MCP_OK = 0,
+    MCP_ERR_ARG = -1,         /* bad argument / malformed tree */
+    MCP_ERR_CUDA = -2,        /* CUDA runtime error (no device, OOM, launch failure) */
+    MCP_ERR_UNSUPPORTED = -3, /* e.g. a state count K without a compiled kernel */
+    MCP_ERR_DATA = -4         /* leaf data that is neither one-hot nor all-ones */
+} mcp_status;
+
+int mcp_abi_version(void);
+
+/* Message of the last failure on this context (ctx == NULL: last failure of a call that had no
+ * context, e.g. mcp_create).  The pointer stays valid until the next call on the context. */
+const char *mcp_last_error(const mcp_ctx *ctx);
+
+/* Binds a context to CUDA device `device`, creates its stream and staging buffers. */
+int mcp_create(mcp_ctx **out, int device);
+int mcp_destroy(mcp_ctx *ctx);
+
+/* Optional: run on a caller-provided cudaStream_t (cast to void*) instead of the context's own.
+ * Pass NULL to go back to the internal stream. */
+int mcp_set_stream(mcp_ctx *ctx, void *cuda_stream);
+
+/*
+ * Leaf data.  Replaces the dense one-hot array `x[:, :, leaf.num]` the reference re-expands on
+ * every call (my_repeat, VectorizedFunctions.jl:13-29) by 1-byte state codes uploaded once.
+ *
+ * from_codes: codes is (n_leaves, S) row-major; code k < K is state k (one-hot column), any code
+ *             >= K is gap/missing (all-ones column, Parser.jl:72-74).  Row i belongs to the leaf
+ *             whose node number is leaf_nums[i].
+ * from_dense: x is the reference's own array, (K, S, NN) column-major Float64; for every leaf in
+ *             leaf_nums each column must be one-hot or all ones (what datafortree produces),
+ *             otherwise MCP_ERR_DATA.
+ */
+int mcp_alignment_from_codes(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t S,
+                             const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
+int mcp_alignment_from_dense(mcp_ctx *ctx, const double *x, int K, int64_t S, int NN,
+                             const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
+int mcp_alignment_destroy(mcp_ctx *ctx, mcp_alignment *aln);
+
+/*
+ * One evaluation = logpdf (want_grad == 0) or gradlogpdf (want_grad != 0) of one PhyloDist.
+ *
+ *   NN             number of tree nodes
+ *   postorder_num  NN node numbers in post_order(tree) order (children in stored order before
+ *                  their mother, root last)
+ *   parent_num     NN, indexed by num: number of the mother, 0 for the root
+ *   blv            NN-1, indexed by num: get_branchlength_vector(tree)
+ *   U, D, Uinv, mu what d.substitution_model(base_freq, substitution_rates) returns
+ *                  (K x K col-major, K, K x K col-major, scalar)
+ *   rates, R       d.rates
+ *   pi             d.base_freq (K)
+ *   ll_out         1 double
+ *   grad_out       NN-1 doubles indexed by num (d logL / d blv[num]); may be NULL if !want_grad
+ */
+int mcp_eval(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_t *postorder_num,
+             const int32_t *parent_num, const double *blv, const double *U, const double *D,
+             const double *Uinv, double mu, const double *rates, int R, const double *pi,
+             int want_grad, double *ll_out, double *grad_out);
+
+/*
+ * Same evaluation, result left on the device: d_out (DEVICE pointer, NN doubles) receives
+ * [logL, grad[1..NN-1]] (grad part zero if !want_grad).  The work is enqueued on the context's
+ * stream and NOT synchronised, so a site-sharded caller can all-reduce d_out across GPUs
+ * (one ncclAllReduce of NN doubles) before reading it.
+ */
+int mcp_eval_device(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_t *postorder_num,
+                    const int32_t *parent_num, const double *blv, const double *U, const double *D,
+                    const double *Uinv, double mu, const double *rates, int R, const double *pi,
+                    int want_grad, double *d_out);
+
+/*
+ * T independent evaluations in one launch (MultiplePhyloDist; also proposal/chain batches).
+ * Every per-tree argument of mcp_eval becomes an array of T entries.  K and R are shared.
+ *   ll_out    T doubles
+ *   grad_out  T pointers to NN[t]-1 doubles each (array or entries may be NULL if !want_grad)
+ */
+int mcp_eval_batch(mcp_ctx *ctx, int T, const mcp_alignment *const *alns, const int32_t *NN,
+                   const int32_t *const *postorder_num, const int32_t *const *parent_num,
+                   const double *const *blv, const double *const *U, const double *const *D,
+                   const double *const *Uinv, const double *mu, const double *const *rates, int R,
+                   const double *const *pi, int want_grad, double *ll_out, double *const *grad_out);
+
+/*
+ * Measurement hooks (bench.py).  Timings are CUDA-event times on the context's stream for the
+ * most recent evaluation: the fused pruning+gradient kernel alone, and the whole device-side
+ * sequence (uploads, transition tables, walk, reduction, download).  Valid after a synchronous
+ * call (mcp_eval / mcp_eval_batch).
+ */
+typedef struct mcp_stats {
+    double walk_ms;            /* kernel felsenstein_walk */
+    double device_ms;          /* first H2D .. last D2H on the stream */
+    int64_t h2d_bytes;         /* bytes copied host->device by the last evaluation */
+    int64_t d2h_bytes;         /* bytes copied device->host by the last evaluation */
+    int32_t kernel_launches;   /* kernels launched by the last evaluation */
+    int32_t grid, block;       /* walk kernel launch shape */
+    int32_t tiles;             /* column tiles processed */
+    int32_t schedule_rebuilt;  /* 1 if the topology differed from the cached one */
+    int64_t scratch_bytes;     /* device scratch currently held for partials */
+} mcp_stats;
+int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
+
+/* Tuning knobs: block = threads per CTA (= columns per tile; 0 = automatic),
+ * ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
+int mcp_set_launch(mcp_ctx *ctx, int block, int ctas_per_sm);
+
+/*
+ * Host-only: emits the device schedule (the flat "walk program") for a topology, so the
+ * scheduler can be checked without a GPU.  leaf_row[num-1] = alignment row of that leaf, or -1
+ * for internal nodes.  Ops are 8 int32 each (layouts in csrc/schedule.hpp).  Pass cap_* =
+ * capacity of the arrays in ops; returns MCP_ERR_ARG if too small.
+ *   info[0]=n_post info[1]=n_pre info[2]=n_slots info[3]=n_stack info[4]=n_dnodes
+ */
+int mcp_schedule_dump(int NN, const int32_t *postorder_num, const int32_t *parent_num,
+                      const int32_t *leaf_row, int want_grad, int32_t *post_ops, int cap_post,
+                      int32_t *pre_ops, int cap_pre, int32_t *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCPHYLO_B200_H */

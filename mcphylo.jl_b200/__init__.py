@@ -13,3 +13,9 @@ from .substitution_models import Restriction, JC, GTR, freeK, setmatrix, freeK_e
 from .rates import discrete_gamma_rates, mean_boundaries, median_boundaries  # noqa: F401
 from .parser import (ParseNexus, ParseCSV, datafortree, codesfortree, dense_to_codes,  # noqa: F401
                      get_alphabet, FileSyntaxError)
+from .phylodist import (PhyloDist, MultiplePhyloDist, DeviceAlignment, DimensionMismatch, logpdf,  # noqa: F401
+                        gradlogpdf, multi_gradlogpdf, minimum, maximum, size, get_context,
+                        set_default_device, release_device_cache)
+from . import phylodist as _phylodist
+globals()["__logpdf"] = getattr(_phylodist, "__logpdf")
+from .synthetic import random_tree, simulate_codes  # noqa: F401,E402

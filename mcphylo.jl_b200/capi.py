@@ -1,0 +1,243 @@
+"""ctypes binding of libmcphylo_b200.so (include/mcphylo_b200.h) — the same calls the Julia
+glue makes with `ccall` (julia/MCPhyloB200.jl).
+
+No fallback of any kind: a missing library raises at load time, a missing GPU raises at
+`Context()` time with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmcphylo_b200.so")
+_lib = None
+
+SYMBOLS = [
+    "mcp_abi_version", "mcp_last_error", "mcp_create", "mcp_destroy", "mcp_set_stream",
+    "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_destroy",
+    "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
+    "mcp_schedule_dump",
+]
+
+
+class McpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libmcphylo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [("walk_ms", C.c_double), ("device_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32), ("grid", C.c_int32),
+                ("block", C.c_int32), ("tiles", C.c_int32), ("schedule_rebuilt", C.c_int32),
+                ("scratch_bytes", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_vp = C.c_void_p
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+def load():
+    """Load the shared library; raises if it has not been built (python -c 'import
+    __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built. There is no CPU "
+            "fallback. Build it with `python -c \"import __graft_entry__ as g; g.build()\"`.")
+    lib = C.CDLL(LIB_PATH)
+    lib.mcp_abi_version.restype = C.c_int
+    lib.mcp_last_error.restype = C.c_char_p
+    lib.mcp_last_error.argtypes = [_vp]
+    lib.mcp_create.argtypes = [C.POINTER(_vp), C.c_int]
+    lib.mcp_destroy.argtypes = [_vp]
+    lib.mcp_set_stream.argtypes = [_vp, _vp]
+    lib.mcp_set_launch.argtypes = [_vp, C.c_int, C.c_int]
+    lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
+    lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
+    lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
+    eval_args = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_int, _vp, C.c_int]
+    lib.mcp_eval.argtypes = eval_args + [_dp, _vp]
+    lib.mcp_eval_device.argtypes = eval_args + [_vp]
+    lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
+    lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    lib.mcp_schedule_dump.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]
+    for name in SYMBOLS:
+        if name != "mcp_last_error":
+            getattr(lib, name).restype = C.c_int
+    if lib.mcp_abi_version() != 1:
+        raise ImportError("libmcphylo_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def _f64(a, order="C"):
+    return np.require(np.asarray(a, dtype=np.float64), requirements=["C"] if order == "C" else ["F"])
+
+
+def _colmajor(a):
+    """Flat column-major copy of a matrix (Julia layout)."""
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+class Alignment:
+    """Leaf data resident on the GPU (mcp_alignment)."""
+
+    def __init__(self, ctx: "Context", handle, K: int, S: int, leaf_nums: np.ndarray):
+        self.ctx, self.handle, self.K, self.S = ctx, handle, K, S
+        self.leaf_nums = leaf_nums
+
+    def close(self):
+        if self.handle is not None and self.ctx.handle is not None:
+            load().mcp_alignment_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One mcp_ctx: a (process, GPU) pair."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _vp()
+        rc = self.lib.mcp_create(C.byref(h), int(device))
+        if rc:
+            raise McpError(rc, self.lib.mcp_last_error(None).decode())
+        self.handle = h
+        self.device = device
+
+    def _check(self, rc: int):
+        if rc:
+            raise McpError(rc, self.lib.mcp_last_error(self.handle).decode())
+
+    def close(self):
+        if self.handle is not None:
+            self.lib.mcp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self.lib.mcp_set_stream(self.handle, _vp(cuda_stream or 0)))
+
+    def set_launch(self, block: int = 0, ctas_per_sm: int = 0):
+        self._check(self.lib.mcp_set_launch(self.handle, int(block), int(ctas_per_sm)))
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.mcp_get_stats(self.handle, C.byref(s)))
+        return s.asdict()
+
+    # ---- leaf data -------------------------------------------------------------------
+    def alignment_from_codes(self, codes, K: int, leaf_nums) -> Alignment:
+        codes = np.ascontiguousarray(np.asarray(codes, dtype=np.uint8))
+        leaf_nums = _i32(leaf_nums)
+        n_leaves, S = codes.shape
+        assert leaf_nums.size == n_leaves
+        h = _vp()
+        self._check(self.lib.mcp_alignment_from_codes(self.handle, codes.ctypes.data, int(K), int(S),
+                                                      leaf_nums.ctypes.data, n_leaves, C.byref(h)))
+        return Alignment(self, h, int(K), int(S), leaf_nums)
+
+    def alignment_from_dense(self, x, leaf_nums) -> Alignment:
+        x = np.asarray(x, dtype=np.float64)
+        K, S, NN = x.shape
+        xf = x if x.flags.f_contiguous else np.asfortranarray(x)
+        leaf_nums = _i32(leaf_nums)
+        h = _vp()
+        self._check(self.lib.mcp_alignment_from_dense(self.handle, xf.ctypes.data, K, S, NN,
+                                                      leaf_nums.ctypes.data, leaf_nums.size, C.byref(h)))
+        return Alignment(self, h, K, S, leaf_nums)
+
+    # ---- evaluation ------------------------------------------------------------------
+    @staticmethod
+    def _pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi):
+        return (_i32(postorder_num), _i32(parent_num), _f64(blv), _colmajor(U), _f64(D), _colmajor(Uinv),
+                _f64(rates), _f64(pi))
+
+    def eval(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
+             want_grad: bool = True):
+        po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
+        NN = po.size
+        assert pa.size == NN and blv.size == NN - 1 and D.size == aln.K and pi.size == aln.K
+        ll = C.c_double()
+        grad = np.zeros(max(NN - 1, 1), dtype=np.float64) if want_grad else None
+        self._check(self.lib.mcp_eval(self.handle, aln.handle, NN, po.ctypes.data, pa.ctypes.data, blv.ctypes.data,
+                                      U.ctypes.data, D.ctypes.data, Uinv.ctypes.data, float(mu),
+                                      rates.ctypes.data, rates.size, pi.ctypes.data, int(want_grad),
+                                      C.byref(ll), grad.ctypes.data if want_grad else None))
+        return ll.value, (grad[:NN - 1] if want_grad else None)
+
+    def eval_device(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
+                    want_grad: bool, d_out_ptr: int):
+        """Result stays on the device at d_out_ptr (NN doubles); not synchronised."""
+        po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
+        NN = po.size
+        self._check(self.lib.mcp_eval_device(self.handle, aln.handle, NN, po.ctypes.data, pa.ctypes.data,
+                                             blv.ctypes.data, U.ctypes.data, D.ctypes.data, Uinv.ctypes.data,
+                                             float(mu), rates.ctypes.data, rates.size, pi.ctypes.data,
+                                             int(want_grad), _vp(d_out_ptr)))
+
+    def eval_batch(self, alns: Sequence[Alignment], trees: Sequence[tuple], want_grad: bool = True):
+        """trees[t] = (postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi)."""
+        T = len(alns)
+        assert T == len(trees) and T >= 1
+        packed = [self._pack(t[0], t[1], t[2], t[3], t[4], t[5], t[7], t[8]) for t in trees]
+        R = packed[0][6].size
+        assert all(p[6].size == R for p in packed), "all trees of a batch must share the number of rates"
+        NN = _i32([p[0].size for p in packed])
+        mu = _f64([t[6] for t in trees])
+
+        def ptrs(i):
+            return (C.c_void_p * T)(*[p[i].ctypes.data for p in packed])
+
+        aln_ptrs = (C.c_void_p * T)(*[a.handle.value for a in alns])
+        ll = np.zeros(T, dtype=np.float64)
+        grads = [np.zeros(max(int(n) - 1, 1), dtype=np.float64) for n in NN] if want_grad else None
+        gptrs = (C.c_void_p * T)(*[g.ctypes.data for g in grads]) if want_grad else None
+        self._check(self.lib.mcp_eval_batch(self.handle, T, aln_ptrs, NN.ctypes.data, ptrs(0), ptrs(1), ptrs(2),
+                                            ptrs(3), ptrs(4), ptrs(5), mu.ctypes.data, ptrs(6), R, ptrs(7),
+                                            int(want_grad), ll.ctypes.data, gptrs))
+        if want_grad:
+            return ll, [g[:int(n) - 1] for g, n in zip(grads, NN)]
+        return ll, None
+
+
+def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool):
+    """Host-only view of the device walk program (no GPU needed)."""
+    lib = load()
+    po, pa, lr = _i32(postorder_num), _i32(parent_num), _i32(leaf_row)
+    NN = po.size
+    cap = 2 * NN + 8
+    post = np.zeros((cap, 8), dtype=np.int32)
+    pre = np.zeros((cap, 8), dtype=np.int32)
+    info = np.zeros(8, dtype=np.int32)
+    rc = lib.mcp_schedule_dump(NN, po.ctypes.data, pa.ctypes.data, lr.ctypes.data, int(want_grad),
+                               post.ctypes.data, cap, pre.ctypes.data, cap, info.ctypes.data)
+    if rc:
+        raise McpError(rc, lib.mcp_last_error(None).decode())
+    return {"post": post[:info[0]].copy(), "pre": pre[:info[1]].copy(), "n_slots": int(info[2]),
+            "n_stack": int(info[3]), "n_dnodes": int(info[4])}

@@ -1,0 +1,1120 @@
+// mcphylo_b200.cu — libmcphylo_b200.so: C ABI (include/mcphylo_b200.h) + sm_100a kernels.
+//
+// Replaces, for one PhyloDist evaluation, the reference's
+//   my_repeat + parallel_transition_prob + FelsensteinFunction (post-order pruning with per-column
+//   rescaling, then the reverse-post-order gradient pass)
+//   /root/reference/src/distributions/Phylodist.jl:107-138
+//   /root/reference/src/Likelihood/LikelihoodCalculator_Node.jl:3-114
+//   /root/reference/src/Likelihood/VectorizedFunctions.jl:13-213
+//
+// Design: alignment columns (site x rate category) are independent through both
+// passes, so ONE thread owns one column for the whole evaluation and walks the flat op program
+// produced by schedule.hpp.  No inter-thread dependency exists, hence one fused persistent kernel
+// (post pass + gradient pass) with no grid- or block-level synchronisation inside a tile.
+// Partials live in a CTA-private scratch region laid out [slot][thread][state] so that a warp's
+// access is one contiguous run of 32*K doubles (256-bit vector ld/st per thread at K = 4).
+// fp64 throughout.  Rescaling uses exact powers of two (exponent extraction) instead of the
+// reference's divide-by-max + log per node; the integer exponent sum is exact and
+// logL = ln2 * sum(exponents) + sum(log(pi . L_root)).
+#include "../../include/mcphylo_b200.h"
+#include "schedule.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+using mcp::PostOp;
+using mcp::PreOp;
+using mcp::Schedule;
+
+// --------------------------------------------------------------------------------------------
+// device-side descriptors
+// --------------------------------------------------------------------------------------------
+struct TreeDev {
+    long long post_off;      // op index (32-byte units) of this tree's post program
+    long long pre_off;       // ... pre program
+    long long ptab_off;      // doubles, into the transition-table buffer
+    long long dyn_off;       // doubles, into the per-evaluation parameter buffer
+    long long out_off;       // doubles, into the result buffer ([logL, grad(NN-1)] per tree)
+    const unsigned char* codes;  // (rows, code_stride) state codes of this tree's alignment
+    long long S;             // sites
+    long long code_stride;
+    int n_post, n_pre;
+    int NN, n_br;            // real nodes; rows of the branch table (device nodes)
+    int tile_begin, tiles_per_rate;
+    int row_lo, row_hi;      // accumulator rows [lo, hi) holding this tree's partial sums
+};
+
+struct LLRow {
+    long long esum;  // sum of binary exponents removed by rescaling (exact)
+    double logsum;   // sum of log(pi . L_root)
+};
+
+struct WalkParams {
+    const TreeDev* trees;
+    const int4* ops;
+    const double* ptab;
+    const double* dyn;
+    double* scratch;
+    long long scratch_per_cta;  // doubles
+    double* rows;               // [row][row_stride] gradient partial sums
+    LLRow* rows_ll;
+    const int* cta_row_base;
+    long long row_stride;
+    int n_slots, n_stack;
+    int n_tiles, T, R, want_grad;
+};
+
+// per-tree layout of the per-evaluation parameter block (offsets in doubles from dyn_off)
+__host__ __device__ inline long long dyn_blv(int) { return 0; }
+__host__ __device__ inline long long dyn_U(int NN) { return NN - 1; }
+__host__ __device__ inline long long dyn_D(int NN, int K) { return NN - 1 + (long long)K * K; }
+__host__ __device__ inline long long dyn_Uinv(int NN, int K) { return NN - 1 + (long long)K * K + K; }
+__host__ __device__ inline long long dyn_mu(int NN, int K) { return NN - 1 + 2LL * K * K + K; }
+__host__ __device__ inline long long dyn_rates(int NN, int K) { return NN + 2LL * K * K + K; }
+__host__ __device__ inline long long dyn_pi(int NN, int K, int R) { return NN + 2LL * K * K + K + R; }
+__host__ __device__ inline long long dyn_size(int NN, int K, int R) {
+    long long n = NN + 2LL * K * K + 2LL * K + R;
+    return (n + 3) & ~3LL;  // keep every tree's block 32-byte aligned
+}
+// transition table entry for one (branch, rate): P columns 0..K (column K = row sums, the
+// all-ones leaf), then dP/dt columns 0..K; column j holds the K parent-state entries.
+__host__ __device__ inline int pst(int K) { return 2 * K * (K + 1); }
+
+// --------------------------------------------------------------------------------------------
+// vector load/store helpers (K doubles per column)
+// --------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void ld_table(const double* __restrict__ p, double (&v)[K]) {
+    // read-only path: tables are written by an earlier kernel
+    if constexpr (K == 4) {
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+    } else if constexpr (K == 2) {
+        asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __ldg(p + k);
+    }
+}
+// Partials: written and re-read by the SAME thread inside one kernel, so they must not go
+// through the non-coherent path; .cg keeps this streaming data out of L1 (tables/ops stay there).
+template <int K>
+__device__ __forceinline__ void ld_partial(const double* p, double (&v)[K]) {
+    if constexpr (K == 4) {
+        asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+    } else if constexpr (K == 2) {
+        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __ldcg(p + k);
+    }
+}
+template <int K>
+__device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
+    if constexpr (K == 4) {
+        asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    } else if constexpr (K == 2) {
+        asm volatile("st.global.cg.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) __stcg(p + k, v[k]);
+    }
+}
+
+// out[s] = sum_j T[j][s] * L[j]   (T = K columns of a table, column-major by child state j)
+template <int K>
+__device__ __forceinline__ void table_times(const double* __restrict__ tab, const double (&L)[K], double (&out)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double col[K];
+        ld_table<K>(tab + j * K, col);
+#pragma unroll
+        for (int s = 0; s < K; ++s) out[s] = (j == 0) ? col[s] * L[0] : fma(col[s], L[j], out[s]);
+    }
+}
+// out[j] = sum_s T[j][s] * q[s]   (transposed product)
+template <int K>
+__device__ __forceinline__ void table_transposed_times(const double* __restrict__ tab, const double (&q)[K], double (&out)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double col[K];
+        ld_table<K>(tab + j * K, col);
+        double acc = col[0] * q[0];
+#pragma unroll
+        for (int s = 1; s < K; ++s) acc = fma(col[s], q[s], acc);
+        out[j] = acc;
+    }
+}
+
+// Multiply a column by the exact power of two that brings its maximum into [1,2); returns the
+// removed binary exponent.  Zero / denormal / non-finite maxima are left alone.
+template <int K>
+__device__ __forceinline__ int rescale_pow2(double (&v)[K]) {
+    double m = v[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) m = fmax(m, v[k]);
+    int e = (__double2hiint(m) >> 20) & 0x7ff;
+    if (e == 0 || e == 0x7ff) return 0;
+    double sc = __hiloint2double((2046 - e) << 20, 0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] *= sc;
+    return e - 1023;
+}
+
+// lane 0 ends with sum(va) over the warp, lane 16 with sum(vb)
+__device__ __forceinline__ double warp_pair_reduce(double va, double vb, int lane) {
+    const bool upper = (lane & 16) != 0;
+    double send = upper ? va : vb;
+    double keep = upper ? vb : va;
+    double v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 1: transition tables P(t), dP/dt for every (tree, branch, rate)
+//   P   = U diag(exp(mu t D r)) Uinv                 VectorizedFunctions.jl:116-168
+//   dP  = U diag(D r mu exp(mu t D r)) Uinv          VectorizedFunctions.jl:89-113, 139-152
+// same operation order as the reference; one thread per (branch, rate).
+// --------------------------------------------------------------------------------------------
+constexpr int KMAX_TABLE = 32;
+
+__global__ void build_transition_tables(const TreeDev* __restrict__ trees, const double* __restrict__ dyn,
+                                        double* __restrict__ ptab, int K, int R) {
+    const TreeDev tr = trees[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= tr.n_br * R) return;
+    const int br = idx / R, r = idx - br * R;
+    const double* d = dyn + tr.dyn_off;
+    const double* U = d + dyn_U(tr.NN);
+    const double* D = d + dyn_D(tr.NN, K);
+    const double* Uinv = d + dyn_Uinv(tr.NN, K);
+    const double mu = d[dyn_mu(tr.NN, K)];
+    const double rate = d[dyn_rates(tr.NN, K) + r];
+    double* P = ptab + tr.ptab_off + ((long long)br * R + r) * pst(K);
+    double* dP = P + K * (K + 1);
+    if (br >= tr.NN - 1) {  // root row (unused) and virtual branches: identity, zero derivative
+        for (int n = 0; n <= K; ++n)
+            for (int m = 0; m < K; ++m) {
+                P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0;
+                dP[n * K + m] = 0.0;
+            }
+        return;
+    }
+    const double t = d[dyn_blv(tr.NN) + br];
+    double e[KMAX_TABLE], de[KMAX_TABLE];
+    for (int i = 0; i < K; ++i) {
+        double ex = exp(mu * t * D[i] * rate);
+        e[i] = ex;
+        de[i] = D[i] * rate * mu * ex;
+    }
+    for (int m = 0; m < K; ++m) {
+        double rs = 0.0, drs = 0.0;
+        for (int n = 0; n < K; ++n) {
+            double c = 0.0, dc = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double u = U[m + K * k], ui = Uinv[k + K * n];
+                c += (u * e[k]) * ui;
+                dc += (u * de[k]) * ui;
+            }
+            P[n * K + m] = c;
+            dP[n * K + m] = dc;
+            rs += c;    // what P * (all-ones leaf) gives: sum_s1 1 * P[s, s1]
+            drs += dc;
+        }
+        P[K * K + m] = rs;
+        dP[K * K + m] = drs;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 2: the fused walk.  grid = persistent CTAs, each takes a contiguous range of column
+// tiles; a tile = blockDim.x columns of one rate category of one tree.
+// --------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) felsenstein_walk(const WalkParams p) {
+    extern __shared__ double s_acc[];  // per-branch gradient sums of this CTA (gradient mode)
+    __shared__ long long s_e[8];
+    __shared__ double s_l[8];
+
+    const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
+    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
+    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
+    if (tile >= tile_end) return;
+
+    double* const slots = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K;
+    double* const stack = slots + (long long)p.n_slots * TW * K;
+    const long long slot_stride = (long long)TW * K;
+    int row = p.cta_row_base[blockIdx.x];
+    const int R = p.R;
+
+    int ti = 0;
+    while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
+
+    while (tile < tile_end) {
+        const TreeDev tr = p.trees[ti];
+        const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
+        if (p.want_grad) {
+            for (int i = tid; i < tr.n_br; i += TW) s_acc[i] = 0.0;
+        }
+        __syncthreads();
+        long long e_total = 0;
+        double logsum = 0.0;
+        const double* const dynp = p.dyn + tr.dyn_off;
+        double pi[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) pi[k] = __ldg(dynp + dyn_pi(tr.NN, K, R) + k);
+        const int4* const post_ops = p.ops + 2 * tr.post_off;
+        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
+        constexpr int PST = 2 * K * (K + 1);
+
+        for (; tile < tree_tile_end; ++tile) {
+            const int local = tile - tr.tile_begin;
+            const int r = local / tr.tiles_per_rate;
+            const long long site = (long long)(local - r * tr.tiles_per_rate) * TW + tid;
+            const bool valid = site < tr.S;
+            const unsigned char* const codes = tr.codes + (valid ? site : 0);
+            const double* const tab_r = p.ptab + tr.ptab_off + (long long)r * PST;
+            const long long br_stride = (long long)R * PST;
+
+            // ------------------------------ post pass ------------------------------
+            double cur[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) cur[k] = 1.0;
+            int e_col = 0;
+            for (int i = 0; i < tr.n_post; ++i) {
+                const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
+                const int flags = o1.y;
+                double Da[K], Db[K];
+                {
+                    const double* tab = tab_r + o0.y * br_stride;
+                    const int kind = flags & 3;
+                    if (kind == mcp::OPK_LEAF) {
+                        int code = (valid && o0.x >= 0) ? (int)__ldg(codes + (long long)o0.x * tr.code_stride) : K;
+                        code = min(code, K);
+                        ld_table<K>(tab + code * K, Da);
+                    } else if (kind == mcp::OPK_REG) {
+                        table_times<K>(tab, cur, Da);
+                    } else {
+                        double L[K];
+                        ld_partial<K>(slots + o0.x * slot_stride, L);
+                        table_times<K>(tab, L, Da);
+                    }
+                }
+                {
+                    const double* tab = tab_r + o0.w * br_stride;
+                    const int kind = (flags >> 2) & 3;
+                    if (kind == mcp::OPK_LEAF) {
+                        int code = (valid && o0.z >= 0) ? (int)__ldg(codes + (long long)o0.z * tr.code_stride) : K;
+                        code = min(code, K);
+                        ld_table<K>(tab + code * K, Db);
+                    } else if (kind == mcp::OPK_REG) {
+                        table_times<K>(tab, cur, Db);
+                    } else {
+                        double L[K];
+                        ld_partial<K>(slots + o0.z * slot_stride, L);
+                        table_times<K>(tab, L, Db);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) cur[k] = Da[k] * Db[k];
+                e_col += rescale_pow2<K>(cur);
+                if (flags & mcp::POST_STORE) st_partial<K>(slots + o1.x * slot_stride, cur);
+            }
+            {
+                double rootv = pi[0] * cur[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) rootv = fma(pi[k], cur[k], rootv);
+                if (valid) {
+                    logsum += log(rootv);
+                    e_total += e_col;
+                }
+            }
+
+            // ------------------------------ gradient pass ------------------------------
+            if (p.want_grad) {
+                for (int i = 0; i < tr.n_pre; ++i) {
+                    const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
+                    const int flags = o1.w;
+                    const int a_br = o0.z, b_br = o1.x;
+                    double pm[K];
+                    {
+                        const int mk = flags & 3;
+                        if (mk == mcp::PREM_ROOT) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) pm[k] = pi[k];
+                        } else if (mk == mcp::PREM_REG) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) pm[k] = cur[k];
+                        } else {
+                            ld_partial<K>(stack + o0.x * slot_stride, pm);
+                        }
+                    }
+                    const double* const tab_a = tab_r + a_br * br_stride;
+                    const double* const tab_b = tab_r + b_br * br_stride;
+                    double Da[K], Ya[K], Db[K], Yb[K];
+                    if (flags & 4) {
+                        double L[K];
+                        ld_partial<K>(slots + o0.y * slot_stride, L);
+                        table_times<K>(tab_a, L, Da);
+                        table_times<K>(tab_a + K * (K + 1), L, Ya);
+                    } else {
+                        int code = (valid && o0.y >= 0) ? (int)__ldg(codes + (long long)o0.y * tr.code_stride) : K;
+                        code = min(code, K);
+                        ld_table<K>(tab_a + code * K, Da);
+                        ld_table<K>(tab_a + K * (K + 1) + code * K, Ya);
+                    }
+                    if (flags & 8) {
+                        double L[K];
+                        ld_partial<K>(slots + o0.w * slot_stride, L);
+                        table_times<K>(tab_b, L, Db);
+                        table_times<K>(tab_b + K * (K + 1), L, Yb);
+                    } else {
+                        int code = (valid && o0.w >= 0) ? (int)__ldg(codes + (long long)o0.w * tr.code_stride) : K;
+                        code = min(code, K);
+                        ld_table<K>(tab_b + code * K, Db);
+                        ld_table<K>(tab_b + K * (K + 1) + code * K, Yb);
+                    }
+                    double qa[K], qb[K];
+                    double den = 0.0, na = 0.0, nb = 0.0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        qa[k] = pm[k] * Db[k];
+                        qb[k] = pm[k] * Da[k];
+                        den = fma(qa[k], Da[k], den);
+                        na = fma(qa[k], Ya[k], na);
+                        nb = fma(qb[k], Yb[k], nb);
+                    }
+                    const double inv = 1.0 / den;
+                    const double ga = valid ? na * inv : 0.0;
+                    const double gb = valid ? nb * inv : 0.0;
+                    const double red = warp_pair_reduce(ga, gb, lane);
+                    if (lane == 0) atomicAdd(&s_acc[a_br], red);
+                    else if (lane == 16) atomicAdd(&s_acc[b_br], red);
+
+                    const int a_out = (flags >> 4) & 3, b_out = (flags >> 6) & 3;
+                    if (a_out != mcp::OUT_NONE) {
+                        double pa[K];
+                        table_transposed_times<K>(tab_a, qa, pa);
+                        rescale_pow2<K>(pa);
+                        if (a_out == mcp::OUT_KEEP) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) cur[k] = pa[k];
+                        } else {
+                            st_partial<K>(stack + o1.y * slot_stride, pa);
+                        }
+                    }
+                    if (b_out != mcp::OUT_NONE) {
+                        double pb[K];
+                        table_transposed_times<K>(tab_b, qb, pb);
+                        rescale_pow2<K>(pb);
+                        if (b_out == mcp::OUT_KEEP) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) cur[k] = pb[k];
+                        } else {
+                            st_partial<K>(stack + o1.z * slot_stride, pb);
+                        }
+                    }
+                }
+            }
+        }  // tiles of this tree
+
+        // ---- flush this CTA's sums for the tree into its accumulator row ----
+        for (int off = 16; off > 0; off >>= 1) {
+            e_total += __shfl_xor_sync(0xffffffffu, e_total, off);
+            logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
+        }
+        if (lane == 0) { s_e[warp] = e_total; s_l[warp] = logsum; }
+        __syncthreads();
+        if (tid == 0) {
+            long long es = 0;
+            double ls = 0.0;
+            for (int w = 0; w < (TW + 31) / 32; ++w) { es += s_e[w]; ls += s_l[w]; }
+            p.rows_ll[row].esum = es;
+            p.rows_ll[row].logsum = ls;
+        }
+        if (p.want_grad) {
+            double* dst = p.rows + (long long)row * p.row_stride;
+            for (int i = tid; i < tr.n_br; i += TW) dst[i] = s_acc[i];
+        }
+        __syncthreads();
+        ++row;
+        ++ti;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel 3: fixed-order reduction of the accumulator rows -> [logL, grad] per tree
+// --------------------------------------------------------------------------------------------
+__global__ void finalize_results(const TreeDev* __restrict__ trees, const double* __restrict__ rows,
+                                 long long row_stride, const LLRow* __restrict__ rows_ll,
+                                 double* __restrict__ out, int want_grad) {
+    const TreeDev tr = trees[blockIdx.y];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= tr.NN) return;
+    double* o = out + tr.out_off;
+    if (j == 0) {
+        long long es = 0;
+        double ls = 0.0;
+        for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) { es += rows_ll[rw].esum; ls += rows_ll[rw].logsum; }
+        o[0] = (double)es * 0.693147180559945309417232121458 + ls;
+    } else {
+        double g = 0.0;
+        if (want_grad)
+            for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) g += rows[(long long)rw * row_stride + (j - 1)];
+        o[j] = g;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+thread_local std::string g_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct mcp_alignment {
+    int K = 0;
+    long long S = 0, stride = 0;
+    int n_leaves = 0;
+    unsigned char* d_codes = nullptr;
+    std::vector<int32_t> leaf_nums;
+    unsigned long long id = 0;
+};
+
+struct mcp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string error;
+    bool pending_async = false;
+    int opt_block = 0, opt_ctas_per_sm = 0;
+    unsigned long long next_aln_id = 1;
+
+    DevBuf d_topo, d_dyn, d_ptab, d_scratch, d_rows, d_rows_ll, d_out;
+    PinBuf h_topo, h_dyn, h_out;
+
+    // cached topology
+    struct TreeSig {
+        unsigned long long aln_id;
+        int NN;
+        std::vector<int32_t> po, pa;
+    };
+    std::vector<TreeSig> sig;
+    int sig_want_grad = -1, sig_block = 0, sig_K = 0, sig_R = 0;
+    // derived launch state kept with the cached topology
+    std::vector<TreeDev> trees;
+    std::vector<Schedule> scheds;
+    size_t topo_bytes = 0, off_trees = 0, off_ops = 0, off_rowbase = 0;
+    int n_tiles = 0, grid = 0, block = 0, n_rows = 0, n_slots = 0, n_stack = 0, max_br = 0;
+    long long total_out = 0, total_dyn = 0, total_ptab = 0, scratch_per_cta = 0, row_stride = 0;
+    size_t smem_bytes = 0;
+
+    mcp_stats stats{};
+};
+
+namespace {
+
+int fail(mcp_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    else g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(ctx, MCP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                     \
+    } while (0)
+
+int ensure_dev(mcp_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (ctx->pending_async) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->pending_async = false;
+    }
+    if (b.p) CUDA_TRY(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(ctx, MCP_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return 0;
+}
+int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CUDA_TRY(ctx, cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    CUDA_TRY(ctx, cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+template <int K>
+int launch_walk(mcp_ctx* ctx, const WalkParams& wp) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)ctx->smem_bytes));
+    felsenstein_walk<K><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
+}
+template <int K>
+int occupancy_for(mcp_ctx* ctx, int block, size_t smem, int* out) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K>, block, smem));
+    return 0;
+}
+
+#define MCP_DISPATCH_K(K, CALL)                      \
+    switch (K) {                                     \
+        case 2: { constexpr int KK = 2; CALL; break; } \
+        case 3: { constexpr int KK = 3; CALL; break; } \
+        case 4: { constexpr int KK = 4; CALL; break; } \
+        case 5: { constexpr int KK = 5; CALL; break; } \
+        case 6: { constexpr int KK = 6; CALL; break; } \
+        default: rc = MCP_ERR_UNSUPPORTED;           \
+    }
+
+bool k_supported(int K) { return K >= 2 && K <= 6; }
+
+struct BatchArgs {
+    int T;
+    const mcp_alignment* const* alns;
+    const int32_t* NN;
+    const int32_t* const* po;
+    const int32_t* const* pa;
+    const double* const* blv;
+    const double* const* U;
+    const double* const* D;
+    const double* const* Uinv;
+    const double* mu;
+    const double* const* rates;
+    int R;
+    const double* const* pi;
+    int want_grad;
+};
+
+// (Re)build schedules, tile/row assignment and the topology upload if anything structural changed.
+int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
+    const int T = a.T, R = a.R;
+    // choose the tile width first: it is part of the signature
+    long long total_cols = 0;
+    for (int t = 0; t < T; ++t) total_cols += a.alns[t]->S * R;
+    int block = ctx->opt_block;
+    if (block <= 0) {
+        block = 128;
+        while (block > 32 && (total_cols + block - 1) / block < 2LL * ctx->sm_count) block >>= 1;
+    }
+    bool same = (int)ctx->sig.size() == T && ctx->sig_want_grad == a.want_grad && ctx->sig_block == block &&
+                ctx->sig_K == K && ctx->sig_R == R;
+    for (int t = 0; same && t < T; ++t) {
+        const auto& s = ctx->sig[t];
+        same = s.aln_id == a.alns[t]->id && s.NN == a.NN[t] &&
+               std::memcmp(s.po.data(), a.po[t], sizeof(int32_t) * a.NN[t]) == 0 &&
+               std::memcmp(s.pa.data(), a.pa[t], sizeof(int32_t) * a.NN[t]) == 0;
+    }
+    *rebuilt = !same;
+    if (same) return 0;
+
+    ctx->sig.clear();
+    ctx->scheds.assign(T, Schedule());
+    ctx->trees.assign(T, TreeDev());
+    long long n_ops = 0, out_off = 0, dyn_off = 0, ptab_off = 0;
+    int tile_cursor = 0, n_slots = 1, n_stack = 1, max_br = 1;
+    std::vector<int32_t> leaf_row;
+    for (int t = 0; t < T; ++t) {
+        const mcp_alignment* al = a.alns[t];
+        const int NN = a.NN[t];
+        if (NN < 2) return fail(ctx, MCP_ERR_ARG, "tree %d: NN must be >= 2", t);
+        leaf_row.assign(NN, -1);
+        for (int i = 0; i < al->n_leaves; ++i) {
+            int num = al->leaf_nums[i];
+            if (num >= 1 && num <= NN) leaf_row[num - 1] = i;
+        }
+        std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, ctx->scheds[t]);
+        if (!err.empty()) return fail(ctx, MCP_ERR_ARG, "tree %d: %s", t, err.c_str());
+        const Schedule& sc = ctx->scheds[t];
+        TreeDev& td = ctx->trees[t];
+        td.post_off = n_ops;
+        n_ops += (long long)sc.post.size();
+        td.pre_off = n_ops;
+        n_ops += (long long)sc.pre.size();
+        td.n_post = (int)sc.post.size();
+        td.n_pre = (int)sc.pre.size();
+        td.NN = NN;
+        td.n_br = sc.n_dnodes;
+        td.codes = al->d_codes;
+        td.S = al->S;
+        td.code_stride = al->stride;
+        td.out_off = out_off;
+        out_off += NN;
+        td.dyn_off = dyn_off;
+        dyn_off += dyn_size(NN, K, R);
+        td.ptab_off = ptab_off;
+        ptab_off += (long long)sc.n_dnodes * R * pst(K);
+        td.tiles_per_rate = (int)((al->S + block - 1) / block);
+        td.tile_begin = tile_cursor;
+        long long nt = (long long)td.tiles_per_rate * R;
+        if (tile_cursor + nt > 0x7fffffffLL) return fail(ctx, MCP_ERR_ARG, "too many column tiles");
+        tile_cursor += (int)nt;
+        n_slots = std::max(n_slots, sc.n_slots);
+        n_stack = std::max(n_stack, sc.n_stack);
+        max_br = std::max(max_br, sc.n_dnodes);
+        mcp_ctx::TreeSig sg;
+        sg.aln_id = al->id;
+        sg.NN = NN;
+        sg.po.assign(a.po[t], a.po[t] + NN);
+        sg.pa.assign(a.pa[t], a.pa[t] + NN);
+        ctx->sig.push_back(std::move(sg));
+    }
+    ctx->sig_want_grad = a.want_grad;
+    ctx->sig_block = block;
+    ctx->sig_K = K;
+    ctx->sig_R = R;
+    ctx->n_tiles = tile_cursor;
+    ctx->block = block;
+    ctx->n_slots = n_slots;
+    ctx->n_stack = a.want_grad ? n_stack : 0;
+    ctx->max_br = max_br;
+    ctx->total_out = out_off;
+    ctx->total_dyn = dyn_off;
+    ctx->total_ptab = ptab_off;
+    ctx->smem_bytes = a.want_grad ? (size_t)max_br * sizeof(double) : 0;
+    if (ctx->smem_bytes > 200 * 1024)
+        return fail(ctx, MCP_ERR_UNSUPPORTED, "tree with %d nodes exceeds the shared-memory gradient accumulator", max_br);
+
+    // persistent grid
+    int occ = 0, rc = 0;
+    MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, ctx->smem_bytes, &occ));
+    if (rc) return rc == MCP_ERR_UNSUPPORTED ? fail(ctx, rc, "no kernel compiled for K = %d states", K) : rc;
+    if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d, smem %zu)", block, ctx->smem_bytes);
+    if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
+    ctx->grid = (int)std::min<long long>((long long)ctx->n_tiles, (long long)occ * ctx->sm_count);
+    if (ctx->grid < 1) ctx->grid = 1;
+
+    // accumulator rows: one per (CTA, tree) pair in CTA order (also tree order)
+    std::vector<int32_t> row_base(ctx->grid, 0);
+    {
+        const int q = ctx->n_tiles / ctx->grid, rem = ctx->n_tiles % ctx->grid;
+        int row = 0, ti = 0;
+        for (int t = 0; t < T; ++t) ctx->trees[t].row_lo = ctx->trees[t].row_hi = 0;
+        std::vector<char> seen(T, 0);
+        for (int c = 0; c < ctx->grid; ++c) {
+            int t0 = c * q + std::min(c, rem), t1 = t0 + q + (c < rem ? 1 : 0);
+            row_base[c] = row;
+            int tile = t0;
+            while (ti < T - 1 && tile >= ctx->trees[ti].tile_begin + R * ctx->trees[ti].tiles_per_rate) ++ti;
+            int tj = ti;
+            while (tile < t1) {
+                int tend = std::min(t1, ctx->trees[tj].tile_begin + R * ctx->trees[tj].tiles_per_rate);
+                if (!seen[tj]) { ctx->trees[tj].row_lo = row; seen[tj] = 1; }
+                ++row;
+                ctx->trees[tj].row_hi = row;
+                tile = tend;
+                ++tj;
+            }
+        }
+        ctx->n_rows = row;
+    }
+    ctx->row_stride = (max_br + 3) & ~3;
+    ctx->scratch_per_cta = (long long)(ctx->n_slots + ctx->n_stack) * block * K;
+
+    // topology upload: [TreeDev x T][ops][row_base]
+    ctx->off_trees = 0;
+    ctx->off_ops = (sizeof(TreeDev) * T + 31) & ~(size_t)31;
+    ctx->off_rowbase = ctx->off_ops + (size_t)n_ops * 32;
+    ctx->topo_bytes = ctx->off_rowbase + sizeof(int32_t) * ctx->grid;
+    int e;
+    if ((e = ensure_pin(ctx, ctx->h_topo, ctx->topo_bytes))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_topo, ctx->topo_bytes))) return e;
+    char* h = (char*)ctx->h_topo.p;
+    std::memcpy(h + ctx->off_trees, ctx->trees.data(), sizeof(TreeDev) * T);
+    char* ho = h + ctx->off_ops;
+    for (int t = 0; t < T; ++t) {
+        const Schedule& sc = ctx->scheds[t];
+        std::memcpy(ho, sc.post.data(), sc.post.size() * 32);
+        ho += sc.post.size() * 32;
+        std::memcpy(ho, sc.pre.data(), sc.pre.size() * 32);
+        ho += sc.pre.size() * 32;
+    }
+    std::memcpy(h + ctx->off_rowbase, row_base.data(), sizeof(int32_t) * ctx->grid);
+    return 0;
+}
+
+int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_out, double* const* grad_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (a.T < 1) return fail(ctx, MCP_ERR_ARG, "batch must hold at least one tree");
+    if (a.R < 1) return fail(ctx, MCP_ERR_ARG, "need at least one rate category");
+    for (int t = 0; t < a.T; ++t) {
+        if (!a.alns[t] || !a.po[t] || !a.pa[t] || !a.blv[t] || !a.U[t] || !a.D[t] || !a.Uinv[t] || !a.rates[t] || !a.pi[t])
+            return fail(ctx, MCP_ERR_ARG, "tree %d: null argument", t);
+        if (a.alns[t]->K != a.alns[0]->K) return fail(ctx, MCP_ERR_ARG, "all alignments of a batch must share K");
+    }
+    const int K = a.alns[0]->K, R = a.R, T = a.T;
+    if (!k_supported(K)) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->pending_async) {  // staging buffers may still be in flight
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->pending_async = false;
+    }
+    bool rebuilt = false;
+    int e = prepare_topology(ctx, a, K, &rebuilt);
+    if (e) { ctx->sig.clear(); return e; }
+
+    // buffers
+    if ((e = ensure_pin(ctx, ctx->h_dyn, sizeof(double) * ctx->total_dyn))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_dyn, sizeof(double) * ctx->total_dyn))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_ptab, sizeof(double) * ctx->total_ptab))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_scratch, sizeof(double) * ctx->scratch_per_cta * ctx->grid))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_rows, sizeof(double) * ctx->row_stride * ctx->n_rows))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_rows_ll, sizeof(LLRow) * ctx->n_rows))) return e;
+    double* d_out = d_out_user;
+    if (!d_out) {
+        if ((e = ensure_dev(ctx, ctx->d_out, sizeof(double) * ctx->total_out))) return e;
+        if ((e = ensure_pin(ctx, ctx->h_out, sizeof(double) * ctx->total_out))) return e;
+        d_out = (double*)ctx->d_out.p;
+    }
+
+    // per-evaluation parameters
+    double* hd = (double*)ctx->h_dyn.p;
+    for (int t = 0; t < T; ++t) {
+        const int NN = a.NN[t];
+        double* d = hd + ctx->trees[t].dyn_off;
+        std::memcpy(d + dyn_blv(NN), a.blv[t], sizeof(double) * (NN - 1));
+        std::memcpy(d + dyn_U(NN), a.U[t], sizeof(double) * K * K);
+        std::memcpy(d + dyn_D(NN, K), a.D[t], sizeof(double) * K);
+        std::memcpy(d + dyn_Uinv(NN, K), a.Uinv[t], sizeof(double) * K * K);
+        d[dyn_mu(NN, K)] = a.mu[t];
+        std::memcpy(d + dyn_rates(NN, K), a.rates[t], sizeof(double) * R);
+        std::memcpy(d + dyn_pi(NN, K, R), a.pi[t], sizeof(double) * K);
+    }
+
+    cudaStream_t st = ctx->stream;
+    mcp_stats& s = ctx->stats;
+    s = mcp_stats{};
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (rebuilt) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_topo.p, ctx->h_topo.p, ctx->topo_bytes, cudaMemcpyHostToDevice, st));
+        s.h2d_bytes += (int64_t)ctx->topo_bytes;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(double) * ctx->total_dyn, cudaMemcpyHostToDevice, st));
+    s.h2d_bytes += (int64_t)(sizeof(double) * ctx->total_dyn);
+
+    const TreeDev* d_trees = (const TreeDev*)((char*)ctx->d_topo.p + ctx->off_trees);
+    {
+        dim3 grid((ctx->max_br * R + 127) / 128, T);
+        build_transition_tables<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_dyn.p, (double*)ctx->d_ptab.p, K, R);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    WalkParams wp;
+    wp.trees = d_trees;
+    wp.ops = (const int4*)((char*)ctx->d_topo.p + ctx->off_ops);
+    wp.ptab = (const double*)ctx->d_ptab.p;
+    wp.dyn = (const double*)ctx->d_dyn.p;
+    wp.scratch = (double*)ctx->d_scratch.p;
+    wp.scratch_per_cta = ctx->scratch_per_cta;
+    wp.rows = (double*)ctx->d_rows.p;
+    wp.rows_ll = (LLRow*)ctx->d_rows_ll.p;
+    wp.cta_row_base = (const int*)((char*)ctx->d_topo.p + ctx->off_rowbase);
+    wp.row_stride = ctx->row_stride;
+    wp.n_slots = ctx->n_slots;
+    wp.n_stack = ctx->n_stack;
+    wp.n_tiles = ctx->n_tiles;
+    wp.T = T;
+    wp.R = R;
+    wp.want_grad = a.want_grad ? 1 : 0;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+    int rc = 0;
+    MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp));
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+    {
+        int maxNN = 0;
+        for (int t = 0; t < T; ++t) maxNN = std::max(maxNN, a.NN[t]);
+        dim3 grid((maxNN + 127) / 128, T);
+        finalize_results<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_rows.p, ctx->row_stride,
+                                               (const LLRow*)ctx->d_rows_ll.p, d_out, wp.want_grad);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    s.kernel_launches = 3;
+    s.grid = ctx->grid;
+    s.block = ctx->block;
+    s.tiles = ctx->n_tiles;
+    s.schedule_rebuilt = rebuilt ? 1 : 0;
+    s.scratch_bytes = (int64_t)ctx->d_scratch.cap;
+    if (d_out_user) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+        ctx->pending_async = true;
+        return 0;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * ctx->total_out, cudaMemcpyDeviceToHost, st));
+    s.d2h_bytes = (int64_t)(sizeof(double) * ctx->total_out);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    const double* ho = (const double*)ctx->h_out.p;
+    for (int t = 0; t < T; ++t) {
+        const double* o = ho + ctx->trees[t].out_off;
+        if (ll_out) ll_out[t] = o[0];
+        if (a.want_grad && grad_out && grad_out[t]) std::memcpy(grad_out[t], o + 1, sizeof(double) * (a.NN[t] - 1));
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) s.walk_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s.device_ms = ms;
+    return 0;
+}
+
+int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, const int32_t* leaf_nums,
+                   int n_leaves, mcp_alignment** out) {
+    mcp_alignment* al = new mcp_alignment();
+    al->K = K;
+    al->S = S;
+    al->stride = (S + 127) & ~127LL;
+    if (al->stride == 0) al->stride = 128;
+    al->n_leaves = n_leaves;
+    al->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
+    al->id = ctx->next_aln_id++;
+    size_t bytes = (size_t)al->stride * (size_t)std::max(n_leaves, 1);
+    cudaError_t e = cudaMalloc((void**)&al->d_codes, bytes);
+    if (e != cudaSuccess) {
+        delete al;
+        return fail(ctx, MCP_ERR_CUDA, "cudaMalloc of %zu bytes for the alignment failed: %s", bytes, cudaGetErrorString(e));
+    }
+    e = cudaMemset(al->d_codes, K, bytes);
+    if (e == cudaSuccess && S > 0 && n_leaves > 0)
+        e = cudaMemcpy2D(al->d_codes, (size_t)al->stride, codes, (size_t)S, (size_t)S, (size_t)n_leaves, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(al->d_codes);
+        delete al;
+        return fail(ctx, MCP_ERR_CUDA, "alignment upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = al;
+    return 0;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------------
+extern "C" {
+
+int mcp_abi_version(void) { return MCP_ABI_VERSION; }
+
+const char* mcp_last_error(const mcp_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int mcp_create(mcp_ctx** out, int device) {
+    if (!out) return fail(nullptr, MCP_ERR_ARG, "mcp_create: null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MCP_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, MCP_ERR_ARG, "device %d out of range (have %d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, MCP_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, MCP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, MCP_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    mcp_ctx* ctx = new mcp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    for (int i = 0; e == cudaSuccess && i < 4; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e != cudaSuccess) {
+        std::string msg = cudaGetErrorString(e);
+        delete ctx;
+        return fail(nullptr, MCP_ERR_CUDA, "stream/event creation failed: %s", msg.c_str());
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return 0;
+}
+
+int mcp_destroy(mcp_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_ptab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out})
+        if (b->p) cudaFree(b->p);
+    for (PinBuf* b : {&ctx->h_topo, &ctx->h_dyn, &ctx->h_out})
+        if (b->p) cudaFreeHost(b->p);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return 0;
+}
+
+int mcp_set_stream(mcp_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (ctx->pending_async) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->pending_async = false;
+    }
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return 0;
+}
+
+int mcp_set_launch(mcp_ctx* ctx, int block, int ctas_per_sm) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (block != 0 && (block < 32 || block > 256 || (block & 31)))
+        return fail(ctx, MCP_ERR_ARG, "block must be 0 or a multiple of 32 in [32, 256]");
+    if (ctas_per_sm < 0) return fail(ctx, MCP_ERR_ARG, "ctas_per_sm must be >= 0");
+    ctx->opt_block = block;
+    ctx->opt_ctas_per_sm = ctas_per_sm;
+    ctx->sig.clear();
+    return 0;
+}
+
+int mcp_alignment_from_codes(mcp_ctx* ctx, const uint8_t* codes, int K, int64_t S, const int32_t* leaf_nums,
+                             int n_leaves, mcp_alignment** out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!out || !codes || !leaf_nums) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_codes: null argument");
+    if (K < 1 || K > 254 || S < 0 || n_leaves < 1) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_codes: bad K/S/n_leaves");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return make_alignment(ctx, codes, K, S, leaf_nums, n_leaves, out);
+}
+
+int mcp_alignment_from_dense(mcp_ctx* ctx, const double* x, int K, int64_t S, int NN, const int32_t* leaf_nums,
+                             int n_leaves, mcp_alignment** out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!out || !x || !leaf_nums) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_dense: null argument");
+    if (K < 1 || K > 254 || S < 0 || n_leaves < 1 || NN < n_leaves) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_dense: bad sizes");
+    std::vector<unsigned char> codes((size_t)n_leaves * (size_t)S);
+    for (int l = 0; l < n_leaves; ++l) {
+        const int num = leaf_nums[l];
+        if (num < 1 || num > NN) return fail(ctx, MCP_ERR_ARG, "leaf number %d out of range", num);
+        const double* slab = x + (size_t)K * (size_t)S * (size_t)(num - 1);
+        for (int64_t s = 0; s < S; ++s) {
+            const double* col = slab + (size_t)K * s;
+            int ones = 0, zeros = 0, first = -1;
+            for (int k = 0; k < K; ++k) {
+                if (col[k] == 1.0) { ++ones; if (first < 0) first = k; }
+                else if (col[k] == 0.0) ++zeros;
+            }
+            unsigned char c;
+            if (ones == K) c = (unsigned char)K;
+            else if (ones == 1 && zeros == K - 1) c = (unsigned char)first;
+            else
+                return fail(ctx, MCP_ERR_DATA, "leaf %d, site %lld: column is neither one-hot nor all ones", num, (long long)s + 1);
+            codes[(size_t)l * S + s] = c;
+        }
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return make_alignment(ctx, codes.data(), K, S, leaf_nums, n_leaves, out);
+}
+
+int mcp_alignment_destroy(mcp_ctx* ctx, mcp_alignment* aln) {
+    if (!aln) return 0;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        ctx->pending_async = false;
+        ctx->sig.clear();
+    }
+    if (aln->d_codes) cudaFree(aln->d_codes);
+    delete aln;
+    return 0;
+}
+
+int mcp_eval(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num, const int32_t* parent_num,
+             const double* blv, const double* U, const double* D, const double* Uinv, double mu, const double* rates,
+             int R, const double* pi, int want_grad, double* ll_out, double* grad_out) {
+    BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
+    double* g = grad_out;
+    return eval_impl(ctx, a, nullptr, ll_out, &g);
+}
+
+int mcp_eval_device(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
+                    const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
+                    double mu, const double* rates, int R, const double* pi, int want_grad, double* d_out) {
+    if (!d_out) return fail(ctx, MCP_ERR_ARG, "mcp_eval_device: null device output pointer");
+    BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
+    return eval_impl(ctx, a, d_out, nullptr, nullptr);
+}
+
+int mcp_eval_batch(mcp_ctx* ctx, int T, const mcp_alignment* const* alns, const int32_t* NN,
+                   const int32_t* const* postorder_num, const int32_t* const* parent_num, const double* const* blv,
+                   const double* const* U, const double* const* D, const double* const* Uinv, const double* mu,
+                   const double* const* rates, int R, const double* const* pi, int want_grad, double* ll_out,
+                   double* const* grad_out) {
+    if (!alns || !NN || !postorder_num || !parent_num || !blv || !U || !D || !Uinv || !mu || !rates || !pi)
+        return fail(ctx, MCP_ERR_ARG, "mcp_eval_batch: null argument array");
+    BatchArgs a{T, alns, NN, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, R, pi, want_grad};
+    return eval_impl(ctx, a, nullptr, ll_out, grad_out);
+}
+
+int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {
+    if (!ctx || !out) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats: null argument");
+    *out = ctx->stats;
+    return 0;
+}
+
+int mcp_schedule_dump(int NN, const int32_t* postorder_num, const int32_t* parent_num, const int32_t* leaf_row,
+                      int want_grad, int32_t* post_ops, int cap_post, int32_t* pre_ops, int cap_pre, int32_t* info) {
+    if (!postorder_num || !parent_num || !leaf_row || !info) return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: null argument");
+    Schedule sc;
+    std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, want_grad != 0, sc);
+    if (!err.empty()) return fail(nullptr, MCP_ERR_ARG, "%s", err.c_str());
+    info[0] = (int32_t)sc.post.size();
+    info[1] = (int32_t)sc.pre.size();
+    info[2] = sc.n_slots;
+    info[3] = sc.n_stack;
+    info[4] = sc.n_dnodes;
+    if ((int)sc.post.size() > cap_post || (int)sc.pre.size() > cap_pre)
+        return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: output arrays too small");
+    if (post_ops) std::memcpy(post_ops, sc.post.data(), sc.post.size() * 32);
+    if (pre_ops) std::memcpy(pre_ops, sc.pre.data(), sc.pre.size() * 32);
+    return 0;
+}
+
+}  // extern "C"

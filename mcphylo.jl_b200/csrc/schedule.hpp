@@ -1,0 +1,247 @@
+// schedule.hpp — host-side compiler from a tree topology to the flat "walk program" the
+// device executes.  Pure C++ (no CUDA) so it can be exercised without a GPU
+// (mcp_schedule_dump, tests/test_schedule_emulator.py).
+//
+// Every alignment column is owned by ONE thread for the whole evaluation: the thread walks all
+// nodes itself, so the program is a straight list of ops with no inter-thread dependencies.
+// The reference walks the same nodes one dense array at a time
+// (/root/reference/src/Likelihood/LikelihoodCalculator_Node.jl:92-111 post-order,
+//  :25-74 reverse post-order); the traversal ORDER here is chosen for locality, the arithmetic
+// per node is the reference's.
+//
+// Device tree: strictly binary.  A node with k >= 3 children (the reference's tests have a
+// trifurcating root) is folded left into k-2 virtual nodes on identity branches, which keeps
+// the reference's product order ((D1*D2)*D3..); a node with one child gets a virtual all-ones
+// leaf on an identity branch.  Virtual branches have P = I, dP = 0 and no gradient output.
+//
+// POST program, one op per internal device node, executed in an order where the child with the
+// larger subtree comes first.  Then the second child (if internal) is always the op executed
+// immediately before (operand kind REG, still in registers) and only the first child may have
+// to be re-read (kind MEM).  In gradient mode every non-root result is stored (slot = op
+// index) because the pre pass needs it; in logL-only mode only results that will be re-read
+// are stored, into a LIFO of depth <= log2(N)+1.
+//
+// PRE program (gradient mode), one op per internal device node = one family {mother, a, b}:
+//   Da = P_a L_a, Db = P_b L_b, qa = pre_m * Db, qb = pre_m * Da, den = sum pre_m*Da*Db,
+//   grad_a += qa.(dP_a L_a)/den, grad_b likewise, pre_a = P_a^T qa, pre_b = P_b^T qb.
+// Depth-first, descending into the child with the SMALLER subtree first (its pre vector stays
+// in registers: KEEP); the other internal child is pushed on a LIFO (PUSH) of depth
+// <= log2(N)+1 and popped when the walk comes back.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mcp {
+
+enum : int { OPK_LEAF = 0, OPK_REG = 1, OPK_MEM = 2 };          // post operand kinds
+enum : int { PREM_ROOT = 0, PREM_REG = 1, PREM_STACK = 2 };     // where pre[mother] comes from
+enum : int { OUT_NONE = 0, OUT_KEEP = 1, OUT_PUSH = 2 };        // what happens to pre[child]
+
+// 8 x int32 each.
+struct PostOp {
+    int32_t a_src, a_br, b_src, b_br;  // LEAF: alignment row (-1 = all ones); MEM: slot; REG: unused
+    int32_t dst;                       // slot to store the result in (if STORE)
+    int32_t flags;                     // bits 0-1 a kind, 2-3 b kind, 4 STORE, 5 ROOT
+    int32_t node;                      // device node id (debug / emulator)
+    int32_t pad;
+};
+struct PreOp {
+    int32_t m_src;                     // STACK: lifo slot
+    int32_t a_src, a_br, b_src, b_br;  // LEAF: alignment row; internal: post slot of the child
+    int32_t a_dst, b_dst;              // PUSH: lifo slot
+    int32_t flags;                     // bits 0-1 m kind, 2 a internal, 3 b internal, 4-5 a out, 6-7 b out
+};
+static_assert(sizeof(PostOp) == 32 && sizeof(PreOp) == 32, "ops are two 16-byte words");
+
+constexpr int POST_STORE = 1 << 4, POST_ROOT = 1 << 5;
+
+struct Schedule {
+    std::vector<PostOp> post;
+    std::vector<PreOp> pre;
+    int n_dnodes = 0;   // device nodes = NN + virtual ones; also the number of branch-table rows
+    int n_slots = 0;    // post result slots needed per column
+    int n_stack = 0;    // pre LIFO depth needed per column
+    int n_real_branches = 0;  // NN-1
+};
+
+// leaf_row[num-1] = alignment row for leaves (must be >= 0 for every childless node).
+// Returns "" on success, else an error message.
+inline std::string build_schedule(int NN, const int32_t* postorder_num, const int32_t* parent_num,
+                                  const int32_t* leaf_row, bool want_grad, Schedule& out) {
+    if (NN < 2) return "tree must have at least two nodes";
+    if (postorder_num[NN - 1] != NN) return "root must come last in post-order and carry num == NN";
+    std::vector<int> pos(NN, -1);
+    for (int i = 0; i < NN; ++i) {
+        int num = postorder_num[i];
+        if (num < 1 || num > NN) return "postorder_num out of range";
+        if (pos[num - 1] >= 0) return "postorder_num has duplicates";
+        pos[num - 1] = i;
+    }
+    if (parent_num[NN - 1] != 0) return "root must have parent 0";
+    std::vector<int> nchild(NN, 0), cstart(NN + 1, 0);
+    for (int n = 0; n < NN - 1; ++n) {
+        int p = parent_num[n];
+        if (p < 1 || p > NN) return "parent_num out of range";
+        if (pos[p - 1] <= pos[n]) return "a mother must come after her children in post-order";
+        nchild[p - 1]++;
+    }
+    for (int n = 0; n < NN; ++n) cstart[n + 1] = cstart[n] + nchild[n];
+    std::vector<int> clist(NN > 1 ? NN - 1 : 1), cfill(NN, 0);
+    for (int i = 0; i < NN; ++i) {  // stored child order == order of appearance in post-order
+        int n = postorder_num[i] - 1;
+        int p = parent_num[n];
+        if (p > 0) clist[cstart[p - 1] + cfill[p - 1]++] = n;
+    }
+
+    // ---- binarise -------------------------------------------------------------------------
+    struct DNode { int left = -1, right = -1, row = -1, isize = 0; };
+    std::vector<DNode> dn(NN);
+    dn.reserve(2 * NN);
+    for (int n = 0; n < NN; ++n) {
+        int k = nchild[n];
+        const int* ch = clist.data() + cstart[n];
+        if (k == 0) {
+            if (leaf_row[n] < 0) return "leaf node " + std::to_string(n + 1) + " has no alignment row";
+            dn[n].row = leaf_row[n];
+        } else if (k == 1) {
+            DNode one;  // virtual all-ones leaf on an identity branch
+            one.row = -1;
+            dn.push_back(one);
+            dn[n].left = ch[0];
+            dn[n].right = (int)dn.size() - 1;
+        } else {
+            int acc = ch[0];
+            for (int i = 1; i < k - 1; ++i) {
+                DNode v;
+                v.left = acc;
+                v.right = ch[i];
+                dn.push_back(v);
+                acc = (int)dn.size() - 1;
+            }
+            dn[n].left = acc;
+            dn[n].right = ch[k - 1];
+        }
+    }
+    const int ND = (int)dn.size();
+    const int root = NN - 1;
+    auto is_leaf = [&](int d) { return dn[d].left < 0; };
+
+    // ---- subtree sizes (internal device nodes), iterative post-order ----------------------
+    std::vector<int> order;  // generic post-order of internal nodes, for isize
+    order.reserve(ND);
+    {
+        std::vector<std::pair<int, int>> st;
+        st.push_back({root, 0});
+        while (!st.empty()) {
+            auto& [d, state] = st.back();
+            if (is_leaf(d)) { st.pop_back(); continue; }
+            if (state == 0) { state = 1; int c = dn[d].left; st.push_back({c, 0}); }
+            else if (state == 1) { state = 2; int c = dn[d].right; st.push_back({c, 0}); }
+            else { dn[d].isize = 1 + dn[dn[d].left].isize + dn[dn[d].right].isize; order.push_back(d); st.pop_back(); }
+        }
+    }
+
+    out = Schedule();
+    out.n_dnodes = ND;
+    out.n_real_branches = NN - 1;
+    const int n_int = (int)order.size();
+    out.post.reserve(n_int);
+    std::vector<int> slot_of(ND, -1);  // where a node's post result lives
+
+    // ---- POST program: larger subtree first --------------------------------------------------
+    {
+        std::vector<std::pair<int, int>> st;
+        st.push_back({root, 0});
+        int last_emitted = -1, depth = 0, max_depth = 0;
+        while (!st.empty()) {
+            auto [d, state] = st.back();
+            if (is_leaf(d)) { st.pop_back(); continue; }
+            int l = dn[d].left, r = dn[d].right;
+            bool left_first = dn[l].isize >= dn[r].isize;
+            int first = left_first ? l : r, second = left_first ? r : l;
+            if (state == 0) { st.back().second = 1; st.push_back({first, 0}); continue; }
+            if (state == 1) {
+                st.back().second = 2;
+                // logL-only: the first child's result must be parked if the second child's
+                // subtree will overwrite the registers
+                if (!want_grad && !is_leaf(first) && !is_leaf(second)) {
+                    PostOp& fop = out.post[slot_of[first]];  // slot_of holds the op index for now
+                    fop.flags |= POST_STORE;
+                    fop.dst = depth++;
+                    if (depth > max_depth) max_depth = depth;
+                }
+                st.push_back({second, 0});
+                continue;
+            }
+            st.pop_back();
+            PostOp op{};
+            op.node = d;
+            auto operand = [&](int c, int32_t& src, int32_t& br) -> int {
+                br = c;
+                if (is_leaf(c)) { src = dn[c].row; return OPK_LEAF; }
+                if (c == last_emitted) { src = 0; return OPK_REG; }
+                src = want_grad ? slot_of[c] : out.post[slot_of[c]].dst;
+                return OPK_MEM;
+            };
+            int ka = operand(l, op.a_src, op.a_br);
+            int kb = operand(r, op.b_src, op.b_br);
+            op.flags = ka | (kb << 2);
+            if (!want_grad && (ka == OPK_MEM || kb == OPK_MEM)) depth--;  // LIFO pop
+            if (d == root) op.flags |= POST_ROOT;
+            int idx = (int)out.post.size();
+            if (want_grad) {
+                if (d != root) { op.flags |= POST_STORE; op.dst = idx; }
+            }
+            slot_of[d] = idx;
+            out.post.push_back(op);
+            last_emitted = d;
+        }
+        out.n_slots = want_grad ? (int)out.post.size() : max_depth;
+        if (out.n_slots < 1) out.n_slots = 1;
+    }
+
+    // ---- PRE program: smaller subtree first, the other child parked on a LIFO ----------------
+    if (want_grad) {
+        out.pre.reserve(n_int);
+        struct Pending { int node, slot; };
+        std::vector<Pending> pending;
+        int level = 0, max_level = 0;
+        int cur = root, cur_kind = PREM_ROOT, cur_src = 0;
+        while (true) {
+            PreOp op{};
+            int a = dn[cur].left, b = dn[cur].right;
+            op.m_src = cur_src;
+            op.a_br = a; op.b_br = b;
+            bool ai = !is_leaf(a), bi = !is_leaf(b);
+            op.a_src = ai ? slot_of[a] : dn[a].row;
+            op.b_src = bi ? slot_of[b] : dn[b].row;
+            int a_out = OUT_NONE, b_out = OUT_NONE;
+            int next = -1;
+            if (cur_kind == PREM_STACK) level--;  // popped; this op may reuse the slot
+            if (ai && bi) {
+                bool a_small = dn[a].isize <= dn[b].isize;
+                int keep = a_small ? a : b, push = a_small ? b : a;
+                (a_small ? a_out : b_out) = OUT_KEEP;
+                (a_small ? b_out : a_out) = OUT_PUSH;
+                (a_small ? op.b_dst : op.a_dst) = level;
+                pending.push_back({push, level});
+                level++;
+                if (level > max_level) max_level = level;
+                next = keep;
+            } else if (ai) { a_out = OUT_KEEP; next = a; }
+            else if (bi) { b_out = OUT_KEEP; next = b; }
+            op.flags = cur_kind | (ai ? 4 : 0) | (bi ? 8 : 0) | (a_out << 4) | (b_out << 6);
+            out.pre.push_back(op);
+            if (next >= 0) { cur = next; cur_kind = PREM_REG; cur_src = 0; }
+            else if (!pending.empty()) {
+                Pending p = pending.back(); pending.pop_back();
+                cur = p.node; cur_kind = PREM_STACK; cur_src = p.slot;
+            } else break;
+        }
+        out.n_stack = max_level < 1 ? 1 : max_level;
+    }
+    return "";
+}
+
+}  // namespace mcp

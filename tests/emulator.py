@@ -1,0 +1,86 @@
+"""numpy emulator of the device walk program (csrc/schedule.hpp op semantics, the arithmetic of
+felsenstein_walk in csrc/mcphylo_b200.cu) — lets the host scheduler be checked without a GPU.
+All columns are processed at once as arrays; `reg` plays the per-thread register `cur`."""
+import numpy as np
+
+OPK_LEAF, OPK_REG, OPK_MEM = 0, 1, 2
+PREM_ROOT, PREM_REG, PREM_STACK = 0, 1, 2
+OUT_NONE, OUT_KEEP, OUT_PUSH = 0, 1, 2
+
+
+def _rescale(v):
+    m = v.max(axis=0)
+    _, e = np.frexp(m)           # m = f * 2**e, f in [0.5, 1)
+    e = e - 1                    # bring the max into [1, 2)
+    return v * np.ldexp(1.0, -e)[None, :], e
+
+
+def run_program(prog, codes, K, P, dP, pi, n_real_branches):
+    """prog: capi.schedule_dump output.  codes (rows, S) uint8.  P, dP: (K, K, R, NB) Fortran
+    arrays [s_parent, s_child, r, branch] for the REAL branches.  Returns (ll, grad_dev) with
+    grad_dev indexed by device branch id."""
+    R = P.shape[2]
+    S = codes.shape[1]
+    nd = prog["n_dnodes"]
+
+    def tables(br, r):
+        if br < n_real_branches:
+            return P[:, :, r, br], dP[:, :, r, br]
+        return np.eye(K), np.zeros((K, K))
+
+    def leaf_down(T, row):
+        # column pick, all-ones -> row sums
+        ext = np.concatenate([T, T.sum(axis=1, keepdims=True)], axis=1)   # (K, K+1)
+        c = np.full(S, K) if row < 0 else np.minimum(codes[row].astype(int), K)
+        return ext[:, c]
+
+    ll = 0.0
+    grad = np.zeros(nd)
+    for r in range(R):
+        slots = {}
+        reg = np.ones((K, S))
+        esum = np.zeros(S, dtype=np.int64)
+        for op in prog["post"]:
+            a_src, a_br, b_src, b_br, dst, flags = (int(v) for v in op[:6])
+
+            def down(kind, src, br):
+                Pm, _ = tables(br, r)
+                if kind == OPK_LEAF:
+                    return leaf_down(Pm, src)
+                L = reg if kind == OPK_REG else slots[src]
+                return Pm @ L
+            Da = down(flags & 3, a_src, a_br)
+            Db = down((flags >> 2) & 3, b_src, b_br)
+            reg, e = _rescale(Da * Db)
+            esum += e
+            if flags & 16:
+                slots[dst] = reg
+        ll += (esum * np.log(2.0) + np.log(pi @ reg)).sum()
+
+        stack = {}
+        for op in prog["pre"]:
+            m_src, a_src, a_br, b_src, b_br, a_dst, b_dst, flags = (int(v) for v in op)
+            mk = flags & 3
+            pm = np.repeat(pi[:, None], S, axis=1) if mk == PREM_ROOT else (reg if mk == PREM_REG else stack[m_src])
+
+            def child(internal, src, br):
+                Pm, dPm = tables(br, r)
+                if internal:
+                    L = slots[src]
+                    return Pm @ L, dPm @ L, Pm
+                return leaf_down(Pm, src), leaf_down(dPm, src), Pm
+            Da, Ya, Pa = child(flags & 4, a_src, a_br)
+            Db, Yb, Pb = child(flags & 8, b_src, b_br)
+            qa, qb = pm * Db, pm * Da
+            den = (qa * Da).sum(axis=0)
+            grad[a_br] += ((qa * Ya).sum(axis=0) / den).sum()
+            grad[b_br] += ((qb * Yb).sum(axis=0) / den).sum()
+            for out, dst, Pm, q in (((flags >> 4) & 3, a_dst, Pa, qa), ((flags >> 6) & 3, b_dst, Pb, qb)):
+                if out == OUT_NONE:
+                    continue
+                v, _ = _rescale(Pm.T @ q)
+                if out == OUT_KEEP:
+                    reg = v
+                else:
+                    stack[dst] = v
+    return ll, grad

@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (capi / PhyloDist API), against the
+CPU oracle on identical trees and alignments, against the reference's goldens, and — at sizes the
+oracle cannot hold — through size-independent properties.
+
+Tolerances (BASELINE.json north_star): logL relative error <= 1e-10, every gradient component
+relative error <= 1e-8 (absolute 1e-8 * max|grad| floor for components that cancel to ~0)."""
+import numpy as np
+import pytest
+
+import mcphylo_jl_b200 as mcp
+from conftest import golden_case
+from synth import random_tree, simulate_codes
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-10
+GRAD_RTOL = 1e-8
+
+
+def _model(K, pi, rng):
+    if K == 2:
+        return mcp.Restriction, pi, np.zeros(1)
+    if K == 4:
+        return mcp.GTR, pi, rng.uniform(0.5, 2.5, size=6)
+    return mcp.JC, pi, np.zeros(1)
+
+
+def _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates, want_grad=True):
+    ft = mcp.flatten(tree)
+    x = oracle.codes_to_dense(codes, leaf_nums, K, ft.NN)
+    U, D, Uinv, mu = model(np.asarray(pi, float), np.asarray(srates, float))
+    return oracle.felsenstein(x, ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu,
+                              np.asarray(rates, float), np.asarray(pi, float), want_grad, 0)
+
+
+def _check(ll, g, ll_o, g_o):
+    assert abs(ll - ll_o) <= LL_RTOL * abs(ll_o), (ll, ll_o)
+    if g_o is not None:
+        scale = np.max(np.abs(g_o))
+        assert np.all(np.abs(g - g_o) <= GRAD_RTOL * np.maximum(np.abs(g_o), 1e-3 * scale)), \
+            np.max(np.abs(g - g_o) / np.maximum(np.abs(g_o), 1e-3 * scale))
+
+
+def test_primates_golden_dense_input():
+    tree, x, _, _, fx = golden_case("primates")
+    pd = mcp.PhyloDist(tree, fx["base_freq"], [1.0], [1.0], mcp.JC)
+    assert pd.size() == tuple(fx["size"])
+    ll = mcp.logpdf(pd, x)
+    assert abs(ll - fx["logpdf"]) <= LL_RTOL * abs(ll)
+    ll2, grad = mcp.gradlogpdf(pd, x)
+    assert abs(ll2 - fx["logpdf"]) <= LL_RTOL * abs(ll)
+    assert grad.shape == (21,) and np.all(np.isfinite(grad))
+
+
+def test_simudata_golden_gradient(oracle):
+    tree, x, codes, leaf_nums, fx = golden_case("simudata")
+    pd = mcp.PhyloDist(tree, fx["base_freq"], [1.0], [1.0], mcp.JC)
+    ll, grad = mcp.gradlogpdf(pd, x)
+    assert np.max(np.abs(grad - fx["grad"]) / np.abs(fx["grad"])) <= GRAD_RTOL
+    assert abs(ll - fx["logpdf_loose"]) <= fx["logpdf_rtol"] * abs(ll)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.JC, fx["base_freq"], [1.0], [1.0])
+    _check(ll, grad, ll_o, g_o)
+    # compact codes give the same answer as the dense array
+    ll_c, grad_c = mcp.gradlogpdf(pd, mcp.DeviceAlignment(codes, leaf_nums, 4))
+    assert ll_c == ll and np.array_equal(grad_c, grad)
+
+
+def test_multiple_phylodist_golden():
+    tree, x, _, _, fx = golden_case("primates")
+    mpd = mcp.MultiplePhyloDist([tree, tree], np.full((4, 2), 0.25), np.ones((1, 2)), np.ones((1, 2)), mcp.JC)
+    assert mpd.size() == (4, 1, 22, 2)
+    mdf = np.asfortranarray(np.stack([x, x], axis=3))
+    assert abs(mcp.logpdf(mpd, mdf) - 2 * fx["logpdf"]) <= LL_RTOL * abs(2 * fx["logpdf"])
+    res = mcp.multi_gradlogpdf(mpd, mdf)
+    assert len(res) == 2
+    for ll, g in res:
+        assert abs(ll - fx["logpdf"]) <= LL_RTOL * abs(ll) and g.shape == (21,)
+    assert np.array_equal(res[0][1], res[1][1])
+    with pytest.raises(mcp.DimensionMismatch):
+        mcp.MultiplePhyloDist([tree, tree], np.full((4, 3), 0.25), [1.0], [1.0], mcp.JC)
+    with pytest.raises(mcp.DimensionMismatch):
+        mcp.MultiplePhyloDist([tree, tree], np.full((4, 2), 0.25), np.ones((1, 3)), [1.0], mcp.JC)
+
+
+@pytest.mark.parametrize("n_taxa,K,R,S,seed,multi,unary", [
+    (10, 2, 1, 1000, 20241, False, False),     # BASELINE config 1 shape
+    (50, 2, 1, 4000, 20242, False, False),     # config 2 shape (sites subsampled)
+    (200, 4, 4, 600, 20243, False, False),     # config 3 shape (sites subsampled)
+    (37, 4, 2, 257, 7, True, False),           # trifurcations, ragged tile
+    (23, 3, 3, 130, 8, True, True),            # K=3, unary node
+    (2, 4, 1, 33, 9, False, False),            # smallest tree
+    (64, 5, 1, 100, 10, False, False),
+    (16, 6, 2, 64, 12, False, False),
+    (300, 2, 1, 31, 11, False, False),         # fewer sites than one warp
+])
+def test_random_cases_vs_oracle(oracle, n_taxa, K, R, S, seed, multi, unary):
+    rng = np.random.default_rng(seed)
+    tree = random_tree(n_taxa, rng, multifurcate=multi, unary=unary)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, S, rng, gap_frac=0.05)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll, grad = mcp.gradlogpdf(pd, aln)
+    ll_only = mcp.logpdf(pd, aln)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    _check(ll, grad, ll_o, g_o)
+    _check(ll_only, None, ll_o, None)
+
+
+def test_every_launch_shape_agrees(oracle):
+    rng = np.random.default_rng(3)
+    tree = random_tree(40, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 3000, rng)
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates)
+    ctx = mcp.get_context()
+    try:
+        for block, ctas in [(32, 1), (64, 0), (128, 2), (256, 0), (256, 1)]:
+            ctx.set_launch(block, ctas)
+            ll, g = mcp.gradlogpdf(pd, aln)
+            _check(ll, g, ll_o, g_o)
+            assert ctx.stats()["block"] == block
+    finally:
+        ctx.set_launch(0, 0)
+
+
+def test_topology_cache_and_branch_updates(oracle):
+    """Same topology, new branch lengths (the leapfrog pattern), then an NNI."""
+    rng = np.random.default_rng(21)
+    tree = random_tree(30, rng)
+    pi = np.array([0.3, 0.7])
+    codes, leaf_nums = simulate_codes(tree, mcp.Restriction(pi, []), pi, np.ones(1), 500, rng)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, 2)
+    ctx = mcp.get_context()
+    for it in range(3):
+        blv = np.clip(rng.exponential(0.1, size=58), 1e-4, 1.0)
+        mcp.set_branchlength_vector(tree, blv)
+        pd = mcp.PhyloDist(tree, pi, [0.0], [1.0], mcp.Restriction)
+        ll, g = mcp.gradlogpdf(pd, aln)
+        assert ctx.stats()["schedule_rebuilt"] == (1 if it == 0 else 0)
+        _check(ll, g, *_oracle_eval(oracle, tree, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0]))
+    target = next(n for n in mcp.post_order(tree) if n.nchild == 2 and not n.root and n.mother.nchild == 2)
+    assert mcp.NNI(tree, target) == 1
+    pd = mcp.PhyloDist(tree, pi, [0.0], [1.0], mcp.Restriction)
+    ll, g = mcp.gradlogpdf(pd, aln)
+    assert ctx.stats()["schedule_rebuilt"] == 1
+    _check(ll, g, *_oracle_eval(oracle, tree, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0]))
+
+
+def test_batch_of_distinct_trees(oracle):
+    """MultiplePhyloDist shape of BASELINE config 5, scaled down: distinct topologies, own data."""
+    rng = np.random.default_rng(5000)
+    pi = np.array([0.3, 0.7])
+    trees, alns, expect = [], [], []
+    for i in range(7):
+        t = random_tree(12 + 3 * i, rng)
+        codes, leaf_nums = simulate_codes(t, mcp.Restriction(pi, []), pi, np.ones(1), 700, rng)
+        trees.append(t)
+        alns.append(mcp.DeviceAlignment(codes, leaf_nums, 2))
+        expect.append(_oracle_eval(oracle, t, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0]))
+    mpd = mcp.MultiplePhyloDist(trees, pi, [0.0], [1.0], mcp.Restriction)
+    res = mcp.multi_gradlogpdf(mpd, alns)
+    for (ll, g), (ll_o, g_o) in zip(res, expect):
+        _check(ll, g, ll_o, g_o)
+    total = mcp.logpdf(mpd, alns)
+    assert abs(total - sum(e[0] for e in expect)) <= LL_RTOL * abs(total)
+
+
+def test_finite_differences_on_device():
+    rng = np.random.default_rng(77)
+    tree = random_tree(9, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 200, rng)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    ll, g = mcp.gradlogpdf(mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR), aln)
+    blv = mcp.get_branchlength_vector(tree)
+    for b in range(blv.size):
+        vals = []
+        for sgn in (1, -1):
+            t = blv.copy()
+            t[b] += sgn * 1e-6
+            mcp.set_branchlength_vector(tree, t)
+            vals.append(mcp.logpdf(mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR), aln))
+        mcp.set_branchlength_vector(tree, blv)
+        assert abs((vals[0] - vals[1]) / 2e-6 - g[b]) <= 2e-6 * max(1.0, abs(g[b]))
+
+
+def test_large_properties_without_oracle():
+    """Sizes the dense oracle cannot hold: additivity over site blocks (the multi-GPU sharding
+    identity), invariance to the launch shape, and rate-category additivity."""
+    rng = np.random.default_rng(20244)
+    n_taxa, S = 1000, 20000
+    tree = random_tree(n_taxa, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, S, rng)
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    full = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    ll, g = mcp.gradlogpdf(pd, full)
+    assert np.isfinite(ll) and np.all(np.isfinite(g)) and g.shape == (2 * n_taxa - 2,)
+    # site blocks add up
+    parts = [mcp.gradlogpdf(pd, full.site_block(lo, hi)) for lo, hi in [(0, 7001), (7001, 7002), (7002, S)]]
+    assert abs(sum(p[0] for p in parts) - ll) <= 1e-12 * abs(ll)
+    gs = sum(p[1] for p in parts)
+    assert np.all(np.abs(gs - g) <= 1e-10 * np.maximum(np.abs(g), 1e-3 * np.max(np.abs(g))))
+    # rate categories are independent replicas (reference semantics: no mixing)
+    per_rate = [mcp.gradlogpdf(mcp.PhyloDist(tree, pi, sr, [r], mcp.GTR), full) for r in rates]
+    assert abs(sum(p[0] for p in per_rate) - ll) <= 1e-12 * abs(ll)
+    # logL-only path (recycled slots) equals the gradient path's logL
+    assert abs(mcp.logpdf(pd, full) - ll) <= 1e-13 * abs(ll)
+
+
+def test_error_paths():
+    tree, x, codes, leaf_nums, fx = golden_case("simudata")
+    pd = mcp.PhyloDist(tree, fx["base_freq"], [1.0], [1.0], mcp.JC)
+    bad = x.copy(order="F")
+    bad[:, 3, 0] = 0.5
+    with pytest.raises(mcp.capi.McpError) as ei:
+        mcp.logpdf(pd, bad)
+    assert ei.value.code == -4
+    with pytest.raises(mcp.DimensionMismatch):
+        mcp.logpdf(mcp.PhyloDist(tree, [0.5, 0.5], [1.0], [1.0], mcp.Restriction), x)
+    # an alignment that lacks one of the tree's leaves
+    with pytest.raises(mcp.capi.McpError) as ei:
+        mcp.logpdf(pd, mcp.DeviceAlignment(codes[:-1], leaf_nums[:-1], 4))
+    assert ei.value.code == -1
+    # 20 states: no compiled kernel, reported not crashed
+    t2 = mcp.ParseNewick("(a:0.1,b:0.2);")
+    with pytest.raises(mcp.capi.McpError) as ei:
+        mcp.logpdf(mcp.PhyloDist(t2, np.full(20, 0.05), [1.0], [1.0], mcp.JC),
+                   mcp.DeviceAlignment(np.zeros((2, 5), np.uint8), [1, 2], 20))
+    assert ei.value.code == -3

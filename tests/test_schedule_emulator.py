@@ -1,0 +1,106 @@
+"""The host scheduler (csrc/schedule.hpp through mcp_schedule_dump) checked on CPU: its walk
+program, executed by a numpy emulator of the kernel's arithmetic, must reproduce the oracle and
+the reference goldens.  Also checks the structural promises the kernel relies on."""
+import numpy as np
+import pytest
+
+import mcphylo_jl_b200 as mcp
+from mcphylo_jl_b200 import capi
+from conftest import golden_case
+from emulator import run_program
+from synth import random_tree, simulate_codes
+
+
+def _leaf_row(ft, leaf_nums):
+    lr = np.full(ft.NN, -1, dtype=np.int32)
+    for i, n in enumerate(leaf_nums):
+        lr[n - 1] = i
+    return lr
+
+
+def _emulate(oracle, tree, codes, leaf_nums, model_out, rates, pi, want_grad=True):
+    ft = mcp.flatten(tree)
+    U, D, Uinv, mu = model_out
+    P, dP = oracle.transition(U, D, Uinv, mu, np.asarray(rates, float), ft.blv, want_dP=True)
+    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, _leaf_row(ft, leaf_nums), want_grad)
+    ll, g = run_program(prog, codes, len(D), P, dP, np.asarray(pi, float), ft.NN - 1)
+    return ll, g[:ft.NN - 1], prog, ft
+
+
+def test_goldens_through_the_schedule(oracle):
+    tree, x, codes, leaf_nums, fx = golden_case("primates")
+    ll, _, prog, ft = _emulate(oracle, tree, codes, leaf_nums, mcp.JC(fx["base_freq"], [1.0]), [1.0], fx["base_freq"])
+    assert abs(ll - fx["logpdf"]) <= 1e-12 * abs(ll)
+    assert prog["n_dnodes"] == ft.NN + 1            # one virtual node for the trifurcating root
+
+    tree, x, codes, leaf_nums, fx = golden_case("simudata")
+    ll, g, _, _ = _emulate(oracle, tree, codes, leaf_nums, mcp.JC(fx["base_freq"], [1.0]), [1.0], fx["base_freq"])
+    assert np.max(np.abs(g - fx["grad"]) / np.abs(fx["grad"])) <= 1e-11
+
+
+@pytest.mark.parametrize("n_taxa,K,R,seed", [(2, 2, 1, 0), (3, 4, 2, 1), (17, 2, 1, 2), (40, 4, 4, 3), (64, 3, 2, 4)])
+def test_random_trees_match_oracle(oracle, n_taxa, K, R, seed):
+    rng = np.random.default_rng(seed)
+    tree = random_tree(n_taxa, rng, multifurcate=(seed % 2 == 1), unary=(seed == 3))
+    pi = rng.dirichlet(np.ones(K) * 5)
+    if K == 2:
+        model = mcp.Restriction(pi, [])
+    elif K == 4:
+        model = mcp.GTR(pi, rng.uniform(0.5, 2.0, size=6))
+    else:
+        model = mcp.JC(pi, [])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model, pi, rates, 37, rng, gap_frac=0.1)
+    ft = mcp.flatten(tree)
+    x = oracle.codes_to_dense(codes, leaf_nums, K, ft.NN)
+    U, D, Uinv, mu = model
+    ll_o, g_o = oracle.felsenstein(x, ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, rates, pi, True, 1)
+    ll, g, prog, _ = _emulate(oracle, tree, codes, leaf_nums, model, rates, pi)
+    assert abs(ll - ll_o) <= 1e-11 * abs(ll_o)
+    assert np.allclose(g, g_o, rtol=1e-9, atol=1e-9)
+    # logL-only program (LIFO slots) gives the same value
+    ll2, _, prog2, _ = _emulate(oracle, tree, codes, leaf_nums, model, rates, pi, want_grad=False)
+    assert abs(ll2 - ll_o) <= 1e-11 * abs(ll_o)
+    assert len(prog2["pre"]) == 0
+    assert prog2["n_slots"] <= int(np.log2(max(n_taxa, 2))) + 2
+
+
+def test_structure_of_the_program():
+    rng = np.random.default_rng(11)
+    tree = random_tree(200, rng)
+    ft = mcp.flatten(tree)
+    lr = _leaf_row(ft, ft.leaf_nums)
+    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, lr, True)
+    post, pre = prog["post"], prog["pre"]
+    n_int = ft.NN - len(ft.leaf_nums)
+    assert len(post) == n_int and len(pre) == n_int
+    # at most one MEM and one REG operand per op; REG only refers to the previous op
+    for i, op in enumerate(post):
+        kinds = [op[5] & 3, (op[5] >> 2) & 3]
+        assert kinds.count(2) <= 1 and kinds.count(1) <= 1
+        if 1 in kinds:
+            assert i > 0
+        for kind, src in zip(kinds, (op[0], op[2])):
+            if kind == 2:
+                assert 0 <= src < i     # a slot is the index of an earlier op
+    assert (post[-1][5] >> 5) & 1 == 1 and sum((op[5] >> 5) & 1 for op in post) == 1
+    # LIFO depth of the gradient pass is logarithmic for any topology
+    assert prog["n_stack"] <= int(np.log2(200)) + 1
+    cat = mcp.ParseNewick("(" * 199 + "t000:1," + ",".join(f"t{i:03d}:1)" for i in range(1, 200)) + ";")
+    ftc = mcp.flatten(cat)
+    progc = capi.schedule_dump(ftc.postorder_num, ftc.parent_num, _leaf_row(ftc, ftc.leaf_nums), True)
+    assert progc["n_stack"] == 1
+    progc0 = capi.schedule_dump(ftc.postorder_num, ftc.parent_num, _leaf_row(ftc, ftc.leaf_nums), False)
+    assert progc0["n_slots"] == 1
+
+
+def test_bad_trees_are_rejected():
+    po = np.array([1, 2, 3], dtype=np.int32)
+    with pytest.raises(capi.McpError):   # leaf without alignment row
+        capi.schedule_dump(po, [3, 3, 0], [-1, 0, -1], True)
+    with pytest.raises(capi.McpError):   # root not last
+        capi.schedule_dump([3, 1, 2], [3, 3, 0], [0, 1, -1], True)
+    with pytest.raises(capi.McpError):   # cycle / mother before child
+        capi.schedule_dump(po, [2, 1, 0], [0, 1, -1], True)
+    with pytest.raises(capi.McpError):
+        capi.schedule_dump([1], [0], [0], True)
