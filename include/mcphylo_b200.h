@@ -78,6 +78,10 @@ int mcp_alignment_from_codes(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t 
                              const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
 int mcp_alignment_from_dense(mcp_ctx *ctx, const double *x, int K, int64_t S, int NN,
                              const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
+/* Re-upload the codes of an existing alignment (same K, S, leaf_nums) from host memory,
+ * asynchronously on the context's stream; evaluations enqueued afterwards see the new data.
+ * With pinned host memory the copy overlaps host work.  The cached schedule stays valid. */
+int mcp_alignment_update_codes(mcp_ctx *ctx, mcp_alignment *aln, const uint8_t *codes);
 int mcp_alignment_destroy(mcp_ctx *ctx, mcp_alignment *aln);
 
 /*

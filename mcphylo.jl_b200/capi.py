@@ -18,7 +18,8 @@ _lib = None
 
 SYMBOLS = [
     "mcp_abi_version", "mcp_last_error", "mcp_create", "mcp_destroy", "mcp_set_stream",
-    "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_destroy",
+    "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
+    "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
     "mcp_schedule_dump",
 ]
@@ -66,6 +67,7 @@ def load():
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
+    lib.mcp_alignment_update_codes.argtypes = [_vp, _vp, _vp]
     eval_args = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_int, _vp, C.c_int]
     lib.mcp_eval.argtypes = eval_args + [_dp, _vp]
     lib.mcp_eval_device.argtypes = eval_args + [_vp]
@@ -100,6 +102,11 @@ class Alignment:
     def __init__(self, ctx: "Context", handle, K: int, S: int, leaf_nums: np.ndarray):
         self.ctx, self.handle, self.K, self.S = ctx, handle, K, S
         self.leaf_nums = leaf_nums
+
+    def update_codes(self, host_ptr: int):
+        """Re-upload (n_leaves, S) uint8 codes from host memory at `host_ptr` (async on the
+        context's stream; pinned memory recommended)."""
+        self.ctx._check(load().mcp_alignment_update_codes(self.ctx.handle, self.handle, _vp(host_ptr)))
 
     def close(self):
         if self.handle is not None and self.ctx.handle is not None:

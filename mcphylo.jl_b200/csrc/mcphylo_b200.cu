@@ -900,9 +900,6 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         if (ll_out) ll_out[t] = o[0];
         if (a.want_grad && grad_out && grad_out[t]) std::memcpy(grad_out[t], o + 1, sizeof(double) * (a.NN[t] - 1));
     }
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) s.walk_ms = ms;
-    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s.device_ms = ms;
     return 0;
 }
 
@@ -1053,6 +1050,17 @@ int mcp_alignment_from_dense(mcp_ctx* ctx, const double* x, int K, int64_t S, in
     return make_alignment(ctx, codes.data(), K, S, leaf_nums, n_leaves, out);
 }
 
+int mcp_alignment_update_codes(mcp_ctx* ctx, mcp_alignment* aln, const uint8_t* codes) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!aln || !codes) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_update_codes: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (aln->S > 0)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(aln->d_codes, (size_t)aln->stride, codes, (size_t)aln->S, (size_t)aln->S,
+                                        (size_t)aln->n_leaves, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->pending_async = true;
+    return 0;
+}
+
 int mcp_alignment_destroy(mcp_ctx* ctx, mcp_alignment* aln) {
     if (!aln) return 0;
     if (ctx) {
@@ -1096,6 +1104,14 @@ int mcp_eval_batch(mcp_ctx* ctx, int T, const mcp_alignment* const* alns, const 
 int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {
     if (!ctx || !out) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats: null argument");
     *out = ctx->stats;
+    // event times are read lazily: they exist once the stream has passed the last event
+    float ms = 0.f;
+    if (ctx->ev[3] && cudaEventQuery(ctx->ev[3]) == cudaSuccess) {
+        if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) out->walk_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) out->device_ms = ms;
+    } else {
+        cudaGetLastError();
+    }
     return 0;
 }
 

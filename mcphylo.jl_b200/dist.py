@@ -1,0 +1,94 @@
+"""Site sharding across GPUs: one process per GPU (torch.distributed), each rank owns a
+contiguous block of alignment columns for all nodes and rate categories, and the only exchange
+per evaluation is one all-reduce (sum) of the NN doubles [logL, grad[1..NN-1]].
+torch is plumbing here (process group, device tensor for the NCCL call); the evaluation itself
+is the C-ABI `mcp_eval_device`, enqueued on torch's current stream so the collective follows it
+in stream order without a host synchronisation in between.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from .phylodist import DeviceAlignment, PhyloDist, _device_alignment, _tree_args, get_context
+
+
+def shard_bounds(S: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Rank g owns sites [g*ceil(S/G), min(S, (g+1)*ceil(S/G)))."""
+    per = -(-S // world_size)
+    lo = min(S, rank * per)
+    return lo, min(S, lo + per)
+
+
+def local_shard(aln: DeviceAlignment, world_size: int, rank: int) -> DeviceAlignment:
+    lo, hi = shard_bounds(aln.S, world_size, rank)
+    return aln.site_block(lo, hi)
+
+
+def allreduce_sum(t, group=None):
+    """Sum of the packed [logL, grad] vector over ranks (NCCL on device tensors, gloo on CPU
+    tensors in the host-logic tests)."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class ShardedEvaluator:
+    """gradlogpdf / logpdf of one PhyloDist whose alignment is split over the ranks of a process
+    group.  Every rank calls with the same tree and gets the same (all-reduced) result."""
+
+    def __init__(self, local_alignment: DeviceAlignment, device: int, group=None):
+        import torch
+
+        self.torch = torch
+        self.aln = local_alignment
+        self.device = device
+        self.group = group
+        self.ctx = get_context(device)
+        self._out = None
+        self._pinned = None
+
+    def _buffers(self, NN: int):
+        torch = self.torch
+        if self._out is None or self._out.numel() != NN:
+            self._out = torch.empty(NN, dtype=torch.float64, device=f"cuda:{self.device}")
+            self._pinned = torch.empty(NN, dtype=torch.float64).pin_memory()
+        return self._out, self._pinned
+
+    def evaluate(self, d: PhyloDist, want_grad: bool = True):
+        torch = self.torch
+        ft, targs = _tree_args(d)
+        out, pinned = self._buffers(ft.NN)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream()
+            self.ctx.set_stream(stream.cuda_stream)
+            aln = _device_alignment(self.aln, ft.leaf_nums, d.nbase, self.ctx)
+            self.ctx.eval_device(aln, *targs, want_grad=want_grad, d_out_ptr=out.data_ptr())
+            allreduce_sum(out, self.group)
+            pinned.copy_(out, non_blocking=True)
+            stream.synchronize()
+        res = pinned.numpy()
+        return float(res[0]), (res[1:].copy() if want_grad else None)
+
+    def gradlogpdf(self, d: PhyloDist):
+        return self.evaluate(d, True)
+
+    def logpdf(self, d: PhyloDist) -> float:
+        return self.evaluate(d, False)[0]
+
+
+def sharded_sum(local_eval: Callable[[], Tuple[float, Optional[np.ndarray]]], NN: int, group=None):
+    """Host-logic twin of ShardedEvaluator.evaluate for CPU tests: packs a rank-local
+    (logL, grad) into the same NN-vector, all-reduces it and unpacks."""
+    import torch
+
+    ll, g = local_eval()
+    t = torch.zeros(NN, dtype=torch.float64)
+    t[0] = ll
+    if g is not None:
+        t[1:] = torch.from_numpy(np.asarray(g, dtype=np.float64))
+    allreduce_sum(t, group)
+    return float(t[0]), t[1:].numpy().copy()
