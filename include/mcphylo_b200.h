@@ -59,9 +59,11 @@ const char *mcp_last_error(const mcp_ctx *ctx);
 int mcp_create(mcp_ctx **out, int device);
 int mcp_destroy(mcp_ctx *ctx);
 
-/* Optional: run on a caller-provided cudaStream_t (cast to void*) instead of the context's own.
- * Pass NULL to go back to the internal stream. */
+/* Optional: run on a caller-provided cudaStream_t (cast to void*) instead of the context's own
+ * non-blocking stream.  NULL selects the CUDA default stream (that is what e.g. torch's default
+ * stream is).  mcp_use_own_stream goes back to the internal stream. */
 int mcp_set_stream(mcp_ctx *ctx, void *cuda_stream);
+int mcp_use_own_stream(mcp_ctx *ctx);
 
 /*
  * Leaf data.  Replaces the dense one-hot array `x[:, :, leaf.num]` the reference re-expands on

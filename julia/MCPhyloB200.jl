@@ -1,0 +1,131 @@
+# MCPhyloB200.jl — the reference-side binding a maintainer adds to MCPhylo.jl so that
+#   logpdf(d::PhyloDist, x), gradlogpdf(d::PhyloDist, x)            (src/distributions/Phylodist.jl:107-138)
+#   logpdf(d::MultiplePhyloDist, x), __logpdf(d::MultiplePhyloDist, x)   (Phylodist.jl:281-297)
+# run on a B200 through libmcphylo_b200.so (include/mcphylo_b200.h).  Samplers, the model graph
+# and everything else keep calling the same generic functions.
+#
+# NOT EXECUTED IN THIS REPO'S CI: the build container has no Julia.  The Python ctypes binding
+# mcphylo.jl_b200/capi.py makes exactly these calls with exactly these argument orders and IS
+# tested on the GPU (tests/test_gpu_parity.py), see INTEGRATION.md.
+#
+# Usage:  using MCPhylo; include("MCPhyloB200.jl"); MCPhyloB200.enable!("/path/to/libmcphylo_b200.so")
+module MCPhyloB200
+
+using MCPhylo
+import MCPhylo: PhyloDist, MultiplePhyloDist, logpdf, gradlogpdf, __logpdf,
+                post_order, get_leaves, get_branchlength_vector, get_mother
+
+const LIB = Ref{String}("libmcphylo_b200")
+# The handle is process-local and created lazily; it is never stored in a PhyloDist / Model, so
+# serialised chains (src/output/fileio.jl:15-35) stay loadable.
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+# One resident device alignment per data array object (the observed node's value is the same
+# Array for the life of a chain, src/model/dependent.jl:344-358).
+const ALIGNMENTS = IdDict{Any,Ptr{Cvoid}}()
+
+last_error(ctx) = unsafe_string(ccall((:mcp_last_error, LIB[]), Cstring, (Ptr{Cvoid},), ctx))
+check(rc::Cint, ctx = CTX[]) = rc == 0 ? nothing : error("libmcphylo_b200 ($rc): " * last_error(ctx))
+
+function context(device::Integer = parse(Int, get(ENV, "MCPHYLO_B200_DEVICE", "0")))
+    if CTX[] == C_NULL
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:mcp_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Cint), out, device)
+        rc == 0 || error("libmcphylo_b200 ($rc): " * last_error(C_NULL))   # no CPU fallback
+        CTX[] = out[]
+    end
+    CTX[]
+end
+
+function alignment(x::Array{Float64,3}, leaf_nums::Vector{Int32})
+    get!(ALIGNMENTS, x) do
+        K, S, NN = size(x)
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mcp_alignment_from_dense, LIB[]), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Cint, Int64, Cint, Ptr{Int32}, Cint, Ref{Ptr{Cvoid}}),
+                    context(), x, K, S, NN, leaf_nums, length(leaf_nums), out))
+        out[]
+    end
+end
+
+# Tree -> flat arrays, using MCPhyloTree's own accessors so the numbering rule is never re-derived.
+function flatten(tree)
+    po = post_order(tree)
+    NN = length(po)
+    postorder_num = Int32[n.num for n in po]
+    parent_num = zeros(Int32, NN)
+    for n in po
+        n.root || (parent_num[n.num] = get_mother(n).num)
+    end
+    leaf_nums = Int32[l.num for l in get_leaves(tree)]
+    NN, postorder_num, parent_num, get_branchlength_vector(tree), leaf_nums
+end
+
+function evaluate(d::PhyloDist, x::Array{Float64,3}, want_grad::Bool)
+    NN, po, pa, blv, leaf_nums = flatten(d.tree)
+    U, D, Uinv, mu = d.substitution_model(d.base_freq, d.substitution_rates)
+    ll = Ref{Float64}(0.0)
+    grad = want_grad ? Vector{Float64}(undef, NN - 1) : Float64[]
+    check(ccall((:mcp_eval, LIB[]), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Cint, Ptr{Float64},
+                 Cint, Ref{Float64}, Ptr{Float64}),
+                context(), alignment(x, leaf_nums), NN, po, pa, Vector{Float64}(blv),
+                Matrix{Float64}(U), Vector{Float64}(D), Matrix{Float64}(Uinv), Float64(mu),
+                d.rates, length(d.rates), d.base_freq,
+                want_grad, ll, want_grad ? pointer(grad) : C_NULL))
+    ll[], grad
+end
+
+function evaluate(d::MultiplePhyloDist, x::Array{Float64,4}, want_grad::Bool)
+    T = length(d.DistCollector)
+    flat = [flatten(pd.tree) for pd in d.DistCollector]
+    models = [pd.substitution_model(pd.base_freq, pd.substitution_rates) for pd in d.DistCollector]
+    slabs = [get!(() -> x[:, :, 1:d.size_array[t], t], SLABS, (x, t)) for t in 1:T]
+    alns = Ptr{Cvoid}[alignment(slabs[t], flat[t][5]) for t in 1:T]
+    NN = Int32[f[1] for f in flat]
+    blv = [Vector{Float64}(f[4]) for f in flat]
+    U = [Matrix{Float64}(m[1]) for m in models]; D = [Vector{Float64}(m[2]) for m in models]
+    Uinv = [Matrix{Float64}(m[3]) for m in models]; mu = Float64[m[4] for m in models]
+    rates = [pd.rates for pd in d.DistCollector]; pis = [pd.base_freq for pd in d.DistCollector]
+    ll = zeros(Float64, T)
+    grads = [Vector{Float64}(undef, NN[t] - 1) for t in 1:T]
+    ptrs(v) = Ptr{Cvoid}[pointer(a) for a in v]
+    GC.@preserve flat blv U D Uinv rates pis grads begin
+        check(ccall((:mcp_eval_batch, LIB[]), Cint,
+                    (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}},
+                     Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Float64},
+                     Ptr{Ptr{Cvoid}}, Cint, Ptr{Ptr{Cvoid}}, Cint, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
+                    context(), T, alns, NN, ptrs([f[2] for f in flat]), ptrs([f[3] for f in flat]),
+                    ptrs(blv), ptrs(U), ptrs(D), ptrs(Uinv), mu, ptrs(rates),
+                    length(rates[1]), ptrs(pis), want_grad, ll, want_grad ? ptrs(grads) : C_NULL))
+    end
+    ll, grads
+end
+const SLABS = IdDict{Any,Any}()
+
+"""Route the four PhyloDist methods through the GPU library (method redefinition)."""
+function enable!(libpath::AbstractString = LIB[])
+    LIB[] = libpath
+    @eval MCPhylo begin
+        logpdf(d::PhyloDist, x::Array{Float64,3})::Float64 = $(evaluate)(d, x, false)[1]
+        gradlogpdf(d::PhyloDist, x::Array{Float64,3}) = $(evaluate)(d, x, true)
+        logpdf(d::MultiplePhyloDist, x::Array{Float64,4})::Float64 = sum($(evaluate)(d, x, false)[1])
+        function __logpdf(d::MultiplePhyloDist, x::Array{Float64,4})
+            ll, g = $(evaluate)(d, x, true)
+            Tuple[(ll[i], g[i]) for i in eachindex(ll)]
+        end
+    end
+    nothing
+end
+
+function shutdown!()
+    for (_, a) in ALIGNMENTS
+        ccall((:mcp_alignment_destroy, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], a)
+    end
+    empty!(ALIGNMENTS); empty!(SLABS)
+    CTX[] == C_NULL || ccall((:mcp_destroy, LIB[]), Cint, (Ptr{Cvoid},), CTX[])
+    CTX[] = C_NULL
+    nothing
+end
+
+end # module

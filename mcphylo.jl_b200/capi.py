@@ -13,11 +13,12 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmcphylo_b200.so")
+LIB_PATH = os.environ.get("MCPHYLO_B200_LIB") or os.path.join(_HERE, "lib", "libmcphylo_b200.so")
 _lib = None
 
 SYMBOLS = [
     "mcp_abi_version", "mcp_last_error", "mcp_create", "mcp_destroy", "mcp_set_stream",
+    "mcp_use_own_stream",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
@@ -63,6 +64,7 @@ def load():
     lib.mcp_create.argtypes = [C.POINTER(_vp), C.c_int]
     lib.mcp_destroy.argtypes = [_vp]
     lib.mcp_set_stream.argtypes = [_vp, _vp]
+    lib.mcp_use_own_stream.argtypes = [_vp]
     lib.mcp_set_launch.argtypes = [_vp, C.c_int, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
@@ -148,7 +150,12 @@ class Context:
             pass
 
     def set_stream(self, cuda_stream: Optional[int]):
-        self._check(self.lib.mcp_set_stream(self.handle, _vp(cuda_stream or 0)))
+        """Run on the given cudaStream_t handle (0 = CUDA default stream); None returns to the
+        context's own stream."""
+        if cuda_stream is None:
+            self._check(self.lib.mcp_use_own_stream(self.handle))
+        else:
+            self._check(self.lib.mcp_set_stream(self.handle, _vp(int(cuda_stream))))
 
     def set_launch(self, block: int = 0, ctas_per_sm: int = 0):
         self._check(self.lib.mcp_set_launch(self.handle, int(block), int(ctas_per_sm)))

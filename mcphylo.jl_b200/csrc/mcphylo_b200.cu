@@ -41,7 +41,7 @@ using mcp::Schedule;
 struct TreeDev {
     long long post_off;      // op index (32-byte units) of this tree's post program
     long long pre_off;       // ... pre program
-    long long ptab_off;      // doubles, into the transition-table buffer
+    long long btab_off;      // doubles, into the branch-table buffer
     long long dyn_off;       // doubles, into the per-evaluation parameter buffer
     long long out_off;       // doubles, into the result buffer ([logL, grad(NN-1)] per tree)
     const unsigned char* codes;  // (rows, code_stride) state codes of this tree's alignment
@@ -61,7 +61,7 @@ struct LLRow {
 struct WalkParams {
     const TreeDev* trees;
     const int4* ops;
-    const double* ptab;
+    const double* btab;
     const double* dyn;
     double* scratch;
     long long scratch_per_cta;  // doubles
@@ -71,6 +71,7 @@ struct WalkParams {
     long long row_stride;
     int n_slots, n_stack;
     int n_tiles, T, R, want_grad;
+    int max_br;
 };
 
 // per-tree layout of the per-evaluation parameter block (offsets in doubles from dyn_off)
@@ -81,13 +82,26 @@ __host__ __device__ inline long long dyn_Uinv(int NN, int K) { return NN - 1 + (
 __host__ __device__ inline long long dyn_mu(int NN, int K) { return NN - 1 + 2LL * K * K + K; }
 __host__ __device__ inline long long dyn_rates(int NN, int K) { return NN + 2LL * K * K + K; }
 __host__ __device__ inline long long dyn_pi(int NN, int K, int R) { return NN + 2LL * K * K + K + R; }
+__host__ __device__ inline long long dyn_slot(int NN, int K, int R) { return NN + 2LL * K * K + 2LL * K + R; }
 __host__ __device__ inline long long dyn_size(int NN, int K, int R) {
-    long long n = NN + 2LL * K * K + 2LL * K + R;
+    long long n = NN + 2LL * K * K + 2LL * K + R + 1;
     return (n + 3) & ~3LL;  // keep every tree's block 32-byte aligned
 }
-// transition table entry for one (branch, rate): P columns 0..K (column K = row sums, the
-// all-ones leaf), then dP/dt columns 0..K; column j holds the K parent-state entries.
-__host__ __device__ inline int pst(int K) { return 2 * K * (K + 1); }
+// Branch table, one entry per (device branch, rate category), BT(K) doubles:
+//   [0, K)                    e_i = exp(mu * t * D_i * rate)     (internal children: P = U diag(e) Uinv)
+//   [K, K + K*(K+1))          P columns 0..K for LEAF children: column j = P[:, j], column K = row sums
+//                             (= P * all-ones leaf); each column holds the K parent-state entries
+//   [K + K*(K+1), K + 2K(K+1)) dP/dt columns, same layout
+__host__ __device__ inline int bt_size(int K) { return K + 2 * K * (K + 1); }
+
+// Model constants of the evaluation, read as CONSTANT-BANK operands (warp-uniform: no per-lane
+// register delivery, DFMA takes them directly).  One slot per distinct substitution model in the
+// batch.  Slot layout (doubles): U (K*K col-major) | Uinv (K*K col-major) | pi (K) | c[r][i] =
+// D_i * mu * rate_r (R*K).
+constexpr int MODEL_SLOT = 256;                 // doubles per slot
+constexpr int MODEL_SLOTS = 32;                 // 64 KB of constant memory
+constexpr int MAX_RATES = 16;
+__constant__ double c_model[MODEL_SLOT * MODEL_SLOTS];
 
 // --------------------------------------------------------------------------------------------
 // vector load/store helpers (K doubles per column)
@@ -96,17 +110,17 @@ template <int K>
 __device__ __forceinline__ void ld_table(const double* __restrict__ p, double (&v)[K]) {
     // read-only path: tables are written by an earlier kernel
     if constexpr (K == 4) {
-        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
     } else if constexpr (K == 2) {
-        asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+        asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
     } else {
 #pragma unroll
         for (int k = 0; k < K; ++k) v[k] = __ldg(p + k);
     }
 }
 // Partials: written and re-read by the SAME thread inside one kernel, so they must not go
-// through the non-coherent path; .cg keeps this streaming data out of L1 (tables/ops stay there).
+// through the non-coherent path; .cg keeps this streaming data out of L1.
 template <int K>
 __device__ __forceinline__ void ld_partial(const double* p, double (&v)[K]) {
     if constexpr (K == 4) {
@@ -132,28 +146,63 @@ __device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
     }
 }
 
-// out[s] = sum_j T[j][s] * L[j]   (T = K columns of a table, column-major by child state j)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Model view: MOFS is the slot offset into c_model; with a compile-time 0 the constant operands
+// fold into the DFMA encodings.
 template <int K>
-__device__ __forceinline__ void table_times(const double* __restrict__ tab, const double (&L)[K], double (&out)[K]) {
+struct Model {
+    int ofs;
+    __device__ __forceinline__ double U(int s, int i) const { return c_model[ofs + s + K * i]; }
+    __device__ __forceinline__ double Ui(int i, int j) const { return c_model[ofs + K * K + i + K * j]; }
+    __device__ __forceinline__ double pi(int k) const { return c_model[ofs + 2 * K * K + k]; }
+    __device__ __forceinline__ double c(int r, int i) const { return c_model[ofs + 2 * K * K + K + r * K + i]; }
+};
+
+// z = e * (Uinv L)       (the eigen-coordinates of P L)
+template <int K>
+__device__ __forceinline__ void eig_project(const Model<K>& m, const double (&L)[K], const double (&e)[K], double (&z)[K]) {
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        double col[K];
-        ld_table<K>(tab + j * K, col);
+    for (int i = 0; i < K; ++i) {
+        double w = m.Ui(i, 0) * L[0];
 #pragma unroll
-        for (int s = 0; s < K; ++s) out[s] = (j == 0) ? col[s] * L[0] : fma(col[s], L[j], out[s]);
+        for (int j = 1; j < K; ++j) w = fma(m.Ui(i, j), L[j], w);
+        z[i] = e[i] * w;
     }
 }
-// out[j] = sum_s T[j][s] * q[s]   (transposed product)
+// out = U z
 template <int K>
-__device__ __forceinline__ void table_transposed_times(const double* __restrict__ tab, const double (&q)[K], double (&out)[K]) {
+__device__ __forceinline__ void eig_expand(const Model<K>& m, const double (&z)[K], double (&out)[K]) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        double a = m.U(s, 0) * z[0];
+#pragma unroll
+        for (int i = 1; i < K; ++i) a = fma(m.U(s, i), z[i], a);
+        out[s] = a;
+    }
+}
+// out = P^T q = Uinv^T (e * (U^T q))
+template <int K>
+__device__ __forceinline__ void eig_transposed(const Model<K>& m, const double (&q)[K], const double (&e)[K], double (&out)[K]) {
+    double z[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double w = m.U(0, i) * q[0];
+#pragma unroll
+        for (int s = 1; s < K; ++s) w = fma(m.U(s, i), q[s], w);
+        z[i] = e[i] * w;
+    }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        double col[K];
-        ld_table<K>(tab + j * K, col);
-        double acc = col[0] * q[0];
+        double a = m.Ui(0, j) * z[0];
 #pragma unroll
-        for (int s = 1; s < K; ++s) acc = fma(col[s], q[s], acc);
-        out[j] = acc;
+        for (int i = 1; i < K; ++i) a = fma(m.Ui(i, j), z[i], a);
+        out[j] = a;
     }
 }
 
@@ -186,15 +235,16 @@ __device__ __forceinline__ double warp_pair_reduce(double va, double vb, int lan
 }
 
 // --------------------------------------------------------------------------------------------
-// kernel 1: transition tables P(t), dP/dt for every (tree, branch, rate)
-//   P   = U diag(exp(mu t D r)) Uinv                 VectorizedFunctions.jl:116-168
-//   dP  = U diag(D r mu exp(mu t D r)) Uinv          VectorizedFunctions.jl:89-113, 139-152
-// same operation order as the reference; one thread per (branch, rate).
+// kernel 1: branch tables for every (tree, branch, rate)
+//   e   = exp(mu t D r)
+//   P   = U diag(e) Uinv                             VectorizedFunctions.jl:116-168
+//   dP  = U diag(D r mu e) Uinv                      VectorizedFunctions.jl:89-113, 139-152
+// (P, dP columns are only read for LEAF children; same operation order as the reference.)
 // --------------------------------------------------------------------------------------------
 constexpr int KMAX_TABLE = 32;
 
-__global__ void build_transition_tables(const TreeDev* __restrict__ trees, const double* __restrict__ dyn,
-                                        double* __restrict__ ptab, int K, int R) {
+__global__ void build_branch_tables(const TreeDev* __restrict__ trees, const double* __restrict__ dyn,
+                                    double* __restrict__ btab, int K, int R) {
     const TreeDev tr = trees[blockIdx.y];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= tr.n_br * R) return;
@@ -205,9 +255,11 @@ __global__ void build_transition_tables(const TreeDev* __restrict__ trees, const
     const double* Uinv = d + dyn_Uinv(tr.NN, K);
     const double mu = d[dyn_mu(tr.NN, K)];
     const double rate = d[dyn_rates(tr.NN, K) + r];
-    double* P = ptab + tr.ptab_off + ((long long)br * R + r) * pst(K);
+    double* ev = btab + tr.btab_off + ((long long)br * R + r) * bt_size(K);
+    double* P = ev + K;
     double* dP = P + K * (K + 1);
     if (br >= tr.NN - 1) {  // root row (unused) and virtual branches: identity, zero derivative
+        for (int i = 0; i < K; ++i) ev[i] = 1.0;
         for (int n = 0; n <= K; ++n)
             for (int m = 0; m < K; ++m) {
                 P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0;
@@ -220,6 +272,7 @@ __global__ void build_transition_tables(const TreeDev* __restrict__ trees, const
     for (int i = 0; i < K; ++i) {
         double ex = exp(mu * t * D[i] * rate);
         e[i] = ex;
+        ev[i] = ex;
         de[i] = D[i] * rate * mu * ex;
     }
     for (int m = 0; m < K; ++m) {
@@ -244,10 +297,38 @@ __global__ void build_transition_tables(const TreeDev* __restrict__ trees, const
 // --------------------------------------------------------------------------------------------
 // kernel 2: the fused walk.  grid = persistent CTAs, each takes a contiguous range of column
 // tiles; a tile = blockDim.x columns of one rate category of one tree.
+//
+// Per-op inputs that are uniform over the tile or byte-sized per column are staged in shared
+// memory CH ops at a time with cp.async, one chunk ahead of the compute:
+//   sdesc  3 x CH op descriptors (ring of 3: descriptors must be resident one chunk before the
+//          data they describe can be requested)
+//   se     2 x CH x 2 x K doubles: the e vectors of INTERNAL children
+//   scode  2 x CH x 2 x TW bytes: the state codes of LEAF children for the tile's columns
+// so the only global accesses on the per-op critical path are the thread's own partials and the
+// leaf-table gathers.  One __syncthreads per chunk.
 // --------------------------------------------------------------------------------------------
+constexpr int CH = 16;
+
 template <int K>
-__global__ void __launch_bounds__(256) felsenstein_walk(const WalkParams p) {
-    extern __shared__ double s_acc[];  // per-branch gradient sums of this CTA (gradient mode)
+struct WalkSmem {
+    // dynamic shared memory carve-up (offsets in bytes)
+    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0; }
+    static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
+    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * K * 8; }
+    static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
+    static __host__ __device__ size_t total(int n_br, int want_grad, int TW) {
+        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + code_bytes(TW);
+    }
+};
+
+// 3 resident CTAs of 256 threads per SM (<= 80 registers): the walk is latency-bound, 24 warps
+// with a few spills beat 16 warps without (profiles/r1_walk_notes.md).
+#ifndef MCP_WALK_MIN_BLOCKS
+#define MCP_WALK_MIN_BLOCKS 3
+#endif
+template <int K, bool DYN_MODEL>
+__global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(const WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
 
@@ -257,11 +338,17 @@ __global__ void __launch_bounds__(256) felsenstein_walk(const WalkParams p) {
     const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
     if (tile >= tile_end) return;
 
+    double* const s_acc = reinterpret_cast<double*>(smem_raw);
+    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
+    double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
+    unsigned char* const scode = reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes();
+
     double* const slots = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K;
     double* const stack = slots + (long long)p.n_slots * TW * K;
     const long long slot_stride = (long long)TW * K;
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
+    constexpr int BT = K + 2 * K * (K + 1);
 
     int ti = 0;
     while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
@@ -272,74 +359,136 @@ __global__ void __launch_bounds__(256) felsenstein_walk(const WalkParams p) {
         if (p.want_grad) {
             for (int i = tid; i < tr.n_br; i += TW) s_acc[i] = 0.0;
         }
-        __syncthreads();
         long long e_total = 0;
         double logsum = 0.0;
-        const double* const dynp = p.dyn + tr.dyn_off;
-        double pi[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) pi[k] = __ldg(dynp + dyn_pi(tr.NN, K, R) + k);
+        Model<K> mdl;
+        mdl.ofs = DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0;
         const int4* const post_ops = p.ops + 2 * tr.post_off;
         const int4* const pre_ops = p.ops + 2 * tr.pre_off;
-        constexpr int PST = 2 * K * (K + 1);
 
         for (; tile < tree_tile_end; ++tile) {
             const int local = tile - tr.tile_begin;
             const int r = local / tr.tiles_per_rate;
-            const long long site = (long long)(local - r * tr.tiles_per_rate) * TW + tid;
-            const bool valid = site < tr.S;
-            const unsigned char* const codes = tr.codes + (valid ? site : 0);
-            const double* const tab_r = p.ptab + tr.ptab_off + (long long)r * PST;
-            const long long br_stride = (long long)R * PST;
+            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TW;
+            const bool valid = site0 + tid < tr.S;
+            const unsigned char* const codes0 = tr.codes + site0;
+            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT;
+            const long long br_stride = (long long)R * BT;
+            double crate[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) crate[i] = mdl.c(r, i);
+
+            // ---- chunk staging (all threads of the CTA) ----
+            auto stage_desc = [&](const int4* ops, int n_ops, int c) {
+                const int base = c * CH, cnt = min(CH, n_ops - base);
+                int4* dst = sdesc + (c % 3) * (CH * 2);
+                for (int i = tid; i < cnt * 2; i += TW) cp_async16(dst + i, ops + 2 * base + i);
+            };
+            auto stage_data = [&](int n_ops, int c) {
+                const int base = c * CH, cnt = min(CH, n_ops - base);
+                const int4* d = sdesc + (c % 3) * (CH * 2);
+                double* eb = se + (c & 1) * (CH * 2 * K);
+                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                const int pieces = TW / 16;                  // 16-byte pieces of one code row segment
+                const int per_child = pieces > (K * 8 + 15) / 16 ? pieces : (K * 8 + 15) / 16;
+                for (int w = tid; w < cnt * 2 * per_child; w += TW) {
+                    const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
+                    const int4 o0 = d[2 * j];
+                    const int fl = d[2 * j + 1].y;
+                    const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
+                    const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
+                    if (kind == mcp::OPK_LEAF) {
+                        if (piece < pieces && src >= 0)
+                            cp_async16(cb + (size_t)(j * 2 + ch) * TW + piece * 16,
+                                       codes0 + (long long)src * tr.code_stride + piece * 16);
+                    } else if (piece * 16 < K * 8) {
+                        if constexpr ((K * 8) % 16 == 0) {
+                            cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * K) + piece * 16,
+                                       reinterpret_cast<const unsigned char*>(tab_r + br * br_stride) + piece * 16);
+                        } else {
+                            if (piece == 0) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) eb[(j * 2 + ch) * K + k] = __ldg(tab_r + br * br_stride + k);
+                            }
+                        }
+                    }
+                }
+            };
+            auto prologue = [&](const int4* ops, int n_ops) {
+                __syncthreads();                              // previous pass / tile done with the buffers
+                stage_desc(ops, n_ops, 0);
+                if (n_ops > CH) stage_desc(ops, n_ops, 1);
+                cp_async_commit();
+                cp_async_wait_all();
+                __syncthreads();
+                stage_data(n_ops, 0);
+                cp_async_commit();
+            };
+            auto chunk_boundary = [&](const int4* ops, int n_ops, int c, int n_chunks) {
+                cp_async_wait_all();
+                __syncthreads();                              // chunk c data + descriptors c, c+1 visible
+                if (c + 1 < n_chunks) stage_data(n_ops, c + 1);
+                if (c + 2 < n_chunks) stage_desc(ops, n_ops, c + 2);
+                cp_async_commit();
+            };
+            auto leaf_code = [&](const unsigned char* cb, int j, int ch, int src) -> int {
+                int code = (valid && src >= 0) ? (int)cb[(size_t)(j * 2 + ch) * TW + tid] : K;
+                return min(code, K);
+            };
 
             // ------------------------------ post pass ------------------------------
             double cur[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) cur[k] = 1.0;
             int e_col = 0;
-            for (int i = 0; i < tr.n_post; ++i) {
-                const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
-                const int flags = o1.y;
-                double Da[K], Db[K];
-                {
-                    const double* tab = tab_r + o0.y * br_stride;
-                    const int kind = flags & 3;
-                    if (kind == mcp::OPK_LEAF) {
-                        int code = (valid && o0.x >= 0) ? (int)__ldg(codes + (long long)o0.x * tr.code_stride) : K;
-                        code = min(code, K);
-                        ld_table<K>(tab + code * K, Da);
-                    } else if (kind == mcp::OPK_REG) {
-                        table_times<K>(tab, cur, Da);
-                    } else {
-                        double L[K];
-                        ld_partial<K>(slots + o0.x * slot_stride, L);
-                        table_times<K>(tab, L, Da);
-                    }
-                }
-                {
-                    const double* tab = tab_r + o0.w * br_stride;
-                    const int kind = (flags >> 2) & 3;
-                    if (kind == mcp::OPK_LEAF) {
-                        int code = (valid && o0.z >= 0) ? (int)__ldg(codes + (long long)o0.z * tr.code_stride) : K;
-                        code = min(code, K);
-                        ld_table<K>(tab + code * K, Db);
-                    } else if (kind == mcp::OPK_REG) {
-                        table_times<K>(tab, cur, Db);
-                    } else {
-                        double L[K];
-                        ld_partial<K>(slots + o0.z * slot_stride, L);
-                        table_times<K>(tab, L, Db);
-                    }
-                }
+            {
+                const int n_post = tr.n_post, n_chunks = (n_post + CH - 1) / CH;
+                prologue(post_ops, n_post);
+                for (int c = 0; c < n_chunks; ++c) {
+                    chunk_boundary(post_ops, n_post, c, n_chunks);
+                    const int4* d = sdesc + (c % 3) * (CH * 2);
+                    const double* eb = se + (c & 1) * (CH * 2 * K);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                    const int cnt = min(CH, n_post - c * CH);
+                    for (int j = 0; j < cnt; ++j) {
+                        const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
+                        const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
+                        // stored operand (at most one per op) first: its latency overlaps the rest
+                        double Lm[K];
+                        if (ka == mcp::OPK_MEM) ld_partial<K>(slots + o0.x * slot_stride, Lm);
+                        else if (kb == mcp::OPK_MEM) ld_partial<K>(slots + o0.z * slot_stride, Lm);
+                        double Da[K], Db[K];
+                        if (ka == mcp::OPK_LEAF) {
+                            ld_table<K>(tab_r + o0.y * br_stride + K + leaf_code(cb, j, 0, o0.x) * K, Da);
+                        } else {
+                            double e[K], z[K];
 #pragma unroll
-                for (int k = 0; k < K; ++k) cur[k] = Da[k] * Db[k];
-                e_col += rescale_pow2<K>(cur);
-                if (flags & mcp::POST_STORE) st_partial<K>(slots + o1.x * slot_stride, cur);
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * K + k];
+                            if (ka == mcp::OPK_REG) eig_project<K>(mdl, cur, e, z);
+                            else eig_project<K>(mdl, Lm, e, z);
+                            eig_expand<K>(mdl, z, Da);
+                        }
+                        if (kb == mcp::OPK_LEAF) {
+                            ld_table<K>(tab_r + o0.w * br_stride + K + leaf_code(cb, j, 1, o0.z) * K, Db);
+                        } else {
+                            double e[K], z[K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * K + k];
+                            if (kb == mcp::OPK_REG) eig_project<K>(mdl, cur, e, z);
+                            else eig_project<K>(mdl, Lm, e, z);
+                            eig_expand<K>(mdl, z, Db);
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; ++k) cur[k] = Da[k] * Db[k];
+                        e_col += rescale_pow2<K>(cur);
+                        if (flags & mcp::POST_STORE) st_partial<K>(slots + o1.x * slot_stride, cur);
+                    }
+                }
             }
             {
-                double rootv = pi[0] * cur[0];
+                double rootv = mdl.pi(0) * cur[0];
 #pragma unroll
-                for (int k = 1; k < K; ++k) rootv = fma(pi[k], cur[k], rootv);
+                for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[k], rootv);
                 if (valid) {
                     logsum += log(rootv);
                     e_total += e_col;
@@ -348,86 +497,101 @@ __global__ void __launch_bounds__(256) felsenstein_walk(const WalkParams p) {
 
             // ------------------------------ gradient pass ------------------------------
             if (p.want_grad) {
-                for (int i = 0; i < tr.n_pre; ++i) {
-                    const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
-                    const int flags = o1.w;
-                    const int a_br = o0.z, b_br = o1.x;
-                    double pm[K];
-                    {
-                        const int mk = flags & 3;
+                const int n_pre = tr.n_pre, n_chunks = (n_pre + CH - 1) / CH;
+                prologue(pre_ops, n_pre);
+                for (int c = 0; c < n_chunks; ++c) {
+                    chunk_boundary(pre_ops, n_pre, c, n_chunks);
+                    const int4* d = sdesc + (c % 3) * (CH * 2);
+                    const double* eb = se + (c & 1) * (CH * 2 * K);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                    const int cnt = min(CH, n_pre - c * CH);
+                    for (int j = 0; j < cnt; ++j) {
+                        const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
+                        const int flags = o1.y;
+                        const int a_br = o0.y, b_br = o0.w;
+                        const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
+                        const int mk = (flags >> 8) & 3;
+                        // all stored operands of the family are requested up front
+                        double pm[K], La[K], Lb[K];
+                        if (mk == mcp::PREM_STACK) ld_partial<K>(stack + o1.x * slot_stride, pm);
+                        if (ai) ld_partial<K>(slots + o0.x * slot_stride, La);
+                        if (bi) ld_partial<K>(slots + o0.z * slot_stride, Lb);
                         if (mk == mcp::PREM_ROOT) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) pm[k] = pi[k];
+                            for (int k = 0; k < K; ++k) pm[k] = mdl.pi(k);
                         } else if (mk == mcp::PREM_REG) {
 #pragma unroll
                             for (int k = 0; k < K; ++k) pm[k] = cur[k];
-                        } else {
-                            ld_partial<K>(stack + o0.x * slot_stride, pm);
                         }
-                    }
-                    const double* const tab_a = tab_r + a_br * br_stride;
-                    const double* const tab_b = tab_r + b_br * br_stride;
-                    double Da[K], Ya[K], Db[K], Yb[K];
-                    if (flags & 4) {
-                        double L[K];
-                        ld_partial<K>(slots + o0.y * slot_stride, L);
-                        table_times<K>(tab_a, L, Da);
-                        table_times<K>(tab_a + K * (K + 1), L, Ya);
-                    } else {
-                        int code = (valid && o0.y >= 0) ? (int)__ldg(codes + (long long)o0.y * tr.code_stride) : K;
-                        code = min(code, K);
-                        ld_table<K>(tab_a + code * K, Da);
-                        ld_table<K>(tab_a + K * (K + 1) + code * K, Ya);
-                    }
-                    if (flags & 8) {
-                        double L[K];
-                        ld_partial<K>(slots + o0.w * slot_stride, L);
-                        table_times<K>(tab_b, L, Db);
-                        table_times<K>(tab_b + K * (K + 1), L, Yb);
-                    } else {
-                        int code = (valid && o0.w >= 0) ? (int)__ldg(codes + (long long)o0.w * tr.code_stride) : K;
-                        code = min(code, K);
-                        ld_table<K>(tab_b + code * K, Db);
-                        ld_table<K>(tab_b + K * (K + 1) + code * K, Yb);
-                    }
-                    double qa[K], qb[K];
-                    double den = 0.0, na = 0.0, nb = 0.0;
+                        double ea[K], ebv[K];
+                        double Da[K], Ya[K], Db[K], Yb[K];
+                        if (ai) {
+                            double z[K], zd[K];
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        qa[k] = pm[k] * Db[k];
-                        qb[k] = pm[k] * Da[k];
-                        den = fma(qa[k], Da[k], den);
-                        na = fma(qa[k], Ya[k], na);
-                        nb = fma(qb[k], Yb[k], nb);
-                    }
-                    const double inv = 1.0 / den;
-                    const double ga = valid ? na * inv : 0.0;
-                    const double gb = valid ? nb * inv : 0.0;
-                    const double red = warp_pair_reduce(ga, gb, lane);
-                    if (lane == 0) atomicAdd(&s_acc[a_br], red);
-                    else if (lane == 16) atomicAdd(&s_acc[b_br], red);
+                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * K + k];
+                            eig_project<K>(mdl, La, ea, z);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) zd[k] = crate[k] * z[k];
+                            eig_expand<K>(mdl, z, Da);
+                            eig_expand<K>(mdl, zd, Ya);
+                        } else {
+                            const double* t = tab_r + a_br * br_stride + K + leaf_code(cb, j, 0, o0.x) * K;
+                            ld_table<K>(t, Da);
+                            ld_table<K>(t + K * (K + 1), Ya);
+                        }
+                        if (bi) {
+                            double z[K], zd[K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * K + k];
+                            eig_project<K>(mdl, Lb, ebv, z);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) zd[k] = crate[k] * z[k];
+                            eig_expand<K>(mdl, z, Db);
+                            eig_expand<K>(mdl, zd, Yb);
+                        } else {
+                            const double* t = tab_r + b_br * br_stride + K + leaf_code(cb, j, 1, o0.z) * K;
+                            ld_table<K>(t, Db);
+                            ld_table<K>(t + K * (K + 1), Yb);
+                        }
+                        double qa[K], qb[K];
+                        double den = 0.0, na = 0.0, nb = 0.0;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            qa[k] = pm[k] * Db[k];
+                            qb[k] = pm[k] * Da[k];
+                            den = fma(qa[k], Da[k], den);
+                            na = fma(qa[k], Ya[k], na);
+                            nb = fma(qb[k], Yb[k], nb);
+                        }
+                        const double inv = 1.0 / den;
+                        const double ga = valid ? na * inv : 0.0;
+                        const double gb = valid ? nb * inv : 0.0;
+                        const double red = warp_pair_reduce(ga, gb, lane);
+                        if (lane == 0) atomicAdd(&s_acc[a_br], red);
+                        else if (lane == 16) atomicAdd(&s_acc[b_br], red);
 
-                    const int a_out = (flags >> 4) & 3, b_out = (flags >> 6) & 3;
-                    if (a_out != mcp::OUT_NONE) {
-                        double pa[K];
-                        table_transposed_times<K>(tab_a, qa, pa);
-                        rescale_pow2<K>(pa);
-                        if (a_out == mcp::OUT_KEEP) {
+                        const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
+                        if (a_out != mcp::OUT_NONE) {
+                            double pa[K];
+                            eig_transposed<K>(mdl, qa, ea, pa);
+                            rescale_pow2<K>(pa);
+                            if (a_out == mcp::OUT_KEEP) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) cur[k] = pa[k];
-                        } else {
-                            st_partial<K>(stack + o1.y * slot_stride, pa);
+                                for (int k = 0; k < K; ++k) cur[k] = pa[k];
+                            } else {
+                                st_partial<K>(stack + o1.z * slot_stride, pa);
+                            }
                         }
-                    }
-                    if (b_out != mcp::OUT_NONE) {
-                        double pb[K];
-                        table_transposed_times<K>(tab_b, qb, pb);
-                        rescale_pow2<K>(pb);
-                        if (b_out == mcp::OUT_KEEP) {
+                        if (b_out != mcp::OUT_NONE) {
+                            double pb[K];
+                            eig_transposed<K>(mdl, qb, ebv, pb);
+                            rescale_pow2<K>(pb);
+                            if (b_out == mcp::OUT_KEEP) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) cur[k] = pb[k];
-                        } else {
-                            st_partial<K>(stack + o1.z * slot_stride, pb);
+                                for (int k = 0; k < K; ++k) cur[k] = pb[k];
+                            } else {
+                                st_partial<K>(stack + o1.w * slot_stride, pb);
+                            }
                         }
                     }
                 }
@@ -516,8 +680,8 @@ struct mcp_ctx {
     int opt_block = 0, opt_ctas_per_sm = 0;
     unsigned long long next_aln_id = 1;
 
-    DevBuf d_topo, d_dyn, d_ptab, d_scratch, d_rows, d_rows_ll, d_out;
-    PinBuf h_topo, h_dyn, h_out;
+    DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out;
+    PinBuf h_topo, h_dyn, h_out, h_model;
 
     // cached topology
     struct TreeSig {
@@ -532,7 +696,7 @@ struct mcp_ctx {
     std::vector<Schedule> scheds;
     size_t topo_bytes = 0, off_trees = 0, off_ops = 0, off_rowbase = 0;
     int n_tiles = 0, grid = 0, block = 0, n_rows = 0, n_slots = 0, n_stack = 0, max_br = 0;
-    long long total_out = 0, total_dyn = 0, total_ptab = 0, scratch_per_cta = 0, row_stride = 0;
+    long long total_out = 0, total_dyn = 0, total_btab = 0, scratch_per_cta = 0, row_stride = 0;
     size_t smem_bytes = 0;
 
     mcp_stats stats{};
@@ -594,18 +758,33 @@ int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
 }
 
 template <int K>
-int launch_walk(mcp_ctx* ctx, const WalkParams& wp) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)ctx->smem_bytes));
-    felsenstein_walk<K><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
+    if (dyn_model) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ctx->smem_bytes));
+        felsenstein_walk<K, true><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    } else {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)ctx->smem_bytes));
+        felsenstein_walk<K, false><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
 template <int K>
 int occupancy_for(mcp_ctx* ctx, int block, size_t smem, int* out) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K>, block, smem));
+    // the dynamic-model variant needs a few more registers: size the persistent grid for it
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int o1 = 0, o2 = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, true>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, false>, block, smem));
+    *out = std::min(o1, o2);
     return 0;
+}
+size_t walk_smem_bytes(int K, int max_br, int want_grad, int block) {
+    size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
+    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 2 * block;
 }
 
 #define MCP_DISPATCH_K(K, CALL)                      \
@@ -645,8 +824,8 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     for (int t = 0; t < T; ++t) total_cols += a.alns[t]->S * R;
     int block = ctx->opt_block;
     if (block <= 0) {
-        block = 128;
-        while (block > 32 && (total_cols + block - 1) / block < 2LL * ctx->sm_count) block >>= 1;
+        block = 256;
+        while (block > 32 && (total_cols + block - 1) / block < 6LL * ctx->sm_count) block >>= 1;
     }
     bool same = (int)ctx->sig.size() == T && ctx->sig_want_grad == a.want_grad && ctx->sig_block == block &&
                 ctx->sig_K == K && ctx->sig_R == R;
@@ -662,7 +841,7 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     ctx->sig.clear();
     ctx->scheds.assign(T, Schedule());
     ctx->trees.assign(T, TreeDev());
-    long long n_ops = 0, out_off = 0, dyn_off = 0, ptab_off = 0;
+    long long n_ops = 0, out_off = 0, dyn_off = 0, btab_off = 0;
     int tile_cursor = 0, n_slots = 1, n_stack = 1, max_br = 1;
     std::vector<int32_t> leaf_row;
     for (int t = 0; t < T; ++t) {
@@ -693,8 +872,8 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         out_off += NN;
         td.dyn_off = dyn_off;
         dyn_off += dyn_size(NN, K, R);
-        td.ptab_off = ptab_off;
-        ptab_off += (long long)sc.n_dnodes * R * pst(K);
+        td.btab_off = btab_off;
+        btab_off += (long long)sc.n_dnodes * R * bt_size(K);
         td.tiles_per_rate = (int)((al->S + block - 1) / block);
         td.tile_begin = tile_cursor;
         long long nt = (long long)td.tiles_per_rate * R;
@@ -721,8 +900,8 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     ctx->max_br = max_br;
     ctx->total_out = out_off;
     ctx->total_dyn = dyn_off;
-    ctx->total_ptab = ptab_off;
-    ctx->smem_bytes = a.want_grad ? (size_t)max_br * sizeof(double) : 0;
+    ctx->total_btab = btab_off;
+    ctx->smem_bytes = walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block);
     if (ctx->smem_bytes > 200 * 1024)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree with %d nodes exceeds the shared-memory gradient accumulator", max_br);
 
@@ -807,7 +986,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     // buffers
     if ((e = ensure_pin(ctx, ctx->h_dyn, sizeof(double) * ctx->total_dyn))) return e;
     if ((e = ensure_dev(ctx, ctx->d_dyn, sizeof(double) * ctx->total_dyn))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_ptab, sizeof(double) * ctx->total_ptab))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_btab, sizeof(double) * ctx->total_btab))) return e;
     if ((e = ensure_dev(ctx, ctx->d_scratch, sizeof(double) * ctx->scratch_per_cta * ctx->grid))) return e;
     if ((e = ensure_dev(ctx, ctx->d_rows, sizeof(double) * ctx->row_stride * ctx->n_rows))) return e;
     if ((e = ensure_dev(ctx, ctx->d_rows_ll, sizeof(LLRow) * ctx->n_rows))) return e;
@@ -832,10 +1011,39 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         std::memcpy(d + dyn_pi(NN, K, R), a.pi[t], sizeof(double) * K);
     }
 
+    // substitution-model constants -> constant memory, one slot per distinct model of the batch
+    if (R > MAX_RATES) return fail(ctx, MCP_ERR_UNSUPPORTED, "more than %d rate categories", MAX_RATES);
+    const int model_doubles = 2 * K * K + K + R * K;
+    if (model_doubles > MODEL_SLOT) return fail(ctx, MCP_ERR_UNSUPPORTED, "model with K=%d, R=%d does not fit a constant slot", K, R);
+    if ((e = ensure_pin(ctx, ctx->h_model, sizeof(double) * MODEL_SLOT * MODEL_SLOTS))) return e;
+    double* hm = (double*)ctx->h_model.p;
+    int n_models = 0;
+    for (int t = 0; t < T; ++t) {
+        double cand[MODEL_SLOT];
+        std::memcpy(cand, a.U[t], sizeof(double) * K * K);
+        std::memcpy(cand + K * K, a.Uinv[t], sizeof(double) * K * K);
+        std::memcpy(cand + 2 * K * K, a.pi[t], sizeof(double) * K);
+        for (int r = 0; r < R; ++r)
+            for (int i = 0; i < K; ++i) cand[2 * K * K + K + r * K + i] = a.D[t][i] * a.rates[t][r] * a.mu[t];
+        int slot = -1;
+        for (int m = 0; m < n_models && slot < 0; ++m)
+            if (std::memcmp(hm + (size_t)m * MODEL_SLOT, cand, sizeof(double) * model_doubles) == 0) slot = m;
+        if (slot < 0) {
+            if (n_models == MODEL_SLOTS)
+                return fail(ctx, MCP_ERR_UNSUPPORTED, "more than %d distinct substitution models in one batch", MODEL_SLOTS);
+            slot = n_models++;
+            std::memcpy(hm + (size_t)slot * MODEL_SLOT, cand, sizeof(double) * model_doubles);
+        }
+        hd[ctx->trees[t].dyn_off + dyn_slot(a.NN[t], K, R)] = (double)slot;
+    }
+    const bool dyn_model = n_models > 1;
+
     cudaStream_t st = ctx->stream;
     mcp_stats& s = ctx->stats;
     s = mcp_stats{};
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+    CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_model, hm, sizeof(double) * MODEL_SLOT * n_models, 0, cudaMemcpyHostToDevice, st));
+    s.h2d_bytes += (int64_t)(sizeof(double) * MODEL_SLOT * n_models);
     if (rebuilt) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_topo.p, ctx->h_topo.p, ctx->topo_bytes, cudaMemcpyHostToDevice, st));
         s.h2d_bytes += (int64_t)ctx->topo_bytes;
@@ -846,13 +1054,13 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     const TreeDev* d_trees = (const TreeDev*)((char*)ctx->d_topo.p + ctx->off_trees);
     {
         dim3 grid((ctx->max_br * R + 127) / 128, T);
-        build_transition_tables<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_dyn.p, (double*)ctx->d_ptab.p, K, R);
+        build_branch_tables<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_dyn.p, (double*)ctx->d_btab.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     WalkParams wp;
     wp.trees = d_trees;
     wp.ops = (const int4*)((char*)ctx->d_topo.p + ctx->off_ops);
-    wp.ptab = (const double*)ctx->d_ptab.p;
+    wp.btab = (const double*)ctx->d_btab.p;
     wp.dyn = (const double*)ctx->d_dyn.p;
     wp.scratch = (double*)ctx->d_scratch.p;
     wp.scratch_per_cta = ctx->scratch_per_cta;
@@ -866,9 +1074,10 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.T = T;
     wp.R = R;
     wp.want_grad = a.want_grad ? 1 : 0;
+    wp.max_br = ctx->max_br;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
     int rc = 0;
-    MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp));
+    MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp, dyn_model));
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
     {
@@ -908,8 +1117,8 @@ int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S,
     mcp_alignment* al = new mcp_alignment();
     al->K = K;
     al->S = S;
-    al->stride = (S + 127) & ~127LL;
-    if (al->stride == 0) al->stride = 128;
+    al->stride = (S + 255) & ~255LL;   // a tile (<= 256 sites) never reads past a row
+    if (al->stride == 0) al->stride = 256;
     al->n_leaves = n_leaves;
     al->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
     al->id = ctx->next_aln_id++;
@@ -980,9 +1189,9 @@ int mcp_destroy(mcp_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_ptab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out})
+    for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out})
         if (b->p) cudaFree(b->p);
-    for (PinBuf* b : {&ctx->h_topo, &ctx->h_dyn, &ctx->h_out})
+    for (PinBuf* b : {&ctx->h_topo, &ctx->h_dyn, &ctx->h_out, &ctx->h_model})
         if (b->p) cudaFreeHost(b->p);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -997,7 +1206,17 @@ int mcp_set_stream(mcp_ctx* ctx, void* cuda_stream) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->pending_async = false;
     }
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;   // NULL is the CUDA default stream, a valid choice
+    return 0;
+}
+
+int mcp_use_own_stream(mcp_ctx* ctx) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (ctx->pending_async) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->pending_async = false;
+    }
+    ctx->stream = ctx->own_stream;
     return 0;
 }
 

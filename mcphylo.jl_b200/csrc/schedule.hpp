@@ -38,19 +38,28 @@ enum : int { OPK_LEAF = 0, OPK_REG = 1, OPK_MEM = 2 };          // post operand 
 enum : int { PREM_ROOT = 0, PREM_REG = 1, PREM_STACK = 2 };     // where pre[mother] comes from
 enum : int { OUT_NONE = 0, OUT_KEEP = 1, OUT_PUSH = 2 };        // what happens to pre[child]
 
-// 8 x int32 each.
+// Both op types are 8 x int32 with a common head so that the kernel's staging code can treat
+// them alike:
+//   word 0..3  a_src, a_br, b_src, b_br   child operands: LEAF -> alignment row (-1 = all ones),
+//                                          MEM -> post slot of the child, REG -> unused;
+//                                          *_br = device node id of the child (branch-table row)
+//   word 4     post: dst slot (if STORE)   pre: m_src (LIFO slot when the mother is on the stack)
+//   word 5     flags: bits 0-1 a kind, 2-3 b kind (OPK_*), 4 POST_STORE, 5 POST_ROOT,
+//              pre only: bits 8-9 where pre[mother] comes from (PREM_*), 10-11 a out, 12-13 b out (OUT_*)
+//   word 6     post: device node id (debug) pre: a_dst (LIFO slot if a is pushed)
+//   word 7     pre: b_dst
 struct PostOp {
-    int32_t a_src, a_br, b_src, b_br;  // LEAF: alignment row (-1 = all ones); MEM: slot; REG: unused
-    int32_t dst;                       // slot to store the result in (if STORE)
-    int32_t flags;                     // bits 0-1 a kind, 2-3 b kind, 4 STORE, 5 ROOT
-    int32_t node;                      // device node id (debug / emulator)
+    int32_t a_src, a_br, b_src, b_br;
+    int32_t dst;
+    int32_t flags;
+    int32_t node;
     int32_t pad;
 };
 struct PreOp {
-    int32_t m_src;                     // STACK: lifo slot
-    int32_t a_src, a_br, b_src, b_br;  // LEAF: alignment row; internal: post slot of the child
-    int32_t a_dst, b_dst;              // PUSH: lifo slot
-    int32_t flags;                     // bits 0-1 m kind, 2 a internal, 3 b internal, 4-5 a out, 6-7 b out
+    int32_t a_src, a_br, b_src, b_br;
+    int32_t m_src;
+    int32_t flags;
+    int32_t a_dst, b_dst;
 };
 static_assert(sizeof(PostOp) == 32 && sizeof(PreOp) == 32, "ops are two 16-byte words");
 
@@ -231,7 +240,8 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
                 next = keep;
             } else if (ai) { a_out = OUT_KEEP; next = a; }
             else if (bi) { b_out = OUT_KEEP; next = b; }
-            op.flags = cur_kind | (ai ? 4 : 0) | (bi ? 8 : 0) | (a_out << 4) | (b_out << 6);
+            op.flags = (ai ? OPK_MEM : OPK_LEAF) | ((bi ? OPK_MEM : OPK_LEAF) << 2) | (cur_kind << 8) |
+                       (a_out << 10) | (b_out << 12);
             out.pre.push_back(op);
             if (next >= 0) { cur = next; cur_kind = PREM_REG; cur_src = 0; }
             else if (!pending.empty()) {

@@ -59,8 +59,8 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches):
 
         stack = {}
         for op in prog["pre"]:
-            m_src, a_src, a_br, b_src, b_br, a_dst, b_dst, flags = (int(v) for v in op)
-            mk = flags & 3
+            a_src, a_br, b_src, b_br, m_src, flags, a_dst, b_dst = (int(v) for v in op)
+            mk = (flags >> 8) & 3
             pm = np.repeat(pi[:, None], S, axis=1) if mk == PREM_ROOT else (reg if mk == PREM_REG else stack[m_src])
 
             def child(internal, src, br):
@@ -69,13 +69,13 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches):
                     L = slots[src]
                     return Pm @ L, dPm @ L, Pm
                 return leaf_down(Pm, src), leaf_down(dPm, src), Pm
-            Da, Ya, Pa = child(flags & 4, a_src, a_br)
-            Db, Yb, Pb = child(flags & 8, b_src, b_br)
+            Da, Ya, Pa = child((flags & 3) == OPK_MEM, a_src, a_br)
+            Db, Yb, Pb = child(((flags >> 2) & 3) == OPK_MEM, b_src, b_br)
             qa, qb = pm * Db, pm * Da
             den = (qa * Da).sum(axis=0)
             grad[a_br] += ((qa * Ya).sum(axis=0) / den).sum()
             grad[b_br] += ((qb * Yb).sum(axis=0) / den).sum()
-            for out, dst, Pm, q in (((flags >> 4) & 3, a_dst, Pa, qa), ((flags >> 6) & 3, b_dst, Pb, qb)):
+            for out, dst, Pm, q in (((flags >> 10) & 3, a_dst, Pa, qa), ((flags >> 12) & 3, b_dst, Pb, qb)):
                 if out == OUT_NONE:
                     continue
                 v, _ = _rescale(Pm.T @ q)

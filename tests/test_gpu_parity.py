@@ -239,3 +239,34 @@ def test_error_paths():
         mcp.logpdf(mcp.PhyloDist(t2, np.full(20, 0.05), [1.0], [1.0], mcp.JC),
                    mcp.DeviceAlignment(np.zeros((2, 5), np.uint8), [1, 2], 20))
     assert ei.value.code == -3
+
+
+def test_sharded_evaluator_follows_torch_streams(oracle):
+    """The multi-GPU entry (mcp_eval_device on torch's current stream, result left on the device)
+    at world size 1, on the default stream and on a side stream."""
+    import torch
+    rng = np.random.default_rng(31)
+    tree = random_tree(60, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 5000, rng)
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates)
+    ev = mcp.ShardedEvaluator(aln, 0)
+    try:
+        ll, g = ev.gradlogpdf(pd)
+        _check(ll, g, ll_o, g_o)
+        assert ev.ctx.stats()["walk_ms"] > 0
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                ll2, g2 = ev.gradlogpdf(pd)
+        assert ll2 == ll and np.array_equal(g2, g)
+        assert abs(ev.logpdf(pd) - ll_o) <= LL_RTOL * abs(ll_o)
+    finally:
+        ev.ctx.set_stream(None)
+    # shards of one alignment add up to the whole (what the all-reduce sums)
+    parts = [mcp.gradlogpdf(pd, mcp.local_shard(aln, 4, r)) for r in range(4)]
+    assert abs(sum(p[0] for p in parts) - ll) <= 1e-12 * abs(ll)
