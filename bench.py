@@ -160,6 +160,10 @@ def cpu_oracle_rate(w, codes, leaf_nums, sample_sites, steps, warmup, threads=0)
     s = min(sample_sites, codes.shape[1])
     x = oracle.codes_to_dense(codes[:, :s], leaf_nums, w["K"], ft.NN)
     U, D, Uinv, mu = w["model"](w["pi"], w["srates"])
+    if threads <= 0:
+        # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle sets
+        # its OpenMP team size explicitly, so that default does not shrink the CPU baseline)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
@@ -167,7 +171,7 @@ def cpu_oracle_rate(w, codes, leaf_nums, sample_sites, steps, warmup, threads=0)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     sec = float(np.mean(times))
-    return 1.0 / (sec * (w["S"] / s)), sec, (threads if threads > 0 else oracle.num_threads()), s
+    return 1.0 / (sec * (w["S"] / s)), sec, threads, s
 
 
 def run_reference(args):
@@ -242,7 +246,7 @@ def run_b200(args):
 
     # alignment upload (one-off, reported separately)
     t_up = time.perf_counter()
-    ll, grad = ev.gradlogpdf(dist_for(0))
+    ll0, grad0 = ev.gradlogpdf(dist_for(0))
     torch.cuda.synchronize()
     t_up = time.perf_counter() - t_up
     pinned_codes = torch.from_numpy(codes).pin_memory()
@@ -341,8 +345,9 @@ def run_b200(args):
                        "scratch_bytes": stats["scratch_bytes"]},
             "setup": {"alignment_generate_s": t_gen, "first_eval_incl_upload_s": t_up,
                       "codes_bytes_per_gpu": int(codes.nbytes)},
-            "result_check": {"logL": ll, "grad_finite": bool(np.all(np.isfinite(grad))),
-                             "e2e_matches": bool(abs(ll_e - ll) <= 1e-9 * abs(ll))},
+            "result_check": {"logL_at_initial_branch_lengths": ll0, "grad_l2_at_initial_branch_lengths":
+                             float(np.linalg.norm(grad0)), "grad_finite": bool(np.all(np.isfinite(grad))),
+                             "e2e_matches_resident": bool(abs(ll_e - ll) <= 1e-9 * abs(ll))},
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = args.cpu_sample or 10000

@@ -206,19 +206,32 @@ __device__ __forceinline__ void eig_transposed(const Model<K>& m, const double (
     }
 }
 
-// Multiply a column by the exact power of two that brings its maximum into [1,2); returns the
-// removed binary exponent.  Zero / denormal / non-finite maxima are left alone.
+// Multiply a column by the exact power of two that brings its largest magnitude into [1,2);
+// returns the removed binary exponent.  Works on the exponent fields with integer ops (fp64 has no
+// native max instruction; fmax() costs ~10 instructions).  Zero / denormal / non-finite maxima are
+// left alone.
 template <int K>
 __device__ __forceinline__ int rescale_pow2(double (&v)[K]) {
-    double m = v[0];
+    unsigned m = (unsigned)__double2hiint(v[0]) & 0x7fffffffu;
 #pragma unroll
-    for (int k = 1; k < K; ++k) m = fmax(m, v[k]);
-    int e = (__double2hiint(m) >> 20) & 0x7ff;
+    for (int k = 1; k < K; ++k) m = max(m, (unsigned)__double2hiint(v[k]) & 0x7fffffffu);
+    const int e = (int)(m >> 20);
     if (e == 0 || e == 0x7ff) return 0;
-    double sc = __hiloint2double((2046 - e) << 20, 0);
+    const double sc = __hiloint2double((2046 - e) << 20, 0);
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] *= sc;
     return e - 1023;
+}
+
+// 1/x for a positive, normal x: hardware seed + two Newton steps (relative error ~1e-16; the
+// quotient only scales a gradient term whose tolerance is 1e-8).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
 }
 
 // lane 0 ends with sum(va) over the warp, lane 16 with sum(vb)
@@ -307,7 +320,26 @@ __global__ void build_branch_tables(const TreeDev* __restrict__ trees, const dou
 // so the only global accesses on the per-op critical path are the thread's own partials and the
 // leaf-table gathers.  One __syncthreads per chunk.
 // --------------------------------------------------------------------------------------------
+#ifndef MCP_WQ
+#define MCP_WQ 0
+#endif
 constexpr int CH = 16;
+
+// Per-op record derived by the staging threads from the raw descriptor (schedule.hpp): everything the
+// compute threads need as ready-to-add byte offsets, so no warp repeats the uniform address math.
+//   xa / xb  LEAF child: byte offset (from the branch-table base) of the child's P columns for this
+//            tile's rate; MEM child: byte offset (from the thread's scratch base) of its stored partial
+//   post: y0 = where to store the result          pre: y0 = pre[mother] on the LIFO, y1 / y2 = where
+//                                                       pre[a] / pre[b] are pushed
+// Offsets are 32-bit: a CTA's scratch region and one tree's branch table are far below 4 GB (checked
+// on the host).
+struct __align__(16) OpRec {
+    int flags;
+    unsigned xa, xb, y0;       // first half: needed at the start of the op
+    int a_br, b_br;
+    unsigned y1, y2;           // second half: needed at its end
+};
+static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 
 template <int K>
 struct WalkSmem {
@@ -316,8 +348,9 @@ struct WalkSmem {
     static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
     static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * K * 8; }
     static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
+    static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
     static __host__ __device__ size_t total(int n_br, int want_grad, int TW) {
-        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + code_bytes(TW);
+        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + rec_bytes() + code_bytes(TW);
     }
 };
 
@@ -341,11 +374,15 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
     int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
     double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
-    unsigned char* const scode = reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes();
+    OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
+    unsigned char* const scode = reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes();
 
-    double* const slots = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K;
-    double* const stack = slots + (long long)p.n_slots * TW * K;
-    const long long slot_stride = (long long)TW * K;
+    // per-thread base of the CTA-private scratch; all slot / LIFO offsets in the records are byte
+    // offsets from here
+    unsigned char* const scr = reinterpret_cast<unsigned char*>(
+        p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K);
+    const unsigned slot_bytes = (unsigned)TW * K * 8;
+    const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
     constexpr int BT = K + 2 * K * (K + 1);
@@ -372,8 +409,9 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
             const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TW;
             const bool valid = site0 + tid < tr.S;
             const unsigned char* const codes0 = tr.codes + site0;
-            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT;
-            const long long br_stride = (long long)R * BT;
+            // this tree's branch table at (branch 0, rate r); record offsets are relative to it
+            const unsigned char* const btab_b = reinterpret_cast<const unsigned char*>(p.btab + tr.btab_off + (long long)r * BT);
+            const unsigned br_bytes = (unsigned)R * BT * 8;
             double crate[K];
 #pragma unroll
             for (int i = 0; i < K; ++i) crate[i] = mdl.c(r, i);
@@ -384,11 +422,14 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                 int4* dst = sdesc + (c % 3) * (CH * 2);
                 for (int i = tid; i < cnt * 2; i += TW) cp_async16(dst + i, ops + 2 * base + i);
             };
-            auto stage_data = [&](int n_ops, int c) {
+            // Copies e vectors / leaf codes of chunk c and derives the per-op records (byte offsets),
+            // once per CTA instead of once per warp.  `pre` selects the pre-program field meaning.
+            auto stage_data = [&](int n_ops, int c, bool pre) {
                 const int base = c * CH, cnt = min(CH, n_ops - base);
                 const int4* d = sdesc + (c % 3) * (CH * 2);
                 double* eb = se + (c & 1) * (CH * 2 * K);
                 unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                OpRec* rb = srec + (c & 1) * CH;
                 const int pieces = TW / 16;                  // 16-byte pieces of one code row segment
                 const int per_child = pieces > (K * 8 + 15) / 16 ? pieces : (K * 8 + 15) / 16;
                 for (int w = tid; w < cnt * 2 * per_child; w += TW) {
@@ -398,42 +439,61 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                     const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
                     const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
                     if (kind == mcp::OPK_LEAF) {
-                        if (piece < pieces && src >= 0)
-                            cp_async16(cb + (size_t)(j * 2 + ch) * TW + piece * 16,
-                                       codes0 + (long long)src * tr.code_stride + piece * 16);
+                        if (piece < pieces) {
+                            unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TW + piece * 16;
+                            if (src >= 0) cp_async16(dstp, codes0 + (long long)src * tr.code_stride + piece * 16);
+                            else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
+                        }
                     } else if (piece * 16 < K * 8) {
+                        const double* esrc = reinterpret_cast<const double*>(btab_b + (unsigned)br * br_bytes);
                         if constexpr ((K * 8) % 16 == 0) {
                             cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * K) + piece * 16,
-                                       reinterpret_cast<const unsigned char*>(tab_r + br * br_stride) + piece * 16);
+                                       reinterpret_cast<const unsigned char*>(esrc) + piece * 16);
                         } else {
                             if (piece == 0) {
 #pragma unroll
-                                for (int k = 0; k < K; ++k) eb[(j * 2 + ch) * K + k] = __ldg(tab_r + br * br_stride + k);
+                                for (int k = 0; k < K; ++k) eb[(j * 2 + ch) * K + k] = __ldg(esrc + k);
                             }
                         }
                     }
                 }
+                for (int j = tid; j < cnt; j += TW) {
+                    const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
+                    const int fl = o1.y, ka = fl & 3, kb = (fl >> 2) & 3;
+                    OpRec rec;
+                    rec.flags = fl;
+                    rec.a_br = o0.y;
+                    rec.b_br = o0.w;
+                    rec.xa = ka == mcp::OPK_LEAF ? (unsigned)o0.y * br_bytes + K * 8 : (unsigned)o0.x * slot_bytes;
+                    rec.xb = kb == mcp::OPK_LEAF ? (unsigned)o0.w * br_bytes + K * 8 : (unsigned)o0.z * slot_bytes;
+                    if (pre) {
+                        rec.y0 = stack_base + (unsigned)o1.x * slot_bytes;     // pre[mother] on the LIFO
+                        rec.y1 = stack_base + (unsigned)o1.z * slot_bytes;     // where pre[a] is pushed
+                        rec.y2 = stack_base + (unsigned)o1.w * slot_bytes;     // where pre[b] is pushed
+                    } else {
+                        rec.y0 = (unsigned)o1.x * slot_bytes;                  // where the result is stored
+                        rec.y1 = 0;
+                        rec.y2 = 0;
+                    }
+                    rb[j] = rec;
+                }
             };
-            auto prologue = [&](const int4* ops, int n_ops) {
+            auto prologue = [&](const int4* ops, int n_ops, bool pre) {
                 __syncthreads();                              // previous pass / tile done with the buffers
                 stage_desc(ops, n_ops, 0);
                 if (n_ops > CH) stage_desc(ops, n_ops, 1);
                 cp_async_commit();
                 cp_async_wait_all();
                 __syncthreads();
-                stage_data(n_ops, 0);
+                stage_data(n_ops, 0, pre);
                 cp_async_commit();
             };
-            auto chunk_boundary = [&](const int4* ops, int n_ops, int c, int n_chunks) {
+            auto chunk_boundary = [&](const int4* ops, int n_ops, int c, int n_chunks, bool pre) {
                 cp_async_wait_all();
                 __syncthreads();                              // chunk c data + descriptors c, c+1 visible
-                if (c + 1 < n_chunks) stage_data(n_ops, c + 1);
+                if (c + 1 < n_chunks) stage_data(n_ops, c + 1, pre);
                 if (c + 2 < n_chunks) stage_desc(ops, n_ops, c + 2);
                 cp_async_commit();
-            };
-            auto leaf_code = [&](const unsigned char* cb, int j, int ch, int src) -> int {
-                int code = (valid && src >= 0) ? (int)cb[(size_t)(j * 2 + ch) * TW + tid] : K;
-                return min(code, K);
             };
 
             // ------------------------------ post pass ------------------------------
@@ -443,23 +503,25 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
             int e_col = 0;
             {
                 const int n_post = tr.n_post, n_chunks = (n_post + CH - 1) / CH;
-                prologue(post_ops, n_post);
+                prologue(post_ops, n_post, false);
                 for (int c = 0; c < n_chunks; ++c) {
-                    chunk_boundary(post_ops, n_post, c, n_chunks);
-                    const int4* d = sdesc + (c % 3) * (CH * 2);
+                    chunk_boundary(post_ops, n_post, c, n_chunks, false);
+                    const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW) + tid;
                     const int cnt = min(CH, n_post - c * CH);
                     for (int j = 0; j < cnt; ++j) {
-                        const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
-                        const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
+                        const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
+                        struct { int flags; unsigned xa, xb, y0; } rec = {(int)rh.x, rh.y, rh.z, rh.w};
+                        const int flags = rec.flags, ka = flags & 3, kb = (flags >> 2) & 3;
                         // stored operand (at most one per op) first: its latency overlaps the rest
                         double Lm[K];
-                        if (ka == mcp::OPK_MEM) ld_partial<K>(slots + o0.x * slot_stride, Lm);
-                        else if (kb == mcp::OPK_MEM) ld_partial<K>(slots + o0.z * slot_stride, Lm);
+                        if (ka == mcp::OPK_MEM) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xa), Lm);
+                        else if (kb == mcp::OPK_MEM) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xb), Lm);
                         double Da[K], Db[K];
                         if (ka == mcp::OPK_LEAF) {
-                            ld_table<K>(tab_r + o0.y * br_stride + K + leaf_code(cb, j, 0, o0.x) * K, Da);
+                            const int code = min((int)cb[(j * 2 + 0) * TW], K);
+                            ld_table<K>(reinterpret_cast<const double*>(btab_b + rec.xa) + code * K, Da);
                         } else {
                             double e[K], z[K];
 #pragma unroll
@@ -469,7 +531,8 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                             eig_expand<K>(mdl, z, Da);
                         }
                         if (kb == mcp::OPK_LEAF) {
-                            ld_table<K>(tab_r + o0.w * br_stride + K + leaf_code(cb, j, 1, o0.z) * K, Db);
+                            const int code = min((int)cb[(j * 2 + 1) * TW], K);
+                            ld_table<K>(reinterpret_cast<const double*>(btab_b + rec.xb) + code * K, Db);
                         } else {
                             double e[K], z[K];
 #pragma unroll
@@ -481,7 +544,7 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
 #pragma unroll
                         for (int k = 0; k < K; ++k) cur[k] = Da[k] * Db[k];
                         e_col += rescale_pow2<K>(cur);
-                        if (flags & mcp::POST_STORE) st_partial<K>(slots + o1.x * slot_stride, cur);
+                        if (flags & mcp::POST_STORE) st_partial<K>(reinterpret_cast<double*>(scr + rec.y0), cur);
                     }
                 }
             }
@@ -498,24 +561,24 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
             // ------------------------------ gradient pass ------------------------------
             if (p.want_grad) {
                 const int n_pre = tr.n_pre, n_chunks = (n_pre + CH - 1) / CH;
-                prologue(pre_ops, n_pre);
+                prologue(pre_ops, n_pre, true);
                 for (int c = 0; c < n_chunks; ++c) {
-                    chunk_boundary(pre_ops, n_pre, c, n_chunks);
-                    const int4* d = sdesc + (c % 3) * (CH * 2);
+                    chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
+                    const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW) + tid;
                     const int cnt = min(CH, n_pre - c * CH);
                     for (int j = 0; j < cnt; ++j) {
-                        const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
-                        const int flags = o1.y;
-                        const int a_br = o0.y, b_br = o0.w;
+                        const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
+                        struct { int flags; unsigned xa, xb, y0; } rec = {(int)rh.x, rh.y, rh.z, rh.w};
+                        const int flags = rec.flags;
                         const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
                         const int mk = (flags >> 8) & 3;
                         // all stored operands of the family are requested up front
                         double pm[K], La[K], Lb[K];
-                        if (mk == mcp::PREM_STACK) ld_partial<K>(stack + o1.x * slot_stride, pm);
-                        if (ai) ld_partial<K>(slots + o0.x * slot_stride, La);
-                        if (bi) ld_partial<K>(slots + o0.z * slot_stride, Lb);
+                        if (mk == mcp::PREM_STACK) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.y0), pm);
+                        if (ai) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xa), La);
+                        if (bi) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xb), Lb);
                         if (mk == mcp::PREM_ROOT) {
 #pragma unroll
                             for (int k = 0; k < K; ++k) pm[k] = mdl.pi(k);
@@ -523,6 +586,120 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
 #pragma unroll
                             for (int k = 0; k < K; ++k) pm[k] = cur[k];
                         }
+#if MCP_WQ
+                        // Da = P_a L_a, Db = P_b L_b.  For an internal child z = e*(Uinv L) is kept:
+                        // q.(dP L) = sum_i c_i z_i (U^T q)_i, and U^T q is needed for pre[child] anyway.
+                        double ea[K], ebv[K], za[K], zb[K];
+                        double Da[K], Db[K], Ya[K], Yb[K];
+                        if (ai) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * K + k];
+                            eig_project<K>(mdl, La, ea, za);
+                            eig_expand<K>(mdl, za, Da);
+                        } else {
+                            const int code = min((int)cb[(j * 2 + 0) * TW], K);
+                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xa) + code * K;
+                            ld_table<K>(t, Da);
+                            ld_table<K>(t + K * (K + 1), Ya);
+                        }
+                        if (bi) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * K + k];
+                            eig_project<K>(mdl, Lb, ebv, zb);
+                            eig_expand<K>(mdl, zb, Db);
+                        } else {
+                            const int code = min((int)cb[(j * 2 + 1) * TW], K);
+                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xb) + code * K;
+                            ld_table<K>(t, Db);
+                            ld_table<K>(t + K * (K + 1), Yb);
+                        }
+                        double qa[K], qb[K];
+                        double den = 0.0;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            qa[k] = pm[k] * Db[k];
+                            qb[k] = pm[k] * Da[k];
+                            den = fma(qa[k], Da[k], den);
+                        }
+                        double na = 0.0, nb = 0.0;
+                        double wa[K], wb[K];   // U^T q (internal children only)
+                        if (ai) {
+#pragma unroll
+                            for (int i = 0; i < K; ++i) {
+                                double w = mdl.U(0, i) * qa[0];
+#pragma unroll
+                                for (int s2 = 1; s2 < K; ++s2) w = fma(mdl.U(s2, i), qa[s2], w);
+                                wa[i] = w;
+                                na = fma(crate[i] * za[i], w, na);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) na = fma(qa[k], Ya[k], na);
+                        }
+                        if (bi) {
+#pragma unroll
+                            for (int i = 0; i < K; ++i) {
+                                double w = mdl.U(0, i) * qb[0];
+#pragma unroll
+                                for (int s2 = 1; s2 < K; ++s2) w = fma(mdl.U(s2, i), qb[s2], w);
+                                wb[i] = w;
+                                nb = fma(crate[i] * zb[i], w, nb);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) nb = fma(qb[k], Yb[k], nb);
+                        }
+                        const double inv = fast_rcp(den);
+                        const double ga = valid ? na * inv : 0.0;
+                        const double gb = valid ? nb * inv : 0.0;
+                        const double red = warp_pair_reduce(ga, gb, lane);
+                        if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
+                        else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
+
+                        // pre[child] = P^T q = Uinv^T (e * (U^T q)), only internal children have one
+                        const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
+                        if (a_out != mcp::OUT_NONE) {
+                            double pa[K];
+#pragma unroll
+                            for (int i = 0; i < K; ++i) wa[i] *= ea[i];
+#pragma unroll
+                            for (int jj = 0; jj < K; ++jj) {
+                                double acc = mdl.Ui(0, jj) * wa[0];
+#pragma unroll
+                                for (int i = 1; i < K; ++i) acc = fma(mdl.Ui(i, jj), wa[i], acc);
+                                pa[jj] = acc;
+                            }
+                            rescale_pow2<K>(pa);
+                            if (a_out == mcp::OUT_KEEP) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) cur[k] = pa[k];
+                            } else {
+                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y1), pa);
+                            }
+                        }
+                        if (b_out != mcp::OUT_NONE) {
+                            double pb[K];
+#pragma unroll
+                            for (int i = 0; i < K; ++i) wb[i] *= ebv[i];
+#pragma unroll
+                            for (int jj = 0; jj < K; ++jj) {
+                                double acc = mdl.Ui(0, jj) * wb[0];
+#pragma unroll
+                                for (int i = 1; i < K; ++i) acc = fma(mdl.Ui(i, jj), wb[i], acc);
+                                pb[jj] = acc;
+                            }
+                            rescale_pow2<K>(pb);
+                            if (b_out == mcp::OUT_KEEP) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) cur[k] = pb[k];
+                            } else {
+                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y2), pb);
+                            }
+                        }
+                    }
+                }
+            }
+#else
                         double ea[K], ebv[K];
                         double Da[K], Ya[K], Db[K], Yb[K];
                         if (ai) {
@@ -535,7 +712,8 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                             eig_expand<K>(mdl, z, Da);
                             eig_expand<K>(mdl, zd, Ya);
                         } else {
-                            const double* t = tab_r + a_br * br_stride + K + leaf_code(cb, j, 0, o0.x) * K;
+                            const int code = min((int)cb[(j * 2 + 0) * TW], K);
+                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xa) + code * K;
                             ld_table<K>(t, Da);
                             ld_table<K>(t + K * (K + 1), Ya);
                         }
@@ -549,7 +727,8 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                             eig_expand<K>(mdl, z, Db);
                             eig_expand<K>(mdl, zd, Yb);
                         } else {
-                            const double* t = tab_r + b_br * br_stride + K + leaf_code(cb, j, 1, o0.z) * K;
+                            const int code = min((int)cb[(j * 2 + 1) * TW], K);
+                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xb) + code * K;
                             ld_table<K>(t, Db);
                             ld_table<K>(t + K * (K + 1), Yb);
                         }
@@ -563,12 +742,12 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                             na = fma(qa[k], Ya[k], na);
                             nb = fma(qb[k], Yb[k], nb);
                         }
-                        const double inv = 1.0 / den;
+                        const double inv = fast_rcp(den);
                         const double ga = valid ? na * inv : 0.0;
                         const double gb = valid ? nb * inv : 0.0;
                         const double red = warp_pair_reduce(ga, gb, lane);
-                        if (lane == 0) atomicAdd(&s_acc[a_br], red);
-                        else if (lane == 16) atomicAdd(&s_acc[b_br], red);
+                        if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
+                        else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
 
                         const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
                         if (a_out != mcp::OUT_NONE) {
@@ -579,7 +758,7 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
 #pragma unroll
                                 for (int k = 0; k < K; ++k) cur[k] = pa[k];
                             } else {
-                                st_partial<K>(stack + o1.z * slot_stride, pa);
+                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y1), pa);
                             }
                         }
                         if (b_out != mcp::OUT_NONE) {
@@ -590,12 +769,13 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
 #pragma unroll
                                 for (int k = 0; k < K; ++k) cur[k] = pb[k];
                             } else {
-                                st_partial<K>(stack + o1.w * slot_stride, pb);
+                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y2), pb);
                             }
                         }
                     }
                 }
             }
+#endif
         }  // tiles of this tree
 
         // ---- flush this CTA's sums for the tree into its accumulator row ----
@@ -784,7 +964,7 @@ int occupancy_for(mcp_ctx* ctx, int block, size_t smem, int* out) {
 }
 size_t walk_smem_bytes(int K, int max_br, int want_grad, int block) {
     size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
-    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 2 * block;
+    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 32 + (size_t)2 * CH * 2 * block;
 }
 
 #define MCP_DISPATCH_K(K, CALL)                      \
@@ -939,6 +1119,8 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         ctx->n_rows = row;
     }
     ctx->row_stride = (max_br + 3) & ~3;
+    if ((double)(ctx->n_slots + n_stack + 1) * block * K * 8.0 >= 4.0e9 || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
+        return fail(ctx, MCP_ERR_UNSUPPORTED, "tree too large for 32-bit scratch offsets (%d nodes)", max_br);
     ctx->scratch_per_cta = (long long)(ctx->n_slots + ctx->n_stack) * block * K;
 
     // topology upload: [TreeDev x T][ops][row_base]
