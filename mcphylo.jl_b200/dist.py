@@ -59,13 +59,19 @@ class ShardedEvaluator:
         return self._out, self._pinned
 
     def evaluate(self, d: PhyloDist, want_grad: bool = True):
-        torch = self.torch
         ft, targs = _tree_args(d)
-        out, pinned = self._buffers(ft.NN)
+        return self.evaluate_flat(ft.leaf_nums, d.nbase, targs, want_grad)
+
+    def evaluate_flat(self, leaf_nums, K: int, targs, want_grad: bool = True):
+        """Same evaluation from already-flattened inputs: targs = (postorder_num, parent_num, blv,
+        U, D, Uinv, mu, rates, pi), exactly the argument list of mcp_eval_device."""
+        torch = self.torch
+        NN = len(targs[0])
+        out, pinned = self._buffers(NN)
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream()
             self.ctx.set_stream(stream.cuda_stream)
-            aln = _device_alignment(self.aln, ft.leaf_nums, d.nbase, self.ctx)
+            aln = _device_alignment(self.aln, leaf_nums, K, self.ctx)
             self.ctx.eval_device(aln, *targs, want_grad=want_grad, d_out_ptr=out.data_ptr())
             allreduce_sum(out, self.group)
             pinned.copy_(out, non_blocking=True)

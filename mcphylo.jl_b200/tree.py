@@ -62,15 +62,15 @@ Node = GeneralNode
 
 def post_order(root: GeneralNode) -> List[GeneralNode]:
     """Children (in stored order) before their mother; the root comes last."""
+    # reversed "root, then children right-to-left" pre-order == left-to-right post-order
     out: List[GeneralNode] = []
-    stack = [(root, 0)]
+    stack = [root]
+    pop, push, extend = stack.pop, out.append, stack.extend
     while stack:
-        node, i = stack.pop()
-        if i < len(node.children):
-            stack.append((node, i + 1))
-            stack.append((node.children[i], 0))
-        else:
-            out.append(node)
+        node = pop()
+        push(node)
+        extend(node.children)
+    out.reverse()
     return out
 
 
@@ -123,18 +123,16 @@ def number_nodes(root: GeneralNode) -> None:
 def get_branchlength_vector(root: GeneralNode) -> np.ndarray:
     """blv[node.num - 1] = node.inc_length for every non-root node (length NN-1)."""
     po = post_order(root)
-    out = np.zeros(len(po) - 1, dtype=np.float64)
-    for n in po:
-        if n is not root:
-            out[n.num - 1] = n.inc_length
-    return out
+    out = np.zeros(len(po), dtype=np.float64)
+    out[np.array([n.num for n in po]) - 1] = [n.inc_length for n in po]
+    return out[:len(po) - 1].copy()
 
 
 def set_branchlength_vector(root: GeneralNode, blv: Iterable[float]) -> None:
-    blv = np.asarray(blv, dtype=np.float64)
+    vals = np.asarray(blv, dtype=np.float64).tolist()
     for n in post_order(root):
         if n is not root:
-            n.inc_length = float(blv[n.num - 1])
+            n.inc_length = vals[n.num - 1]
 
 
 def tree_length(root: GeneralNode) -> float:
@@ -281,19 +279,17 @@ class FlatTree:
 def flatten(root: GeneralNode) -> FlatTree:
     po = post_order(root)
     NN = len(po)
-    postorder_num = np.fromiter((n.num for n in po), dtype=np.int32, count=NN)
-    parent_num = np.zeros(NN, dtype=np.int32)
-    blv = np.zeros(max(NN - 1, 0), dtype=np.float64)
-    leaf_nums = []
-    leaf_names = []
-    for n in po:
-        if n.mother is not None:
-            parent_num[n.num - 1] = n.mother.num
-            blv[n.num - 1] = n.inc_length
-        if n.nchild == 0:
-            leaf_nums.append(n.num)
-            leaf_names.append(n.name)
     if po[-1].num != NN:
         raise ValueError("root must carry the largest node number (run number_nodes)")
-    return FlatTree(NN, postorder_num, parent_num, blv,
-                    np.asarray(leaf_nums, dtype=np.int32), leaf_names)
+    nums = [n.num for n in po]
+    parents = [n.mother.num if n.mother is not None else 0 for n in po]
+    lengths = [n.inc_length for n in po]
+    postorder_num = np.array(nums, dtype=np.int32)
+    idx = postorder_num - 1
+    parent_num = np.zeros(NN, dtype=np.int32)
+    parent_num[idx] = parents
+    blv_full = np.zeros(NN, dtype=np.float64)
+    blv_full[idx] = lengths
+    leaves = [n for n in po if not n.children]
+    return FlatTree(NN, postorder_num, parent_num, blv_full[:NN - 1].copy(),
+                    np.array([n.num for n in leaves], dtype=np.int32), [n.name for n in leaves])
