@@ -151,6 +151,8 @@ int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
 /* Tuning knobs: block = threads per CTA (= columns per tile; 0 = automatic),
  * ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
 int mcp_set_launch(mcp_ctx *ctx, int block, int ctas_per_sm);
+/* Alignment columns walked by one thread: 1, 2, or 0 = automatic (2 once the GPU is full). */
+int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);
 
 /*
  * Host-only: emits the device schedule (the flat "walk program") for a topology, so the

@@ -22,6 +22,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
+    "mcp_set_columns_per_thread",
     "mcp_schedule_dump",
 ]
 
@@ -66,6 +67,7 @@ def load():
     lib.mcp_set_stream.argtypes = [_vp, _vp]
     lib.mcp_use_own_stream.argtypes = [_vp]
     lib.mcp_set_launch.argtypes = [_vp, C.c_int, C.c_int]
+    lib.mcp_set_columns_per_thread.argtypes = [_vp, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
@@ -159,6 +161,9 @@ class Context:
 
     def set_launch(self, block: int = 0, ctas_per_sm: int = 0):
         self._check(self.lib.mcp_set_launch(self.handle, int(block), int(ctas_per_sm)))
+
+    def set_columns_per_thread(self, cpt: int = 0):
+        self._check(self.lib.mcp_set_columns_per_thread(self.handle, int(cpt)))
 
     def stats(self) -> dict:
         s = Stats()

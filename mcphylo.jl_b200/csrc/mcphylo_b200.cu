@@ -164,45 +164,61 @@ struct Model {
     __device__ __forceinline__ double c(int r, int i) const { return c_model[ofs + 2 * K * K + K + r * K + i]; }
 };
 
-// z = e * (Uinv L)       (the eigen-coordinates of P L)
-template <int K>
-__device__ __forceinline__ void eig_project(const Model<K>& m, const double (&L)[K], const double (&e)[K], double (&z)[K]) {
+// ---- eigen-space products for C columns at once (column index innermost, so one constant /
+// uniform-register operand feeds C independent DFMAs) ----
+// z[c] = e * (Uinv L[c])
+template <int K, int C>
+__device__ __forceinline__ void eig_project(const Model<K>& m, const double (&L)[C][K], const double (&e)[K], double (&z)[C][K]) {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        double w = m.Ui(i, 0) * L[0];
+        double w[C];
 #pragma unroll
-        for (int j = 1; j < K; ++j) w = fma(m.Ui(i, j), L[j], w);
-        z[i] = e[i] * w;
+        for (int c = 0; c < C; ++c) w[c] = m.Ui(i, 0) * L[c][0];
+#pragma unroll
+        for (int j = 1; j < K; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = fma(m.Ui(i, j), L[c][j], w[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c][i] = e[i] * w[c];
     }
 }
-// out = U z
-template <int K>
-__device__ __forceinline__ void eig_expand(const Model<K>& m, const double (&z)[K], double (&out)[K]) {
+// out[c] = U z[c]
+template <int K, int C>
+__device__ __forceinline__ void eig_expand(const Model<K>& m, const double (&z)[C][K], double (&out)[C][K]) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
-        double a = m.U(s, 0) * z[0];
 #pragma unroll
-        for (int i = 1; i < K; ++i) a = fma(m.U(s, i), z[i], a);
-        out[s] = a;
+        for (int c = 0; c < C; ++c) out[c][s] = m.U(s, 0) * z[c][0];
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
     }
 }
-// out = P^T q = Uinv^T (e * (U^T q))
-template <int K>
-__device__ __forceinline__ void eig_transposed(const Model<K>& m, const double (&q)[K], const double (&e)[K], double (&out)[K]) {
-    double z[K];
+// out[c] = P^T q[c] = Uinv^T (e * (U^T q[c]))
+template <int K, int C>
+__device__ __forceinline__ void eig_transposed(const Model<K>& m, const double (&q)[C][K], const double (&e)[K], double (&out)[C][K]) {
+    double z[C][K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        double w = m.U(0, i) * q[0];
+        double w[C];
 #pragma unroll
-        for (int s = 1; s < K; ++s) w = fma(m.U(s, i), q[s], w);
-        z[i] = e[i] * w;
+        for (int c = 0; c < C; ++c) w[c] = m.U(0, i) * q[c][0];
+#pragma unroll
+        for (int s = 1; s < K; ++s)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = fma(m.U(s, i), q[c][s], w[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c][i] = e[i] * w[c];
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        double a = m.Ui(0, j) * z[0];
 #pragma unroll
-        for (int i = 1; i < K; ++i) a = fma(m.Ui(i, j), z[i], a);
-        out[j] = a;
+        for (int c = 0; c < C; ++c) out[c][j] = m.Ui(0, j) * z[c][0];
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(i, j), z[c][i], out[c][j]);
     }
 }
 
@@ -320,9 +336,6 @@ __global__ void build_branch_tables(const TreeDev* __restrict__ trees, const dou
 // so the only global accesses on the per-op critical path are the thread's own partials and the
 // leaf-table gathers.  One __syncthreads per chunk.
 // --------------------------------------------------------------------------------------------
-#ifndef MCP_WQ
-#define MCP_WQ 0
-#endif
 constexpr int CH = 16;
 
 // Per-op record derived by the staging threads from the raw descriptor (schedule.hpp): everything the
@@ -359,13 +372,19 @@ struct WalkSmem {
 #ifndef MCP_WALK_MIN_BLOCKS
 #define MCP_WALK_MIN_BLOCKS 3
 #endif
-template <int K, bool DYN_MODEL>
-__global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(const WalkParams p) {
+// Heavier per-thread state (K * columns per thread > 4 doubles per vector) gets 2 CTAs per SM
+// (<= 128 registers) instead of 3.
+#ifndef MCP_WALK_MIN_BLOCKS2
+#define MCP_WALK_MIN_BLOCKS2 2
+#endif
+template <int K, int CPT, bool DYN_MODEL>
+__global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
 
     const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int TS = TW * CPT;                          // sites per tile; column c of a thread = site0 + c*TW + tid
     const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
     int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
     const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
@@ -377,11 +396,14 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
     OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
     unsigned char* const scode = reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes();
 
-    // per-thread base of the CTA-private scratch; all slot / LIFO offsets in the records are byte
-    // offsets from here
+    // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state]; all
+    // slot / LIFO offsets in the records are byte offsets from here
     unsigned char* const scr = reinterpret_cast<unsigned char*>(
         p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K);
-    const unsigned slot_bytes = (unsigned)TW * K * 8;
+    constexpr int COLB = 1;                           // (documentation) one column = K doubles per thread
+    (void)COLB;
+    const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
+    const unsigned slot_bytes = col_bytes * CPT;
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
@@ -406,8 +428,10 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
         for (; tile < tree_tile_end; ++tile) {
             const int local = tile - tr.tile_begin;
             const int r = local / tr.tiles_per_rate;
-            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TW;
-            const bool valid = site0 + tid < tr.S;
+            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TS;
+            bool valid[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) valid[c] = site0 + c * TW + tid < tr.S;
             const unsigned char* const codes0 = tr.codes + site0;
             // this tree's branch table at (branch 0, rate r); record offsets are relative to it
             const unsigned char* const btab_b = reinterpret_cast<const unsigned char*>(p.btab + tr.btab_off + (long long)r * BT);
@@ -428,9 +452,9 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                 const int base = c * CH, cnt = min(CH, n_ops - base);
                 const int4* d = sdesc + (c % 3) * (CH * 2);
                 double* eb = se + (c & 1) * (CH * 2 * K);
-                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW);
+                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS);
                 OpRec* rb = srec + (c & 1) * CH;
-                const int pieces = TW / 16;                  // 16-byte pieces of one code row segment
+                const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
                 const int per_child = pieces > (K * 8 + 15) / 16 ? pieces : (K * 8 + 15) / 16;
                 for (int w = tid; w < cnt * 2 * per_child; w += TW) {
                     const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
@@ -440,7 +464,7 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                     const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
                     if (kind == mcp::OPK_LEAF) {
                         if (piece < pieces) {
-                            unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TW + piece * 16;
+                            unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TS + piece * 16;
                             if (src >= 0) cp_async16(dstp, codes0 + (long long)src * tr.code_stride + piece * 16);
                             else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
                         }
@@ -495,12 +519,24 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                 if (c + 2 < n_chunks) stage_desc(ops, n_ops, c + 2);
                 cp_async_commit();
             };
+            auto ld_cols = [&](unsigned off, double (&v)[CPT][K]) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) ld_partial<K>(reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
+            };
+            auto st_cols = [&](unsigned off, const double (&v)[CPT][K]) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) st_partial<K>(reinterpret_cast<double*>(scr + off + c * col_bytes), v[c]);
+            };
 
             // ------------------------------ post pass ------------------------------
-            double cur[K];
+            double cur[CPT][K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) cur[k] = 1.0;
-            int e_col = 0;
+            for (int c = 0; c < CPT; ++c)
+#pragma unroll
+                for (int k = 0; k < K; ++k) cur[c][k] = 1.0;
+            int e_col[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) e_col[c] = 0;
             {
                 const int n_post = tr.n_post, n_chunks = (n_post + CH - 1) / CH;
                 prologue(post_ops, n_post, false);
@@ -508,53 +544,62 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                     chunk_boundary(post_ops, n_post, c, n_chunks, false);
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW) + tid;
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
                     const int cnt = min(CH, n_post - c * CH);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
-                        struct { int flags; unsigned xa, xb, y0; } rec = {(int)rh.x, rh.y, rh.z, rh.w};
-                        const int flags = rec.flags, ka = flags & 3, kb = (flags >> 2) & 3;
+                        const int flags = (int)rh.x, ka = flags & 3, kb = (flags >> 2) & 3;
                         // stored operand (at most one per op) first: its latency overlaps the rest
-                        double Lm[K];
-                        if (ka == mcp::OPK_MEM) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xa), Lm);
-                        else if (kb == mcp::OPK_MEM) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xb), Lm);
-                        double Da[K], Db[K];
+                        double Lm[CPT][K];
+                        if (ka == mcp::OPK_MEM) ld_cols(rh.y, Lm);
+                        else if (kb == mcp::OPK_MEM) ld_cols(rh.z, Lm);
+                        double Da[CPT][K], Db[CPT][K];
                         if (ka == mcp::OPK_LEAF) {
-                            const int code = min((int)cb[(j * 2 + 0) * TW], K);
-                            ld_table<K>(reinterpret_cast<const double*>(btab_b + rec.xa) + code * K, Da);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
+                                ld_table<K>(reinterpret_cast<const double*>(btab_b + rh.y) + code * K, Da[cc]);
+                            }
                         } else {
-                            double e[K], z[K];
+                            double e[K], z[CPT][K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * K + k];
-                            if (ka == mcp::OPK_REG) eig_project<K>(mdl, cur, e, z);
-                            else eig_project<K>(mdl, Lm, e, z);
-                            eig_expand<K>(mdl, z, Da);
+                            if (ka == mcp::OPK_REG) eig_project<K, CPT>(mdl, cur, e, z);
+                            else eig_project<K, CPT>(mdl, Lm, e, z);
+                            eig_expand<K, CPT>(mdl, z, Da);
                         }
                         if (kb == mcp::OPK_LEAF) {
-                            const int code = min((int)cb[(j * 2 + 1) * TW], K);
-                            ld_table<K>(reinterpret_cast<const double*>(btab_b + rec.xb) + code * K, Db);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
+                                ld_table<K>(reinterpret_cast<const double*>(btab_b + rh.z) + code * K, Db[cc]);
+                            }
                         } else {
-                            double e[K], z[K];
+                            double e[K], z[CPT][K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * K + k];
-                            if (kb == mcp::OPK_REG) eig_project<K>(mdl, cur, e, z);
-                            else eig_project<K>(mdl, Lm, e, z);
-                            eig_expand<K>(mdl, z, Db);
+                            if (kb == mcp::OPK_REG) eig_project<K, CPT>(mdl, cur, e, z);
+                            else eig_project<K, CPT>(mdl, Lm, e, z);
+                            eig_expand<K, CPT>(mdl, z, Db);
                         }
 #pragma unroll
-                        for (int k = 0; k < K; ++k) cur[k] = Da[k] * Db[k];
-                        e_col += rescale_pow2<K>(cur);
-                        if (flags & mcp::POST_STORE) st_partial<K>(reinterpret_cast<double*>(scr + rec.y0), cur);
+                        for (int cc = 0; cc < CPT; ++cc) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) cur[cc][k] = Da[cc][k] * Db[cc][k];
+                            e_col[cc] += rescale_pow2<K>(cur[cc]);
+                        }
+                        if (flags & mcp::POST_STORE) st_cols(rh.w, cur);
                     }
                 }
             }
-            {
-                double rootv = mdl.pi(0) * cur[0];
 #pragma unroll
-                for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[k], rootv);
-                if (valid) {
+            for (int cc = 0; cc < CPT; ++cc) {
+                double rootv = mdl.pi(0) * cur[cc][0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[cc][k], rootv);
+                if (valid[cc]) {
                     logsum += log(rootv);
-                    e_total += e_col;
+                    e_total += e_col[cc];
                 }
             }
 
@@ -566,216 +611,127 @@ __global__ void __launch_bounds__(256, MCP_WALK_MIN_BLOCKS) felsenstein_walk(con
                     chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TW) + tid;
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
                     const int cnt = min(CH, n_pre - c * CH);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
-                        struct { int flags; unsigned xa, xb, y0; } rec = {(int)rh.x, rh.y, rh.z, rh.w};
-                        const int flags = rec.flags;
+                        const int flags = (int)rh.x;
                         const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
                         const int mk = (flags >> 8) & 3;
                         // all stored operands of the family are requested up front
-                        double pm[K], La[K], Lb[K];
-                        if (mk == mcp::PREM_STACK) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.y0), pm);
-                        if (ai) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xa), La);
-                        if (bi) ld_partial<K>(reinterpret_cast<const double*>(scr + rec.xb), Lb);
+                        double pm[CPT][K], La[CPT][K], Lb[CPT][K];
+                        if (mk == mcp::PREM_STACK) ld_cols(rh.w, pm);
+                        if (ai) ld_cols(rh.y, La);
+                        if (bi) ld_cols(rh.z, Lb);
                         if (mk == mcp::PREM_ROOT) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) pm[k] = mdl.pi(k);
+                            for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) pm[cc][k] = mdl.pi(k);
                         } else if (mk == mcp::PREM_REG) {
 #pragma unroll
-                            for (int k = 0; k < K; ++k) pm[k] = cur[k];
+                            for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) pm[cc][k] = cur[cc][k];
                         }
-#if MCP_WQ
-                        // Da = P_a L_a, Db = P_b L_b.  For an internal child z = e*(Uinv L) is kept:
-                        // q.(dP L) = sum_i c_i z_i (U^T q)_i, and U^T q is needed for pre[child] anyway.
-                        double ea[K], ebv[K], za[K], zb[K];
-                        double Da[K], Db[K], Ya[K], Yb[K];
-                        if (ai) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * K + k];
-                            eig_project<K>(mdl, La, ea, za);
-                            eig_expand<K>(mdl, za, Da);
-                        } else {
-                            const int code = min((int)cb[(j * 2 + 0) * TW], K);
-                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xa) + code * K;
-                            ld_table<K>(t, Da);
-                            ld_table<K>(t + K * (K + 1), Ya);
-                        }
-                        if (bi) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * K + k];
-                            eig_project<K>(mdl, Lb, ebv, zb);
-                            eig_expand<K>(mdl, zb, Db);
-                        } else {
-                            const int code = min((int)cb[(j * 2 + 1) * TW], K);
-                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xb) + code * K;
-                            ld_table<K>(t, Db);
-                            ld_table<K>(t + K * (K + 1), Yb);
-                        }
-                        double qa[K], qb[K];
-                        double den = 0.0;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            qa[k] = pm[k] * Db[k];
-                            qb[k] = pm[k] * Da[k];
-                            den = fma(qa[k], Da[k], den);
-                        }
-                        double na = 0.0, nb = 0.0;
-                        double wa[K], wb[K];   // U^T q (internal children only)
-                        if (ai) {
-#pragma unroll
-                            for (int i = 0; i < K; ++i) {
-                                double w = mdl.U(0, i) * qa[0];
-#pragma unroll
-                                for (int s2 = 1; s2 < K; ++s2) w = fma(mdl.U(s2, i), qa[s2], w);
-                                wa[i] = w;
-                                na = fma(crate[i] * za[i], w, na);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) na = fma(qa[k], Ya[k], na);
-                        }
-                        if (bi) {
-#pragma unroll
-                            for (int i = 0; i < K; ++i) {
-                                double w = mdl.U(0, i) * qb[0];
-#pragma unroll
-                                for (int s2 = 1; s2 < K; ++s2) w = fma(mdl.U(s2, i), qb[s2], w);
-                                wb[i] = w;
-                                nb = fma(crate[i] * zb[i], w, nb);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) nb = fma(qb[k], Yb[k], nb);
-                        }
-                        const double inv = fast_rcp(den);
-                        const double ga = valid ? na * inv : 0.0;
-                        const double gb = valid ? nb * inv : 0.0;
-                        const double red = warp_pair_reduce(ga, gb, lane);
-                        if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
-                        else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
-
-                        // pre[child] = P^T q = Uinv^T (e * (U^T q)), only internal children have one
-                        const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
-                        if (a_out != mcp::OUT_NONE) {
-                            double pa[K];
-#pragma unroll
-                            for (int i = 0; i < K; ++i) wa[i] *= ea[i];
-#pragma unroll
-                            for (int jj = 0; jj < K; ++jj) {
-                                double acc = mdl.Ui(0, jj) * wa[0];
-#pragma unroll
-                                for (int i = 1; i < K; ++i) acc = fma(mdl.Ui(i, jj), wa[i], acc);
-                                pa[jj] = acc;
-                            }
-                            rescale_pow2<K>(pa);
-                            if (a_out == mcp::OUT_KEEP) {
-#pragma unroll
-                                for (int k = 0; k < K; ++k) cur[k] = pa[k];
-                            } else {
-                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y1), pa);
-                            }
-                        }
-                        if (b_out != mcp::OUT_NONE) {
-                            double pb[K];
-#pragma unroll
-                            for (int i = 0; i < K; ++i) wb[i] *= ebv[i];
-#pragma unroll
-                            for (int jj = 0; jj < K; ++jj) {
-                                double acc = mdl.Ui(0, jj) * wb[0];
-#pragma unroll
-                                for (int i = 1; i < K; ++i) acc = fma(mdl.Ui(i, jj), wb[i], acc);
-                                pb[jj] = acc;
-                            }
-                            rescale_pow2<K>(pb);
-                            if (b_out == mcp::OUT_KEEP) {
-#pragma unroll
-                                for (int k = 0; k < K; ++k) cur[k] = pb[k];
-                            } else {
-                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y2), pb);
-                            }
-                        }
-                    }
-                }
-            }
-#else
                         double ea[K], ebv[K];
-                        double Da[K], Ya[K], Db[K], Yb[K];
+                        double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
                         if (ai) {
-                            double z[K], zd[K];
+                            double z[CPT][K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * K + k];
-                            eig_project<K>(mdl, La, ea, z);
+                            eig_project<K, CPT>(mdl, La, ea, z);
+                            eig_expand<K, CPT>(mdl, z, Da);
 #pragma unroll
-                            for (int k = 0; k < K; ++k) zd[k] = crate[k] * z[k];
-                            eig_expand<K>(mdl, z, Da);
-                            eig_expand<K>(mdl, zd, Ya);
+                            for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) z[cc][k] *= crate[k];
+                            eig_expand<K, CPT>(mdl, z, Ya);
                         } else {
-                            const int code = min((int)cb[(j * 2 + 0) * TW], K);
-                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xa) + code * K;
-                            ld_table<K>(t, Da);
-                            ld_table<K>(t + K * (K + 1), Ya);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
+                                const double* t = reinterpret_cast<const double*>(btab_b + rh.y) + code * K;
+                                ld_table<K>(t, Da[cc]);
+                                ld_table<K>(t + K * (K + 1), Ya[cc]);
+                            }
                         }
                         if (bi) {
-                            double z[K], zd[K];
+                            double z[CPT][K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * K + k];
-                            eig_project<K>(mdl, Lb, ebv, z);
+                            eig_project<K, CPT>(mdl, Lb, ebv, z);
+                            eig_expand<K, CPT>(mdl, z, Db);
 #pragma unroll
-                            for (int k = 0; k < K; ++k) zd[k] = crate[k] * z[k];
-                            eig_expand<K>(mdl, z, Db);
-                            eig_expand<K>(mdl, zd, Yb);
+                            for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) z[cc][k] *= crate[k];
+                            eig_expand<K, CPT>(mdl, z, Yb);
                         } else {
-                            const int code = min((int)cb[(j * 2 + 1) * TW], K);
-                            const double* t = reinterpret_cast<const double*>(btab_b + rec.xb) + code * K;
-                            ld_table<K>(t, Db);
-                            ld_table<K>(t + K * (K + 1), Yb);
-                        }
-                        double qa[K], qb[K];
-                        double den = 0.0, na = 0.0, nb = 0.0;
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            qa[k] = pm[k] * Db[k];
-                            qb[k] = pm[k] * Da[k];
-                            den = fma(qa[k], Da[k], den);
-                            na = fma(qa[k], Ya[k], na);
-                            nb = fma(qb[k], Yb[k], nb);
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
+                                const double* t = reinterpret_cast<const double*>(btab_b + rh.z) + code * K;
+                                ld_table<K>(t, Db[cc]);
+                                ld_table<K>(t + K * (K + 1), Yb[cc]);
+                            }
                         }
-                        const double inv = fast_rcp(den);
-                        const double ga = valid ? na * inv : 0.0;
-                        const double gb = valid ? nb * inv : 0.0;
+                        double qa[CPT][K], qb[CPT][K];
+                        double ga = 0.0, gb = 0.0;
+#pragma unroll
+                        for (int cc = 0; cc < CPT; ++cc) {
+                            double den = 0.0, na = 0.0, nb = 0.0;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                qa[cc][k] = pm[cc][k] * Db[cc][k];
+                                qb[cc][k] = pm[cc][k] * Da[cc][k];
+                                den = fma(qa[cc][k], Da[cc][k], den);
+                                na = fma(qa[cc][k], Ya[cc][k], na);
+                                nb = fma(qb[cc][k], Yb[cc][k], nb);
+                            }
+                            const double inv = fast_rcp(den);
+                            if (valid[cc]) {
+                                ga = fma(na, inv, ga);
+                                gb = fma(nb, inv, gb);
+                            }
+                        }
                         const double red = warp_pair_reduce(ga, gb, lane);
                         if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
                         else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
 
+                        // pre[child] = P^T q, only internal children have one
                         const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
                         if (a_out != mcp::OUT_NONE) {
-                            double pa[K];
-                            eig_transposed<K>(mdl, qa, ea, pa);
-                            rescale_pow2<K>(pa);
+                            double pa[CPT][K];
+                            eig_transposed<K, CPT>(mdl, qa, ea, pa);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pa[cc]);
                             if (a_out == mcp::OUT_KEEP) {
 #pragma unroll
-                                for (int k = 0; k < K; ++k) cur[k] = pa[k];
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = pa[cc][k];
                             } else {
-                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y1), pa);
+                                st_cols(rb[j].y1, pa);
                             }
                         }
                         if (b_out != mcp::OUT_NONE) {
-                            double pb[K];
-                            eig_transposed<K>(mdl, qb, ebv, pb);
-                            rescale_pow2<K>(pb);
+                            double pb[CPT][K];
+                            eig_transposed<K, CPT>(mdl, qb, ebv, pb);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pb[cc]);
                             if (b_out == mcp::OUT_KEEP) {
 #pragma unroll
-                                for (int k = 0; k < K; ++k) cur[k] = pb[k];
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = pb[cc][k];
                             } else {
-                                st_partial<K>(reinterpret_cast<double*>(scr + rb[j].y2), pb);
+                                st_cols(rb[j].y2, pb);
                             }
                         }
                     }
                 }
             }
-#endif
         }  // tiles of this tree
 
         // ---- flush this CTA's sums for the tree into its accumulator row ----
@@ -857,7 +813,8 @@ struct mcp_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string error;
     bool pending_async = false;
-    int opt_block = 0, opt_ctas_per_sm = 0;
+    int opt_block = 0, opt_ctas_per_sm = 0, opt_cpt = 0;
+    int cpt = 1;   // columns per thread of the cached launch
     unsigned long long next_aln_id = 1;
 
     DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out;
@@ -870,7 +827,7 @@ struct mcp_ctx {
         std::vector<int32_t> po, pa;
     };
     std::vector<TreeSig> sig;
-    int sig_want_grad = -1, sig_block = 0, sig_K = 0, sig_R = 0;
+    int sig_want_grad = -1, sig_block = 0, sig_K = 0, sig_R = 0, sig_cpt = 0;
     // derived launch state kept with the cached topology
     std::vector<TreeDev> trees;
     std::vector<Schedule> scheds;
@@ -937,34 +894,37 @@ int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
     return 0;
 }
 
-template <int K>
-int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
-    if (dyn_model) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)ctx->smem_bytes));
-        felsenstein_walk<K, true><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
-    } else {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)ctx->smem_bytes));
-        felsenstein_walk<K, false><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
-    }
+template <int K, int CPT, bool DYN>
+int launch_walk_inst(mcp_ctx* ctx, const WalkParams& wp) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, CPT, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)ctx->smem_bytes));
+    felsenstein_walk<K, CPT, DYN><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
 template <int K>
-int occupancy_for(mcp_ctx* ctx, int block, size_t smem, int* out) {
+int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
+    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true>(ctx, wp) : launch_walk_inst<K, 2, false>(ctx, wp);
+    return dyn_model ? launch_walk_inst<K, 1, true>(ctx, wp) : launch_walk_inst<K, 1, false>(ctx, wp);
+}
+template <int K, int CPT>
+int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, int* out) {
     // the dynamic-model variant needs a few more registers: size the persistent grid for it
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, CPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, CPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int o1 = 0, o2 = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, true>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, false>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false>, block, smem));
     *out = std::min(o1, o2);
     return 0;
 }
-size_t walk_smem_bytes(int K, int max_br, int want_grad, int block) {
+template <int K>
+int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, int* out) {
+    return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, out) : occupancy_inst<K, 1>(ctx, block, smem, out);
+}
+size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
     size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
-    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 32 + (size_t)2 * CH * 2 * block;
+    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 32 + (size_t)2 * CH * 2 * block * cpt;
 }
 
 #define MCP_DISPATCH_K(K, CALL)                      \
@@ -1007,8 +967,13 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         block = 256;
         while (block > 32 && (total_cols + block - 1) / block < 6LL * ctx->sm_count) block >>= 1;
     }
+    // Two columns per thread amortise the per-op overhead (descriptor decode, constant loads, warp
+    // reduction) once there is enough work to fill the GPU.  Measured: 1.2x at K = 2; at K = 4 the
+    // doubled register state costs more occupancy than it saves (profiles/r1_walk_notes.md).
+    int cpt = ctx->opt_cpt;
+    if (cpt <= 0) cpt = (K <= 3 && total_cols / (2LL * block) >= 12LL * ctx->sm_count) ? 2 : 1;
     bool same = (int)ctx->sig.size() == T && ctx->sig_want_grad == a.want_grad && ctx->sig_block == block &&
-                ctx->sig_K == K && ctx->sig_R == R;
+                ctx->sig_K == K && ctx->sig_R == R && ctx->sig_cpt == cpt;
     for (int t = 0; same && t < T; ++t) {
         const auto& s = ctx->sig[t];
         same = s.aln_id == a.alns[t]->id && s.NN == a.NN[t] &&
@@ -1054,7 +1019,7 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         dyn_off += dyn_size(NN, K, R);
         td.btab_off = btab_off;
         btab_off += (long long)sc.n_dnodes * R * bt_size(K);
-        td.tiles_per_rate = (int)((al->S + block - 1) / block);
+        td.tiles_per_rate = (int)((al->S + (long long)block * cpt - 1) / ((long long)block * cpt));
         td.tile_begin = tile_cursor;
         long long nt = (long long)td.tiles_per_rate * R;
         if (tile_cursor + nt > 0x7fffffffLL) return fail(ctx, MCP_ERR_ARG, "too many column tiles");
@@ -1071,6 +1036,8 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     }
     ctx->sig_want_grad = a.want_grad;
     ctx->sig_block = block;
+    ctx->sig_cpt = cpt;
+    ctx->cpt = cpt;
     ctx->sig_K = K;
     ctx->sig_R = R;
     ctx->n_tiles = tile_cursor;
@@ -1081,13 +1048,13 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     ctx->total_out = out_off;
     ctx->total_dyn = dyn_off;
     ctx->total_btab = btab_off;
-    ctx->smem_bytes = walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block);
+    ctx->smem_bytes = walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block, cpt);
     if (ctx->smem_bytes > 200 * 1024)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree with %d nodes exceeds the shared-memory gradient accumulator", max_br);
 
     // persistent grid
     int occ = 0, rc = 0;
-    MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, ctx->smem_bytes, &occ));
+    MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, &occ));
     if (rc) return rc == MCP_ERR_UNSUPPORTED ? fail(ctx, rc, "no kernel compiled for K = %d states", K) : rc;
     if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d, smem %zu)", block, ctx->smem_bytes);
     if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
@@ -1119,9 +1086,9 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         ctx->n_rows = row;
     }
     ctx->row_stride = (max_br + 3) & ~3;
-    if ((double)(ctx->n_slots + n_stack + 1) * block * K * 8.0 >= 4.0e9 || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
+    if ((double)(ctx->n_slots + n_stack + 1) * block * cpt * K * 8.0 >= 4.0e9 || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree too large for 32-bit scratch offsets (%d nodes)", max_br);
-    ctx->scratch_per_cta = (long long)(ctx->n_slots + ctx->n_stack) * block * K;
+    ctx->scratch_per_cta = (long long)(ctx->n_slots + ctx->n_stack) * block * cpt * K;
 
     // topology upload: [TreeDev x T][ops][row_base]
     ctx->off_trees = 0;
@@ -1299,8 +1266,8 @@ int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S,
     mcp_alignment* al = new mcp_alignment();
     al->K = K;
     al->S = S;
-    al->stride = (S + 255) & ~255LL;   // a tile (<= 256 sites) never reads past a row
-    if (al->stride == 0) al->stride = 256;
+    al->stride = (S + 1023) & ~1023LL;   // a tile (<= 256 threads x 4 columns) never reads past a row
+    if (al->stride == 0) al->stride = 1024;
     al->n_leaves = n_leaves;
     al->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
     al->id = ctx->next_aln_id++;
@@ -1409,6 +1376,14 @@ int mcp_set_launch(mcp_ctx* ctx, int block, int ctas_per_sm) {
     if (ctas_per_sm < 0) return fail(ctx, MCP_ERR_ARG, "ctas_per_sm must be >= 0");
     ctx->opt_block = block;
     ctx->opt_ctas_per_sm = ctas_per_sm;
+    ctx->sig.clear();
+    return 0;
+}
+
+int mcp_set_columns_per_thread(mcp_ctx* ctx, int cpt) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (cpt != 0 && cpt != 1 && cpt != 2) return fail(ctx, MCP_ERR_ARG, "columns per thread must be 0 (automatic), 1 or 2");
+    ctx->opt_cpt = cpt;
     ctx->sig.clear();
     return 0;
 }

@@ -121,13 +121,41 @@ def test_every_launch_shape_agrees(oracle):
     ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates)
     ctx = mcp.get_context()
     try:
-        for block, ctas in [(32, 1), (64, 0), (128, 2), (256, 0), (256, 1)]:
+        for block, ctas, cpt in [(32, 1, 1), (64, 0, 2), (128, 2, 1), (256, 0, 2), (256, 1, 1), (128, 0, 2)]:
             ctx.set_launch(block, ctas)
+            ctx.set_columns_per_thread(cpt)
             ll, g = mcp.gradlogpdf(pd, aln)
             _check(ll, g, ll_o, g_o)
             assert ctx.stats()["block"] == block
+            _check(mcp.logpdf(pd, aln), None, ll_o, None)
     finally:
         ctx.set_launch(0, 0)
+        ctx.set_columns_per_thread(0)
+
+
+@pytest.mark.parametrize("K,R,S", [(2, 1, 1500), (3, 2, 700), (5, 1, 300)])
+def test_two_columns_per_thread(oracle, K, R, S):
+    """The two-columns-per-thread instantiation (automatic only for large K <= 3 problems) against
+    the oracle, with a ragged last tile."""
+    rng = np.random.default_rng(100 + K)
+    tree = random_tree(33, rng, multifurcate=True)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, S, rng, gap_frac=0.05)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_columns_per_thread(2)
+        for block in (32, 128):
+            ctx.set_launch(block, 0)
+            ll, g = mcp.gradlogpdf(pd, aln)
+            _check(ll, g, ll_o, g_o)
+    finally:
+        ctx.set_launch(0, 0)
+        ctx.set_columns_per_thread(0)
 
 
 def test_topology_cache_and_branch_updates(oracle):

@@ -25,8 +25,10 @@ pd = mcp.PhyloDist(w["tree"], w["pi"], w["srates"], w["rates"], w["model"])
 ctx = mcp.get_context(0)
 balg = bench.algorithmic_bytes(w["n_taxa"], w["S"], w["K"], w["R"], not a.nograd)
 for shape in a.shapes.split(","):
-    blk, cps = (int(v) for v in shape.split(":"))
+    parts = [int(v) for v in shape.split(":")]
+    blk, cps = parts[0], parts[1]
     ctx.set_launch(blk, cps)
+    ctx.set_columns_per_thread(parts[2] if len(parts) > 2 else 0)
     ts = []
     for r in range(a.reps + 1):
         res = mcp.logpdf(pd, aln) if a.nograd else mcp.gradlogpdf(pd, aln)[0]
@@ -34,5 +36,5 @@ for shape in a.shapes.split(","):
         if r:
             ts.append(st["walk_ms"])
     t = float(np.median(ts))
-    print(f"block={st['block']:4d} grid={st['grid']:5d} tiles={st['tiles']:6d} walk_ms={t:9.3f} "
+    print(f"shape={shape:10s} block={st['block']:4d} grid={st['grid']:5d} tiles={st['tiles']:6d} walk_ms={t:9.3f} "
           f"alg_GB/s={balg / t / 1e6:8.1f} device_ms={st['device_ms']:.3f} ll={res:.6f}", flush=True)
