@@ -109,6 +109,24 @@ def test_random_cases_vs_oracle(oracle, n_taxa, K, R, S, seed, multi, unary):
     _check(ll_only, None, ll_o, None)
 
 
+@pytest.mark.parametrize("K,R,n_taxa,S", [(7, 1, 12, 150), (20, 2, 25, 200), (32, 1, 9, 70)])
+def test_large_alphabets_generic_kernel(oracle, K, R, n_taxa, S):
+    """K > 6 (e.g. 20-state protein alphabets) runs on the runtime-K kernel."""
+    rng = np.random.default_rng(200 + K)
+    tree = random_tree(n_taxa, rng, multifurcate=True, unary=(K == 20))
+    pi = rng.dirichlet(np.ones(K) * 5)
+    # a reversible K-state model: symmetric exchangeabilities times pi (GTR with K states)
+    srates = rng.uniform(0.2, 3.0, size=K * (K - 1) // 2)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, srates), pi, rates, S, rng, gap_frac=0.05)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, mcp.GTR)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll, g = mcp.gradlogpdf(pd, aln)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, mcp.GTR, pi, srates, rates)
+    _check(ll, g, ll_o, g_o)
+    _check(mcp.logpdf(pd, aln), None, ll_o, None)
+
+
 def test_every_launch_shape_agrees(oracle):
     rng = np.random.default_rng(3)
     tree = random_tree(40, rng)
@@ -261,11 +279,11 @@ def test_error_paths():
     with pytest.raises(mcp.capi.McpError) as ei:
         mcp.logpdf(pd, mcp.DeviceAlignment(codes[:-1], leaf_nums[:-1], 4))
     assert ei.value.code == -1
-    # 20 states: no compiled kernel, reported not crashed
+    # 40 states: beyond the generic kernel's limit, reported not crashed
     t2 = mcp.ParseNewick("(a:0.1,b:0.2);")
     with pytest.raises(mcp.capi.McpError) as ei:
-        mcp.logpdf(mcp.PhyloDist(t2, np.full(20, 0.05), [1.0], [1.0], mcp.JC),
-                   mcp.DeviceAlignment(np.zeros((2, 5), np.uint8), [1, 2], 20))
+        mcp.logpdf(mcp.PhyloDist(t2, np.full(40, 0.025), [1.0], [1.0], mcp.JC),
+                   mcp.DeviceAlignment(np.zeros((2, 5), np.uint8), [1, 2], 40))
     assert ei.value.code == -3
 
 
