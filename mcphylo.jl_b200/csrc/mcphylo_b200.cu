@@ -72,6 +72,11 @@ struct WalkParams {
     int n_slots, n_stack;
     int n_tiles, T, R, want_grad;
     int max_br;
+    int pad_;
+    // Substitution-model constants when the whole batch shares ONE model (the common case): kernel
+    // parameters live in constant bank 0, so they reach the FP64 pipe as uniform operands without
+    // a separate host-to-device copy.  Layout as in c_model (below).
+    double model[176];
 };
 
 // per-tree layout of the per-evaluation parameter block (offsets in doubles from dyn_off)
@@ -155,20 +160,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Model view: MOFS is the slot offset into c_model; with a compile-time 0 the constant operands
 // fold into the DFMA encodings.
-template <int K>
-struct Model {
+// DYN = false: the single model embedded in the kernel parameters; DYN = true: slot `ofs` of c_model.
+template <int K, bool DYN>
+struct ModelT {
+    const WalkParams& p;
     int ofs;
-    __device__ __forceinline__ double U(int s, int i) const { return c_model[ofs + s + K * i]; }
-    __device__ __forceinline__ double Ui(int i, int j) const { return c_model[ofs + K * K + i + K * j]; }
-    __device__ __forceinline__ double pi(int k) const { return c_model[ofs + 2 * K * K + k]; }
-    __device__ __forceinline__ double c(int r, int i) const { return c_model[ofs + 2 * K * K + K + r * K + i]; }
+    __device__ __forceinline__ double U(int s, int i) const { return DYN ? c_model[ofs + s + K * i] : p.model[s + K * i]; }
+    __device__ __forceinline__ double Ui(int i, int j) const { return DYN ? c_model[ofs + K * K + i + K * j] : p.model[K * K + i + K * j]; }
+    __device__ __forceinline__ double pi(int k) const { return DYN ? c_model[ofs + 2 * K * K + k] : p.model[2 * K * K + k]; }
+    __device__ __forceinline__ double c(int r, int i) const {
+        return DYN ? c_model[ofs + 2 * K * K + K + r * K + i] : p.model[2 * K * K + K + r * K + i];
+    }
 };
 
 // ---- eigen-space products for C columns at once (column index innermost, so one constant /
 // uniform-register operand feeds C independent DFMAs) ----
 // z[c] = e * (Uinv L[c])
-template <int K, int C>
-__device__ __forceinline__ void eig_project(const Model<K>& m, const double (&L)[C][K], const double (&e)[K], double (&z)[C][K]) {
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K], const double (&e)[K], double (&z)[C][K]) {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         double w[C];
@@ -183,8 +192,8 @@ __device__ __forceinline__ void eig_project(const Model<K>& m, const double (&L)
     }
 }
 // out[c] = U z[c]
-template <int K, int C>
-__device__ __forceinline__ void eig_expand(const Model<K>& m, const double (&z)[C][K], double (&out)[C][K]) {
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], double (&out)[C][K]) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
 #pragma unroll
@@ -196,8 +205,8 @@ __device__ __forceinline__ void eig_expand(const Model<K>& m, const double (&z)[
     }
 }
 // out[c] = P^T q[c] = Uinv^T (e * (U^T q[c]))
-template <int K, int C>
-__device__ __forceinline__ void eig_transposed(const Model<K>& m, const double (&q)[C][K], const double (&e)[K], double (&out)[C][K]) {
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][K], const double (&e)[K], double (&out)[C][K]) {
     double z[C][K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
@@ -378,7 +387,7 @@ struct WalkSmem {
 #define MCP_WALK_MIN_BLOCKS2 2
 #endif
 template <int K, int CPT, bool DYN_MODEL>
-__global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const WalkParams p) {
+__global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
@@ -420,8 +429,7 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
         }
         long long e_total = 0;
         double logsum = 0.0;
-        Model<K> mdl;
-        mdl.ofs = DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0;
+        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
         const int4* const post_ops = p.ops + 2 * tr.post_off;
         const int4* const pre_ops = p.ops + 2 * tr.pre_off;
 
@@ -1411,7 +1419,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     mcp_stats& s = ctx->stats;
     s = mcp_stats{};
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-    if (n_models > 0) {
+    if (n_models > 1) {   // several models: slots in constant memory; one model travels as a kernel parameter
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_model, hm, sizeof(double) * MODEL_SLOT * n_models, 0, cudaMemcpyHostToDevice, st));
         s.h2d_bytes += (int64_t)(sizeof(double) * MODEL_SLOT * n_models);
     }
@@ -1446,6 +1454,10 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.R = R;
     wp.want_grad = a.want_grad ? 1 : 0;
     wp.max_br = ctx->max_br;
+    wp.pad_ = 0;
+    static_assert(sizeof(wp.model) / sizeof(double) >= 2 * 6 * 6 + 6 + MAX_RATES * 6, "model parameter block too small");
+    std::memset(wp.model, 0, sizeof wp.model);
+    if (n_models == 1) std::memcpy(wp.model, hm, sizeof(double) * model_doubles);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
     int rc = 0;
     if (k_templated(K)) {

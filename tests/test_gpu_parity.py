@@ -316,3 +316,46 @@ def test_sharded_evaluator_follows_torch_streams(oracle):
     # shards of one alignment add up to the whole (what the all-reduce sums)
     parts = [mcp.gradlogpdf(pd, mcp.local_shard(aln, 4, r)) for r in range(4)]
     assert abs(sum(p[0] for p in parts) - ll) <= 1e-12 * abs(ll)
+
+
+@pytest.mark.parametrize("K", [2, 4])
+def test_extreme_branch_lengths(oracle, K):
+    """Near-zero and saturated branches (no clamping anywhere, like the reference): P ~ I and
+    P ~ stationary both have to survive the eigen-factored form and the power-of-two rescaling."""
+    rng = np.random.default_rng(300 + K)
+    tree = random_tree(40, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4) if K == 4 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, 400, rng, gap_frac=0.02)
+    blv = mcp.get_branchlength_vector(tree)
+    idx = rng.permutation(blv.size)
+    blv[idx[:6]] = [1e-9, 1e-7, 1e-5, 30.0, 80.0, 5.0]
+    mcp.set_branchlength_vector(tree, blv)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll, g = mcp.gradlogpdf(pd, aln)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    assert np.isfinite(ll) and np.all(np.isfinite(g))
+    assert abs(ll - ll_o) <= LL_RTOL * abs(ll_o)
+    scale = np.max(np.abs(g_o))
+    assert np.all(np.abs(g - g_o) <= 1e-7 * np.maximum(np.abs(g_o), 1e-3 * scale))
+
+
+def test_long_chain_does_not_underflow(oracle):
+    """A 1200-taxon caterpillar with long branches: per-column likelihoods below 1e-308, which an
+    unscaled double cannot hold; the exponent bookkeeping must carry them (the reference rescales
+    at every node too)."""
+    n = 1200
+    nwk = "(" * (n - 1) + "t0000:0.4," + ",".join(f"t{i:04d}:0.4):0.3" for i in range(1, n))
+    nwk = nwk[:nwk.rfind(":")] + ";"
+    tree = mcp.ParseNewick(nwk)
+    rng = np.random.default_rng(9)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, np.ones(1), 32, rng, gap_frac=0.0)
+    pd = mcp.PhyloDist(tree, pi, sr, [1.0], mcp.GTR)
+    ll, g = mcp.gradlogpdf(pd, mcp.DeviceAlignment(codes, leaf_nums, 4))
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, [1.0])
+    assert ll_o / 32 < -720        # exp(-720) < smallest normal double
+    _check(ll, g, ll_o, g_o)
