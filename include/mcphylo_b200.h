@@ -153,6 +153,9 @@ int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
 int mcp_set_launch(mcp_ctx *ctx, int block, int ctas_per_sm);
 /* Alignment columns walked by one thread: 1, 2, or 0 = automatic (2 once the GPU is full). */
 int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);
+/* Where a CTA keeps its partial-likelihood scratch: -1 automatic (shared memory for small inputs
+ * whose scratch fits, HBM otherwise), 0 always HBM, 1 shared memory whenever it fits. */
+int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
 
 /*
  * Host-only: emits the device schedule (the flat "walk program") for a topology, so the

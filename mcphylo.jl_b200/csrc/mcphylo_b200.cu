@@ -371,8 +371,10 @@ struct WalkSmem {
     static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * K * 8; }
     static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
     static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
+    // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
+    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
     static __host__ __device__ size_t total(int n_br, int want_grad, int TW) {
-        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + rec_bytes() + code_bytes(TW);
+        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
     }
 };
 
@@ -386,7 +388,10 @@ struct WalkSmem {
 #ifndef MCP_WALK_MIN_BLOCKS2
 #define MCP_WALK_MIN_BLOCKS2 2
 #endif
-template <int K, int CPT, bool DYN_MODEL>
+// SSCR = true keeps the CTA's partials scratch in SHARED memory instead of HBM: the latency path for
+// small problems (MCMC-sized trees), where a lone warp would otherwise wait an L2 round trip for
+// every partial it has just written.
+template <int K, int CPT, bool DYN_MODEL, bool SSCR>
 __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
@@ -403,12 +408,15 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
     int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
     double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
     OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
-    unsigned char* const scode = reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes();
+    double* const stab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes());
+    unsigned char* const scode = reinterpret_cast<unsigned char*>(stab) + WalkSmem<K>::tab_bytes();
+    constexpr int KK1 = K * (K + 1);                  // doubles of one leaf table (P or dP columns)
 
     // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state]; all
     // slot / LIFO offsets in the records are byte offsets from here
-    unsigned char* const scr = reinterpret_cast<unsigned char*>(
-        p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K);
+    unsigned char* const scr = SSCR
+        ? scode + WalkSmem<K>::code_bytes(TS) + (size_t)tid * K * 8
+        : reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K);
     constexpr int COLB = 1;                           // (documentation) one column = K doubles per thread
     (void)COLB;
     const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
@@ -462,29 +470,43 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
                 double* eb = se + (c & 1) * (CH * 2 * K);
                 unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS);
                 OpRec* rb = srec + (c & 1) * CH;
+                double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                 const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
-                const int per_child = pieces > (K * 8 + 15) / 16 ? pieces : (K * 8 + 15) / 16;
+                const int tab_doubles = pre ? 2 * KK1 : KK1; // P columns (+ dP columns in the gradient pass)
+                const int tpieces = (tab_doubles + 1) / 2;   // 16-byte pieces of one leaf table
+                const int epieces = (K * 8 + 15) / 16;
+                const int per_child = pieces + tpieces > epieces ? pieces + tpieces : epieces;
                 for (int w = tid; w < cnt * 2 * per_child; w += TW) {
                     const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
                     const int4 o0 = d[2 * j];
                     const int fl = d[2 * j + 1].y;
                     const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
                     const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
+                    const double* bsrc = reinterpret_cast<const double*>(btab_b + (unsigned)br * br_bytes);
                     if (kind == mcp::OPK_LEAF) {
                         if (piece < pieces) {
                             unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TS + piece * 16;
                             if (src >= 0) cp_async16(dstp, codes0 + (long long)src * tr.code_stride + piece * 16);
                             else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
+                        } else if (piece < pieces + tpieces) {
+                            const int tp = piece - pieces;
+                            double* dstp = tb + (size_t)(j * 2 + ch) * 2 * KK1 + tp * 2;
+                            const double* srcp = bsrc + K + tp * 2;
+                            if constexpr ((K * 8) % 16 == 0) {
+                                cp_async16(dstp, srcp);
+                            } else {
+                                dstp[0] = __ldg(srcp);
+                                if (tp * 2 + 1 < tab_doubles) dstp[1] = __ldg(srcp + 1);
+                            }
                         }
-                    } else if (piece * 16 < K * 8) {
-                        const double* esrc = reinterpret_cast<const double*>(btab_b + (unsigned)br * br_bytes);
+                    } else if (piece < epieces) {
                         if constexpr ((K * 8) % 16 == 0) {
                             cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * K) + piece * 16,
-                                       reinterpret_cast<const unsigned char*>(esrc) + piece * 16);
+                                       reinterpret_cast<const unsigned char*>(bsrc) + piece * 16);
                         } else {
                             if (piece == 0) {
 #pragma unroll
-                                for (int k = 0; k < K; ++k) eb[(j * 2 + ch) * K + k] = __ldg(esrc + k);
+                                for (int k = 0; k < K; ++k) eb[(j * 2 + ch) * K + k] = __ldg(bsrc + k);
                             }
                         }
                     }
@@ -529,11 +551,27 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
             };
             auto ld_cols = [&](unsigned off, double (&v)[CPT][K]) {
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) ld_partial<K>(reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
+                for (int c = 0; c < CPT; ++c) {
+                    if constexpr (SSCR) {
+                        const double* src = reinterpret_cast<const double*>(scr + off + c * col_bytes);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v[c][k] = src[k];
+                    } else {
+                        ld_partial<K>(reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
+                    }
+                }
             };
             auto st_cols = [&](unsigned off, const double (&v)[CPT][K]) {
 #pragma unroll
-                for (int c = 0; c < CPT; ++c) st_partial<K>(reinterpret_cast<double*>(scr + off + c * col_bytes), v[c]);
+                for (int c = 0; c < CPT; ++c) {
+                    if constexpr (SSCR) {
+                        double* dst = reinterpret_cast<double*>(scr + off + c * col_bytes);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) dst[k] = v[c][k];
+                    } else {
+                        st_partial<K>(reinterpret_cast<double*>(scr + off + c * col_bytes), v[c]);
+                    }
+                }
             };
 
             // ------------------------------ post pass ------------------------------
@@ -553,6 +591,7 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * K);
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
+                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_post - c * CH);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
@@ -566,7 +605,9 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
                                 const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
-                                ld_table<K>(reinterpret_cast<const double*>(btab_b + rh.y) + code * K, Da[cc]);
+                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) Da[cc][k] = t[k];
                             }
                         } else {
                             double e[K], z[CPT][K];
@@ -580,7 +621,9 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
                                 const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
-                                ld_table<K>(reinterpret_cast<const double*>(btab_b + rh.z) + code * K, Db[cc]);
+                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) Db[cc][k] = t[k];
                             }
                         } else {
                             double e[K], z[CPT][K];
@@ -620,6 +663,7 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * K);
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
+                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_pre - c * CH);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
@@ -659,9 +703,9 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
                                 const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
-                                const double* t = reinterpret_cast<const double*>(btab_b + rh.y) + code * K;
-                                ld_table<K>(t, Da[cc]);
-                                ld_table<K>(t + K * (K + 1), Ya[cc]);
+                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) { Da[cc][k] = t[k]; Ya[cc][k] = t[KK1 + k]; }
                             }
                         }
                         if (bi) {
@@ -679,9 +723,9 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
                                 const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
-                                const double* t = reinterpret_cast<const double*>(btab_b + rh.z) + code * K;
-                                ld_table<K>(t, Db[cc]);
-                                ld_table<K>(t + K * (K + 1), Yb[cc]);
+                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) { Db[cc][k] = t[k]; Yb[cc][k] = t[KK1 + k]; }
                             }
                         }
                         double qa[CPT][K], qb[CPT][K];
@@ -1032,6 +1076,8 @@ struct mcp_ctx {
     bool pending_async = false;
     int opt_block = 0, opt_ctas_per_sm = 0, opt_cpt = 0;
     int cpt = 1;   // columns per thread of the cached launch
+    bool smem_scratch = false;   // partials scratch in shared memory (small-problem latency path)
+    int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
     unsigned long long next_aln_id = 1;
 
     DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out;
@@ -1111,37 +1157,60 @@ int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
     return 0;
 }
 
-template <int K, int CPT, bool DYN>
+// cudaFuncSetAttribute is only needed when a kernel's dynamic shared memory grows
+template <class Kern>
+int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
+    static thread_local std::vector<std::pair<const void*, size_t>> done;
+    for (auto& d : done)
+        if (d.first == (const void*)kern) {
+            if (d.second >= smem) return 0;
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            d.second = smem;
+            return 0;
+        }
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done.push_back({(const void*)kern, smem});
+    return 0;
+}
+template <int K, int CPT, bool DYN, bool SSCR>
 int launch_walk_inst(mcp_ctx* ctx, const WalkParams& wp) {
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, CPT, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)ctx->smem_bytes));
-    felsenstein_walk<K, CPT, DYN><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    int e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, DYN, SSCR>, ctx->smem_bytes);
+    if (e) return e;
+    felsenstein_walk<K, CPT, DYN, SSCR><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
 template <int K>
 int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
-    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true>(ctx, wp) : launch_walk_inst<K, 2, false>(ctx, wp);
-    return dyn_model ? launch_walk_inst<K, 1, true>(ctx, wp) : launch_walk_inst<K, 1, false>(ctx, wp);
+    if (ctx->smem_scratch && !dyn_model && ctx->cpt == 1) return launch_walk_inst<K, 1, false, true>(ctx, wp);
+    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true, false>(ctx, wp) : launch_walk_inst<K, 2, false, false>(ctx, wp);
+    return dyn_model ? launch_walk_inst<K, 1, true, false>(ctx, wp) : launch_walk_inst<K, 1, false, false>(ctx, wp);
 }
 template <int K, int CPT>
-int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, int* out) {
+int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, bool sscr, int* out) {
+    int e;
+    if (sscr) {
+        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, false, true>, smem))) return e;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K, 1, false, true>, block, smem));
+        return 0;
+    }
     // the dynamic-model variant needs a few more registers: size the persistent grid for it
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, CPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk<K, CPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, false, false>, smem))) return e;
     int o1 = 0, o2 = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true, false>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false, false>, block, smem));
     *out = std::min(o1, o2);
     return 0;
 }
 template <int K>
-int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, int* out) {
-    return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, out) : occupancy_inst<K, 1>(ctx, block, smem, out);
+int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, bool sscr, int* out) {
+    return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, false, out) : occupancy_inst<K, 1>(ctx, block, smem, sscr, out);
 }
 size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
     size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
-    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 32 + (size_t)2 * CH * 2 * block * cpt;
+    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 32 +
+           (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
 }
 
 #define MCP_DISPATCH_K(K, CALL)                      \
@@ -1272,13 +1341,23 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     ctx->total_btab = btab_off;
     ctx->smem_bytes = k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block, cpt)
                                      : (a.want_grad ? (size_t)max_br * sizeof(double) : 0);
+    // Small problems: keep the partials scratch in shared memory (latency path).  Automatic when the
+    // whole input is a handful of tiles per SM and the scratch of one CTA fits next to the staging
+    // buffers.
+    {
+        const size_t scr_bytes = (size_t)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8;
+        const bool fits = k_templated(K) && cpt == 1 && ctx->smem_bytes + scr_bytes <= 96 * 1024;
+        ctx->smem_scratch = fits && (ctx->opt_smem_scratch == 1 ||
+                                     (ctx->opt_smem_scratch < 0 && ctx->n_tiles <= 4 * ctx->sm_count));
+        if (ctx->smem_scratch) ctx->smem_bytes += scr_bytes;
+    }
     if (ctx->smem_bytes > 200 * 1024)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree with %d nodes exceeds the shared-memory gradient accumulator", max_br);
 
     // persistent grid
     int occ = 0, rc = 0;
     if (k_templated(K)) {
-        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, &occ));
+        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, ctx->smem_scratch, &occ));
     } else {
         CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, felsenstein_walk_generic, block, ctx->smem_bytes));
@@ -1615,6 +1694,14 @@ int mcp_set_launch(mcp_ctx* ctx, int block, int ctas_per_sm) {
     if (ctas_per_sm < 0) return fail(ctx, MCP_ERR_ARG, "ctas_per_sm must be >= 0");
     ctx->opt_block = block;
     ctx->opt_ctas_per_sm = ctas_per_sm;
+    ctx->sig.clear();
+    return 0;
+}
+
+int mcp_set_scratch_mode(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "scratch mode must be -1 (automatic), 0 (HBM) or 1 (shared memory when it fits)");
+    ctx->opt_smem_scratch = mode;
     ctx->sig.clear();
     return 0;
 }

@@ -359,3 +359,33 @@ def test_long_chain_does_not_underflow(oracle):
     ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, [1.0])
     assert ll_o / 32 < -720        # exp(-720) < smallest normal double
     _check(ll, g, ll_o, g_o)
+
+
+@pytest.mark.parametrize("K,R", [(2, 1), (4, 4), (3, 2)])
+def test_scratch_in_shared_memory_and_in_hbm_agree(oracle, K, R):
+    """Small inputs keep the partials scratch in shared memory (latency path); forcing it to HBM
+    must give the same numbers, and both must match the oracle."""
+    rng = np.random.default_rng(400 + K)
+    tree = random_tree(50, rng, multifurcate=True)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, 1000, rng, gap_frac=0.03)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    ctx = mcp.get_context()
+    res = {}
+    try:
+        for mode in (0, 1):
+            ctx.set_scratch_mode(mode)
+            for block in (32, 64):
+                ctx.set_launch(block, 0)
+                ll, g = mcp.gradlogpdf(pd, aln)
+                _check(ll, g, ll_o, g_o)
+                _check(mcp.logpdf(pd, aln), None, ll_o, None)
+                res[(mode, block)] = (ll, g)
+    finally:
+        ctx.set_scratch_mode(-1)
+        ctx.set_launch(0, 0)
+    assert res[(0, 32)][0] == res[(1, 32)][0]          # identical arithmetic, identical logL
