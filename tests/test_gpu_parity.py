@@ -389,3 +389,16 @@ def test_scratch_in_shared_memory_and_in_hbm_agree(oracle, K, R):
         ctx.set_scratch_mode(-1)
         ctx.set_launch(0, 0)
     assert res[(0, 32)][0] == res[(1, 32)][0]          # identical arithmetic, identical logL
+
+
+def test_empty_and_single_site_alignments(oracle):
+    """S = 0 (the reference returns 0.0: empty sums) and S = 1."""
+    tree = mcp.ParseNewick("((a:0.1,b:0.2)e:0.05,(c:0.3,d:0.1)f:0.2)g;")
+    pd = mcp.PhyloDist(tree, [0.25] * 4, [1.0], [1.0, 2.0], mcp.JC)
+    leaf_nums = np.array([1, 2, 3, 4], dtype=np.int32)
+    ll, g = mcp.gradlogpdf(pd, mcp.DeviceAlignment(np.zeros((4, 0), np.uint8), leaf_nums, 4))
+    assert ll == 0.0 and np.all(g == 0.0) and g.shape == (6,)
+    codes = np.array([[0], [1], [4], [3]], dtype=np.uint8)
+    ll, g = mcp.gradlogpdf(pd, mcp.DeviceAlignment(codes, leaf_nums, 4))
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.JC, [0.25] * 4, [1.0], [1.0, 2.0])
+    _check(ll, g, ll_o, g_o)
