@@ -8,12 +8,14 @@
 //   /root/reference/src/Likelihood/VectorizedFunctions.jl:13-213
 //
 // Design: alignment columns (site x rate category) are independent through both
-// passes, so ONE thread owns one column for the whole evaluation and walks the flat op program
-// produced by schedule.hpp.  No inter-thread dependency exists, hence one fused persistent kernel
-// (post pass + gradient pass) with no grid- or block-level synchronisation inside a tile.
-// Partials live in a CTA-private scratch region laid out [slot][thread][state] so that a warp's
-// access is one contiguous run of 32*K doubles (256-bit vector ld/st per thread at K = 4).
-// fp64 throughout.  Rescaling uses exact powers of two (exponent extraction) instead of the
+// passes, so ONE thread owns one (or two) columns for the whole evaluation and walks the flat op
+// program produced by schedule.hpp.  No inter-thread data dependency exists, hence one fused
+// persistent kernel (post pass + gradient pass); the only CTA-level synchronisation is the
+// chunk-wise staging of per-op inputs (descriptors, leaf codes, branch data) in shared memory.
+// Partials live in a CTA-private scratch region laid out [slot][column][thread][state] so that a
+// warp's access is one contiguous run of 32*K doubles (256-bit vector ld/st per thread at K = 4).
+// fp64 throughout.  Transitions are applied in eigen-space, P L = U (e * (Uinv L)), with U / Uinv as
+// constant-bank operands.  Rescaling uses exact powers of two (exponent extraction) instead of the
 // reference's divide-by-max + log per node; the integer exponent sum is exact and
 // logL = ln2 * sum(exponents) + sum(log(pi . L_root)).
 #include "../../include/mcphylo_b200.h"
@@ -111,19 +113,6 @@ __constant__ double c_model[MODEL_SLOT * MODEL_SLOTS];
 // --------------------------------------------------------------------------------------------
 // vector load/store helpers (K doubles per column)
 // --------------------------------------------------------------------------------------------
-template <int K>
-__device__ __forceinline__ void ld_table(const double* __restrict__ p, double (&v)[K]) {
-    // read-only path: tables are written by an earlier kernel
-    if constexpr (K == 4) {
-        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-            : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
-    } else if constexpr (K == 2) {
-        asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = __ldg(p + k);
-    }
-}
 // Partials: written and re-read by the SAME thread inside one kernel, so they must not go
 // through the non-coherent path; .cg keeps this streaming data out of L1.
 template <int K>
@@ -417,8 +406,6 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
     unsigned char* const scr = SSCR
         ? scode + WalkSmem<K>::code_bytes(TS) + (size_t)tid * K * 8
         : reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K);
-    constexpr int COLB = 1;                           // (documentation) one column = K doubles per thread
-    (void)COLB;
     const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
     const unsigned slot_bytes = col_bytes * CPT;
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;

@@ -402,3 +402,29 @@ def test_empty_and_single_site_alignments(oracle):
     ll, g = mcp.gradlogpdf(pd, mcp.DeviceAlignment(codes, leaf_nums, 4))
     ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.JC, [0.25] * 4, [1.0], [1.0, 2.0])
     _check(ll, g, ll_o, g_o)
+
+
+def test_config3_full_size_properties(oracle):
+    """BASELINE config 3 at full size (200 taxa x 100 000 sites, GTR + Gamma4): too large for the
+    dense oracle as a whole, so (i) a contiguous 400-site window is checked against the oracle and
+    (ii) the full result must equal the sum over an uneven partition into site blocks, which also
+    exercises different tile counts / launch shapes of the same data."""
+    rng = np.random.default_rng(20243)
+    tree = random_tree(200, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    S = 100_000
+    pool, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 8192, rng)
+    codes = np.take(pool, rng.integers(0, 8192, size=S), axis=1)
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    full = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    ll, g = mcp.gradlogpdf(pd, full)
+    cuts = [0, 400, 33_333, 33_334, 77_001, S]
+    parts = [mcp.gradlogpdf(pd, full.site_block(a, b)) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert abs(sum(p[0] for p in parts) - ll) <= 1e-12 * abs(ll)
+    gs = sum(p[1] for p in parts)
+    assert np.all(np.abs(gs - g) <= 1e-10 * np.maximum(np.abs(g), 1e-3 * np.max(np.abs(g))))
+    ll_o, g_o = _oracle_eval(oracle, tree, codes[:, :400], leaf_nums, 4, mcp.GTR, pi, sr, rates)
+    _check(parts[0][0], parts[0][1], ll_o, g_o)
+    assert abs(mcp.logpdf(pd, full) - ll) <= 1e-13 * abs(ll)
