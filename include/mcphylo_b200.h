@@ -64,6 +64,9 @@ int mcp_destroy(mcp_ctx *ctx);
  * stream is).  mcp_use_own_stream goes back to the internal stream. */
 int mcp_set_stream(mcp_ctx *ctx, void *cuda_stream);
 int mcp_use_own_stream(mcp_ctx *ctx);
+/* Blocks until everything enqueued by this context (mcp_eval_device, mcp_alignment_update_codes)
+ * has finished. */
+int mcp_synchronize(mcp_ctx *ctx);
 
 /*
  * Leaf data.  Replaces the dense one-hot array `x[:, :, leaf.num]` the reference re-expands on
@@ -82,7 +85,8 @@ int mcp_alignment_from_dense(mcp_ctx *ctx, const double *x, int K, int64_t S, in
                              const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
 /* Re-upload the codes of an existing alignment (same K, S, leaf_nums) from host memory,
  * asynchronously on the context's stream; evaluations enqueued afterwards see the new data.
- * With pinned host memory the copy overlaps host work.  The cached schedule stays valid. */
+ * With pinned host memory the copy overlaps host work; `codes` must stay valid until the context
+ * is synchronised (mcp_synchronize or a synchronous mcp_eval).  The cached schedule stays valid. */
 int mcp_alignment_update_codes(mcp_ctx *ctx, mcp_alignment *aln, const uint8_t *codes);
 int mcp_alignment_destroy(mcp_ctx *ctx, mcp_alignment *aln);
 

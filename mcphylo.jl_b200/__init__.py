@@ -19,4 +19,4 @@ from .phylodist import (PhyloDist, MultiplePhyloDist, DeviceAlignment, Dimension
 from . import phylodist as _phylodist
 globals()["__logpdf"] = getattr(_phylodist, "__logpdf")
 from .synthetic import random_tree, simulate_codes  # noqa: F401,E402
-from .dist import ShardedEvaluator, shard_bounds, local_shard  # noqa: F401,E402
+from .dist import ShardedEvaluator, PipelinedEvaluator, shard_bounds, local_shard  # noqa: F401,E402

@@ -18,7 +18,7 @@ _lib = None
 
 SYMBOLS = [
     "mcp_abi_version", "mcp_last_error", "mcp_create", "mcp_destroy", "mcp_set_stream",
-    "mcp_use_own_stream",
+    "mcp_use_own_stream", "mcp_synchronize",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
@@ -66,6 +66,7 @@ def load():
     lib.mcp_destroy.argtypes = [_vp]
     lib.mcp_set_stream.argtypes = [_vp, _vp]
     lib.mcp_use_own_stream.argtypes = [_vp]
+    lib.mcp_synchronize.argtypes = [_vp]
     lib.mcp_set_launch.argtypes = [_vp, C.c_int, C.c_int]
     lib.mcp_set_columns_per_thread.argtypes = [_vp, C.c_int]
     lib.mcp_set_scratch_mode.argtypes = [_vp, C.c_int]
@@ -159,6 +160,9 @@ class Context:
             self._check(self.lib.mcp_use_own_stream(self.handle))
         else:
             self._check(self.lib.mcp_set_stream(self.handle, _vp(int(cuda_stream))))
+
+    def synchronize(self):
+        self._check(self.lib.mcp_synchronize(self.handle))
 
     def set_launch(self, block: int = 0, ctas_per_sm: int = 0):
         self._check(self.lib.mcp_set_launch(self.handle, int(block), int(ctas_per_sm)))

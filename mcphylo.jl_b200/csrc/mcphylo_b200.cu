@@ -1059,6 +1059,8 @@ struct mcp_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_staged = nullptr;   // the pinned staging buffers of the last evaluation have been consumed
+    bool staged_pending = false;
     std::string error;
     bool pending_async = false;
     int opt_block = 0, opt_ctas_per_sm = 0, opt_cpt = 0;
@@ -1086,6 +1088,7 @@ struct mcp_ctx {
     long long total_out = 0, total_dyn = 0, total_btab = 0, scratch_per_cta = 0, row_stride = 0;
     size_t smem_bytes = 0;
 
+    std::vector<std::pair<const void*, size_t>> smem_attr;   // per kernel: dynamic smem already opted in
     mcp_stats stats{};
 };
 
@@ -1144,11 +1147,11 @@ int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
     return 0;
 }
 
-// cudaFuncSetAttribute is only needed when a kernel's dynamic shared memory grows
+// cudaFuncSetAttribute is only needed when a kernel's dynamic shared memory grows; the attribute is
+// per device, so the high-water marks live in the context.
 template <class Kern>
 int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
-    static thread_local std::vector<std::pair<const void*, size_t>> done;
-    for (auto& d : done)
+    for (auto& d : ctx->smem_attr)
         if (d.first == (const void*)kern) {
             if (d.second >= smem) return 0;
             CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1156,7 +1159,7 @@ int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
             return 0;
         }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done.push_back({(const void*)kern, smem});
+    ctx->smem_attr.push_back({(const void*)kern, smem});
     return 0;
 }
 template <int K, int CPT, bool DYN, bool SSCR>
@@ -1346,7 +1349,7 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     if (k_templated(K)) {
         MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, ctx->smem_scratch, &occ));
     } else {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(felsenstein_walk_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_bytes));
+        if ((rc = ensure_smem_attr(ctx, felsenstein_walk_generic, ctx->smem_bytes))) return rc;
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, felsenstein_walk_generic, block, ctx->smem_bytes));
     }
     if (rc) return rc == MCP_ERR_UNSUPPORTED ? fail(ctx, rc, "no kernel compiled for K = %d states", K) : rc;
@@ -1354,6 +1357,16 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
     ctx->grid = (int)std::min<long long>((long long)ctx->n_tiles, (long long)occ * ctx->sm_count);
     if (ctx->grid < 1) ctx->grid = 1;
+    {   // very large trees: fewer persistent CTAs rather than a scratch allocation that cannot succeed
+        size_t free_b = 0, total_b = 0;
+        const double per_cta = (double)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8.0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_cta > 0) {
+            const double budget = 0.6 * ((double)free_b + (double)ctx->d_scratch.cap);
+            if (per_cta * ctx->grid > budget) ctx->grid = (int)std::max(1.0, std::floor(budget / per_cta));
+        } else {
+            cudaGetLastError();
+        }
+    }
 
     // accumulator rows: one per (CTA, tree) pair in CTA order (also tree order)
     std::vector<int32_t> row_base(ctx->grid, 0);
@@ -1418,9 +1431,9 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     const int K = a.alns[0]->K, R = a.R, T = a.T;
     if (!k_supported(K)) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (ctx->pending_async) {  // staging buffers may still be in flight
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->pending_async = false;
+    if (ctx->staged_pending) {  // the previous (asynchronous) evaluation may still be reading the staging buffers
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_staged));
+        ctx->staged_pending = false;
     }
     bool rebuilt = false;
     int e = prepare_topology(ctx, a, K, &rebuilt);
@@ -1496,6 +1509,9 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(double) * ctx->total_dyn, cudaMemcpyHostToDevice, st));
     s.h2d_bytes += (int64_t)(sizeof(double) * ctx->total_dyn);
 
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged, st));
+    ctx->staged_pending = true;
+
     const TreeDev* d_trees = (const TreeDev*)((char*)ctx->d_topo.p + ctx->off_trees);
     {
         dim3 grid((ctx->max_br * R + 127) / 128, T);
@@ -1557,6 +1573,8 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     s.d2h_bytes = (int64_t)(sizeof(double) * ctx->total_out);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->staged_pending = false;
+    ctx->pending_async = false;
     const double* ho = (const double*)ctx->h_out.p;
     for (int t = 0; t < T; ++t) {
         const double* o = ho + ctx->trees[t].out_off;
@@ -1629,6 +1647,7 @@ int mcp_create(mcp_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; e == cudaSuccess && i < 4; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string msg = cudaGetErrorString(e);
         delete ctx;
@@ -1649,6 +1668,7 @@ int mcp_destroy(mcp_ctx* ctx) {
         if (b->p) cudaFreeHost(b->p);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return 0;
@@ -1661,6 +1681,14 @@ int mcp_set_stream(mcp_ctx* ctx, void* cuda_stream) {
         ctx->pending_async = false;
     }
     ctx->stream = (cudaStream_t)cuda_stream;   // NULL is the CUDA default stream, a valid choice
+    return 0;
+}
+
+int mcp_synchronize(mcp_ctx* ctx) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->pending_async = false;
     return 0;
 }
 
@@ -1746,7 +1774,7 @@ int mcp_alignment_update_codes(mcp_ctx* ctx, mcp_alignment* aln, const uint8_t* 
     if (aln->S > 0)
         CUDA_TRY(ctx, cudaMemcpy2DAsync(aln->d_codes, (size_t)aln->stride, codes, (size_t)aln->S, (size_t)aln->S,
                                         (size_t)aln->n_leaves, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->pending_async = true;
+    ctx->pending_async = true;   // only consulted before buffers are freed / the stream is changed
     return 0;
 }
 

@@ -98,3 +98,68 @@ def sharded_sum(local_eval: Callable[[], Tuple[float, Optional[np.ndarray]]], NN
         t[1:] = torch.from_numpy(np.asarray(g, dtype=np.float64))
     allreduce_sum(t, group)
     return float(t[0]), t[1:].numpy().copy()
+
+
+class PipelinedEvaluator:
+    """Evaluation of an alignment that has to be (re-)uploaded from host memory for the call: the
+    site axis is cut into `n_blocks` blocks handled alternately by two contexts (two CUDA streams),
+    so block b+1 crosses PCIe while block b is being evaluated.  Results of the blocks are summed on
+    the device, all-reduced over the process group if there is one, and read back once.
+
+    `codes` is the rank's (n_leaves, S) uint8 block; pinned per-block copies are made once here."""
+
+    def __init__(self, codes: np.ndarray, leaf_nums, K: int, device: int, n_blocks: int = 4, group=None):
+        import torch
+
+        from . import capi
+
+        self.torch = torch
+        self.device, self.group, self.K = device, group, int(K)
+        self.leaf_nums = np.asarray(leaf_nums, dtype=np.int32)
+        S = codes.shape[1]
+        n_blocks = max(1, min(n_blocks, S if S > 0 else 1))
+        self.ctxs = [capi.Context(device) for _ in range(min(2, n_blocks))]
+        self.blocks = []
+        for b in range(n_blocks):
+            lo, hi = shard_bounds(S, n_blocks, b)
+            if hi <= lo:
+                continue
+            host = torch.from_numpy(np.ascontiguousarray(codes[:, lo:hi])).pin_memory()
+            ctx = self.ctxs[len(self.blocks) % len(self.ctxs)]
+            aln = ctx.alignment_from_codes(host.numpy(), self.K, self.leaf_nums)
+            self.blocks.append((ctx, aln, host))
+        self._out = None
+
+    def evaluate(self, d: PhyloDist, want_grad: bool = True, upload: bool = True):
+        torch = self.torch
+        ft, targs = _tree_args(d)
+        NN = ft.NN
+        if self._out is None or self._out.shape[1] != NN:
+            self._out = torch.empty((len(self.blocks), NN), dtype=torch.float64, device=f"cuda:{self.device}")
+            self._pinned = torch.empty(NN, dtype=torch.float64).pin_memory()
+        with torch.cuda.device(self.device):
+            for i, (ctx, aln, host) in enumerate(self.blocks):
+                if upload:
+                    aln.update_codes(host.data_ptr())
+                ctx.eval_device(aln, *targs, want_grad=want_grad, d_out_ptr=self._out[i].data_ptr())
+            for ctx in self.ctxs:
+                ctx.synchronize()
+            total = self._out.sum(dim=0)
+            allreduce_sum(total, self.group)
+            self._pinned.copy_(total, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        res = self._pinned.numpy()
+        return float(res[0]), (res[1:].copy() if want_grad else None)
+
+    def gradlogpdf(self, d: PhyloDist):
+        return self.evaluate(d, True)
+
+    def logpdf(self, d: PhyloDist) -> float:
+        return self.evaluate(d, False)[0]
+
+    def close(self):
+        for ctx, aln, _ in self.blocks:
+            aln.close()
+        for ctx in self.ctxs:
+            ctx.close()
+        self.blocks, self.ctxs = [], []

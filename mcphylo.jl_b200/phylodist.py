@@ -7,7 +7,9 @@ The reference re-expands `x` and recomputes everything on the CPU in every call;
 call flattens the tree, evaluates the substitution model's eigendecomposition on the host
 and hands both to the C-ABI (capi.py -> libmcphylo_b200.so).  The leaf data `x` is uploaded
 once per array object and stays resident on the GPU (the reference passes the same Array for
-the life of a chain, /root/reference/src/model/dependent.jl:344-358).
+the life of a chain, /root/reference/src/model/dependent.jl:344-358).  The cache is keyed by the
+array OBJECT: an array modified in place after its first use must be re-registered with
+`release_device_cache()`.
 
 No CPU fallback exists: without the CUDA library or a GPU these functions raise.
 """

@@ -428,3 +428,24 @@ def test_config3_full_size_properties(oracle):
     ll_o, g_o = _oracle_eval(oracle, tree, codes[:, :400], leaf_nums, 4, mcp.GTR, pi, sr, rates)
     _check(parts[0][0], parts[0][1], ll_o, g_o)
     assert abs(mcp.logpdf(pd, full) - ll) <= 1e-13 * abs(ll)
+
+
+def test_pipelined_evaluator_matches_resident(oracle):
+    """Upload-overlapped evaluation in site blocks (dist.PipelinedEvaluator) vs the resident path."""
+    rng = np.random.default_rng(41)
+    tree = random_tree(30, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 3001, rng)
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates)
+    for n_blocks in (1, 3, 4):
+        pipe = mcp.PipelinedEvaluator(codes, leaf_nums, 4, 0, n_blocks=n_blocks)
+        try:
+            for _ in range(2):                      # second call re-uploads into the same buffers
+                ll, g = pipe.gradlogpdf(pd)
+                _check(ll, g, ll_o, g_o)
+            assert abs(pipe.logpdf(pd) - ll_o) <= LL_RTOL * abs(ll_o)
+        finally:
+            pipe.close()
