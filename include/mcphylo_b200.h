@@ -160,6 +160,10 @@ int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);
 /* Where a CTA keeps its partial-likelihood scratch: -1 automatic (shared memory for small inputs
  * whose scratch fits, HBM otherwise), 0 always HBM, 1 shared memory whenever it fits. */
 int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
+/* Level-parallel small-tree kernel (all warps of a CTA share one 32-column tile, one barrier per
+ * tree level): -1 automatic (inputs of at most a few tiles per SM whose tree fits in shared memory),
+ * 0 never, 1 whenever the tree fits. */
+int mcp_set_level_mode(mcp_ctx *ctx, int mode);
 
 /*
  * Host-only: emits the device schedule (the flat "walk program") for a topology, so the
@@ -167,6 +171,9 @@ int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
  * for internal nodes.  Ops are 8 int32 each (layouts in csrc/schedule.hpp).  Pass cap_* =
  * capacity of the arrays in ops; returns MCP_ERR_ARG if too small.
  *   info[0]=n_post info[1]=n_pre info[2]=n_slots info[3]=n_stack info[4]=n_dnodes
+ *   info[5]=post levels info[6]=pre levels (info must hold 8 ints)
+ * want_grad: bit 0 = gradient program wanted, bit 1 = emit the level-ordered variant used by the
+ * small-tree kernel instead of the depth-first one.
  */
 int mcp_schedule_dump(int NN, const int32_t *postorder_num, const int32_t *parent_num,
                       const int32_t *leaf_row, int want_grad, int32_t *post_ops, int cap_post,

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
-    "mcp_set_columns_per_thread", "mcp_set_scratch_mode",
+    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_level_mode",
     "mcp_schedule_dump",
 ]
 
@@ -70,6 +70,7 @@ def load():
     lib.mcp_set_launch.argtypes = [_vp, C.c_int, C.c_int]
     lib.mcp_set_columns_per_thread.argtypes = [_vp, C.c_int]
     lib.mcp_set_scratch_mode.argtypes = [_vp, C.c_int]
+    lib.mcp_set_level_mode.argtypes = [_vp, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
@@ -170,6 +171,9 @@ class Context:
     def set_columns_per_thread(self, cpt: int = 0):
         self._check(self.lib.mcp_set_columns_per_thread(self.handle, int(cpt)))
 
+    def set_level_mode(self, mode: int = -1):
+        self._check(self.lib.mcp_set_level_mode(self.handle, int(mode)))
+
     def set_scratch_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_scratch_mode(self.handle, int(mode)))
 
@@ -253,7 +257,7 @@ class Context:
         return ll, None
 
 
-def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool):
+def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool, by_levels: bool = False):
     """Host-only view of the device walk program (no GPU needed)."""
     lib = load()
     po, pa, lr = _i32(postorder_num), _i32(parent_num), _i32(leaf_row)
@@ -262,9 +266,10 @@ def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool):
     post = np.zeros((cap, 8), dtype=np.int32)
     pre = np.zeros((cap, 8), dtype=np.int32)
     info = np.zeros(8, dtype=np.int32)
-    rc = lib.mcp_schedule_dump(NN, po.ctypes.data, pa.ctypes.data, lr.ctypes.data, int(want_grad),
+    rc = lib.mcp_schedule_dump(NN, po.ctypes.data, pa.ctypes.data, lr.ctypes.data, int(bool(want_grad)) | (2 if by_levels else 0),
                                post.ctypes.data, cap, pre.ctypes.data, cap, info.ctypes.data)
     if rc:
         raise McpError(rc, lib.mcp_last_error(None).decode())
     return {"post": post[:info[0]].copy(), "pre": pre[:info[1]].copy(), "n_slots": int(info[2]),
-            "n_stack": int(info[3]), "n_dnodes": int(info[4])}
+            "n_stack": int(info[3]), "n_dnodes": int(info[4]), "post_levels": int(info[5]),
+            "pre_levels": int(info[6])}

@@ -28,6 +28,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,8 @@ struct TreeDev {
     int NN, n_br;            // real nodes; rows of the branch table (device nodes)
     int tile_begin, tiles_per_rate;
     int row_lo, row_hi;      // accumulator rows [lo, hi) holding this tree's partial sums
+    int lvl_off, n_post_lvl, n_pre_lvl;   // level-ordered program: offsets into WalkParams::levels
+    int n_rows;              // leaf rows of the alignment
 };
 
 struct LLRow {
@@ -70,11 +73,12 @@ struct WalkParams {
     double* rows;               // [row][row_stride] gradient partial sums
     LLRow* rows_ll;
     const int* cta_row_base;
+    const int* levels;          // level offsets of the level-ordered programs (small-tree kernel)
     long long row_stride;
     int n_slots, n_stack;
     int n_tiles, T, R, want_grad;
     int max_br;
-    int pad_;
+    int max_rows;               // largest number of leaf rows in the batch
     // Substitution-model constants when the whole batch shares ONE model (the common case): kernel
     // parameters live in constant bank 0, so they reach the FP64 pipe as uniform operands without
     // a separate host-to-device copy.  Layout as in c_model (below).
@@ -381,7 +385,10 @@ struct WalkSmem {
 // small problems (MCMC-sized trees), where a lone warp would otherwise wait an L2 round trip for
 // every partial it has just written.
 template <int K, int CPT, bool DYN_MODEL, bool SSCR>
-__global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
+#ifndef MCP_WALK_MAXT
+#define MCP_WALK_MAXT 256
+#endif
+__global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
@@ -798,6 +805,237 @@ __global__ void __launch_bounds__(256, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_
 }
 
 // --------------------------------------------------------------------------------------------
+// kernel 2c: small-tree latency path.  A tile is ONE warp wide (32 columns) but is worked on by all
+// W warps of the CTA: the level-ordered program (schedule.hpp, by_levels) lists ops of equal height
+// (post pass) / depth (gradient pass) together, the warps split each level's ops, and a
+// __syncthreads separates levels.  All partials and pre vectors of the tile live in shared memory.
+// The critical path is the tree height instead of the node count; used when the whole input is only
+// a few tiles per SM (MCMC-sized problems), where the depth-first walk runs at single-warp latency.
+// --------------------------------------------------------------------------------------------
+struct LevelSmem {
+    // byte offsets into dynamic shared memory
+    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 127) & ~(size_t)127) : 0; }
+    static __host__ __device__ size_t exp_bytes() { return 128; }
+    static __host__ __device__ size_t code_bytes(int n_rows) { return (((size_t)n_rows * 32) + 127) & ~(size_t)127; }
+    static __host__ __device__ size_t slot_bytes(int K) { return (size_t)32 * K * 8; }
+    static __host__ __device__ size_t total(int n_br, int want_grad, int n_rows, int n_slots, int n_stack, int K) {
+        return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + (size_t)(n_slots + n_stack) * slot_bytes(K);
+    }
+};
+
+template <int K, bool DYN_MODEL>
+__global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_constant__ WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_e[8];
+    __shared__ double s_l[8];
+
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, W = NT >> 5;
+    const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
+    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
+    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
+    if (tile >= tile_end) return;
+
+    double* const s_acc = reinterpret_cast<double*>(smem_raw);
+    int* const s_exp = reinterpret_cast<int*>(smem_raw + LevelSmem::acc_bytes(p.max_br, p.want_grad));
+    unsigned char* const s_code = reinterpret_cast<unsigned char*>(s_exp) + LevelSmem::exp_bytes();
+    double* const s_post = reinterpret_cast<double*>(s_code + LevelSmem::code_bytes(p.max_rows)) + lane * K;
+    double* const s_pre = s_post + (size_t)p.n_slots * 32 * K;
+    constexpr int SLOT = 32 * K;                  // doubles per slot
+    constexpr int BT = K + 2 * K * (K + 1), KK1 = K * (K + 1);
+    int row = p.cta_row_base[blockIdx.x];
+    const int R = p.R;
+
+    int ti = 0;
+    while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
+
+    while (tile < tile_end) {
+        const TreeDev tr = p.trees[ti];
+        const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
+        if (p.want_grad) {
+            for (int i = tid; i < tr.n_br; i += NT) s_acc[i] = 0.0;
+        }
+        long long e_total = 0;
+        double logsum = 0.0;
+        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
+        const int4* const post_ops = p.ops + 2 * tr.post_off;
+        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
+        const int* const post_lvl = p.levels + tr.lvl_off;
+        const int* const pre_lvl = post_lvl + tr.n_post_lvl + 1;
+
+        for (; tile < tree_tile_end; ++tile) {
+            const int local = tile - tr.tile_begin;
+            const int r = local / tr.tiles_per_rate;
+            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * 32;
+            const bool valid = site0 + lane < tr.S;
+            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT;
+            const long long br_stride = (long long)R * BT;
+
+            __syncthreads();                                   // previous tile done with the shared buffers
+            for (int i = tid; i < tr.n_rows * 32; i += NT) {   // this tile's state codes, all leaves
+                const int rw = i >> 5, l = i & 31;
+                s_code[i] = (site0 + l < tr.S) ? __ldg(tr.codes + (long long)rw * tr.code_stride + site0 + l) : (unsigned char)K;
+            }
+            if (tid < 32) s_exp[tid] = 0;
+            __syncthreads();
+
+            auto leaf_code = [&](int src) -> int { return src >= 0 ? min((int)s_code[src * 32 + lane], K) : K; };
+            auto ld_slot = [&](const double* base, int slot, double (&v)[1][K]) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) v[0][k] = base[(size_t)slot * SLOT + k];
+            };
+            auto st_slot = [&](double* base, int slot, const double (&v)[1][K]) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) base[(size_t)slot * SLOT + k] = v[0][k];
+            };
+            auto ld_vec = [&](const double* g, double (&v)[K]) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) v[k] = __ldg(g + k);
+            };
+
+            // ------------------------------ post pass ------------------------------
+            for (int lv = 0; lv < tr.n_post_lvl; ++lv) {
+                const int lo = __ldg(post_lvl + lv), hi = __ldg(post_lvl + lv + 1);
+                for (int i = lo + warp; i < hi; i += W) {
+                    const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
+                    const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
+                    double Da[1][K], Db[1][K];
+                    if (ka == mcp::OPK_LEAF) {
+                        ld_vec(tab_r + o0.y * br_stride + K + leaf_code(o0.x) * K, Da[0]);
+                    } else {
+                        double L[1][K], z[1][K], e[K];
+                        ld_slot(s_post, o0.x, L);
+                        ld_vec(tab_r + o0.y * br_stride, e);
+                        eig_project<K, 1>(mdl, L, e, z);
+                        eig_expand<K, 1>(mdl, z, Da);
+                    }
+                    if (kb == mcp::OPK_LEAF) {
+                        ld_vec(tab_r + o0.w * br_stride + K + leaf_code(o0.z) * K, Db[0]);
+                    } else {
+                        double L[1][K], z[1][K], e[K];
+                        ld_slot(s_post, o0.z, L);
+                        ld_vec(tab_r + o0.w * br_stride, e);
+                        eig_project<K, 1>(mdl, L, e, z);
+                        eig_expand<K, 1>(mdl, z, Db);
+                    }
+                    double cur[1][K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) cur[0][k] = Da[0][k] * Db[0][k];
+                    const int ex = rescale_pow2<K>(cur[0]);
+                    if (ex != 0) atomicAdd(&s_exp[lane], ex);
+                    if (flags & mcp::POST_STORE) st_slot(s_post, o1.x, cur);
+                    if (flags & mcp::POST_ROOT) {
+                        double rootv = mdl.pi(0) * cur[0][0];
+#pragma unroll
+                        for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[0][k], rootv);
+                        if (valid) logsum += log(rootv);
+                    }
+                }
+                __syncthreads();
+            }
+            if (warp == 0 && valid) e_total += s_exp[lane];
+
+            // ------------------------------ gradient pass ------------------------------
+            if (p.want_grad) {
+                for (int lv = 0; lv < tr.n_pre_lvl; ++lv) {
+                    const int lo = __ldg(pre_lvl + lv), hi = __ldg(pre_lvl + lv + 1);
+                    for (int i = lo + warp; i < hi; i += W) {
+                        const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
+                        const int flags = o1.y;
+                        const int a_br = o0.y, b_br = o0.w;
+                        const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
+                        double pm[1][K];
+                        if (((flags >> 8) & 3) == mcp::PREM_ROOT) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) pm[0][k] = mdl.pi(k);
+                        } else {
+                            ld_slot(s_pre, o1.x, pm);
+                        }
+                        double ea[K], ebv[K];
+                        double Da[1][K], Ya[1][K], Db[1][K], Yb[1][K];
+                        if (ai) {
+                            double L[1][K], z[1][K];
+                            ld_slot(s_post, o0.x, L);
+                            ld_vec(tab_r + a_br * br_stride, ea);
+                            eig_project<K, 1>(mdl, L, ea, z);
+                            eig_expand<K, 1>(mdl, z, Da);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) z[0][k] *= mdl.c(r, k);
+                            eig_expand<K, 1>(mdl, z, Ya);
+                        } else {
+                            const double* t = tab_r + a_br * br_stride + K + leaf_code(o0.x) * K;
+                            ld_vec(t, Da[0]);
+                            ld_vec(t + KK1, Ya[0]);
+                        }
+                        if (bi) {
+                            double L[1][K], z[1][K];
+                            ld_slot(s_post, o0.z, L);
+                            ld_vec(tab_r + b_br * br_stride, ebv);
+                            eig_project<K, 1>(mdl, L, ebv, z);
+                            eig_expand<K, 1>(mdl, z, Db);
+#pragma unroll
+                            for (int k = 0; k < K; ++k) z[0][k] *= mdl.c(r, k);
+                            eig_expand<K, 1>(mdl, z, Yb);
+                        } else {
+                            const double* t = tab_r + b_br * br_stride + K + leaf_code(o0.z) * K;
+                            ld_vec(t, Db[0]);
+                            ld_vec(t + KK1, Yb[0]);
+                        }
+                        double qa[1][K], qb[1][K];
+                        double den = 0.0, na = 0.0, nb = 0.0;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            qa[0][k] = pm[0][k] * Db[0][k];
+                            qb[0][k] = pm[0][k] * Da[0][k];
+                            den = fma(qa[0][k], Da[0][k], den);
+                            na = fma(qa[0][k], Ya[0][k], na);
+                            nb = fma(qb[0][k], Yb[0][k], nb);
+                        }
+                        const double inv = fast_rcp(den);
+                        const double red = warp_pair_reduce(valid ? na * inv : 0.0, valid ? nb * inv : 0.0, lane);
+                        if (lane == 0) atomicAdd(&s_acc[a_br], red);
+                        else if (lane == 16) atomicAdd(&s_acc[b_br], red);
+                        if (((flags >> 10) & 3) != mcp::OUT_NONE) {
+                            double pa[1][K];
+                            eig_transposed<K, 1>(mdl, qa, ea, pa);
+                            rescale_pow2<K>(pa[0]);
+                            st_slot(s_pre, o1.z, pa);
+                        }
+                        if (((flags >> 12) & 3) != mcp::OUT_NONE) {
+                            double pb[1][K];
+                            eig_transposed<K, 1>(mdl, qb, ebv, pb);
+                            rescale_pow2<K>(pb[0]);
+                            st_slot(s_pre, o1.w, pb);
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }  // tiles of this tree
+
+        for (int off = 16; off > 0; off >>= 1) {
+            e_total += __shfl_xor_sync(0xffffffffu, e_total, off);
+            logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
+        }
+        if (lane == 0) { s_e[warp] = e_total; s_l[warp] = logsum; }
+        __syncthreads();
+        if (tid == 0) {
+            long long es = 0;
+            double ls = 0.0;
+            for (int w = 0; w < W; ++w) { es += s_e[w]; ls += s_l[w]; }
+            p.rows_ll[row].esum = es;
+            p.rows_ll[row].logsum = ls;
+        }
+        if (p.want_grad) {
+            double* dst = p.rows + (long long)row * p.row_stride;
+            for (int i = tid; i < tr.n_br; i += NT) dst[i] = s_acc[i];
+        }
+        __syncthreads();
+        ++row;
+        ++ti;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 // kernel 2b: generic state count (6 < K <= KMAX_GENERIC), runtime K.  Same op program, same scratch
 // layout and accumulator rows as the templated kernel, but dense-table arithmetic straight from the
 // branch table (P / dP columns are stored for every branch) and per-thread vectors in local memory.
@@ -1066,6 +1304,11 @@ struct mcp_ctx {
     int opt_block = 0, opt_ctas_per_sm = 0, opt_cpt = 0;
     int cpt = 1;   // columns per thread of the cached launch
     bool smem_scratch = false;   // partials scratch in shared memory (small-problem latency path)
+    bool level_mode = false;     // level-parallel small-tree kernel
+    int opt_levels = -1;         // -1 automatic, 0 never, 1 whenever it fits
+    int sig_levels = -1;
+    int max_rows = 1;
+    size_t off_levels = 0;
     int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
     unsigned long long next_aln_id = 1;
 
@@ -1088,7 +1331,6 @@ struct mcp_ctx {
     long long total_out = 0, total_dyn = 0, total_btab = 0, scratch_per_cta = 0, row_stride = 0;
     size_t smem_bytes = 0;
 
-    std::vector<std::pair<const void*, size_t>> smem_attr;   // per kernel: dynamic smem already opted in
     mcp_stats stats{};
 };
 
@@ -1147,19 +1389,24 @@ int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
     return 0;
 }
 
-// cudaFuncSetAttribute is only needed when a kernel's dynamic shared memory grows; the attribute is
-// per device, so the high-water marks live in the context.
+// cudaFuncSetAttribute is only needed when a kernel's dynamic shared memory grows.  The attribute
+// belongs to the (device, function) pair and is shared by every context of the process, so the
+// high-water marks are process-global and only ever raised.
 template <class Kern>
 int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
-    for (auto& d : ctx->smem_attr)
-        if (d.first == (const void*)kern) {
-            if (d.second >= smem) return 0;
+    struct Mark { int device; const void* fn; size_t bytes; };
+    static std::mutex mu;
+    static std::vector<Mark> marks;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& m : marks)
+        if (m.device == ctx->device && m.fn == (const void*)kern) {
+            if (m.bytes >= smem) return 0;
             CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            d.second = smem;
+            m.bytes = smem;
             return 0;
         }
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->smem_attr.push_back({(const void*)kern, smem});
+    marks.push_back({ctx->device, (const void*)kern, smem});
     return 0;
 }
 template <int K, int CPT, bool DYN, bool SSCR>
@@ -1196,6 +1443,24 @@ int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, bool sscr, int* out) {
 template <int K>
 int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, bool sscr, int* out) {
     return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, false, out) : occupancy_inst<K, 1>(ctx, block, smem, sscr, out);
+}
+template <int K>
+int occupancy_levels(mcp_ctx* ctx, int block, size_t smem, int* out) {
+    int e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk_levels<K, true>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk_levels<K, false>, smem))) return e;
+    int o1 = 0, o2 = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk_levels<K, true>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk_levels<K, false>, block, smem));
+    *out = std::min(o1, o2);
+    return 0;
+}
+template <int K>
+int launch_levels(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
+    if (dyn_model) felsenstein_walk_levels<K, true><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    else felsenstein_walk_levels<K, false><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return 0;
 }
 size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
     size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
@@ -1253,8 +1518,12 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         cpt = 1;
         if (block > 128) block = 128;
     }
+    // Small inputs (a few one-warp tiles per SM): level-parallel kernel, a tile is 32 columns wide
+    // and is worked on by all 8 warps of a 256-thread CTA.
+    const bool try_levels = k_templated(K) && ctx->opt_levels != 0 &&
+                            (ctx->opt_levels == 1 || (ctx->opt_block == 0 && total_cols <= 32LL * 4 * ctx->sm_count));
     bool same = (int)ctx->sig.size() == T && ctx->sig_want_grad == a.want_grad && ctx->sig_block == block &&
-                ctx->sig_K == K && ctx->sig_R == R && ctx->sig_cpt == cpt;
+                ctx->sig_K == K && ctx->sig_R == R && ctx->sig_cpt == cpt && ctx->sig_levels == (int)try_levels;
     for (int t = 0; same && t < T; ++t) {
         const auto& s = ctx->sig[t];
         same = s.aln_id == a.alns[t]->id && s.NN == a.NN[t] &&
@@ -1265,11 +1534,16 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     if (same) return 0;
 
     ctx->sig.clear();
+    long long n_ops = 0, out_off = 0, dyn_off = 0, btab_off = 0, n_lvl_ints = 0;
+    int tile_cursor = 0, n_slots = 1, n_stack = 1, max_br = 1, max_rows = 1;
+    std::vector<int32_t> leaf_row;
+    bool level_mode = try_levels;
+    auto build_all = [&](bool by_levels, int tile_w) -> int {
+    ctx->sig.clear();
     ctx->scheds.assign(T, Schedule());
     ctx->trees.assign(T, TreeDev());
-    long long n_ops = 0, out_off = 0, dyn_off = 0, btab_off = 0;
-    int tile_cursor = 0, n_slots = 1, n_stack = 1, max_br = 1;
-    std::vector<int32_t> leaf_row;
+    n_ops = out_off = dyn_off = btab_off = n_lvl_ints = 0;
+    tile_cursor = 0; n_slots = 1; n_stack = 1; max_br = 1; max_rows = 1;
     for (int t = 0; t < T; ++t) {
         const mcp_alignment* al = a.alns[t];
         const int NN = a.NN[t];
@@ -1279,7 +1553,7 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
             int num = al->leaf_nums[i];
             if (num >= 1 && num <= NN) leaf_row[num - 1] = i;
         }
-        std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, ctx->scheds[t]);
+        std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, ctx->scheds[t], by_levels);
         if (!err.empty()) return fail(ctx, MCP_ERR_ARG, "tree %d: %s", t, err.c_str());
         const Schedule& sc = ctx->scheds[t];
         TreeDev& td = ctx->trees[t];
@@ -1300,7 +1574,13 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         dyn_off += dyn_size(NN, K, R);
         td.btab_off = btab_off;
         btab_off += (long long)sc.n_dnodes * R * bt_size(K);
-        td.tiles_per_rate = (int)((al->S + (long long)block * cpt - 1) / ((long long)block * cpt));
+        td.tiles_per_rate = (int)((al->S + (long long)tile_w - 1) / (long long)tile_w);
+        td.n_rows = al->n_leaves;
+        td.lvl_off = (int)n_lvl_ints;
+        td.n_post_lvl = sc.post_levels.empty() ? 0 : (int)sc.post_levels.size() - 1;
+        td.n_pre_lvl = sc.pre_levels.empty() ? 0 : (int)sc.pre_levels.size() - 1;
+        n_lvl_ints += (long long)sc.post_levels.size() + (long long)sc.pre_levels.size();
+        max_rows = std::max(max_rows, al->n_leaves);
         td.tile_begin = tile_cursor;
         long long nt = (long long)td.tiles_per_rate * R;
         if (tile_cursor + nt > 0x7fffffffLL) return fail(ctx, MCP_ERR_ARG, "too many column tiles");
@@ -1315,9 +1595,23 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         sg.pa.assign(a.pa[t], a.pa[t] + NN);
         ctx->sig.push_back(std::move(sg));
     }
+    return 0;
+    };  // build_all
+    int be = 0;
+    if (level_mode) {
+        if ((be = build_all(true, 32))) { ctx->sig.clear(); return be; }
+        const size_t need = LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K);
+        if (need > 160 * 1024) level_mode = false;     // tree too large for the shared-memory path
+    }
+    if (!level_mode && (be = build_all(false, block * cpt))) { ctx->sig.clear(); return be; }
+    const int sig_block = block, sig_cpt = cpt;
+    if (level_mode) { block = 256; cpt = 1; }
+    ctx->level_mode = level_mode;
+    ctx->sig_levels = (int)try_levels;
+    ctx->max_rows = max_rows;
     ctx->sig_want_grad = a.want_grad;
-    ctx->sig_block = block;
-    ctx->sig_cpt = cpt;
+    ctx->sig_block = sig_block;
+    ctx->sig_cpt = sig_cpt;
     ctx->cpt = cpt;
     ctx->sig_K = K;
     ctx->sig_R = R;
@@ -1329,14 +1623,15 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     ctx->total_out = out_off;
     ctx->total_dyn = dyn_off;
     ctx->total_btab = btab_off;
-    ctx->smem_bytes = k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block, cpt)
-                                     : (a.want_grad ? (size_t)max_br * sizeof(double) : 0);
+    ctx->smem_bytes = level_mode ? LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K)
+                      : k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block, cpt)
+                                       : (a.want_grad ? (size_t)max_br * sizeof(double) : 0);
     // Small problems: keep the partials scratch in shared memory (latency path).  Automatic when the
     // whole input is a handful of tiles per SM and the scratch of one CTA fits next to the staging
     // buffers.
     {
         const size_t scr_bytes = (size_t)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8;
-        const bool fits = k_templated(K) && cpt == 1 && ctx->smem_bytes + scr_bytes <= 96 * 1024;
+        const bool fits = !level_mode && k_templated(K) && cpt == 1 && ctx->smem_bytes + scr_bytes <= 96 * 1024;
         ctx->smem_scratch = fits && (ctx->opt_smem_scratch == 1 ||
                                      (ctx->opt_smem_scratch < 0 && ctx->n_tiles <= 4 * ctx->sm_count));
         if (ctx->smem_scratch) ctx->smem_bytes += scr_bytes;
@@ -1346,7 +1641,9 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
 
     // persistent grid
     int occ = 0, rc = 0;
-    if (k_templated(K)) {
+    if (level_mode) {
+        MCP_DISPATCH_K(K, rc = occupancy_levels<KK>(ctx, block, ctx->smem_bytes, &occ));
+    } else if (k_templated(K)) {
         MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, ctx->smem_scratch, &occ));
     } else {
         if ((rc = ensure_smem_attr(ctx, felsenstein_walk_generic, ctx->smem_bytes))) return rc;
@@ -1359,7 +1656,7 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     if (ctx->grid < 1) ctx->grid = 1;
     {   // very large trees: fewer persistent CTAs rather than a scratch allocation that cannot succeed
         size_t free_b = 0, total_b = 0;
-        const double per_cta = (double)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8.0;
+        const double per_cta = level_mode ? 0.0 : (double)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8.0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_cta > 0) {
             const double budget = 0.6 * ((double)free_b + (double)ctx->d_scratch.cap);
             if (per_cta * ctx->grid > budget) ctx->grid = (int)std::max(1.0, std::floor(budget / per_cta));
@@ -1393,15 +1690,16 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         ctx->n_rows = row;
     }
     ctx->row_stride = (max_br + 3) & ~3;
-    if ((double)(ctx->n_slots + n_stack + 1) * block * cpt * K * 8.0 >= 4.0e9 || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
+    if ((!level_mode && (double)(ctx->n_slots + n_stack + 1) * block * cpt * K * 8.0 >= 4.0e9) || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree too large for 32-bit scratch offsets (%d nodes)", max_br);
-    ctx->scratch_per_cta = (long long)(ctx->n_slots + ctx->n_stack) * block * cpt * K;
+    ctx->scratch_per_cta = level_mode ? 4 : (long long)(ctx->n_slots + ctx->n_stack) * block * cpt * K;
 
     // topology upload: [TreeDev x T][ops][row_base]
     ctx->off_trees = 0;
     ctx->off_ops = (sizeof(TreeDev) * T + 31) & ~(size_t)31;
     ctx->off_rowbase = ctx->off_ops + (size_t)n_ops * 32;
-    ctx->topo_bytes = ctx->off_rowbase + sizeof(int32_t) * ctx->grid;
+    ctx->off_levels = ctx->off_rowbase + sizeof(int32_t) * ctx->grid;
+    ctx->topo_bytes = ctx->off_levels + sizeof(int32_t) * (size_t)std::max<long long>(n_lvl_ints, 1);
     int e;
     if ((e = ensure_pin(ctx, ctx->h_topo, ctx->topo_bytes))) return e;
     if ((e = ensure_dev(ctx, ctx->d_topo, ctx->topo_bytes))) return e;
@@ -1416,6 +1714,14 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         ho += sc.pre.size() * 32;
     }
     std::memcpy(h + ctx->off_rowbase, row_base.data(), sizeof(int32_t) * ctx->grid);
+    {
+        int32_t* hl = (int32_t*)(h + ctx->off_levels);
+        for (int t = 0; t < T; ++t) {
+            const Schedule& sc = ctx->scheds[t];
+            for (int32_t v : sc.post_levels) *hl++ = v;
+            for (int32_t v : sc.pre_levels) *hl++ = v;
+        }
+    }
     return 0;
 }
 
@@ -1528,6 +1834,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.rows = (double*)ctx->d_rows.p;
     wp.rows_ll = (LLRow*)ctx->d_rows_ll.p;
     wp.cta_row_base = (const int*)((char*)ctx->d_topo.p + ctx->off_rowbase);
+    wp.levels = (const int*)((char*)ctx->d_topo.p + ctx->off_levels);
     wp.row_stride = ctx->row_stride;
     wp.n_slots = ctx->n_slots;
     wp.n_stack = ctx->n_stack;
@@ -1536,13 +1843,15 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.R = R;
     wp.want_grad = a.want_grad ? 1 : 0;
     wp.max_br = ctx->max_br;
-    wp.pad_ = 0;
+    wp.max_rows = ctx->max_rows;
     static_assert(sizeof(wp.model) / sizeof(double) >= 2 * 6 * 6 + 6 + MAX_RATES * 6, "model parameter block too small");
     std::memset(wp.model, 0, sizeof wp.model);
     if (n_models == 1) std::memcpy(wp.model, hm, sizeof(double) * model_doubles);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
     int rc = 0;
-    if (k_templated(K)) {
+    if (ctx->level_mode) {
+        MCP_DISPATCH_K(K, rc = launch_levels<KK>(ctx, wp, dyn_model));
+    } else if (k_templated(K)) {
         MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp, dyn_model));
     } else {
         felsenstein_walk_generic<<<ctx->grid, ctx->block, ctx->smem_bytes, st>>>(wp, K);
@@ -1721,6 +2030,14 @@ int mcp_set_scratch_mode(mcp_ctx* ctx, int mode) {
     return 0;
 }
 
+int mcp_set_level_mode(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "level mode must be -1 (automatic), 0 (off) or 1 (whenever the tree fits)");
+    ctx->opt_levels = mode;
+    ctx->sig.clear();
+    return 0;
+}
+
 int mcp_set_columns_per_thread(mcp_ctx* ctx, int cpt) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (cpt != 0 && cpt != 1 && cpt != 2) return fail(ctx, MCP_ERR_ARG, "columns per thread must be 0 (automatic), 1 or 2");
@@ -1836,13 +2153,17 @@ int mcp_schedule_dump(int NN, const int32_t* postorder_num, const int32_t* paren
                       int want_grad, int32_t* post_ops, int cap_post, int32_t* pre_ops, int cap_pre, int32_t* info) {
     if (!postorder_num || !parent_num || !leaf_row || !info) return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: null argument");
     Schedule sc;
-    std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, want_grad != 0, sc);
+    const bool by_levels = (want_grad & 2) != 0;   // bit 1 of want_grad selects the level-ordered program
+    want_grad &= 1;
+    std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, want_grad != 0, sc, by_levels);
     if (!err.empty()) return fail(nullptr, MCP_ERR_ARG, "%s", err.c_str());
     info[0] = (int32_t)sc.post.size();
     info[1] = (int32_t)sc.pre.size();
     info[2] = sc.n_slots;
     info[3] = sc.n_stack;
     info[4] = sc.n_dnodes;
+    info[5] = (int32_t)(sc.post_levels.empty() ? 0 : sc.post_levels.size() - 1);
+    info[6] = (int32_t)(sc.pre_levels.empty() ? 0 : sc.pre_levels.size() - 1);
     if ((int)sc.post.size() > cap_post || (int)sc.pre.size() > cap_pre)
         return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: output arrays too small");
     if (post_ops) std::memcpy(post_ops, sc.post.data(), sc.post.size() * 32);

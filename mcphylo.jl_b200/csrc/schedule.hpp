@@ -28,6 +28,7 @@
 // in registers: KEEP); the other internal child is pushed on a LIFO (PUSH) of depth
 // <= log2(N)+1 and popped when the walk comes back.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -72,12 +73,19 @@ struct Schedule {
     int n_slots = 0;    // post result slots needed per column
     int n_stack = 0;    // pre LIFO depth needed per column
     int n_real_branches = 0;  // NN-1
+    // level-ordered variant only: ops [levels[l], levels[l+1]) are mutually independent
+    std::vector<int32_t> post_levels, pre_levels;
 };
 
 // leaf_row[num-1] = alignment row for leaves (must be >= 0 for every childless node).
 // Returns "" on success, else an error message.
+//
+// by_levels = true emits the LEVEL-ORDERED variant for the small-tree latency kernel: the same op
+// semantics, but ops sorted by height (post) / depth (pre) so that all ops of a level can run in
+// parallel on different warps; every operand goes through a slot (no REG / KEEP), post result of
+// internal node i lives in post slot i, its pre vector in pre ("LIFO") slot i.
 inline std::string build_schedule(int NN, const int32_t* postorder_num, const int32_t* parent_num,
-                                  const int32_t* leaf_row, bool want_grad, Schedule& out) {
+                                  const int32_t* leaf_row, bool want_grad, Schedule& out, bool by_levels = false) {
     if (NN < 2) return "tree must have at least two nodes";
     if (postorder_num[NN - 1] != NN) return "root must come last in post-order and carry num == NN";
     std::vector<int> pos(NN, -1);
@@ -157,6 +165,62 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
     const int n_int = (int)order.size();
     out.post.reserve(n_int);
     std::vector<int> slot_of(ND, -1);  // where a node's post result lives
+
+    if (by_levels) {
+        std::vector<int> height(ND, 0), depth(ND, 0);
+        for (int d : order) height[d] = 1 + std::max(height[dn[d].left], height[dn[d].right]);
+        std::vector<int> byh(order);
+        std::stable_sort(byh.begin(), byh.end(), [&](int x, int y) { return height[x] < height[y]; });
+        for (int i = 0; i < n_int; ++i) slot_of[byh[i]] = i;
+        for (int i = 0; i < n_int; ++i) {
+            const int d = byh[i];
+            PostOp op{};
+            op.node = d;
+            auto operand = [&](int c, int32_t& src, int32_t& br) -> int {
+                br = c;
+                if (is_leaf(c)) { src = dn[c].row; return OPK_LEAF; }
+                src = slot_of[c];
+                return OPK_MEM;
+            };
+            int ka = operand(dn[d].left, op.a_src, op.a_br);
+            int kb = operand(dn[d].right, op.b_src, op.b_br);
+            op.flags = ka | (kb << 2);
+            if (d == root) op.flags |= POST_ROOT;
+            else { op.flags |= POST_STORE; op.dst = i; }
+            if (i == 0 || height[d] != height[byh[i - 1]]) out.post_levels.push_back(i);
+            out.post.push_back(op);
+        }
+        out.post_levels.push_back(n_int);
+        out.n_slots = n_int;
+        if (want_grad) {
+            for (auto it = order.rbegin(); it != order.rend(); ++it) {   // mothers before children
+                depth[dn[*it].left] = depth[*it] + 1;
+                depth[dn[*it].right] = depth[*it] + 1;
+            }
+            std::vector<int> byd(order.rbegin(), order.rend());
+            std::stable_sort(byd.begin(), byd.end(), [&](int x, int y) { return depth[x] < depth[y]; });
+            for (int i = 0; i < n_int; ++i) {
+                const int m = byd[i];
+                PreOp op{};
+                const int a = dn[m].left, b = dn[m].right;
+                const bool ai = !is_leaf(a), bi = !is_leaf(b);
+                op.a_br = a; op.b_br = b;
+                op.a_src = ai ? slot_of[a] : dn[a].row;
+                op.b_src = bi ? slot_of[b] : dn[b].row;
+                op.m_src = slot_of[m];
+                op.a_dst = ai ? slot_of[a] : 0;
+                op.b_dst = bi ? slot_of[b] : 0;
+                op.flags = (ai ? OPK_MEM : OPK_LEAF) | ((bi ? OPK_MEM : OPK_LEAF) << 2) |
+                           ((m == root ? PREM_ROOT : PREM_STACK) << 8) |
+                           ((ai ? OUT_PUSH : OUT_NONE) << 10) | ((bi ? OUT_PUSH : OUT_NONE) << 12);
+                if (i == 0 || depth[m] != depth[byd[i - 1]]) out.pre_levels.push_back(i);
+                out.pre.push_back(op);
+            }
+            out.pre_levels.push_back(n_int);
+            out.n_stack = n_int;
+        }
+        return "";
+    }
 
     // ---- POST program: larger subtree first --------------------------------------------------
     {

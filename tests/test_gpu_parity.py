@@ -449,3 +449,32 @@ def test_pipelined_evaluator_matches_resident(oracle):
             assert abs(pipe.logpdf(pd) - ll_o) <= LL_RTOL * abs(ll_o)
         finally:
             pipe.close()
+
+
+@pytest.mark.parametrize("n_taxa,K,R,S,multi", [(10, 2, 1, 1000, False), (50, 2, 1, 3000, True), (40, 4, 4, 500, True),
+                                                (2, 4, 1, 40, False), (60, 3, 2, 300, False), (25, 6, 1, 100, False)])
+def test_level_parallel_kernel(oracle, n_taxa, K, R, S, multi):
+    """The small-tree kernel (warps of a CTA split the ops of a tree level) forced on, against the
+    oracle and against the depth-first kernel on the same input."""
+    rng = np.random.default_rng(500 + n_taxa + K)
+    tree = random_tree(n_taxa, rng, multifurcate=multi, unary=(K == 3))
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, S, rng, gap_frac=0.05)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_level_mode(1)
+        ll1, g1 = mcp.gradlogpdf(pd, aln)
+        assert ctx.stats()["block"] == 256
+        l1 = mcp.logpdf(pd, aln)
+        ctx.set_level_mode(0)
+        ll0, g0 = mcp.gradlogpdf(pd, aln)
+    finally:
+        ctx.set_level_mode(-1)
+    _check(ll1, g1, ll_o, g_o)
+    _check(l1, None, ll_o, None)
+    _check(ll0, g0, ll_o, g_o)

@@ -104,3 +104,32 @@ def test_bad_trees_are_rejected():
         capi.schedule_dump(po, [2, 1, 0], [0, 1, -1], True)
     with pytest.raises(capi.McpError):
         capi.schedule_dump([1], [0], [0], True)
+
+
+@pytest.mark.parametrize("n_taxa,K,seed", [(2, 2, 0), (9, 4, 1), (50, 2, 2), (33, 3, 3)])
+def test_level_ordered_program(oracle, n_taxa, K, seed):
+    """The level-ordered variant (small-tree kernel) has the same op semantics: executed
+    sequentially by the emulator it must reproduce the oracle, and its level count is the tree
+    height, not the node count."""
+    rng = np.random.default_rng(50 + seed)
+    tree = random_tree(n_taxa, rng, multifurcate=(seed % 2 == 1), unary=(seed == 3))
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model = mcp.Restriction(pi, []) if K == 2 else (mcp.GTR(pi, rng.uniform(0.5, 2.0, size=6)) if K == 4 else mcp.JC(pi, []))
+    codes, leaf_nums = simulate_codes(tree, model, pi, np.ones(1), 29, rng, gap_frac=0.1)
+    ft = mcp.flatten(tree)
+    x = oracle.codes_to_dense(codes, leaf_nums, K, ft.NN)
+    U, D, Uinv, mu = model
+    ll_o, g_o = oracle.felsenstein(x, ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, np.ones(1), pi, True, 1)
+    P, dP = oracle.transition(U, D, Uinv, mu, np.ones(1), ft.blv, want_dP=True)
+    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, _leaf_row(ft, leaf_nums), True, by_levels=True)
+    ll, g = run_program(prog, codes, K, P, dP, pi, ft.NN - 1)
+    assert abs(ll - ll_o) <= 1e-11 * abs(ll_o)
+    assert np.allclose(g[:ft.NN - 1], g_o, rtol=1e-9, atol=1e-9)
+    n_int = len(prog["post"])
+    assert prog["n_slots"] == n_int and prog["n_stack"] == n_int
+    assert 1 <= prog["post_levels"] <= n_int and prog["pre_levels"] == prog["post_levels"]
+    if n_taxa >= 33:
+        assert prog["post_levels"] < n_int // 2
+    # no REG / KEEP in this variant
+    assert all((op[5] & 3) != 1 and ((op[5] >> 2) & 3) != 1 for op in prog["post"])
+    assert all(((op[5] >> 10) & 3) != 1 and ((op[5] >> 12) & 3) != 1 and ((op[5] >> 8) & 3) != 1 for op in prog["pre"])

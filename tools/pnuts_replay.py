@@ -37,7 +37,7 @@ class State:
         self.x, self.r, self.g, self.lf = x, r, g, lf
 
 
-def ref_NNI(s, tmpB, epsilon, blv, delta, logf, rng, counters):
+def ref_NNI(s, tmpB, epsilon, blv, delta, logf, rng, counters, logf_pair=None):
     po = mcp.post_order(s.x)
     intext = np.zeros(len(po) - 1)
     by_num = {n.num: n for n in po}
@@ -54,15 +54,22 @@ def ref_NNI(s, tmpB, epsilon, blv, delta, logf, rng, counters):
         s.r[ref] *= -1.0
         if intext[ref] == 1:
             mcp.set_branchlength_vector(s.x, molifier(blv, delta))
-            U_before = logf(s.x)
-            counters["logpdf"] += 1
             v_copy = copy.deepcopy(s.x)
             target = next(n for n in mcp.post_order(v_copy) if n.num == ref + 1)
             made = mcp.NNI(v_copy, target, bool(rng.integers(0, 2)))
+            if made and logf_pair is not None:
+                # both sides of the NNI in ONE batched launch (mcp_eval_batch, two trees, same alignment)
+                U_before, U_after = logf_pair(s.x, v_copy)
+                counters["logpdf"] += 2
+                counters["batched_pairs"] += 1
+            else:
+                U_before = logf(s.x)
+                counters["logpdf"] += 1
+                if made:
+                    U_after = logf(v_copy)
+                    counters["logpdf"] += 1
             if made:
                 att += 1
-                U_after = logf(v_copy)
-                counters["logpdf"] += 1
                 delta_U = 2.0 * (U_before - U_after)
                 my_v = s.r[ref] ** 2
                 if my_v > delta_U:
@@ -74,11 +81,11 @@ def ref_NNI(s, tmpB, epsilon, blv, delta, logf, rng, counters):
     return tmpB, nni, att
 
 
-def refraction(s, epsilon, logfgrad, logf, delta, rng, counters):
+def refraction(s, epsilon, logfgrad, logf, delta, rng, counters, logf_pair=None):
     blenvec = mcp.get_branchlength_vector(s.x)
     s.r += (epsilon * 0.5) * s.g
     tmpB = blenvec + epsilon * s.r
-    tmpB, nni, att = ref_NNI(s, tmpB, epsilon, blenvec, delta, logf, rng, counters)
+    tmpB, nni, att = ref_NNI(s, tmpB, epsilon, blenvec, delta, logf, rng, counters, logf_pair)
     blenvec = molifier(tmpB, delta)
     mcp.set_branchlength_vector(s.x, blenvec)
     lf, grad = logfgrad(s.x)
@@ -98,6 +105,8 @@ def main():
     ap.add_argument("--epsilon", type=float, default=0.002)
     ap.add_argument("--delta", type=float, default=0.003)
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--batch-nni", action="store_true",
+                    help="evaluate the two logpdf calls of an NNI attempt as one mcp_eval_batch launch")
     a = ap.parse_args()
     w = bench.make_workload(a.workload, a.sites)
     codes, leaf_nums = bench.make_codes(w, 0, w["S"])
@@ -122,10 +131,16 @@ def main():
         note()
         return v
 
+    def logf_pair(t1, t2):
+        mpd = mcp.MultiplePhyloDist([t1, t2], w["pi"], w["srates"], w["rates"], w["model"])
+        v = mcp.phylodist._multi(mpd, [aln, aln], False, None)[0]
+        note()
+        return float(v[0]), float(v[1])
+
     tree = w["tree"]
     lf, g = logfgrad(tree)
     n = g.size
-    counters = {"gradlogpdf": 0, "logpdf": 0}
+    counters = {"gradlogpdf": 0, "logpdf": 0, "batched_pairs": 0}
     s = State(tree, rng.standard_normal(n), g * scale_fac(mcp.get_branchlength_vector(tree), a.delta), lf)
     H0 = -s.lf + 0.5 * float(s.r @ s.r)
     for k in dev:
@@ -133,16 +148,17 @@ def main():
     nni = att = 0
     t0 = time.perf_counter()
     for i in range(a.leapfrogs):
-        dn, da = refraction(s, a.epsilon, logfgrad, logf, a.delta, rng, counters)
+        dn, da = refraction(s, a.epsilon, logfgrad, logf, a.delta, rng, counters, logf_pair if a.batch_nni else None)
         nni += dn
         att += da
     wall = time.perf_counter() - t0
     H1 = -s.lf + 0.5 * float(s.r @ s.r)
-    calls = counters["gradlogpdf"] + counters["logpdf"]
+    calls = counters["gradlogpdf"] + counters["logpdf"] - counters["batched_pairs"]   # library calls
     print(json.dumps({
         "workload": f"{a.workload}: {w['n_taxa']} taxa x {w['S']} sites, K={w['K']}, R={w['R']}; tree-space leapfrog replay",
         "leapfrogs": a.leapfrogs, "epsilon": a.epsilon, "gradlogpdf_calls": counters["gradlogpdf"],
-        "logpdf_calls": counters["logpdf"], "nni_attempted": att, "nni_accepted": nni,
+        "logpdf_calls": counters["logpdf"], "batched_nni_pairs": counters["batched_pairs"],
+        "nni_attempted": att, "nni_accepted": nni,
         "schedule_rebuilds": dev["rebuilds"],
         "us_per_leapfrog_wall": wall / a.leapfrogs * 1e6,
         "us_per_call_wall": wall / calls * 1e6,
