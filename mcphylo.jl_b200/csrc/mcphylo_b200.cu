@@ -74,6 +74,8 @@ struct WalkParams {
     LLRow* rows_ll;
     const int* cta_row_base;
     const int* levels;          // level offsets of the level-ordered programs (small-tree kernel)
+    double* out;                // small-tree kernel: [logL, grad] per tree, device or pinned host memory
+    unsigned int* done_counter; // small-tree kernel: CTAs finished (the last one reduces the rows)
     long long row_stride;
     int n_slots, n_stack;
     int n_tiles, T, R, want_grad;
@@ -818,8 +820,10 @@ struct LevelSmem {
     static __host__ __device__ size_t exp_bytes() { return 128; }
     static __host__ __device__ size_t code_bytes(int n_rows) { return (((size_t)n_rows * 32) + 127) & ~(size_t)127; }
     static __host__ __device__ size_t slot_bytes(int K) { return (size_t)32 * K * 8; }
+    static __host__ __device__ size_t tab_bytes(int n_br, int K) { return (((size_t)n_br * bt_size(K) * 8) + 127) & ~(size_t)127; }
     static __host__ __device__ size_t total(int n_br, int want_grad, int n_rows, int n_slots, int n_stack, int K) {
-        return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + (size_t)(n_slots + n_stack) * slot_bytes(K);
+        return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + tab_bytes(n_br, K) +
+               (size_t)(n_slots + n_stack) * slot_bytes(K);
     }
 };
 
@@ -833,12 +837,13 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
     int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
     const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
-    if (tile >= tile_end) return;
+    __shared__ unsigned s_ticket;
 
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
     int* const s_exp = reinterpret_cast<int*>(smem_raw + LevelSmem::acc_bytes(p.max_br, p.want_grad));
     unsigned char* const s_code = reinterpret_cast<unsigned char*>(s_exp) + LevelSmem::exp_bytes();
-    double* const s_post = reinterpret_cast<double*>(s_code + LevelSmem::code_bytes(p.max_rows)) + lane * K;
+    double* const s_tab = reinterpret_cast<double*>(s_code + LevelSmem::code_bytes(p.max_rows));
+    double* const s_post = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K)) + lane * K;
     double* const s_pre = s_post + (size_t)p.n_slots * 32 * K;
     constexpr int SLOT = 32 * K;                  // doubles per slot
     constexpr int BT = K + 2 * K * (K + 1), KK1 = K * (K + 1);
@@ -846,7 +851,7 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     const int R = p.R;
 
     int ti = 0;
-    while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
+    while (tile < tile_end && ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
 
     while (tile < tile_end) {
         const TreeDev tr = p.trees[ti];
@@ -861,16 +866,65 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
         const int4* const pre_ops = p.ops + 2 * tr.pre_off;
         const int* const post_lvl = p.levels + tr.lvl_off;
         const int* const pre_lvl = post_lvl + tr.n_post_lvl + 1;
+        int built_rate = -1;
 
         for (; tile < tree_tile_end; ++tile) {
             const int local = tile - tr.tile_begin;
             const int r = local / tr.tiles_per_rate;
             const long long site0 = (long long)(local - r * tr.tiles_per_rate) * 32;
             const bool valid = site0 + lane < tr.S;
-            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT;
-            const long long br_stride = (long long)R * BT;
+            const double* const tab_r = s_tab;                 // this tree's branch table for rate r, in shared memory
+            constexpr long long br_stride = BT;
 
             __syncthreads();                                   // previous tile done with the shared buffers
+            if (r != built_rate) {
+                // branch table of (tree, rate r), built here instead of by a separate kernel:
+                // e = exp(t * D mu rate), P = U diag(e) Uinv, dP = U diag(D mu rate e) Uinv, plus the
+                // row-sum columns (same operation order as build_branch_tables)
+                const double* const blv = p.dyn + tr.dyn_off;
+                for (int br = tid; br < tr.n_br; br += NT) {
+                    double* ev = s_tab + (size_t)br * BT;
+                    double* P = ev + K;
+                    double* dP = P + KK1;
+                    if (br >= tr.NN - 1) {
+#pragma unroll
+                        for (int i = 0; i < K; ++i) ev[i] = 1.0;
+#pragma unroll
+                        for (int n = 0; n <= K; ++n)
+#pragma unroll
+                            for (int m = 0; m < K; ++m) { P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0; dP[n * K + m] = 0.0; }
+                        continue;
+                    }
+                    const double t = __ldg(blv + br);
+                    double e[K], de[K];
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        e[i] = exp(t * mdl.c(r, i));
+                        de[i] = mdl.c(r, i) * e[i];
+                        ev[i] = e[i];
+                    }
+#pragma unroll
+                    for (int m = 0; m < K; ++m) {
+                        double rs = 0.0, drs = 0.0;
+#pragma unroll
+                        for (int n = 0; n < K; ++n) {
+                            double c = 0.0, dc = 0.0;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                c += (mdl.U(m, k) * e[k]) * mdl.Ui(k, n);
+                                dc += (mdl.U(m, k) * de[k]) * mdl.Ui(k, n);
+                            }
+                            P[n * K + m] = c;
+                            dP[n * K + m] = dc;
+                            rs += c;
+                            drs += dc;
+                        }
+                        P[K * K + m] = rs;
+                        dP[K * K + m] = drs;
+                    }
+                }
+                built_rate = r;
+            }
             for (int i = tid; i < tr.n_rows * 32; i += NT) {   // this tile's state codes, all leaves
                 const int rw = i >> 5, l = i & 31;
                 s_code[i] = (site0 + l < tr.S) ? __ldg(tr.codes + (long long)rw * tr.code_stride + site0 + l) : (unsigned char)K;
@@ -889,7 +943,7 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
             };
             auto ld_vec = [&](const double* g, double (&v)[K]) {
 #pragma unroll
-                for (int k = 0; k < K; ++k) v[k] = __ldg(g + k);
+                for (int k = 0; k < K; ++k) v[k] = g[k];
             };
 
             // ------------------------------ post pass ------------------------------
@@ -1032,6 +1086,38 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
         __syncthreads();
         ++row;
         ++ti;
+    }
+
+    // ---- fused final reduction: the last CTA to finish sums the accumulator rows in fixed order
+    // and writes [logL, grad] per tree to p.out (device memory, or pinned host memory for the
+    // synchronous entry points: no separate kernel, no device-to-host copy) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {
+        __threadfence();
+        for (int t = 0; t < p.T; ++t) {
+            const TreeDev tr = p.trees[t];
+            double* o = p.out + tr.out_off;
+            for (int j = tid; j < tr.NN; j += NT) {
+                if (j == 0) {
+                    long long es = 0;
+                    double ls = 0.0;
+                    for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) {
+                        es += __ldcg(&p.rows_ll[rw].esum);
+                        ls += __ldcg(&p.rows_ll[rw].logsum);
+                    }
+                    o[0] = (double)es * 0.693147180559945309417232121458 + ls;
+                } else {
+                    double g = 0.0;
+                    if (p.want_grad)
+                        for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) g += __ldcg(p.rows + (long long)rw * p.row_stride + (j - 1));
+                    o[j] = g;
+                }
+            }
+        }
+        if (tid == 0) *p.done_counter = 0;   // ready for the next launch
     }
 }
 
@@ -1312,7 +1398,7 @@ struct mcp_ctx {
     int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
     unsigned long long next_aln_id = 1;
 
-    DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out;
+    DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out, d_counter;
     PinBuf h_topo, h_dyn, h_out, h_model;
 
     // cached topology
@@ -1819,7 +1905,12 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     ctx->staged_pending = true;
 
     const TreeDev* d_trees = (const TreeDev*)((char*)ctx->d_topo.p + ctx->off_trees);
-    {
+    const bool fused = ctx->level_mode;   // small-tree kernel: tables, walk and final reduction in ONE launch
+    if (fused && !ctx->d_counter.p) {
+        if ((e = ensure_dev(ctx, ctx->d_counter, 256))) return e;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, st));
+    }
+    if (!fused) {
         dim3 grid((ctx->max_br * R + 127) / 128, T);
         build_branch_tables<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_dyn.p, (double*)ctx->d_btab.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
@@ -1835,6 +1926,9 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.rows_ll = (LLRow*)ctx->d_rows_ll.p;
     wp.cta_row_base = (const int*)((char*)ctx->d_topo.p + ctx->off_rowbase);
     wp.levels = (const int*)((char*)ctx->d_topo.p + ctx->off_levels);
+    // pinned host memory is device-addressable (unified addressing): the fused kernel writes results there
+    wp.out = d_out_user ? d_out_user : (double*)ctx->h_out.p;
+    wp.done_counter = (unsigned int*)ctx->d_counter.p;
     wp.row_stride = ctx->row_stride;
     wp.n_slots = ctx->n_slots;
     wp.n_stack = ctx->n_stack;
@@ -1859,7 +1953,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     }
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
-    {
+    if (!fused) {
         int maxNN = 0;
         for (int t = 0; t < T; ++t) maxNN = std::max(maxNN, a.NN[t]);
         dim3 grid((maxNN + 127) / 128, T);
@@ -1867,7 +1961,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
                                                (const LLRow*)ctx->d_rows_ll.p, d_out, wp.want_grad);
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    s.kernel_launches = 3;
+    s.kernel_launches = fused ? 1 : 3;
     s.grid = ctx->grid;
     s.block = ctx->block;
     s.tiles = ctx->n_tiles;
@@ -1878,7 +1972,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         ctx->pending_async = true;
         return 0;
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * ctx->total_out, cudaMemcpyDeviceToHost, st));
+    if (!fused) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * ctx->total_out, cudaMemcpyDeviceToHost, st));
     s.d2h_bytes = (int64_t)(sizeof(double) * ctx->total_out);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -1971,7 +2065,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out})
+    for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter})
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : {&ctx->h_topo, &ctx->h_dyn, &ctx->h_out, &ctx->h_model})
         if (b->p) cudaFreeHost(b->p);
