@@ -146,6 +146,9 @@ __device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
     }
 }
 
+// L2 prefetch of a line the thread will read a few ops later (HBM -> L2 ahead of the demand load)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
@@ -389,6 +392,9 @@ struct WalkSmem {
 template <int K, int CPT, bool DYN_MODEL, bool SSCR>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
+#endif
+#ifndef MCP_PREFETCH_DIST
+#define MCP_PREFETCH_DIST 0   // L2 prefetch hints for gradient-pass operands: measured slower (22.3 vs 21.0 ms), kept for experiments
 #endif
 __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -665,6 +671,21 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
                         const int flags = (int)rh.x;
                         const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
+                        if constexpr (!SSCR && MCP_PREFETCH_DIST > 0) {
+                            // the children partials of a later family were written in the post pass, long ago:
+                            // pull them from HBM into L2 now (one request per 128-byte line)
+                            if (j + MCP_PREFETCH_DIST < cnt && (lane * K * 8) % 128 == 0) {
+                                const uint4 rf = *reinterpret_cast<const uint4*>(rb + j + MCP_PREFETCH_DIST);
+                                if (((int)rf.x & 3) == mcp::OPK_MEM) {
+#pragma unroll
+                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.y + cc * col_bytes);
+                                }
+                                if ((((int)rf.x >> 2) & 3) == mcp::OPK_MEM) {
+#pragma unroll
+                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.z + cc * col_bytes);
+                                }
+                            }
+                        }
                         const int mk = (flags >> 8) & 3;
                         // all stored operands of the family are requested up front
                         double pm[CPT][K], La[CPT][K], Lb[CPT][K];
