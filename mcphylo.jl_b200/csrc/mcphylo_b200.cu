@@ -146,6 +146,19 @@ __device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
     }
 }
 
+// Identity moves the compiler cannot see through: a value passed through them is kept in a register
+// (or spilled as one word) instead of being RE-COMPUTED at every use.  ptxas otherwise rematerialises
+// the per-thread scratch base (blockIdx * scratch_per_cta + tid * K * 8, ~13 instructions) in front of
+// every partial load/store of the walk.
+__device__ __forceinline__ unsigned char* keep_ptr(unsigned char* p) {
+    asm volatile("mov.u64 %0, %0;" : "+l"(p));
+    return p;
+}
+__device__ __forceinline__ double keep_f64(double v) {
+    asm volatile("mov.f64 %0, %0;" : "+d"(v));
+    return v;
+}
+
 // L2 prefetch of a line the thread will read a few ops later (HBM -> L2 ahead of the demand load)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
@@ -420,7 +433,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     // slot / LIFO offsets in the records are byte offsets from here
     unsigned char* const scr = SSCR
         ? scode + WalkSmem<K>::code_bytes(TS) + (size_t)tid * K * 8
-        : reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K);
+        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K));
     const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
     const unsigned slot_bytes = col_bytes * CPT;
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
@@ -448,8 +461,12 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             const int r = local / tr.tiles_per_rate;
             const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TS;
             bool valid[CPT];
+            double vmask[CPT];                 // 1.0 for real columns, 0.0 for the padding of a ragged tile
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) valid[c] = site0 + c * TW + tid < tr.S;
+            for (int c = 0; c < CPT; ++c) {
+                valid[c] = site0 + c * TW + tid < tr.S;
+                vmask[c] = keep_f64(valid[c] ? 1.0 : 0.0);
+            }
             const unsigned char* const codes0 = tr.codes + site0;
             // this tree's branch table at (branch 0, rate r); record offsets are relative to it
             const unsigned char* const btab_b = reinterpret_cast<const unsigned char*>(p.btab + tr.btab_off + (long long)r * BT);
@@ -758,11 +775,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 na = fma(qa[cc][k], Ya[cc][k], na);
                                 nb = fma(qb[cc][k], Yb[cc][k], nb);
                             }
-                            const double inv = fast_rcp(den);
-                            if (valid[cc]) {
-                                ga = fma(na, inv, ga);
-                                gb = fma(nb, inv, gb);
-                            }
+                            const double inv = fast_rcp(den) * vmask[cc];
+                            ga = fma(na, inv, ga);
+                            gb = fma(nb, inv, gb);
                         }
                         const double red = warp_pair_reduce(ga, gb, lane);
                         if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
