@@ -101,11 +101,12 @@ __host__ __device__ inline long long dyn_size(int NN, int K, int R) {
     return (n + 3) & ~3LL;  // keep every tree's block 32-byte aligned
 }
 // Branch table, one entry per (device branch, rate category), BT(K) doubles:
-//   [0, K)                    e_i = exp(mu * t * D_i * rate)     (internal children: P = U diag(e) Uinv)
-//   [K, K + K*(K+1))          P columns 0..K for LEAF children: column j = P[:, j], column K = row sums
+//   [0, K)                    em1_i = expm1(mu * t * D_i * rate) (internal children: P = I + U diag(em1) Uinv)
+//   [K, 2K)                   de_i = D_i mu rate * exp(mu t D_i rate)  (internal children: dP/dt = U diag(de) Uinv)
+//   [2K, 2K + K*(K+1))        P columns 0..K for LEAF children: column j = P[:, j], column K = row sums
 //                             (= P * all-ones leaf); each column holds the K parent-state entries
-//   [K + K*(K+1), K + 2K(K+1)) dP/dt columns, same layout
-__host__ __device__ inline int bt_size(int K) { return K + 2 * K * (K + 1); }
+//   [2K + K*(K+1), 2K + 2K(K+1)) dP/dt columns, same layout
+__host__ __device__ inline int bt_size(int K) { return 2 * K + 2 * K * (K + 1); }
 
 // Model constants of the evaluation, read as CONSTANT-BANK operands (warp-uniform: no per-lane
 // register delivery, DFMA takes them directly).  One slot per distinct substitution model in the
@@ -186,9 +187,19 @@ struct ModelT {
 
 // ---- eigen-space products for C columns at once (column index innermost, so one constant /
 // uniform-register operand feeds C independent DFMAs) ----
-// z[c] = e * (Uinv L[c])
-template <int K, int C, class M>
-__device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K], const double (&e)[K], double (&z)[C][K]) {
+//
+// Transitions are applied as  P L = L + U (em1 * (Uinv L)),  em1_i = expm1(mu t D_i r),  not as
+// U (e * (Uinv L)): the latter is accurate only relative to |L|_max, and a partial likelihood vector
+// routinely holds components 1e-20 of its maximum that still decide the likelihood of a site further
+// up (a mismatch selects exactly that component).  The reference multiplies by an explicit
+// non-negative P, which is component-wise accurate; adding the (accurately formed) deviation P - I
+// onto L keeps that property, costs no extra instruction (the leading multiply becomes an FMA onto
+// L), and makes identity branches exact.
+//
+// z[c] = em1 * w[c],  w[c] = Uinv L[c];  WD also returns zd[c] = de * w[c]  (the eigen-coordinates of dP L)
+template <int K, int C, bool WD, class M>
+__device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K], const double (&em1)[K], const double* de,
+                                            double (&z)[C][K], double (&zd)[C][K]) {
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         double w[C];
@@ -199,12 +210,28 @@ __device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K],
 #pragma unroll
             for (int c = 0; c < C; ++c) w[c] = fma(m.Ui(i, j), L[c][j], w[c]);
 #pragma unroll
-        for (int c = 0; c < C; ++c) z[c][i] = e[i] * w[c];
+        for (int c = 0; c < C; ++c) {
+            z[c][i] = em1[i] * w[c];
+            if constexpr (WD) zd[c][i] = de[i] * w[c];
+        }
+    }
+}
+// out[c] = base[c] + U z[c]
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], const double (&base)[C][K], double (&out)[C][K]) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, 0), z[c][0], base[c][s]);
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
     }
 }
 // out[c] = U z[c]
 template <int K, int C, class M>
-__device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], double (&out)[C][K]) {
+__device__ __forceinline__ void eig_expand0(const M& m, const double (&z)[C][K], double (&out)[C][K]) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
 #pragma unroll
@@ -215,9 +242,9 @@ __device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], 
             for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
     }
 }
-// out[c] = P^T q[c] = Uinv^T (e * (U^T q[c]))
+// out[c] = P^T q[c] = q[c] + Uinv^T (em1 * (U^T q[c]))
 template <int K, int C, class M>
-__device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][K], const double (&e)[K], double (&out)[C][K]) {
+__device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][K], const double (&em1)[K], double (&out)[C][K]) {
     double z[C][K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
@@ -229,12 +256,12 @@ __device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][
 #pragma unroll
             for (int c = 0; c < C; ++c) w[c] = fma(m.U(s, i), q[c][s], w[c]);
 #pragma unroll
-        for (int c = 0; c < C; ++c) z[c][i] = e[i] * w[c];
+        for (int c = 0; c < C; ++c) z[c][i] = em1[i] * w[c];
     }
 #pragma unroll
     for (int j = 0; j < K; ++j) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) out[c][j] = m.Ui(0, j) * z[c][0];
+        for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(0, j), z[c][0], q[c][j]);
 #pragma unroll
         for (int i = 1; i < K; ++i)
 #pragma unroll
@@ -305,10 +332,10 @@ __global__ void build_branch_tables(const TreeDev* __restrict__ trees, const dou
     const double mu = d[dyn_mu(tr.NN, K)];
     const double rate = d[dyn_rates(tr.NN, K) + r];
     double* ev = btab + tr.btab_off + ((long long)br * R + r) * bt_size(K);
-    double* P = ev + K;
+    double* P = ev + 2 * K;
     double* dP = P + K * (K + 1);
     if (br >= tr.NN - 1) {  // root row (unused) and virtual branches: identity, zero derivative
-        for (int i = 0; i < K; ++i) ev[i] = 1.0;
+        for (int i = 0; i < K; ++i) { ev[i] = 0.0; ev[K + i] = 0.0; }   // expm1(0) and zero derivative: identity branch
         for (int n = 0; n <= K; ++n)
             for (int m = 0; m < K; ++m) {
                 P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0;
@@ -317,12 +344,13 @@ __global__ void build_branch_tables(const TreeDev* __restrict__ trees, const dou
         return;
     }
     const double t = d[dyn_blv(tr.NN) + br];
-    double e[KMAX_TABLE], de[KMAX_TABLE];
+    double em1[KMAX_TABLE], de[KMAX_TABLE];
     for (int i = 0; i < K; ++i) {
-        double ex = exp(mu * t * D[i] * rate);
-        e[i] = ex;
-        ev[i] = ex;
-        de[i] = D[i] * rate * mu * ex;
+        const double x = mu * t * D[i] * rate;
+        em1[i] = expm1(x);
+        ev[i] = em1[i];
+        de[i] = D[i] * rate * mu * exp(x);
+        ev[K + i] = de[i];
     }
     for (int m = 0; m < K; ++m) {
         double rs = 0.0, drs = 0.0;
@@ -330,9 +358,10 @@ __global__ void build_branch_tables(const TreeDev* __restrict__ trees, const dou
             double c = 0.0, dc = 0.0;
             for (int k = 0; k < K; ++k) {
                 const double u = U[m + K * k], ui = Uinv[k + K * n];
-                c += (u * e[k]) * ui;
+                c += (u * em1[k]) * ui;      // P - I, formed without cancellation against the identity
                 dc += (u * de[k]) * ui;
             }
+            c += (m == n) ? 1.0 : 0.0;
             P[n * K + m] = c;
             dP[n * K + m] = dc;
             rs += c;    // what P * (all-ones leaf) gives: sum_s1 1 * P[s, s1]
@@ -351,7 +380,7 @@ __global__ void build_branch_tables(const TreeDev* __restrict__ trees, const dou
 // memory CH ops at a time with cp.async, one chunk ahead of the compute:
 //   sdesc  3 x CH op descriptors (ring of 3: descriptors must be resident one chunk before the
 //          data they describe can be requested)
-//   se     2 x CH x 2 x K doubles: the e vectors of INTERNAL children
+//   se     2 x CH x 2 x 2K doubles: (em1, de) eigen-coefficient vectors of INTERNAL children
 //   scode  2 x CH x 2 x TW bytes: the state codes of LEAF children for the tile's columns
 // so the only global accesses on the per-op critical path are the thread's own partials and the
 // leaf-table gathers.  One __syncthreads per chunk.
@@ -379,7 +408,7 @@ struct WalkSmem {
     // dynamic shared memory carve-up (offsets in bytes)
     static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0; }
     static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
-    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * K * 8; }
+    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
     static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
     static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
     // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
@@ -439,7 +468,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
-    constexpr int BT = K + 2 * K * (K + 1);
+    constexpr int BT = 2 * K + 2 * K * (K + 1);
 
     int ti = 0;
     while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
@@ -471,9 +500,6 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             // this tree's branch table at (branch 0, rate r); record offsets are relative to it
             const unsigned char* const btab_b = reinterpret_cast<const unsigned char*>(p.btab + tr.btab_off + (long long)r * BT);
             const unsigned br_bytes = (unsigned)R * BT * 8;
-            double crate[K];
-#pragma unroll
-            for (int i = 0; i < K; ++i) crate[i] = mdl.c(r, i);
 
             // ---- chunk staging (all threads of the CTA) ----
             auto stage_desc = [&](const int4* ops, int n_ops, int c) {
@@ -486,14 +512,14 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             auto stage_data = [&](int n_ops, int c, bool pre) {
                 const int base = c * CH, cnt = min(CH, n_ops - base);
                 const int4* d = sdesc + (c % 3) * (CH * 2);
-                double* eb = se + (c & 1) * (CH * 2 * K);
+                double* eb = se + (c & 1) * (CH * 2 * 2 * K);
                 unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS);
                 OpRec* rb = srec + (c & 1) * CH;
                 double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                 const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
                 const int tab_doubles = pre ? 2 * KK1 : KK1; // P columns (+ dP columns in the gradient pass)
                 const int tpieces = (tab_doubles + 1) / 2;   // 16-byte pieces of one leaf table
-                const int epieces = (K * 8 + 15) / 16;
+                const int epieces = K;                       // em1 and de: 2K doubles = K 16-byte pieces
                 const int per_child = pieces + tpieces > epieces ? pieces + tpieces : epieces;
                 for (int w = tid; w < cnt * 2 * per_child; w += TW) {
                     const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
@@ -510,7 +536,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         } else if (piece < pieces + tpieces) {
                             const int tp = piece - pieces;
                             double* dstp = tb + (size_t)(j * 2 + ch) * 2 * KK1 + tp * 2;
-                            const double* srcp = bsrc + K + tp * 2;
+                            const double* srcp = bsrc + 2 * K + tp * 2;
                             if constexpr ((K * 8) % 16 == 0) {
                                 cp_async16(dstp, srcp);
                             } else {
@@ -519,15 +545,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             }
                         }
                     } else if (piece < epieces) {
-                        if constexpr ((K * 8) % 16 == 0) {
-                            cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * K) + piece * 16,
-                                       reinterpret_cast<const unsigned char*>(bsrc) + piece * 16);
-                        } else {
-                            if (piece == 0) {
-#pragma unroll
-                                for (int k = 0; k < K; ++k) eb[(j * 2 + ch) * K + k] = __ldg(bsrc + k);
-                            }
-                        }
+                        // 2K doubles = K 16-byte pieces; entries are 16-byte aligned (bt_size is even)
+                        cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * 2 * K) + piece * 16,
+                                   reinterpret_cast<const unsigned char*>(bsrc) + piece * 16);
                     }
                 }
                 for (int j = tid; j < cnt; j += TW) {
@@ -537,8 +557,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     rec.flags = fl;
                     rec.a_br = o0.y;
                     rec.b_br = o0.w;
-                    rec.xa = ka == mcp::OPK_LEAF ? (unsigned)o0.y * br_bytes + K * 8 : (unsigned)o0.x * slot_bytes;
-                    rec.xb = kb == mcp::OPK_LEAF ? (unsigned)o0.w * br_bytes + K * 8 : (unsigned)o0.z * slot_bytes;
+                    rec.xa = ka == mcp::OPK_LEAF ? (unsigned)o0.y * br_bytes + 2 * K * 8 : (unsigned)o0.x * slot_bytes;
+                    rec.xb = kb == mcp::OPK_LEAF ? (unsigned)o0.w * br_bytes + 2 * K * 8 : (unsigned)o0.z * slot_bytes;
                     if (pre) {
                         rec.y0 = stack_base + (unsigned)o1.x * slot_bytes;     // pre[mother] on the LIFO
                         rec.y1 = stack_base + (unsigned)o1.z * slot_bytes;     // where pre[a] is pushed
@@ -608,7 +628,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 for (int c = 0; c < n_chunks; ++c) {
                     chunk_boundary(post_ops, n_post, c, n_chunks, false);
                     const OpRec* rb = srec + (c & 1) * CH;
-                    const double* eb = se + (c & 1) * (CH * 2 * K);
+                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
                     const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_post - c * CH);
@@ -631,10 +651,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         } else {
                             double e[K], z[CPT][K];
 #pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * K + k];
-                            if (ka == mcp::OPK_REG) eig_project<K, CPT>(mdl, cur, e, z);
-                            else eig_project<K, CPT>(mdl, Lm, e, z);
-                            eig_expand<K, CPT>(mdl, z, Da);
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * 2 * K + k];
+                            if (ka == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Da); }
+                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Da); }
                         }
                         if (kb == mcp::OPK_LEAF) {
 #pragma unroll
@@ -647,10 +666,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         } else {
                             double e[K], z[CPT][K];
 #pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * K + k];
-                            if (kb == mcp::OPK_REG) eig_project<K, CPT>(mdl, cur, e, z);
-                            else eig_project<K, CPT>(mdl, Lm, e, z);
-                            eig_expand<K, CPT>(mdl, z, Db);
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * 2 * K + k];
+                            if (kb == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Db); }
+                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Db); }
                         }
 #pragma unroll
                         for (int cc = 0; cc < CPT; ++cc) {
@@ -680,7 +698,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 for (int c = 0; c < n_chunks; ++c) {
                     chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
                     const OpRec* rb = srec + (c & 1) * CH;
-                    const double* eb = se + (c & 1) * (CH * 2 * K);
+                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
                     const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_pre - c * CH);
@@ -723,16 +741,12 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         double ea[K], ebv[K];
                         double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
                         if (ai) {
-                            double z[CPT][K];
+                            double z[CPT][K], zd[CPT][K];
 #pragma unroll
-                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * K + k];
-                            eig_project<K, CPT>(mdl, La, ea, z);
-                            eig_expand<K, CPT>(mdl, z, Da);
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                for (int k = 0; k < K; ++k) z[cc][k] *= crate[k];
-                            eig_expand<K, CPT>(mdl, z, Ya);
+                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * 2 * K + k];
+                            eig_project<K, CPT, true>(mdl, La, ea, eb + (j * 2 + 0) * 2 * K + K, z, zd);
+                            eig_expand<K, CPT>(mdl, z, La, Da);
+                            eig_expand0<K, CPT>(mdl, zd, Ya);
                         } else {
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
@@ -743,16 +757,12 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             }
                         }
                         if (bi) {
-                            double z[CPT][K];
+                            double z[CPT][K], zd[CPT][K];
 #pragma unroll
-                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * K + k];
-                            eig_project<K, CPT>(mdl, Lb, ebv, z);
-                            eig_expand<K, CPT>(mdl, z, Db);
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                for (int k = 0; k < K; ++k) z[cc][k] *= crate[k];
-                            eig_expand<K, CPT>(mdl, z, Yb);
+                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * 2 * K + k];
+                            eig_project<K, CPT, true>(mdl, Lb, ebv, eb + (j * 2 + 1) * 2 * K + K, z, zd);
+                            eig_expand<K, CPT>(mdl, z, Lb, Db);
+                            eig_expand0<K, CPT>(mdl, zd, Yb);
                         } else {
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
@@ -882,7 +892,7 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     double* const s_post = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K)) + lane * K;
     double* const s_pre = s_post + (size_t)p.n_slots * 32 * K;
     constexpr int SLOT = 32 * K;                  // doubles per slot
-    constexpr int BT = K + 2 * K * (K + 1), KK1 = K * (K + 1);
+    constexpr int BT = 2 * K + 2 * K * (K + 1), KK1 = K * (K + 1);
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
 
@@ -920,11 +930,11 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                 const double* const blv = p.dyn + tr.dyn_off;
                 for (int br = tid; br < tr.n_br; br += NT) {
                     double* ev = s_tab + (size_t)br * BT;
-                    double* P = ev + K;
+                    double* P = ev + 2 * K;
                     double* dP = P + KK1;
                     if (br >= tr.NN - 1) {
 #pragma unroll
-                        for (int i = 0; i < K; ++i) ev[i] = 1.0;
+                        for (int i = 0; i < K; ++i) { ev[i] = 0.0; ev[K + i] = 0.0; }
 #pragma unroll
                         for (int n = 0; n <= K; ++n)
 #pragma unroll
@@ -932,12 +942,13 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                         continue;
                     }
                     const double t = __ldg(blv + br);
-                    double e[K], de[K];
+                    double em1[K], de[K];
 #pragma unroll
                     for (int i = 0; i < K; ++i) {
-                        e[i] = exp(t * mdl.c(r, i));
-                        de[i] = mdl.c(r, i) * e[i];
-                        ev[i] = e[i];
+                        em1[i] = expm1(t * mdl.c(r, i));
+                        de[i] = mdl.c(r, i) * exp(t * mdl.c(r, i));
+                        ev[i] = em1[i];
+                        ev[K + i] = de[i];
                     }
 #pragma unroll
                     for (int m = 0; m < K; ++m) {
@@ -947,9 +958,10 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                             double c = 0.0, dc = 0.0;
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
-                                c += (mdl.U(m, k) * e[k]) * mdl.Ui(k, n);
+                                c += (mdl.U(m, k) * em1[k]) * mdl.Ui(k, n);
                                 dc += (mdl.U(m, k) * de[k]) * mdl.Ui(k, n);
                             }
+                            c += (m == n) ? 1.0 : 0.0;
                             P[n * K + m] = c;
                             dP[n * K + m] = dc;
                             rs += c;
@@ -990,22 +1002,22 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                     const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
                     double Da[1][K], Db[1][K];
                     if (ka == mcp::OPK_LEAF) {
-                        ld_vec(tab_r + o0.y * br_stride + K + leaf_code(o0.x) * K, Da[0]);
+                        ld_vec(tab_r + o0.y * br_stride + 2 * K + leaf_code(o0.x) * K, Da[0]);
                     } else {
                         double L[1][K], z[1][K], e[K];
                         ld_slot(s_post, o0.x, L);
                         ld_vec(tab_r + o0.y * br_stride, e);
-                        eig_project<K, 1>(mdl, L, e, z);
-                        eig_expand<K, 1>(mdl, z, Da);
+                        eig_project<K, 1, false>(mdl, L, e, nullptr, z, z);
+                        eig_expand<K, 1>(mdl, z, L, Da);
                     }
                     if (kb == mcp::OPK_LEAF) {
-                        ld_vec(tab_r + o0.w * br_stride + K + leaf_code(o0.z) * K, Db[0]);
+                        ld_vec(tab_r + o0.w * br_stride + 2 * K + leaf_code(o0.z) * K, Db[0]);
                     } else {
                         double L[1][K], z[1][K], e[K];
                         ld_slot(s_post, o0.z, L);
                         ld_vec(tab_r + o0.w * br_stride, e);
-                        eig_project<K, 1>(mdl, L, e, z);
-                        eig_expand<K, 1>(mdl, z, Db);
+                        eig_project<K, 1, false>(mdl, L, e, nullptr, z, z);
+                        eig_expand<K, 1>(mdl, z, L, Db);
                     }
                     double cur[1][K];
 #pragma unroll
@@ -1043,30 +1055,26 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                         double ea[K], ebv[K];
                         double Da[1][K], Ya[1][K], Db[1][K], Yb[1][K];
                         if (ai) {
-                            double L[1][K], z[1][K];
+                            double L[1][K], z[1][K], zd[1][K];
                             ld_slot(s_post, o0.x, L);
                             ld_vec(tab_r + a_br * br_stride, ea);
-                            eig_project<K, 1>(mdl, L, ea, z);
-                            eig_expand<K, 1>(mdl, z, Da);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) z[0][k] *= mdl.c(r, k);
-                            eig_expand<K, 1>(mdl, z, Ya);
+                            eig_project<K, 1, true>(mdl, L, ea, tab_r + a_br * br_stride + K, z, zd);
+                            eig_expand<K, 1>(mdl, z, L, Da);
+                            eig_expand0<K, 1>(mdl, zd, Ya);
                         } else {
-                            const double* t = tab_r + a_br * br_stride + K + leaf_code(o0.x) * K;
+                            const double* t = tab_r + a_br * br_stride + 2 * K + leaf_code(o0.x) * K;
                             ld_vec(t, Da[0]);
                             ld_vec(t + KK1, Ya[0]);
                         }
                         if (bi) {
-                            double L[1][K], z[1][K];
+                            double L[1][K], z[1][K], zd[1][K];
                             ld_slot(s_post, o0.z, L);
                             ld_vec(tab_r + b_br * br_stride, ebv);
-                            eig_project<K, 1>(mdl, L, ebv, z);
-                            eig_expand<K, 1>(mdl, z, Db);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) z[0][k] *= mdl.c(r, k);
-                            eig_expand<K, 1>(mdl, z, Yb);
+                            eig_project<K, 1, true>(mdl, L, ebv, tab_r + b_br * br_stride + K, z, zd);
+                            eig_expand<K, 1>(mdl, z, L, Db);
+                            eig_expand0<K, 1>(mdl, zd, Yb);
                         } else {
-                            const double* t = tab_r + b_br * br_stride + K + leaf_code(o0.z) * K;
+                            const double* t = tab_r + b_br * br_stride + 2 * K + leaf_code(o0.z) * K;
                             ld_vec(t, Db[0]);
                             ld_vec(t + KK1, Yb[0]);
                         }
@@ -1225,7 +1233,7 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
             const long long site = (long long)(local - r * tr.tiles_per_rate) * TW + tid;
             const bool valid = site < tr.S;
             const unsigned char* const codes = tr.codes + (valid ? site : 0);
-            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT + K;   // P columns of (branch 0, rate r)
+            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT + 2 * K;   // P columns of (branch 0, rate r)
             const long long br_stride = (long long)R * BT;
             auto leaf_code = [&](int src) -> int {
                 int code = (valid && src >= 0) ? (int)__ldg(codes + (long long)src * tr.code_stride) : K;
@@ -1586,7 +1594,7 @@ int launch_levels(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
 }
 size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
     size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
-    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * K * 8 + (size_t)2 * CH * 32 +
+    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
            (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
 }
 
@@ -2039,9 +2047,14 @@ int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S,
         delete al;
         return fail(ctx, MCP_ERR_CUDA, "cudaMalloc of %zu bytes for the alignment failed: %s", bytes, cudaGetErrorString(e));
     }
-    e = cudaMemset(al->d_codes, K, bytes);
+    // On the context's own stream and synchronised: a "synchronous" pageable host-to-device copy
+    // on the default stream may return before the DMA has landed, and evaluations run on a
+    // non-blocking stream that does not wait for the default stream.
+    e = cudaMemsetAsync(al->d_codes, K, bytes, ctx->stream);
     if (e == cudaSuccess && S > 0 && n_leaves > 0)
-        e = cudaMemcpy2D(al->d_codes, (size_t)al->stride, codes, (size_t)S, (size_t)S, (size_t)n_leaves, cudaMemcpyHostToDevice);
+        e = cudaMemcpy2DAsync(al->d_codes, (size_t)al->stride, codes, (size_t)S, (size_t)S, (size_t)n_leaves,
+                              cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         cudaFree(al->d_codes);
         delete al;
