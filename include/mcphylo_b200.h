@@ -111,6 +111,28 @@ int mcp_eval(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_t *post
              int want_grad, double *ll_out, double *grad_out);
 
 /*
+ * Likelihood + branch-length prior in one call: the body of logpdfgrad!(::Type{provided}, ...)
+ * (/root/reference/src/samplers/sampler.jl:172-190), which adds gradlogpdf of the tree's length
+ * prior (/root/reference/src/Likelihood/Prior.jl:1-57, evaluated there through Zygote on every
+ * leapfrog) to the PhyloDist gradient.  Here the prior is folded into the final reduction on the
+ * device.  prior_kind / prior_params:
+ *   MCP_PRIOR_NONE                 (UniformBranchLength, Prior.jl:59-66)  params ignored
+ *   MCP_PRIOR_EXPONENTIAL          exponentialBL(scale)                   params = {scale}
+ *   MCP_PRIOR_COMPOUND_DIRICHLET   CompoundDirichlet(alpha, a, beta, c)   params = {alpha, a, beta, c}
+ *                                  (src/distributions/TreeDistribution.jl:23-39; a branch is
+ *                                  "internal" when the node below it has children)
+ * lp_out receives logL + log prior; grad_out (NN-1 doubles, or NULL for the value only) receives
+ * the summed gradient indexed by num-1.  No support check is made (the reference does that in
+ * logpdf_sub / insupport, Prior.jl:85-92, before it gets here): non-positive branch lengths give
+ * NaN / -Inf from the logarithms exactly as they would in the reference's formula.
+ */
+enum mcp_prior_kind { MCP_PRIOR_NONE = 0, MCP_PRIOR_EXPONENTIAL = 1, MCP_PRIOR_COMPOUND_DIRICHLET = 2 };
+int mcp_eval_posterior(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_t *postorder_num,
+                       const int32_t *parent_num, const double *blv, const double *U, const double *D,
+                       const double *Uinv, double mu, const double *rates, int R, const double *pi,
+                       int prior_kind, const double *prior_params, double *lp_out, double *grad_out);
+
+/*
  * Same evaluation, result left on the device: d_out (DEVICE pointer, NN doubles) receives
  * [logL, grad[1..NN-1]] (grad part zero if !want_grad).  The work is enqueued on the context's
  * stream and NOT synchronised, so a site-sharded caller can all-reduce d_out across GPUs

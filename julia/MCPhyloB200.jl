@@ -76,6 +76,29 @@ function evaluate(d::PhyloDist, x::Array{Float64,3}, want_grad::Bool)
     ll[], grad
 end
 
+# Likelihood + branch-length prior in one device call: what logpdfgrad!(::Type{provided}, ...)
+# (src/samplers/sampler.jl:172-190) assembles from gradlogpdf(m, target) and the Zygote-differentiated
+# prior (src/Likelihood/Prior.jl:39-57).  Topology priors contribute (0, zeros) (Prior.jl:59-66).
+prior_spec(::MCPhylo.UniformBranchLength) = (Cint(0), Float64[0.0])
+prior_spec(p::MCPhylo.exponentialBL) = (Cint(1), Float64[p.scale])
+prior_spec(p::MCPhylo.CompoundDirichlet) = (Cint(2), Float64[p.alpha, p.a, p.beta, p.c])
+
+function posterior(d::PhyloDist, x::Array{Float64,3}, prior)
+    NN, po, pa, blv, leaf_nums = flatten(d.tree)
+    U, D, Uinv, mu = d.substitution_model(d.base_freq, d.substitution_rates)
+    kind, pp = prior_spec(prior)
+    lp = Ref{Float64}(0.0)
+    grad = Vector{Float64}(undef, NN - 1)
+    check(ccall((:mcp_eval_posterior, LIB[]), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Cint, Ptr{Float64},
+                 Cint, Ptr{Float64}, Ref{Float64}, Ptr{Float64}),
+                context(), alignment(x, leaf_nums), NN, po, pa, Vector{Float64}(blv),
+                Matrix{Float64}(U), Vector{Float64}(D), Matrix{Float64}(Uinv), Float64(mu),
+                d.rates, length(d.rates), d.base_freq, kind, pp, lp, grad))
+    lp[], grad
+end
+
 function evaluate(d::MultiplePhyloDist, x::Array{Float64,4}, want_grad::Bool)
     T = length(d.DistCollector)
     flat = [flatten(pd.tree) for pd in d.DistCollector]
@@ -113,6 +136,23 @@ function enable!(libpath::AbstractString = LIB[])
         function __logpdf(d::MultiplePhyloDist, x::Array{Float64,4})
             ll, g = $(evaluate)(d, x, true)
             Tuple[(ll[i], g[i]) for i in eachindex(ll)]
+        end
+        # tree-space HMC target: one PhyloDist-distributed data node + the tree's own prior
+        function logpdfgrad!(::Type{provided}, m::Model, x::T, params::ElementOrVector{Symbol},
+                             target::ElementOrVector{Symbol}, transform::Bool) where {T<:GeneralNode}
+            m[params] = relist(m, x, params, transform)
+            tgt = asvec(target)
+            t_node = m[asvec(params)[1]]
+            if length(tgt) == 1 && t_node.distr isa TreeDistribution
+                m[tgt[1]] = update!(m[tgt[1]], m)
+                node = m[tgt[1]]
+                if node.distr isa PhyloDist && node.value isa Array{Float64,3}
+                    return $(posterior)(node.distr, node.value, t_node.distr.length_distr)
+                end
+            end
+            v, grad = gradlogpdf(m, tgt)                    # anything else: the stock composition
+            vp, gradp = gradlogpdf(t_node, x)
+            vp + v, gradp .+ grad
         end
     end
     nothing

@@ -18,5 +18,7 @@ from .phylodist import (PhyloDist, MultiplePhyloDist, DeviceAlignment, Dimension
                         set_default_device, release_device_cache)
 from . import phylodist as _phylodist
 globals()["__logpdf"] = getattr(_phylodist, "__logpdf")
+from .prior import (exponentialBL, CompoundDirichlet, UniformBranchLength, internal_external,  # noqa: F401,E402
+                    internal_logpdf, insupport, logpdfgrad)
 from .synthetic import random_tree, simulate_codes  # noqa: F401,E402
 from .dist import ShardedEvaluator, PipelinedEvaluator, shard_bounds, local_shard  # noqa: F401,E402

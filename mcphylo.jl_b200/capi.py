@@ -21,7 +21,7 @@ SYMBOLS = [
     "mcp_use_own_stream", "mcp_synchronize",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
-    "mcp_eval", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
+    "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
     "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_level_mode",
     "mcp_schedule_dump",
 ]
@@ -78,6 +78,7 @@ def load():
     eval_args = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_int, _vp, C.c_int]
     lib.mcp_eval.argtypes = eval_args + [_dp, _vp]
     lib.mcp_eval_device.argtypes = eval_args + [_vp]
+    lib.mcp_eval_posterior.argtypes = eval_args[:-1] + [C.c_int, _vp, _dp, _vp]
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     lib.mcp_schedule_dump.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]
@@ -221,6 +222,23 @@ class Context:
                                       rates.ctypes.data, rates.size, pi.ctypes.data, int(want_grad),
                                       C.byref(ll), grad.ctypes.data if want_grad else None))
         return ll.value, (grad[:NN - 1] if want_grad else None)
+
+    def eval_posterior(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
+                       prior_kind: int, prior_params, want_grad: bool = True):
+        """logL + branch-length prior (and the summed gradient) in one call; the prior is added in the
+        final reduction on the device (mcp_eval_posterior)."""
+        po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
+        NN = po.size
+        assert pa.size == NN and blv.size == NN - 1 and D.size == aln.K and pi.size == aln.K
+        pp = _f64(list(prior_params) + [0.0] * 4)[:4].copy()
+        lp = C.c_double()
+        grad = np.zeros(max(NN - 1, 1), dtype=np.float64) if want_grad else None
+        self._check(self.lib.mcp_eval_posterior(self.handle, aln.handle, NN, po.ctypes.data, pa.ctypes.data,
+                                                blv.ctypes.data, U.ctypes.data, D.ctypes.data, Uinv.ctypes.data,
+                                                float(mu), rates.ctypes.data, rates.size, pi.ctypes.data,
+                                                int(prior_kind), pp.ctypes.data, C.byref(lp),
+                                                grad.ctypes.data if want_grad else None))
+        return lp.value, (grad[:NN - 1] if want_grad else None)
 
     def eval_device(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
                     want_grad: bool, d_out_ptr: int):

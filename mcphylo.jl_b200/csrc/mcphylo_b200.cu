@@ -96,8 +96,12 @@ __host__ __device__ inline long long dyn_mu(int NN, int K) { return NN - 1 + 2LL
 __host__ __device__ inline long long dyn_rates(int NN, int K) { return NN + 2LL * K * K + K; }
 __host__ __device__ inline long long dyn_pi(int NN, int K, int R) { return NN + 2LL * K * K + K + R; }
 __host__ __device__ inline long long dyn_slot(int NN, int K, int R) { return NN + 2LL * K * K + 2LL * K + R; }
+// branch-length prior (fused posterior epilogue, mcp_eval_posterior): 4 header doubles
+// [enabled, c0, beta, k4] and NN-1 per-branch weights w_j, for the prior written as
+//   log p(t) = c0 - beta * T + sum_j w_j log t_j + k4 log T,   T = sum_j t_j
+__host__ __device__ inline long long dyn_prior(int NN, int K, int R) { return NN + 2LL * K * K + 2LL * K + R + 1; }
 __host__ __device__ inline long long dyn_size(int NN, int K, int R) {
-    long long n = NN + 2LL * K * K + 2LL * K + R + 1;
+    long long n = dyn_prior(NN, K, R) + 4 + (NN - 1);
     return (n + 3) & ~3LL;  // keep every tree's block 32-byte aligned
 }
 // Branch table, one entry per (device branch, rate category), BT(K) doubles:
@@ -853,6 +857,39 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 }
 
 // --------------------------------------------------------------------------------------------
+// Branch-length prior epilogue (CompoundDirichlet / exponentialBL,
+// /root/reference/src/Likelihood/Prior.jl:1-57): the whole block reduces T = sum t_j and
+// W = sum w_j log t_j in a fixed order (thread-strided partial sums, then a serial sum over the
+// threads), so the value is reproducible.  s_red: 2 * blockDim.x doubles.  Returns {T, W} to
+// every thread.
+// --------------------------------------------------------------------------------------------
+struct PriorSums { double T, W; };
+__device__ inline PriorSums prior_block_sums(const double* __restrict__ blv, const double* __restrict__ w, int nb,
+                                             int tid, int nt, double* s_red) {
+    double a = 0.0, b = 0.0;
+    for (int j = tid; j < nb; j += nt) {
+        const double t = blv[j], wj = w[j];
+        a += t;
+        if (wj != 0.0) b += wj * log(t);
+    }
+    s_red[tid] = a;
+    s_red[nt + tid] = b;
+    __syncthreads();
+    PriorSums r{0.0, 0.0};
+    for (int i = 0; i < nt; ++i) { r.T += s_red[i]; r.W += s_red[nt + i]; }
+    __syncthreads();
+    return r;
+}
+// contribution of the prior to output slot j (0 = log density, j >= 1 = d/dt_j)
+__device__ inline double prior_term(const double* __restrict__ hdr, const double* __restrict__ blv,
+                                    const double* __restrict__ w, const PriorSums& ps, int j) {
+    const double c0 = hdr[1], beta = hdr[2], k4 = hdr[3];
+    if (j == 0) return c0 - beta * ps.T + ps.W + (k4 != 0.0 ? k4 * log(ps.T) : 0.0);
+    const double wj = w[j - 1];
+    return -beta + (wj != 0.0 ? wj / blv[j - 1] : 0.0) + (k4 != 0.0 ? k4 / ps.T : 0.0);
+}
+
+// --------------------------------------------------------------------------------------------
 // kernel 2c: small-tree latency path.  A tile is ONE warp wide (32 columns) but is worked on by all
 // W warps of the CTA: the level-ordered program (schedule.hpp, by_levels) lists ops of equal height
 // (post pass) / depth (gradient pass) together, the warps split each level's ops, and a
@@ -878,6 +915,7 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
+    __shared__ double s_prior[2 * 256];   // block reduction of the branch-length prior (final reduction only)
 
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, W = NT >> 5;
     const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
@@ -1144,7 +1182,13 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
         for (int t = 0; t < p.T; ++t) {
             const TreeDev tr = p.trees[t];
             double* o = p.out + tr.out_off;
+            const double* d = p.dyn + tr.dyn_off;
+            const double* hdr = d + dyn_prior(tr.NN, K, R);
+            const bool prior = hdr[0] != 0.0;
+            PriorSums ps{0.0, 0.0};
+            if (prior) ps = prior_block_sums(d + dyn_blv(tr.NN), hdr + 4, tr.NN - 1, tid, NT, s_prior);
             for (int j = tid; j < tr.NN; j += NT) {
+                double v = 0.0;
                 if (j == 0) {
                     long long es = 0;
                     double ls = 0.0;
@@ -1152,13 +1196,12 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                         es += __ldcg(&p.rows_ll[rw].esum);
                         ls += __ldcg(&p.rows_ll[rw].logsum);
                     }
-                    o[0] = (double)es * 0.693147180559945309417232121458 + ls;
-                } else {
-                    double g = 0.0;
-                    if (p.want_grad)
-                        for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) g += __ldcg(p.rows + (long long)rw * p.row_stride + (j - 1));
-                    o[j] = g;
+                    v = (double)es * 0.693147180559945309417232121458 + ls;
+                } else if (p.want_grad) {
+                    for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) v += __ldcg(p.rows + (long long)rw * p.row_stride + (j - 1));
                 }
+                if (prior && (j == 0 || p.want_grad)) v += prior_term(hdr, d + dyn_blv(tr.NN), hdr + 4, ps, j);
+                o[j] = v;
             }
         }
         if (tid == 0) *p.done_counter = 0;   // ready for the next launch
@@ -1379,22 +1422,29 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
 // --------------------------------------------------------------------------------------------
 __global__ void finalize_results(const TreeDev* __restrict__ trees, const double* __restrict__ rows,
                                  long long row_stride, const LLRow* __restrict__ rows_ll,
-                                 double* __restrict__ out, int want_grad) {
+                                 double* __restrict__ out, int want_grad, const double* __restrict__ dyn, int K, int R) {
+    __shared__ double s_red[2 * 128];
     const TreeDev tr = trees[blockIdx.y];
+    if ((long long)blockIdx.x * blockDim.x >= tr.NN) return;   // whole block idle (batch of unequal trees)
+    const double* d = dyn + tr.dyn_off;
+    const double* hdr = d + dyn_prior(tr.NN, K, R);
+    const bool prior = hdr[0] != 0.0;
+    PriorSums ps{0.0, 0.0};
+    if (prior) ps = prior_block_sums(d + dyn_blv(tr.NN), hdr + 4, tr.NN - 1, threadIdx.x, blockDim.x, s_red);
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= tr.NN) return;
     double* o = out + tr.out_off;
+    double v = 0.0;
     if (j == 0) {
         long long es = 0;
         double ls = 0.0;
         for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) { es += rows_ll[rw].esum; ls += rows_ll[rw].logsum; }
-        o[0] = (double)es * 0.693147180559945309417232121458 + ls;
-    } else {
-        double g = 0.0;
-        if (want_grad)
-            for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) g += rows[(long long)rw * row_stride + (j - 1)];
-        o[j] = g;
+        v = (double)es * 0.693147180559945309417232121458 + ls;
+    } else if (want_grad) {
+        for (int rw = tr.row_lo; rw < tr.row_hi; ++rw) v += rows[(long long)rw * row_stride + (j - 1)];
     }
+    if (prior && (j == 0 || want_grad)) v += prior_term(hdr, d + dyn_blv(tr.NN), hdr + 4, ps, j);
+    o[j] = v;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1626,6 +1676,9 @@ struct BatchArgs {
     int R;
     const double* const* pi;
     int want_grad;
+    // optional branch-length prior (mcp_eval_posterior); applies to every tree of the batch
+    int prior_kind = MCP_PRIOR_NONE;
+    const double* prior_params = nullptr;
 };
 
 // (Re)build schedules, tile/row assignment and the topology upload if anything structural changed.
@@ -1901,6 +1954,45 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         d[dyn_mu(NN, K)] = a.mu[t];
         std::memcpy(d + dyn_rates(NN, K), a.rates[t], sizeof(double) * R);
         std::memcpy(d + dyn_pi(NN, K, R), a.pi[t], sizeof(double) * K);
+        double* pr = d + dyn_prior(NN, K, R);
+        pr[0] = 0.0;
+        if (a.prior_kind != MCP_PRIOR_NONE) {
+            // The prior is brought to the form  c0 - beta*T + sum_j w_j log t_j + k4 log T  on the host
+            // (topology-only constants); sums over the branch lengths and the gradient are formed
+            // on the device in the final reduction.
+            if (!a.prior_params) return fail(ctx, MCP_ERR_ARG, "branch-length prior without parameters");
+            double* w = pr + 4;
+            if (a.prior_kind == MCP_PRIOR_EXPONENTIAL) {
+                const double scale = a.prior_params[0];
+                if (!(scale > 0.0)) return fail(ctx, MCP_ERR_ARG, "exponentialBL: scale must be positive");
+                pr[1] = -(double)(NN - 1) * std::log(scale);
+                pr[2] = 1.0 / scale;
+                pr[3] = 0.0;
+                for (int j = 0; j < NN - 1; ++j) w[j] = 0.0;
+            } else if (a.prior_kind == MCP_PRIOR_COMPOUND_DIRICHLET) {
+                const double alpha = a.prior_params[0], aa = a.prior_params[1], beta = a.prior_params[2], c = a.prior_params[3];
+                if (!(alpha > 0.0 && aa > 0.0 && beta > 0.0 && c > 0.0))
+                    return fail(ctx, MCP_ERR_ARG, "CompoundDirichlet: alpha, a, beta, c must be positive");
+                // internal_external: 1 = the branch leads to an internal node, 0 = to a leaf (Prior.jl:15-23)
+                std::vector<char> internal(NN, 0);
+                for (int j = 0; j < NN; ++j) {
+                    const int m = a.pa[t][j];
+                    if (m >= 1 && m <= NN) internal[m - 1] = 1;
+                }
+                double nterm = 0.0;
+                for (int j = 0; j < NN - 1; ++j) {
+                    w[j] = internal[j] ? aa * c - 1.0 : aa - 1.0;
+                    if (!internal[j]) nterm += 1.0;
+                }
+                const double n_int = nterm - 3.0;
+                pr[1] = alpha * std::log(beta) - std::lgamma(alpha) - std::lgamma(aa) - std::lgamma(c) + std::lgamma(aa + c);
+                pr[2] = beta;
+                pr[3] = alpha - aa * nterm - aa * c * n_int;
+            } else {
+                return fail(ctx, MCP_ERR_ARG, "unknown branch-length prior kind %d", a.prior_kind);
+            }
+            pr[0] = 1.0;
+        }
     }
 
     // substitution-model constants -> constant memory, one slot per distinct model of the batch
@@ -2002,7 +2094,8 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         for (int t = 0; t < T; ++t) maxNN = std::max(maxNN, a.NN[t]);
         dim3 grid((maxNN + 127) / 128, T);
         finalize_results<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_rows.p, ctx->row_stride,
-                                               (const LLRow*)ctx->d_rows_ll.p, d_out, wp.want_grad);
+                                               (const LLRow*)ctx->d_rows_ll.p, d_out, wp.want_grad,
+                                               (const double*)ctx->d_dyn.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     s.kernel_launches = fused ? 1 : 3;
@@ -2257,6 +2350,17 @@ int mcp_eval(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* post
     BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
     double* g = grad_out;
     return eval_impl(ctx, a, nullptr, ll_out, &g);
+}
+
+int mcp_eval_posterior(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
+                       const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
+                       double mu, const double* rates, int R, const double* pi, int prior_kind, const double* prior_params,
+                       double* lp_out, double* grad_out) {
+    BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, grad_out ? 1 : 0};
+    a.prior_kind = prior_kind;
+    a.prior_params = prior_params;
+    double* g = grad_out;
+    return eval_impl(ctx, a, nullptr, lp_out, &g);
 }
 
 int mcp_eval_device(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,

@@ -152,6 +152,9 @@ class PhyloDist:
         return (self.nbase, 1, self.nnodes)
 
 
+from . import prior as _prior  # noqa: E402
+
+
 def minimum(d) -> float:
     return -np.inf
 
@@ -171,7 +174,10 @@ def _tree_args(d: PhyloDist):
 
 
 def logpdf(d, x, device: Optional[int] = None) -> float:
-    """log-likelihood; `x` is the reference's (K, S, NN) array or a DeviceAlignment."""
+    """log-likelihood; `x` is the reference's (K, S, NN) array or a DeviceAlignment.
+    With a branch-length distribution and a tree it is the prior's log density (Prior.jl:68-83)."""
+    if isinstance(d, _prior.LengthDistribution):
+        return _prior.prior_logpdf(d, x)
     if isinstance(d, MultiplePhyloDist):
         return float(np.sum(_multi(d, x, False, device)[0]))
     ctx = get_context(device)
@@ -183,6 +189,8 @@ def logpdf(d, x, device: Optional[int] = None) -> float:
 
 def gradlogpdf(d: PhyloDist, x, device: Optional[int] = None) -> Tuple[float, np.ndarray]:
     """(logL, d logL / d branch length indexed by node.num) — a tuple, like the reference."""
+    if isinstance(d, _prior.LengthDistribution):
+        return _prior.prior_gradlogpdf(d, x)
     ctx = get_context(device)
     ft, targs = _tree_args(d)
     aln = _device_alignment(x, ft.leaf_nums, d.nbase, ctx)

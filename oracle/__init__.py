@@ -3,4 +3,5 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.  See felsenstein_oracle.c for what it restates and how it is pinned.
 """
-from .oracle import (build, codes_to_dense, felsenstein, num_threads, transition)  # noqa: F401
+from .oracle import (build, codes_to_dense, felsenstein, num_threads, transition,  # noqa: F401
+                     compound_dirichlet_logpdf, compound_dirichlet_gradlogpdf, exponential_bl_gradlogpdf)

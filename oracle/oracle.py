@@ -107,3 +107,53 @@ def felsenstein(x, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi, wa
     if rc:
         raise RuntimeError(f"oracle_felsenstein failed ({rc})")
     return ll.value, (grad[:NN - 1] if want_grad else None)
+
+
+# ---------------------------------------------------------------------------------------------
+# Branch-length prior of the tree node.  Test infrastructure like the rest
+# of this file.  Restates internal_logpdf, /root/reference/src/Likelihood/Prior.jl:1-37, as the
+# same scalar loop; the reference obtains the gradient by reverse-mode AD of that function
+# (Prior.jl:39-48), which is reproduced here to machine precision by complex-step differentiation
+# of the restated loop (no hand-derived formula on the checking side).
+# Pinned by test/distributions/treedists.jl:61-69 (tests/test_prior_host.py, test_oracle_prior).
+# ---------------------------------------------------------------------------------------------
+def compound_dirichlet_logpdf(alpha, a, beta, c, b_lens, int_leave_map):
+    import cmath
+    import math
+
+    blen_int = blen_leave = blen_int_log = blen_leave_log = 0.0
+    nterm = 0.0
+    for i in range(len(int_leave_map)):
+        if int_leave_map[i] == 1:
+            blen_int += b_lens[i]
+            blen_int_log += cmath.log(b_lens[i])
+        else:
+            blen_leave += b_lens[i]
+            blen_leave_log += cmath.log(b_lens[i])
+            nterm += 1
+    t_l = blen_int + blen_leave
+    n_int = nterm - 3.0
+    first = (alpha * math.log(beta)) - math.log(math.gamma(alpha)) - (t_l * beta)
+    second = -math.log(math.gamma(a)) - math.log(math.gamma(c)) + math.log(math.gamma(a + c))
+    third = blen_leave_log * (a - 1.0) + blen_int_log * (a * c - 1.0)
+    fourth = (alpha - a * nterm - a * c * n_int) * cmath.log(t_l)
+    return first + second + third + fourth
+
+
+def compound_dirichlet_gradlogpdf(alpha, a, beta, c, b_lens, int_leave_map):
+    b = [complex(v) for v in b_lens]
+    val = compound_dirichlet_logpdf(alpha, a, beta, c, b, int_leave_map).real
+    h = 1e-30
+    grad = np.zeros(len(b))
+    for j in range(len(b)):
+        bj = list(b)
+        bj[j] = b[j] + 1j * h
+        grad[j] = compound_dirichlet_logpdf(alpha, a, beta, c, bj, int_leave_map).imag / h
+    return val, grad
+
+
+def exponential_bl_gradlogpdf(scale, b_lens):
+    import math
+
+    b = np.asarray(b_lens, dtype=np.float64)           # Prior.jl:50-57, 80-83
+    return float(np.sum(-math.log(scale) - b / scale)), np.full(b.size, -1.0 / scale)

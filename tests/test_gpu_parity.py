@@ -478,3 +478,64 @@ def test_level_parallel_kernel(oracle, n_taxa, K, R, S, multi):
     _check(ll1, g1, ll_o, g_o)
     _check(l1, None, ll_o, None)
     _check(ll0, g0, ll_o, g_o)
+
+
+# ---------------------------------------------------------------------------------------------
+# likelihood + branch-length prior in one device call (mcp_eval_posterior; SURVEY.md §8f row 4,
+# the body of logpdfgrad!(::Type{provided}), /root/reference/src/samplers/sampler.jl:172-190)
+# ---------------------------------------------------------------------------------------------
+def _oracle_prior(oracle, prior, tree):
+    blv, ie = mcp.get_branchlength_vector(tree), mcp.internal_external(tree)
+    if prior is None or isinstance(prior, mcp.UniformBranchLength):
+        return 0.0, np.zeros(blv.size)
+    if isinstance(prior, mcp.exponentialBL):
+        return oracle.exponential_bl_gradlogpdf(prior.scale, blv)
+    return oracle.compound_dirichlet_gradlogpdf(prior.alpha, prior.a, prior.beta, prior.c, blv, ie)
+
+
+@pytest.mark.parametrize("prior", [
+    mcp.CompoundDirichlet(1.0, 1.0, 0.100, 1.0),      # the reference's test prior (tree_samplers.jl:22)
+    mcp.CompoundDirichlet(2.5, 0.7, 0.3, 1.9),
+    mcp.exponentialBL(0.25),
+    mcp.UniformBranchLength(),
+    None,
+])
+def test_posterior_golden_tree(oracle, prior):
+    tree, x, codes, leaf_nums, fx = golden_case("simudata")
+    pd = mcp.PhyloDist(tree, fx["base_freq"], [1.0], [1.0], mcp.JC)
+    lp, grad = mcp.logpdfgrad(pd, x, prior)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.JC, fx["base_freq"], [1.0], [1.0])
+    vp, gp = _oracle_prior(oracle, prior, tree)
+    _check(lp, grad, ll_o + vp, g_o + gp)
+    lp_only, none = mcp.logpdfgrad(pd, x, prior, want_grad=False)
+    assert none is None and abs(lp_only - (ll_o + vp)) <= LL_RTOL * abs(ll_o + vp)
+    # the sampler's sum, piece by piece: likelihood call + prior mirror
+    ll, g = mcp.gradlogpdf(pd, x)
+    if prior is not None:
+        v_h, g_h = mcp.gradlogpdf(prior, tree)
+        assert abs(lp - (ll + v_h)) <= 1e-12 * abs(lp)
+        assert np.allclose(grad, g + g_h, rtol=1e-11, atol=1e-9)
+
+
+@pytest.mark.parametrize("level_mode", [0, 1])
+def test_posterior_random_tree_both_kernels(oracle, level_mode):
+    """Same prior epilogue in the three-launch path (finalize_results) and in the fused small-tree kernel."""
+    rng = np.random.default_rng(77)
+    tree = random_tree(40, rng)
+    pi = rng.dirichlet(np.ones(4) * 5)
+    srates = rng.uniform(0.5, 2.5, size=6)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, srates), pi, rates, 500, rng, gap_frac=0.02)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, mcp.GTR)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    ctx = mcp.get_context()
+    ctx.set_level_mode(level_mode)
+    try:
+        prior = mcp.CompoundDirichlet(1.3, 0.9, 0.2, 1.4)
+        lp, grad = mcp.logpdfgrad(pd, aln, prior)
+        assert ctx.stats()["kernel_launches"] == (1 if level_mode else 3)
+    finally:
+        ctx.set_level_mode(-1)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, srates, rates)
+    vp, gp = _oracle_prior(oracle, prior, tree)
+    _check(lp, grad, ll_o + vp, g_o + gp)

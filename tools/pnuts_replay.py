@@ -107,13 +107,26 @@ def main():
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--batch-nni", action="store_true",
                     help="evaluate the two logpdf calls of an NNI attempt as one mcp_eval_batch launch")
+    ap.add_argument("--prior", action="store_true",
+                    help="target = likelihood + CompoundDirichlet(1, 1, 0.1, 1) branch-length prior (the reference's "
+                         "sampler test, test/samplers/tree_samplers.jl:22), evaluated in the same device call "
+                         "(mcp_eval_posterior) as logpdfgrad!(::Type{provided}) would combine them")
     a = ap.parse_args()
+    prior = mcp.CompoundDirichlet(1.0, 1.0, 0.100, 1.0) if a.prior else None
     w = bench.make_workload(a.workload, a.sites)
     codes, leaf_nums = bench.make_codes(w, 0, w["S"])
     aln = mcp.DeviceAlignment(codes, leaf_nums, w["K"])
     rng = np.random.default_rng(a.seed)
     ctx = mcp.get_context(0)
-    dev = {"walk_ms": 0.0, "device_ms": 0.0, "rebuilds": 0}
+    dev = {"walk_ms": 0.0, "device_ms": 0.0, "rebuilds": 0, "api_s": 0.0}
+
+    def timed(fn):
+        def wrapped(*args):
+            t0 = time.perf_counter()
+            out = fn(*args)
+            dev["api_s"] += time.perf_counter() - t0
+            return out
+        return wrapped
 
     def note():
         st = ctx.stats()
@@ -121,20 +134,27 @@ def main():
         dev["device_ms"] += st["device_ms"]
         dev["rebuilds"] += st["schedule_rebuilt"]
 
+    @timed
     def logf(tree):
-        v = mcp.logpdf(mcp.PhyloDist(tree, w["pi"], w["srates"], w["rates"], w["model"]), aln)
+        pd = mcp.PhyloDist(tree, w["pi"], w["srates"], w["rates"], w["model"])
+        v = mcp.logpdfgrad(pd, aln, prior, want_grad=False)[0] if prior else mcp.logpdf(pd, aln)
         note()
         return v
 
+    @timed
     def logfgrad(tree):
-        v = mcp.gradlogpdf(mcp.PhyloDist(tree, w["pi"], w["srates"], w["rates"], w["model"]), aln)
+        pd = mcp.PhyloDist(tree, w["pi"], w["srates"], w["rates"], w["model"])
+        v = mcp.logpdfgrad(pd, aln, prior) if prior else mcp.gradlogpdf(pd, aln)
         note()
         return v
 
+    @timed
     def logf_pair(t1, t2):
         mpd = mcp.MultiplePhyloDist([t1, t2], w["pi"], w["srates"], w["rates"], w["model"])
         v = mcp.phylodist._multi(mpd, [aln, aln], False, None)[0]
         note()
+        if prior:   # the batched entry point carries no prior: add the O(NN) host mirror
+            return float(v[0]) + mcp.logpdf(prior, t1), float(v[1]) + mcp.logpdf(prior, t2)
         return float(v[0]), float(v[1])
 
     tree = w["tree"]
@@ -156,17 +176,19 @@ def main():
     calls = counters["gradlogpdf"] + counters["logpdf"] - counters["batched_pairs"]   # library calls
     print(json.dumps({
         "workload": f"{a.workload}: {w['n_taxa']} taxa x {w['S']} sites, K={w['K']}, R={w['R']}; tree-space leapfrog replay",
+        "target": "likelihood + CompoundDirichlet(1,1,0.1,1) prior, one device call" if prior else "likelihood",
         "leapfrogs": a.leapfrogs, "epsilon": a.epsilon, "gradlogpdf_calls": counters["gradlogpdf"],
         "logpdf_calls": counters["logpdf"], "batched_nni_pairs": counters["batched_pairs"],
         "nni_attempted": att, "nni_accepted": nni,
         "schedule_rebuilds": dev["rebuilds"],
         "us_per_leapfrog_wall": wall / a.leapfrogs * 1e6,
         "us_per_call_wall": wall / calls * 1e6,
+        "us_per_call_api": dev["api_s"] / calls * 1e6,
         "us_per_call_device": dev["device_ms"] / calls * 1e3,
         "us_per_call_walk_kernel": dev["walk_ms"] / calls * 1e3,
         "leapfrogs_per_s": a.leapfrogs / wall,
         "hamiltonian_drift": H1 - H0, "final_logL": s.lf,
-        "note": "wall includes this harness's Python tree handling (deepcopy per NNI attempt, flatten per call)",
+        "note": "wall includes this harness's Python tree handling (refraction loop, deepcopy per NNI attempt); api = time inside the PhyloDist calls (PhyloDist construction, flatten, eigendecomposition, library call)",
     }))
 
 
