@@ -284,9 +284,10 @@ def run_b200(args):
     stats = ctx.stats()
 
     # ---- end to end through the public API with host buffers -------------------------------
-    # PipelinedEvaluator: every step uploads the whole alignment from pinned host memory in 4 site
-    # blocks (block b+1 crosses PCIe while block b is evaluated), flattens the tree, runs the
-    # eigendecomposition, evaluates, all-reduces and reads the result back.
+    # PipelinedEvaluator: every step uploads the whole alignment from pinned host memory in site
+    # blocks of 2, 4, 8, ... grid waves (block b+1 crosses PCIe on the copy stream while block b is
+    # evaluated), flattens the tree, runs the eigendecomposition, evaluates, all-reduces and reads the
+    # result back.
     pipe = mcp.PipelinedEvaluator(codes, leaf_nums, w["K"], local_rank, n_blocks=args.e2e_blocks)
 
     def e2e_step(i):
@@ -351,11 +352,13 @@ def run_b200(args):
             "e2e": {"value": e2e_per_s, "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(codes.nbytes + stats["h2d_bytes"]),
                     "d2h_bytes_per_step": int(NN * 8),
-                    "what": f"per step: alignment codes re-uploaded from pinned host memory in {args.e2e_blocks} site "
-                            "blocks overlapped with the evaluation of the previous block, tree flattened, "
-                            "eigendecomposition, mcp_eval_device per block, all-reduce, result read back"},
+                    "site_blocks": [hi - lo for lo, hi in pipe.bounds],
+                    "what": f"per step: alignment codes re-uploaded from pinned host memory in {len(pipe.bounds)} site "
+                            "blocks (2, 4, 8, ... grid waves) on the copy stream, each overlapped with the evaluation "
+                            "of the previous block; tree flattened, eigendecomposition, mcp_eval_device per block, "
+                            "all-reduce, result read back"},
             "gpu_launches": int(stats["kernel_launches"] * ((args.steps + args.warmup + 1) +
-                                                            args.e2e_blocks * (args.steps + min(args.warmup, 3)))),
+                                                            len(pipe.bounds) * (args.steps + min(args.warmup, 3)))),
             "gpu_launches_timed": int(stats["kernel_launches"] * args.steps),
             "clocks": sampler.summary(),
             "launch": {"grid": stats["grid"], "block": stats["block"], "tiles": stats["tiles"],
@@ -501,7 +504,7 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--trees", type=int, default=0, help="cfg5: number of trees in the batch")
-    ap.add_argument("--e2e-blocks", type=int, default=4, help="site blocks of the pipelined end-to-end path")
+    ap.add_argument("--e2e-blocks", type=int, default=5, help="site blocks of the pipelined end-to-end path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

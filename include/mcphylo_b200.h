@@ -84,9 +84,11 @@ int mcp_alignment_from_codes(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t 
 int mcp_alignment_from_dense(mcp_ctx *ctx, const double *x, int K, int64_t S, int NN,
                              const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
 /* Re-upload the codes of an existing alignment (same K, S, leaf_nums) from host memory,
- * asynchronously on the context's stream; evaluations enqueued afterwards see the new data.
- * With pinned host memory the copy overlaps host work; `codes` must stay valid until the context
- * is synchronised (mcp_synchronize or a synchronous mcp_eval).  The cached schedule stays valid. */
+ * asynchronously on the context's COPY stream: the transfer overlaps evaluations of other
+ * alignments that are already enqueued (site-block pipelining, dist.PipelinedEvaluator), waits for
+ * evaluations of this alignment enqueued earlier, and evaluations of this alignment enqueued
+ * afterwards wait for it.  Use pinned host memory; `codes` must stay valid until an evaluation of
+ * this alignment has completed or mcp_synchronize has returned.  The cached schedule stays valid. */
 int mcp_alignment_update_codes(mcp_ctx *ctx, mcp_alignment *aln, const uint8_t *codes);
 int mcp_alignment_destroy(mcp_ctx *ctx, mcp_alignment *aln);
 
@@ -173,6 +175,15 @@ typedef struct mcp_stats {
     int64_t scratch_bytes;     /* device scratch currently held for partials */
 } mcp_stats;
 int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
+
+/*
+ * Columns (sites x rate categories) that ONE full wave of the persistent walk grid covers for a large
+ * input with K states and a tree of n_nodes nodes: resident CTAs x columns per tile.  A caller that
+ * cuts an alignment into site blocks (to overlap mcp_alignment_update_codes of one block with the
+ * evaluation of another) keeps every launch free of a ragged last wave by making each block a
+ * multiple of columns / R sites.
+ */
+int mcp_wave_columns(mcp_ctx *ctx, int K, int n_nodes, int want_grad, int64_t *columns);
 
 /* Tuning knobs: block = threads per CTA (= columns per tile; 0 = automatic),
  * ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */

@@ -21,7 +21,7 @@ SYMBOLS = [
     "mcp_use_own_stream", "mcp_synchronize",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
-    "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_set_launch",
+    "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
     "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_level_mode",
     "mcp_schedule_dump",
 ]
@@ -81,6 +81,7 @@ def load():
     lib.mcp_eval_posterior.argtypes = eval_args[:-1] + [C.c_int, _vp, _dp, _vp]
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    lib.mcp_wave_columns.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.mcp_schedule_dump.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]
     for name in SYMBOLS:
         if name != "mcp_last_error":
@@ -177,6 +178,12 @@ class Context:
 
     def set_scratch_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_scratch_mode(self.handle, int(mode)))
+
+    def wave_columns(self, K: int, n_nodes: int, want_grad: bool = True) -> int:
+        """Columns (sites x rates) one full wave of the persistent grid covers (mcp_wave_columns)."""
+        out = C.c_int64()
+        self._check(self.lib.mcp_wave_columns(self.handle, int(K), int(n_nodes), int(want_grad), C.byref(out)))
+        return out.value
 
     def stats(self) -> dict:
         s = Stats()

@@ -1470,12 +1470,21 @@ struct mcp_alignment {
     unsigned char* d_codes = nullptr;
     std::vector<int32_t> leaf_nums;
     unsigned long long id = 0;
+    // Re-uploads (mcp_alignment_update_codes) run on the context's copy stream so that they overlap
+    // evaluations of OTHER alignments; these order them against the evaluations of THIS one.
+    cudaEvent_t ev_uploaded = nullptr;
+    cudaEvent_t ev_read_done = nullptr;      // recorded after every walk that read d_codes, once `streamed`
+    mutable bool upload_pending = false;     // an upload has been enqueued that no evaluation has waited for yet
+    mutable bool read_since_upload = false;  // an evaluation reading d_codes was enqueued after the last upload
+    mutable bool streamed = false;           // has been re-uploaded at least once: evaluations record ev_read_done
 };
 
 struct mcp_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // alignment re-uploads (overlap with evaluations)
+    cudaEvent_t ev_walk_done = nullptr;     // the walk kernel of the last evaluation has finished reading the codes
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_staged = nullptr;   // the pinned staging buffers of the last evaluation have been consumed
     bool staged_pending = false;
@@ -1840,7 +1849,10 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     {   // very large trees: fewer persistent CTAs rather than a scratch allocation that cannot succeed
         size_t free_b = 0, total_b = 0;
         const double per_cta = level_mode ? 0.0 : (double)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8.0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_cta > 0) {
+        if (per_cta * ctx->grid <= (double)ctx->d_scratch.cap) {
+            // fits the scratch already held: nothing to allocate, no need to ask the driver
+            // (cudaMemGetInfo costs milliseconds on a GPU with many live allocations)
+        } else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_cta > 0) {
             const double budget = 0.6 * ((double)free_b + (double)ctx->d_scratch.cap);
             if (per_cta * ctx->grid > budget) ctx->grid = (int)std::max(1.0, std::floor(budget / per_cta));
         } else {
@@ -2039,6 +2051,11 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
 
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged, st));
     ctx->staged_pending = true;
+    for (int t = 0; t < T; ++t)   // re-uploads of these alignments that are still in flight on the copy stream
+        if (a.alns[t]->upload_pending) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(st, a.alns[t]->ev_uploaded, 0));
+            a.alns[t]->upload_pending = false;
+        }
 
     const TreeDev* d_trees = (const TreeDev*)((char*)ctx->d_topo.p + ctx->off_trees);
     const bool fused = ctx->level_mode;   // small-tree kernel: tables, walk and final reduction in ONE launch
@@ -2089,6 +2106,11 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     }
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_done, st));
+    for (int t = 0; t < T; ++t) {
+        a.alns[t]->read_since_upload = true;
+        if (a.alns[t]->streamed) CUDA_TRY(ctx, cudaEventRecord(a.alns[t]->ev_read_done, st));
+    }
     if (!fused) {
         int maxNN = 0;
         for (int t = 0; t < T; ++t) maxNN = std::max(maxNN, a.NN[t]);
@@ -2148,7 +2170,11 @@ int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S,
         e = cudaMemcpy2DAsync(al->d_codes, (size_t)al->stride, codes, (size_t)S, (size_t)S, (size_t)n_leaves,
                               cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&al->ev_uploaded, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&al->ev_read_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
+        if (al->ev_uploaded) cudaEventDestroy(al->ev_uploaded);
+        if (al->ev_read_done) cudaEventDestroy(al->ev_read_done);
         cudaFree(al->d_codes);
         delete al;
         return fail(ctx, MCP_ERR_CUDA, "alignment upload failed: %s", cudaGetErrorString(e));
@@ -2193,6 +2219,8 @@ int mcp_create(mcp_ctx** out, int device) {
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; e == cudaSuccess && i < 4; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_walk_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         std::string msg = cudaGetErrorString(e);
         delete ctx;
@@ -2207,6 +2235,7 @@ int mcp_destroy(mcp_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter})
         if (b->p) cudaFree(b->p);
     for (PinBuf* b : {&ctx->h_topo, &ctx->h_dyn, &ctx->h_out, &ctx->h_model})
@@ -2214,6 +2243,8 @@ int mcp_destroy(mcp_ctx* ctx) {
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
+    if (ctx->ev_walk_done) cudaEventDestroy(ctx->ev_walk_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return 0;
@@ -2233,6 +2264,7 @@ int mcp_synchronize(mcp_ctx* ctx) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     ctx->pending_async = false;
     return 0;
 }
@@ -2324,9 +2356,21 @@ int mcp_alignment_update_codes(mcp_ctx* ctx, mcp_alignment* aln, const uint8_t* 
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!aln || !codes) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_update_codes: null argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // On the copy stream: the transfer overlaps whatever the evaluation stream is doing (the
+    // evaluation of another site block, typically).  It must not overtake an evaluation that still
+    // reads this buffer, and the next evaluation of this alignment waits for it (eval_impl).
+    if (aln->read_since_upload) {
+        // first re-upload: only the context-wide "last walk finished" event exists (conservative);
+        // afterwards every evaluation of this alignment records the alignment's own event
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, aln->streamed ? aln->ev_read_done : ctx->ev_walk_done, 0));
+        aln->read_since_upload = false;
+    }
+    aln->streamed = true;
     if (aln->S > 0)
         CUDA_TRY(ctx, cudaMemcpy2DAsync(aln->d_codes, (size_t)aln->stride, codes, (size_t)aln->S, (size_t)aln->S,
-                                        (size_t)aln->n_leaves, cudaMemcpyHostToDevice, ctx->stream));
+                                        (size_t)aln->n_leaves, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(aln->ev_uploaded, ctx->copy_stream));
+    aln->upload_pending = true;
     ctx->pending_async = true;   // only consulted before buffers are freed / the stream is changed
     return 0;
 }
@@ -2336,9 +2380,12 @@ int mcp_alignment_destroy(mcp_ctx* ctx, mcp_alignment* aln) {
     if (ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
         ctx->pending_async = false;
         ctx->sig.clear();
     }
+    if (aln->ev_uploaded) cudaEventDestroy(aln->ev_uploaded);
+    if (aln->ev_read_done) cudaEventDestroy(aln->ev_read_done);
     if (aln->d_codes) cudaFree(aln->d_codes);
     delete aln;
     return 0;
@@ -2380,6 +2427,30 @@ int mcp_eval_batch(mcp_ctx* ctx, int T, const mcp_alignment* const* alns, const 
         return fail(ctx, MCP_ERR_ARG, "mcp_eval_batch: null argument array");
     BatchArgs a{T, alns, NN, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, R, pi, want_grad};
     return eval_impl(ctx, a, nullptr, ll_out, grad_out);
+}
+
+int mcp_wave_columns(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* columns) {
+    if (!ctx || !columns) return fail(ctx, MCP_ERR_ARG, "mcp_wave_columns: null argument");
+    if (!k_supported(K)) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int block = ctx->opt_block > 0 ? ctx->opt_block : 256;
+    int cpt = ctx->opt_cpt > 0 ? ctx->opt_cpt : (K <= 3 ? 2 : 1);
+    int occ = 0, rc = 0;
+    if (k_templated(K)) {
+        const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad ? 1 : 0, block, cpt);
+        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, smem, false, &occ));
+        if (rc) return rc;
+    } else {
+        cpt = 1;
+        block = std::min(block, 128);
+        const size_t smem = want_grad ? (size_t)std::max(n_nodes, 1) * sizeof(double) : 0;
+        if ((rc = ensure_smem_attr(ctx, felsenstein_walk_generic, smem))) return rc;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, felsenstein_walk_generic, block, smem));
+    }
+    if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d)", block);
+    if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
+    *columns = (int64_t)occ * ctx->sm_count * block * cpt;
+    return 0;
 }
 
 int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {

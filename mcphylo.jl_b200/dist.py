@@ -101,14 +101,19 @@ def sharded_sum(local_eval: Callable[[], Tuple[float, Optional[np.ndarray]]], NN
 
 
 class PipelinedEvaluator:
-    """Evaluation of an alignment that has to be (re-)uploaded from host memory for the call: the
-    site axis is cut into `n_blocks` blocks handled alternately by two contexts (two CUDA streams),
-    so block b+1 crosses PCIe while block b is being evaluated.  Results of the blocks are summed on
-    the device, all-reduced over the process group if there is one, and read back once.
+    """Evaluation of an alignment that has to be (re-)uploaded from host memory for the call.  The
+    site axis is cut into blocks; `mcp_alignment_update_codes` puts every block's transfer on the
+    context's copy stream, the evaluations follow on the compute stream and each waits only for its
+    own block, so block b+1 crosses PCIe while block b is evaluated.  Block sizes are multiples of
+    one wave of the persistent grid (`mcp_wave_columns`) and grow geometrically (2, 4, 8, ... waves,
+    then the rest): the first evaluation starts after a millisecond of transfer and no launch ends
+    in a ragged wave.  Block results are summed on the device, all-reduced over the
+    process group if there is one, and read back once.
 
-    `codes` is the rank's (n_leaves, S) uint8 block; pinned per-block copies are made once here."""
+    `codes` is the rank's (n_leaves, S) uint8 block; pinned per-block copies are made at the first
+    evaluation (the wave size depends on the number of rate categories and the tree size)."""
 
-    def __init__(self, codes: np.ndarray, leaf_nums, K: int, device: int, n_blocks: int = 4, group=None):
+    def __init__(self, codes: np.ndarray, leaf_nums, K: int, device: int, n_blocks: int = 5, group=None):
         import torch
 
         from . import capi
@@ -116,38 +121,66 @@ class PipelinedEvaluator:
         self.torch = torch
         self.device, self.group, self.K = device, group, int(K)
         self.leaf_nums = np.asarray(leaf_nums, dtype=np.int32)
-        S = codes.shape[1]
-        n_blocks = max(1, min(n_blocks, S if S > 0 else 1))
-        self.ctxs = [capi.Context(device) for _ in range(min(2, n_blocks))]
+        self.codes = codes
+        self.n_blocks = max(1, int(n_blocks))
+        self.ctx = capi.Context(device)
         self.blocks = []
-        for b in range(n_blocks):
-            lo, hi = shard_bounds(S, n_blocks, b)
-            if hi <= lo:
-                continue
-            host = torch.from_numpy(np.ascontiguousarray(codes[:, lo:hi])).pin_memory()
-            ctx = self.ctxs[len(self.blocks) % len(self.ctxs)]
-            aln = ctx.alignment_from_codes(host.numpy(), self.K, self.leaf_nums)
-            self.blocks.append((ctx, aln, host))
+        self.bounds = []
         self._out = None
+
+    @staticmethod
+    def plan_blocks(S: int, wave_sites: int, n_blocks: int):
+        """[(lo, hi)] site ranges: 2, 4, 8, ... waves, the last block takes the rest."""
+        wave_sites = max(1, int(wave_sites))
+        waves = S // wave_sites
+        if n_blocks <= 1 or waves < 4:
+            return [(0, S)] if S > 0 else []
+        sizes, w = [], 2
+        while len(sizes) < n_blocks - 1 and sum(sizes) + w < waves:
+            sizes.append(w)
+            w *= 2
+        bounds, lo = [], 0
+        for sz in sizes:
+            bounds.append((lo, lo + sz * wave_sites))
+            lo += sz * wave_sites
+        bounds.append((lo, S))
+        return bounds
+
+    def _build(self, R: int, NN: int):
+        torch = self.torch
+        S = self.codes.shape[1]
+        wave_sites = self.ctx.wave_columns(self.K, NN, True) // max(R, 1)
+        self.bounds = self.plan_blocks(S, wave_sites, self.n_blocks)
+        for lo, hi in self.bounds:
+            host = torch.from_numpy(np.ascontiguousarray(self.codes[:, lo:hi])).pin_memory()
+            aln = self.ctx.alignment_from_codes(host.numpy(), self.K, self.leaf_nums)
+            self.blocks.append((aln, host))
+        self.codes = None
 
     def evaluate(self, d: PhyloDist, want_grad: bool = True, upload: bool = True):
         torch = self.torch
         ft, targs = _tree_args(d)
         NN = ft.NN
+        if not self.blocks:
+            self._build(len(d.rates), NN)
         if self._out is None or self._out.shape[1] != NN:
             self._out = torch.empty((len(self.blocks), NN), dtype=torch.float64, device=f"cuda:{self.device}")
             self._pinned = torch.empty(NN, dtype=torch.float64).pin_memory()
         with torch.cuda.device(self.device):
-            for i, (ctx, aln, host) in enumerate(self.blocks):
+            stream = torch.cuda.current_stream()
+            self.ctx.set_stream(stream.cuda_stream)
+            # Issue order matters: host-to-device transfers are served first-in first-out, and every
+            # evaluation starts with a small parameter upload of its own.  Transfer b, evaluation b,
+            # transfer b+1, ...: the parameters of evaluation b queue right behind the block they
+            # need anyway, and transfer b+1 then runs under the kernels of evaluation b.
+            for i, (aln, host) in enumerate(self.blocks):
                 if upload:
                     aln.update_codes(host.data_ptr())
-                ctx.eval_device(aln, *targs, want_grad=want_grad, d_out_ptr=self._out[i].data_ptr())
-            for ctx in self.ctxs:
-                ctx.synchronize()
+                self.ctx.eval_device(aln, *targs, want_grad=want_grad, d_out_ptr=self._out[i].data_ptr())
             total = self._out.sum(dim=0)
             allreduce_sum(total, self.group)
             self._pinned.copy_(total, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            stream.synchronize()
         res = self._pinned.numpy()
         return float(res[0]), (res[1:].copy() if want_grad else None)
 
@@ -158,8 +191,8 @@ class PipelinedEvaluator:
         return self.evaluate(d, False)[0]
 
     def close(self):
-        for ctx, aln, _ in self.blocks:
+        for aln, _ in self.blocks:
             aln.close()
-        for ctx in self.ctxs:
-            ctx.close()
-        self.blocks, self.ctxs = [], []
+        if self.ctx is not None:
+            self.ctx.close()
+        self.blocks, self.ctx = [], None

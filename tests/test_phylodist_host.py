@@ -90,3 +90,19 @@ def test_device_alignment_site_blocks():
     parts = [mcp.local_shard(aln, 3, r) for r in range(3)]
     assert [p.S for p in parts] == [4, 4, 2]
     assert np.array_equal(np.concatenate([p.codes for p in parts], axis=1), codes)
+
+
+def test_pipelined_block_plan_covers_sites_in_wave_multiples():
+    from mcphylo_jl_b200.dist import PipelinedEvaluator as P
+
+    for S, wave, nb in [(1000000, 28416, 5), (1000, 28416, 5), (60000, 28416, 5), (125000, 28416, 3), (0, 100, 4),
+                        (999, 1, 6), (28416 * 7, 28416, 8)]:
+        b = P.plan_blocks(S, wave, nb)
+        assert len(b) <= max(nb, 1)
+        if S == 0:
+            assert b == []
+            continue
+        assert b[0][0] == 0 and b[-1][1] == S
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        assert all(hi > lo for lo, hi in b)
+        assert all((hi - lo) % wave == 0 for lo, hi in b[:-1])         # only the last block is ragged
