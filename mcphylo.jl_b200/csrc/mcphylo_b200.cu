@@ -407,10 +407,21 @@ struct __align__(16) OpRec {
 };
 static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 
+// Where a CTA accumulates its branch-gradient sums.  K <= 3: directly in its accumulator row in
+// global memory with fire-and-forget RED.ADD.F64 (the row stays in L2); a shared-memory fp64 atomic
+// add is a compare-and-swap loop (~10 instructions, 38 % retries when the 8 warps of a CTA hit the
+// same branch).  Measured (profiles/r1_walk_notes.md): 5 % faster at K = 2, but 2.5-5 % SLOWER at
+// K = 4, where the kernel sits on a register knife-edge and the extra 64-bit row pointer spills.
+__host__ __device__ constexpr bool grad_in_l2(int K) { return K <= 3; }
+
 template <int K>
 struct WalkSmem {
     // dynamic shared memory carve-up (offsets in bytes)
-    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0; }
+    // branch-gradient accumulator of the CTA: in shared memory for K >= 4; for K <= 3 it is the CTA's
+    // row in global memory (see grad_in_l2)
+    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) {
+        return (want_grad && !grad_in_l2(K)) ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0;
+    }
     static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
     static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
     static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
@@ -455,6 +466,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     if (tile >= tile_end) return;
 
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
+    constexpr bool GL2 = grad_in_l2(K);
     int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
     double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
     OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
@@ -480,8 +492,10 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     while (tile < tile_end) {
         const TreeDev tr = p.trees[ti];
         const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
-        if (p.want_grad) {
-            for (int i = tid; i < tr.n_br; i += TW) s_acc[i] = 0.0;
+        // this CTA's gradient accumulator row for the tree (global memory, stays in L2)
+        double* const grow = p.rows + (long long)row * p.row_stride;
+        if (p.want_grad) {   // ordered before the first update by the barriers below
+            for (int i = tid; i < tr.n_br; i += TW) (GL2 ? grow : s_acc)[i] = 0.0;
         }
         long long e_total = 0;
         double logsum = 0.0;
@@ -793,9 +807,13 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             ga = fma(na, inv, ga);
                             gb = fma(nb, inv, gb);
                         }
-                        const double red = warp_pair_reduce(ga, gb, lane);
-                        if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
-                        else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
+                        const double red = warp_pair_reduce(ga, gb, lane);   // lane 0: sum of ga, lane 16: sum of gb
+                        if constexpr (GL2) {
+                            if ((lane & 15) == 0) atomicAdd(grow + ((lane >> 4) ? rb[j].b_br : rb[j].a_br), red);
+                        } else {
+                            if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
+                            else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
+                        }
 
                         // pre[child] = P^T q, only internal children have one
                         const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
@@ -846,9 +864,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             p.rows_ll[row].esum = es;
             p.rows_ll[row].logsum = ls;
         }
-        if (p.want_grad) {
-            double* dst = p.rows + (long long)row * p.row_stride;
-            for (int i = tid; i < tr.n_br; i += TW) dst[i] = s_acc[i];
+        if constexpr (!GL2) {
+            if (p.want_grad)
+                for (int i = tid; i < tr.n_br; i += TW) grow[i] = s_acc[i];
         }
         __syncthreads();
         ++row;
@@ -1652,7 +1670,7 @@ int launch_levels(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
     return 0;
 }
 size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
-    size_t acc = want_grad ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
+    const size_t acc = (want_grad && !grad_in_l2(K)) ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
     return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
            (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
 }
