@@ -223,6 +223,8 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL's banner / debug lines go to stderr: stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     w = make_workload(args.workload, args.sites)
     lo, hi = mcp.shard_bounds(w["S"], world, rank)
@@ -399,6 +401,8 @@ def run_batch(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL's banner / debug lines go to stderr: stdout carries exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n_taxa, S, K, R, tseed, dseed = WORKLOADS["cfg5"]
     if args.sites:
