@@ -97,6 +97,27 @@ def algorithmic_bytes(n_taxa, S, K, R, want_grad=True):
     return b_post + (b_pre if want_grad else 0)
 
 
+def init_nccl(local_rank):
+    """Process group + communicator creation with stdout pointed at stderr at the file-descriptor
+    level: NCCL prints its version banner to stdout (NCCL_DEBUG=VERSION on the bench boxes), and
+    stdout must carry exactly one JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        t = torch.zeros(1, device=f"cuda:{local_rank}")
+        dist.all_reduce(t)                      # forces communicator creation now
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class ClockSampler:
     """nvidia-smi style clock / throttle-reason sampling during the timed region (NVML)."""
 
@@ -223,9 +244,7 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's banner / debug lines go to stderr: stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        init_nccl(local_rank)
     w = make_workload(args.workload, args.sites)
     lo, hi = mcp.shard_bounds(w["S"], world, rank)
     t_gen = time.perf_counter()
@@ -401,9 +420,7 @@ def run_batch(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL's banner / debug lines go to stderr: stdout carries exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        init_nccl(local_rank)
     n_taxa, S, K, R, tseed, dseed = WORKLOADS["cfg5"]
     if args.sites:
         S = args.sites
