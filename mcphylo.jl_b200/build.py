@@ -10,7 +10,9 @@ SRC_DIR = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmcphylo_b200.so")
 SOURCES = ["mcphylo_b200.cu"]
-DEPS = ["mcphylo_b200.cu", "schedule.hpp", os.path.join("..", "..", "include", "mcphylo_b200.h")]
+DEPS = ["mcphylo_b200.cu", "schedule.hpp", "device_layout.cuh", "device_math.cuh", "kernel_tables.cuh",
+        "kernel_walk.cuh", "epilogue_prior.cuh", "kernel_levels.cuh", "kernel_generic.cuh", "kernel_finalize.cuh",
+        os.path.join("..", "..", "include", "mcphylo_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-cudart", "static"]

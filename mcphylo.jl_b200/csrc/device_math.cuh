@@ -1,0 +1,200 @@
+// device_math.cuh — per-thread arithmetic: partial-vector loads/stores, eigen-space products, power-of-two rescaling, reductions.
+// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+#pragma once
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// vector load/store helpers (K doubles per column)
+// --------------------------------------------------------------------------------------------
+// Partials: written and re-read by the SAME thread inside one kernel, so they must not go
+// through the non-coherent path; .cg keeps this streaming data out of L1.
+template <int K>
+__device__ __forceinline__ void ld_partial(const double* p, double (&v)[K]) {
+    if constexpr (K == 4) {
+        asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+    } else if constexpr (K == 2) {
+        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = __ldcg(p + k);
+    }
+}
+template <int K>
+__device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
+    if constexpr (K == 4) {
+        asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+    } else if constexpr (K == 2) {
+        asm volatile("st.global.cg.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) __stcg(p + k, v[k]);
+    }
+}
+
+// Identity moves the compiler cannot see through: a value passed through them is kept in a register
+// (or spilled as one word) instead of being RE-COMPUTED at every use.  ptxas otherwise rematerialises
+// the per-thread scratch base (blockIdx * scratch_per_cta + tid * K * 8, ~13 instructions) in front of
+// every partial load/store of the walk.
+__device__ __forceinline__ unsigned char* keep_ptr(unsigned char* p) {
+    asm volatile("mov.u64 %0, %0;" : "+l"(p));
+    return p;
+}
+__device__ __forceinline__ double keep_f64(double v) {
+    asm volatile("mov.f64 %0, %0;" : "+d"(v));
+    return v;
+}
+
+// L2 prefetch of a line the thread will read a few ops later (HBM -> L2 ahead of the demand load)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Model view: MOFS is the slot offset into c_model; with a compile-time 0 the constant operands
+// fold into the DFMA encodings.
+// DYN = false: the single model embedded in the kernel parameters; DYN = true: slot `ofs` of c_model.
+template <int K, bool DYN>
+struct ModelT {
+    const WalkParams& p;
+    int ofs;
+    __device__ __forceinline__ double U(int s, int i) const { return DYN ? c_model[ofs + s + K * i] : p.model[s + K * i]; }
+    __device__ __forceinline__ double Ui(int i, int j) const { return DYN ? c_model[ofs + K * K + i + K * j] : p.model[K * K + i + K * j]; }
+    __device__ __forceinline__ double pi(int k) const { return DYN ? c_model[ofs + 2 * K * K + k] : p.model[2 * K * K + k]; }
+    __device__ __forceinline__ double c(int r, int i) const {
+        return DYN ? c_model[ofs + 2 * K * K + K + r * K + i] : p.model[2 * K * K + K + r * K + i];
+    }
+};
+
+// ---- eigen-space products for C columns at once (column index innermost, so one constant /
+// uniform-register operand feeds C independent DFMAs) ----
+//
+// Transitions are applied as  P L = L + U (em1 * (Uinv L)),  em1_i = expm1(mu t D_i r),  not as
+// U (e * (Uinv L)): the latter is accurate only relative to |L|_max, and a partial likelihood vector
+// routinely holds components 1e-20 of its maximum that still decide the likelihood of a site further
+// up (a mismatch selects exactly that component).  The reference multiplies by an explicit
+// non-negative P, which is component-wise accurate; adding the (accurately formed) deviation P - I
+// onto L keeps that property, costs no extra instruction (the leading multiply becomes an FMA onto
+// L), and makes identity branches exact.
+//
+// z[c] = em1 * w[c],  w[c] = Uinv L[c];  WD also returns zd[c] = de * w[c]  (the eigen-coordinates of dP L)
+template <int K, int C, bool WD, class M>
+__device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K], const double (&em1)[K], const double* de,
+                                            double (&z)[C][K], double (&zd)[C][K]) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double w[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = m.Ui(i, 0) * L[c][0];
+#pragma unroll
+        for (int j = 1; j < K; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = fma(m.Ui(i, j), L[c][j], w[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            z[c][i] = em1[i] * w[c];
+            if constexpr (WD) zd[c][i] = de[i] * w[c];
+        }
+    }
+}
+// out[c] = base[c] + U z[c]
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], const double (&base)[C][K], double (&out)[C][K]) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, 0), z[c][0], base[c][s]);
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
+    }
+}
+// out[c] = U z[c]
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_expand0(const M& m, const double (&z)[C][K], double (&out)[C][K]) {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][s] = m.U(s, 0) * z[c][0];
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
+    }
+}
+// out[c] = P^T q[c] = q[c] + Uinv^T (em1 * (U^T q[c]))
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][K], const double (&em1)[K], double (&out)[C][K]) {
+    double z[C][K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double w[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = m.U(0, i) * q[c][0];
+#pragma unroll
+        for (int s = 1; s < K; ++s)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = fma(m.U(s, i), q[c][s], w[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) z[c][i] = em1[i] * w[c];
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(0, j), z[c][0], q[c][j]);
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(i, j), z[c][i], out[c][j]);
+    }
+}
+
+// Multiply a column by the exact power of two that brings its largest magnitude into [1,2);
+// returns the removed binary exponent.  Works on the exponent fields with integer ops (fp64 has no
+// native max instruction; fmax() costs ~10 instructions).  Zero / denormal / non-finite maxima are
+// left alone.
+template <int K>
+__device__ __forceinline__ int rescale_pow2(double (&v)[K]) {
+    unsigned m = (unsigned)__double2hiint(v[0]) & 0x7fffffffu;
+#pragma unroll
+    for (int k = 1; k < K; ++k) m = max(m, (unsigned)__double2hiint(v[k]) & 0x7fffffffu);
+    const int e = (int)(m >> 20);
+    if (e == 0 || e == 0x7ff) return 0;
+    const double sc = __hiloint2double((2046 - e) << 20, 0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] *= sc;
+    return e - 1023;
+}
+
+// 1/x for a positive, normal x: hardware seed + two Newton steps (relative error ~1e-16; the
+// quotient only scales a gradient term whose tolerance is 1e-8).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+
+// lane 0 ends with sum(va) over the warp, lane 16 with sum(vb)
+__device__ __forceinline__ double warp_pair_reduce(double va, double vb, int lane) {
+    const bool upper = (lane & 16) != 0;
+    double send = upper ? va : vb;
+    double keep = upper ? vb : va;
+    double v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+}  // namespace

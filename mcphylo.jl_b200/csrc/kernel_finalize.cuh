@@ -1,0 +1,53 @@
+// kernel_finalize.cuh — kernel 3: fixed-order reduction of the accumulator rows.
+// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+#pragma once
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// kernel 3: fixed-order reduction of the accumulator rows -> [logL, grad] per tree
+// --------------------------------------------------------------------------------------------
+constexpr int FIN_J = 32, FIN_G = 8;   // outputs per block x row groups (blockDim = 32 x 8)
+__global__ void finalize_results(const TreeDev* __restrict__ trees, const double* __restrict__ rows,
+                                 long long row_stride, const LLRow* __restrict__ rows_ll,
+                                 double* __restrict__ out, int want_grad, const double* __restrict__ dyn, int K, int R) {
+    // Block = 32 consecutive outputs x 8 row groups: group g sums rows row_lo + g, row_lo + g + 8, ...
+    // (a warp reads 32 consecutive doubles of one row), the 8 partial sums meet in shared memory and
+    // are added in group order: fixed order, 8x shorter dependent chain than one thread per output.
+    __shared__ double s_red[2 * FIN_J * FIN_G];
+    __shared__ double s_g[FIN_G][FIN_J];
+    __shared__ long long s_es[FIN_G];
+    const TreeDev tr = trees[blockIdx.y];
+    if ((long long)blockIdx.x * FIN_J >= tr.NN) return;   // whole block idle (batch of unequal trees)
+    const int jl = threadIdx.x, g = threadIdx.y, tid = g * FIN_J + jl;
+    const double* d = dyn + tr.dyn_off;
+    const double* hdr = d + dyn_prior(tr.NN, K, R);
+    const bool prior = hdr[0] != 0.0;
+    PriorSums ps{0.0, 0.0};
+    if (prior) ps = prior_block_sums(d + dyn_blv(tr.NN), hdr + 4, tr.NN - 1, tid, FIN_J * FIN_G, s_red);
+    const int j = blockIdx.x * FIN_J + jl;
+    double v = 0.0;
+    long long es = 0;
+    if (j < tr.NN) {
+        if (j == 0) {
+            for (int rw = tr.row_lo + g; rw < tr.row_hi; rw += FIN_G) { es += rows_ll[rw].esum; v += rows_ll[rw].logsum; }
+        } else if (want_grad) {
+            for (int rw = tr.row_lo + g; rw < tr.row_hi; rw += FIN_G) v += rows[(long long)rw * row_stride + (j - 1)];
+        }
+    }
+    s_g[g][jl] = v;
+    if (j == 0) s_es[g] = es;
+    __syncthreads();
+    if (g != 0 || j >= tr.NN) return;
+    v = 0.0;
+    for (int gg = 0; gg < FIN_G; ++gg) v += s_g[gg][jl];
+    if (j == 0) {
+        es = 0;
+        for (int gg = 0; gg < FIN_G; ++gg) es += s_es[gg];
+        v += (double)es * 0.693147180559945309417232121458;
+    }
+    if (prior && (j == 0 || want_grad)) v += prior_term(hdr, d + dyn_blv(tr.NN), hdr + 4, ps, j);
+    out[tr.out_off + j] = v;
+}
+
+}  // namespace

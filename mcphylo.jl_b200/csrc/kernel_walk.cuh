@@ -1,0 +1,505 @@
+// kernel_walk.cuh — kernel 2: the persistent fused walk (post pass + gradient pass), one thread per column.
+// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+#pragma once
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// kernel 2: the fused walk.  grid = persistent CTAs, each takes a contiguous range of column
+// tiles; a tile = blockDim.x columns of one rate category of one tree.
+//
+// Per-op inputs that are uniform over the tile or byte-sized per column are staged in shared
+// memory CH ops at a time with cp.async, one chunk ahead of the compute:
+//   sdesc  3 x CH op descriptors (ring of 3: descriptors must be resident one chunk before the
+//          data they describe can be requested)
+//   se     2 x CH x 2 x 2K doubles: (em1, de) eigen-coefficient vectors of INTERNAL children
+//   scode  2 x CH x 2 x TW bytes: the state codes of LEAF children for the tile's columns
+// so the only global accesses on the per-op critical path are the thread's own partials and the
+// leaf-table gathers.  One __syncthreads per chunk.
+// --------------------------------------------------------------------------------------------
+constexpr int CH = 16;
+
+// Per-op record derived by the staging threads from the raw descriptor (schedule.hpp): everything the
+// compute threads need as ready-to-add byte offsets, so no warp repeats the uniform address math.
+//   xa / xb  LEAF child: byte offset (from the branch-table base) of the child's P columns for this
+//            tile's rate; MEM child: byte offset (from the thread's scratch base) of its stored partial
+//   post: y0 = where to store the result          pre: y0 = pre[mother] on the LIFO, y1 / y2 = where
+//                                                       pre[a] / pre[b] are pushed
+// Offsets are 32-bit: a CTA's scratch region and one tree's branch table are far below 4 GB (checked
+// on the host).
+struct __align__(16) OpRec {
+    int flags;
+    unsigned xa, xb, y0;       // first half: needed at the start of the op
+    int a_br, b_br;
+    unsigned y1, y2;           // second half: needed at its end
+};
+static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
+
+// Where a CTA accumulates its branch-gradient sums.  K <= 3: directly in its accumulator row in
+// global memory with fire-and-forget RED.ADD.F64 (the row stays in L2); a shared-memory fp64 atomic
+// add is a compare-and-swap loop (~10 instructions, 38 % retries when the 8 warps of a CTA hit the
+// same branch).  Measured (profiles/r1_walk_notes.md): 5 % faster at K = 2, but 2.5-5 % SLOWER at
+// K = 4, where the kernel sits on a register knife-edge and the extra 64-bit row pointer spills.
+__host__ __device__ constexpr bool grad_in_l2(int K) { return K <= 3; }
+
+template <int K>
+struct WalkSmem {
+    // dynamic shared memory carve-up (offsets in bytes)
+    // branch-gradient accumulator of the CTA: in shared memory for K >= 4; for K <= 3 it is the CTA's
+    // row in global memory (see grad_in_l2)
+    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) {
+        return (want_grad && !grad_in_l2(K)) ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0;
+    }
+    static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
+    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
+    static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
+    static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
+    // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
+    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
+    static __host__ __device__ size_t total(int n_br, int want_grad, int TW) {
+        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
+    }
+};
+
+// 3 resident CTAs of 256 threads per SM (<= 80 registers): the walk is latency-bound, 24 warps
+// with a few spills beat 16 warps without (profiles/r1_walk_notes.md).
+#ifndef MCP_WALK_MIN_BLOCKS
+#define MCP_WALK_MIN_BLOCKS 3
+#endif
+// Heavier per-thread state (K * columns per thread > 4 doubles per vector) gets 2 CTAs per SM
+// (<= 128 registers) instead of 3.
+#ifndef MCP_WALK_MIN_BLOCKS2
+#define MCP_WALK_MIN_BLOCKS2 2
+#endif
+// SSCR = true keeps the CTA's partials scratch in SHARED memory instead of HBM: the latency path for
+// small problems (MCMC-sized trees), where a lone warp would otherwise wait an L2 round trip for
+// every partial it has just written.
+template <int K, int CPT, bool DYN_MODEL, bool SSCR>
+#ifndef MCP_WALK_MAXT
+#define MCP_WALK_MAXT 256
+#endif
+#ifndef MCP_PREFETCH_DIST
+#define MCP_PREFETCH_DIST 0   // L2 prefetch hints for gradient-pass operands: measured slower (22.3 vs 21.0 ms), kept for experiments
+#endif
+__global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_e[8];
+    __shared__ double s_l[8];
+
+    const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int TS = TW * CPT;                          // sites per tile; column c of a thread = site0 + c*TW + tid
+    const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
+    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
+    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
+    if (tile >= tile_end) return;
+
+    double* const s_acc = reinterpret_cast<double*>(smem_raw);
+    constexpr bool GL2 = grad_in_l2(K);
+    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
+    double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
+    OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
+    double* const stab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes());
+    unsigned char* const scode = reinterpret_cast<unsigned char*>(stab) + WalkSmem<K>::tab_bytes();
+    constexpr int KK1 = K * (K + 1);                  // doubles of one leaf table (P or dP columns)
+
+    // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state]; all
+    // slot / LIFO offsets in the records are byte offsets from here
+    unsigned char* const scr = SSCR
+        ? scode + WalkSmem<K>::code_bytes(TS) + (size_t)tid * K * 8
+        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K));
+    const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
+    const unsigned slot_bytes = col_bytes * CPT;
+    const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
+    int row = p.cta_row_base[blockIdx.x];
+    const int R = p.R;
+    constexpr int BT = 2 * K + 2 * K * (K + 1);
+
+    int ti = 0;
+    while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
+
+    while (tile < tile_end) {
+        const TreeDev tr = p.trees[ti];
+        const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
+        // this CTA's gradient accumulator row for the tree (global memory, stays in L2)
+        double* const grow = p.rows + (long long)row * p.row_stride;
+        if (p.want_grad) {   // ordered before the first update by the barriers below
+            for (int i = tid; i < tr.n_br; i += TW) (GL2 ? grow : s_acc)[i] = 0.0;
+        }
+        long long e_total = 0;
+        double logsum = 0.0;
+        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
+        const int4* const post_ops = p.ops + 2 * tr.post_off;
+        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
+
+        for (; tile < tree_tile_end; ++tile) {
+            const int local = tile - tr.tile_begin;
+            const int r = local / tr.tiles_per_rate;
+            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TS;
+            bool valid[CPT];
+            double vmask[CPT];                 // 1.0 for real columns, 0.0 for the padding of a ragged tile
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                valid[c] = site0 + c * TW + tid < tr.S;
+                vmask[c] = keep_f64(valid[c] ? 1.0 : 0.0);
+            }
+            const unsigned char* const codes0 = tr.codes + site0;
+            // this tree's branch table at (branch 0, rate r); record offsets are relative to it
+            const unsigned char* const btab_b = reinterpret_cast<const unsigned char*>(p.btab + tr.btab_off + (long long)r * BT);
+            const unsigned br_bytes = (unsigned)R * BT * 8;
+
+            // ---- chunk staging (all threads of the CTA) ----
+            auto stage_desc = [&](const int4* ops, int n_ops, int c) {
+                const int base = c * CH, cnt = min(CH, n_ops - base);
+                int4* dst = sdesc + (c % 3) * (CH * 2);
+                for (int i = tid; i < cnt * 2; i += TW) cp_async16(dst + i, ops + 2 * base + i);
+            };
+            // Copies e vectors / leaf codes of chunk c and derives the per-op records (byte offsets),
+            // once per CTA instead of once per warp.  `pre` selects the pre-program field meaning.
+            auto stage_data = [&](int n_ops, int c, bool pre) {
+                const int base = c * CH, cnt = min(CH, n_ops - base);
+                const int4* d = sdesc + (c % 3) * (CH * 2);
+                double* eb = se + (c & 1) * (CH * 2 * 2 * K);
+                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS);
+                OpRec* rb = srec + (c & 1) * CH;
+                double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
+                const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
+                const int tab_doubles = pre ? 2 * KK1 : KK1; // P columns (+ dP columns in the gradient pass)
+                const int tpieces = (tab_doubles + 1) / 2;   // 16-byte pieces of one leaf table
+                const int epieces = K;                       // em1 and de: 2K doubles = K 16-byte pieces
+                const int per_child = pieces + tpieces > epieces ? pieces + tpieces : epieces;
+                for (int w = tid; w < cnt * 2 * per_child; w += TW) {
+                    const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
+                    const int4 o0 = d[2 * j];
+                    const int fl = d[2 * j + 1].y;
+                    const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
+                    const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
+                    const double* bsrc = reinterpret_cast<const double*>(btab_b + (unsigned)br * br_bytes);
+                    if (kind == mcp::OPK_LEAF) {
+                        if (piece < pieces) {
+                            unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TS + piece * 16;
+                            if (src >= 0) cp_async16(dstp, codes0 + (long long)src * tr.code_stride + piece * 16);
+                            else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
+                        } else if (piece < pieces + tpieces) {
+                            const int tp = piece - pieces;
+                            double* dstp = tb + (size_t)(j * 2 + ch) * 2 * KK1 + tp * 2;
+                            const double* srcp = bsrc + 2 * K + tp * 2;
+                            if constexpr ((K * 8) % 16 == 0) {
+                                cp_async16(dstp, srcp);
+                            } else {
+                                dstp[0] = __ldg(srcp);
+                                if (tp * 2 + 1 < tab_doubles) dstp[1] = __ldg(srcp + 1);
+                            }
+                        }
+                    } else if (piece < epieces) {
+                        // 2K doubles = K 16-byte pieces; entries are 16-byte aligned (bt_size is even)
+                        cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * 2 * K) + piece * 16,
+                                   reinterpret_cast<const unsigned char*>(bsrc) + piece * 16);
+                    }
+                }
+                for (int j = tid; j < cnt; j += TW) {
+                    const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
+                    const int fl = o1.y, ka = fl & 3, kb = (fl >> 2) & 3;
+                    OpRec rec;
+                    rec.flags = fl;
+                    rec.a_br = o0.y;
+                    rec.b_br = o0.w;
+                    rec.xa = ka == mcp::OPK_LEAF ? (unsigned)o0.y * br_bytes + 2 * K * 8 : (unsigned)o0.x * slot_bytes;
+                    rec.xb = kb == mcp::OPK_LEAF ? (unsigned)o0.w * br_bytes + 2 * K * 8 : (unsigned)o0.z * slot_bytes;
+                    if (pre) {
+                        rec.y0 = stack_base + (unsigned)o1.x * slot_bytes;     // pre[mother] on the LIFO
+                        rec.y1 = stack_base + (unsigned)o1.z * slot_bytes;     // where pre[a] is pushed
+                        rec.y2 = stack_base + (unsigned)o1.w * slot_bytes;     // where pre[b] is pushed
+                    } else {
+                        rec.y0 = (unsigned)o1.x * slot_bytes;                  // where the result is stored
+                        rec.y1 = 0;
+                        rec.y2 = 0;
+                    }
+                    rb[j] = rec;
+                }
+            };
+            auto prologue = [&](const int4* ops, int n_ops, bool pre) {
+                __syncthreads();                              // previous pass / tile done with the buffers
+                stage_desc(ops, n_ops, 0);
+                if (n_ops > CH) stage_desc(ops, n_ops, 1);
+                cp_async_commit();
+                cp_async_wait_all();
+                __syncthreads();
+                stage_data(n_ops, 0, pre);
+                cp_async_commit();
+            };
+            auto chunk_boundary = [&](const int4* ops, int n_ops, int c, int n_chunks, bool pre) {
+                cp_async_wait_all();
+                __syncthreads();                              // chunk c data + descriptors c, c+1 visible
+                if (c + 1 < n_chunks) stage_data(n_ops, c + 1, pre);
+                if (c + 2 < n_chunks) stage_desc(ops, n_ops, c + 2);
+                cp_async_commit();
+            };
+            auto ld_cols = [&](unsigned off, double (&v)[CPT][K]) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    if constexpr (SSCR) {
+                        const double* src = reinterpret_cast<const double*>(scr + off + c * col_bytes);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) v[c][k] = src[k];
+                    } else {
+                        ld_partial<K>(reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
+                    }
+                }
+            };
+            auto st_cols = [&](unsigned off, const double (&v)[CPT][K]) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    if constexpr (SSCR) {
+                        double* dst = reinterpret_cast<double*>(scr + off + c * col_bytes);
+#pragma unroll
+                        for (int k = 0; k < K; ++k) dst[k] = v[c][k];
+                    } else {
+                        st_partial<K>(reinterpret_cast<double*>(scr + off + c * col_bytes), v[c]);
+                    }
+                }
+            };
+
+            // ------------------------------ post pass ------------------------------
+            double cur[CPT][K];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c)
+#pragma unroll
+                for (int k = 0; k < K; ++k) cur[c][k] = 1.0;
+            int e_col[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) e_col[c] = 0;
+            {
+                const int n_post = tr.n_post, n_chunks = (n_post + CH - 1) / CH;
+                prologue(post_ops, n_post, false);
+                for (int c = 0; c < n_chunks; ++c) {
+                    chunk_boundary(post_ops, n_post, c, n_chunks, false);
+                    const OpRec* rb = srec + (c & 1) * CH;
+                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
+                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
+                    const int cnt = min(CH, n_post - c * CH);
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
+                        const int flags = (int)rh.x, ka = flags & 3, kb = (flags >> 2) & 3;
+                        // stored operand (at most one per op) first: its latency overlaps the rest
+                        double Lm[CPT][K];
+                        if (ka == mcp::OPK_MEM) ld_cols(rh.y, Lm);
+                        else if (kb == mcp::OPK_MEM) ld_cols(rh.z, Lm);
+                        double Da[CPT][K], Db[CPT][K];
+                        if (ka == mcp::OPK_LEAF) {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
+                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) Da[cc][k] = t[k];
+                            }
+                        } else {
+                            double e[K], z[CPT][K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * 2 * K + k];
+                            if (ka == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Da); }
+                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Da); }
+                        }
+                        if (kb == mcp::OPK_LEAF) {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
+                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) Db[cc][k] = t[k];
+                            }
+                        } else {
+                            double e[K], z[CPT][K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * 2 * K + k];
+                            if (kb == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Db); }
+                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Db); }
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < CPT; ++cc) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) cur[cc][k] = Da[cc][k] * Db[cc][k];
+                            e_col[cc] += rescale_pow2<K>(cur[cc]);
+                        }
+                        if (flags & mcp::POST_STORE) st_cols(rh.w, cur);
+                    }
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < CPT; ++cc) {
+                double rootv = mdl.pi(0) * cur[cc][0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[cc][k], rootv);
+                if (valid[cc]) {
+                    logsum += log(rootv);
+                    e_total += e_col[cc];
+                }
+            }
+
+            // ------------------------------ gradient pass ------------------------------
+            if (p.want_grad) {
+                const int n_pre = tr.n_pre, n_chunks = (n_pre + CH - 1) / CH;
+                prologue(pre_ops, n_pre, true);
+                for (int c = 0; c < n_chunks; ++c) {
+                    chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
+                    const OpRec* rb = srec + (c & 1) * CH;
+                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
+                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
+                    const int cnt = min(CH, n_pre - c * CH);
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
+                        const int flags = (int)rh.x;
+                        const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
+                        if constexpr (!SSCR && MCP_PREFETCH_DIST > 0) {
+                            // the children partials of a later family were written in the post pass, long ago:
+                            // pull them from HBM into L2 now (one request per 128-byte line)
+                            if (j + MCP_PREFETCH_DIST < cnt && (lane * K * 8) % 128 == 0) {
+                                const uint4 rf = *reinterpret_cast<const uint4*>(rb + j + MCP_PREFETCH_DIST);
+                                if (((int)rf.x & 3) == mcp::OPK_MEM) {
+#pragma unroll
+                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.y + cc * col_bytes);
+                                }
+                                if ((((int)rf.x >> 2) & 3) == mcp::OPK_MEM) {
+#pragma unroll
+                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.z + cc * col_bytes);
+                                }
+                            }
+                        }
+                        const int mk = (flags >> 8) & 3;
+                        // all stored operands of the family are requested up front
+                        double pm[CPT][K], La[CPT][K], Lb[CPT][K];
+                        if (mk == mcp::PREM_STACK) ld_cols(rh.w, pm);
+                        if (ai) ld_cols(rh.y, La);
+                        if (bi) ld_cols(rh.z, Lb);
+                        if (mk == mcp::PREM_ROOT) {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) pm[cc][k] = mdl.pi(k);
+                        } else if (mk == mcp::PREM_REG) {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) pm[cc][k] = cur[cc][k];
+                        }
+                        double ea[K], ebv[K];
+                        double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
+                        if (ai) {
+                            double z[CPT][K], zd[CPT][K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * 2 * K + k];
+                            eig_project<K, CPT, true>(mdl, La, ea, eb + (j * 2 + 0) * 2 * K + K, z, zd);
+                            eig_expand<K, CPT>(mdl, z, La, Da);
+                            eig_expand0<K, CPT>(mdl, zd, Ya);
+                        } else {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
+                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) { Da[cc][k] = t[k]; Ya[cc][k] = t[KK1 + k]; }
+                            }
+                        }
+                        if (bi) {
+                            double z[CPT][K], zd[CPT][K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * 2 * K + k];
+                            eig_project<K, CPT, true>(mdl, Lb, ebv, eb + (j * 2 + 1) * 2 * K + K, z, zd);
+                            eig_expand<K, CPT>(mdl, z, Lb, Db);
+                            eig_expand0<K, CPT>(mdl, zd, Yb);
+                        } else {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
+                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) { Db[cc][k] = t[k]; Yb[cc][k] = t[KK1 + k]; }
+                            }
+                        }
+                        double qa[CPT][K], qb[CPT][K];
+                        double ga = 0.0, gb = 0.0;
+#pragma unroll
+                        for (int cc = 0; cc < CPT; ++cc) {
+                            double den = 0.0, na = 0.0, nb = 0.0;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                qa[cc][k] = pm[cc][k] * Db[cc][k];
+                                qb[cc][k] = pm[cc][k] * Da[cc][k];
+                                den = fma(qa[cc][k], Da[cc][k], den);
+                                na = fma(qa[cc][k], Ya[cc][k], na);
+                                nb = fma(qb[cc][k], Yb[cc][k], nb);
+                            }
+                            const double inv = fast_rcp(den) * vmask[cc];
+                            ga = fma(na, inv, ga);
+                            gb = fma(nb, inv, gb);
+                        }
+                        const double red = warp_pair_reduce(ga, gb, lane);   // lane 0: sum of ga, lane 16: sum of gb
+                        if constexpr (GL2) {
+                            if ((lane & 15) == 0) atomicAdd(grow + ((lane >> 4) ? rb[j].b_br : rb[j].a_br), red);
+                        } else {
+                            if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
+                            else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
+                        }
+
+                        // pre[child] = P^T q, only internal children have one
+                        const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
+                        if (a_out != mcp::OUT_NONE) {
+                            double pa[CPT][K];
+                            eig_transposed<K, CPT>(mdl, qa, ea, pa);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pa[cc]);
+                            if (a_out == mcp::OUT_KEEP) {
+#pragma unroll
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = pa[cc][k];
+                            } else {
+                                st_cols(rb[j].y1, pa);
+                            }
+                        }
+                        if (b_out != mcp::OUT_NONE) {
+                            double pb[CPT][K];
+                            eig_transposed<K, CPT>(mdl, qb, ebv, pb);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pb[cc]);
+                            if (b_out == mcp::OUT_KEEP) {
+#pragma unroll
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = pb[cc][k];
+                            } else {
+                                st_cols(rb[j].y2, pb);
+                            }
+                        }
+                    }
+                }
+            }
+        }  // tiles of this tree
+
+        // ---- flush this CTA's sums for the tree into its accumulator row ----
+        for (int off = 16; off > 0; off >>= 1) {
+            e_total += __shfl_xor_sync(0xffffffffu, e_total, off);
+            logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
+        }
+        if (lane == 0) { s_e[warp] = e_total; s_l[warp] = logsum; }
+        __syncthreads();
+        if (tid == 0) {
+            long long es = 0;
+            double ls = 0.0;
+            for (int w = 0; w < (TW + 31) / 32; ++w) { es += s_e[w]; ls += s_l[w]; }
+            p.rows_ll[row].esum = es;
+            p.rows_ll[row].logsum = ls;
+        }
+        if constexpr (!GL2) {
+            if (p.want_grad)
+                for (int i = tid; i < tr.n_br; i += TW) grow[i] = s_acc[i];
+        }
+        __syncthreads();
+        ++row;
+        ++ti;
+    }
+}
+
+}  // namespace

@@ -32,1486 +32,16 @@
 #include <string>
 #include <vector>
 
+#include "device_layout.cuh"
+#include "device_math.cuh"
+#include "kernel_tables.cuh"
+#include "kernel_walk.cuh"
+#include "epilogue_prior.cuh"
+#include "kernel_levels.cuh"
+#include "kernel_generic.cuh"
+#include "kernel_finalize.cuh"
+
 namespace {
-
-using mcp::PostOp;
-using mcp::PreOp;
-using mcp::Schedule;
-
-// --------------------------------------------------------------------------------------------
-// device-side descriptors
-// --------------------------------------------------------------------------------------------
-struct TreeDev {
-    long long post_off;      // op index (32-byte units) of this tree's post program
-    long long pre_off;       // ... pre program
-    long long btab_off;      // doubles, into the branch-table buffer
-    long long dyn_off;       // doubles, into the per-evaluation parameter buffer
-    long long out_off;       // doubles, into the result buffer ([logL, grad(NN-1)] per tree)
-    const unsigned char* codes;  // (rows, code_stride) state codes of this tree's alignment
-    long long S;             // sites
-    long long code_stride;
-    int n_post, n_pre;
-    int NN, n_br;            // real nodes; rows of the branch table (device nodes)
-    int tile_begin, tiles_per_rate;
-    int row_lo, row_hi;      // accumulator rows [lo, hi) holding this tree's partial sums
-    int lvl_off, n_post_lvl, n_pre_lvl;   // level-ordered program: offsets into WalkParams::levels
-    int n_rows;              // leaf rows of the alignment
-};
-
-struct LLRow {
-    long long esum;  // sum of binary exponents removed by rescaling (exact)
-    double logsum;   // sum of log(pi . L_root)
-};
-
-struct WalkParams {
-    const TreeDev* trees;
-    const int4* ops;
-    const double* btab;
-    const double* dyn;
-    double* scratch;
-    long long scratch_per_cta;  // doubles
-    double* rows;               // [row][row_stride] gradient partial sums
-    LLRow* rows_ll;
-    const int* cta_row_base;
-    const int* levels;          // level offsets of the level-ordered programs (small-tree kernel)
-    double* out;                // small-tree kernel: [logL, grad] per tree, device or pinned host memory
-    unsigned int* done_counter; // small-tree kernel: CTAs finished (the last one reduces the rows)
-    long long row_stride;
-    int n_slots, n_stack;
-    int n_tiles, T, R, want_grad;
-    int max_br;
-    int max_rows;               // largest number of leaf rows in the batch
-    // Substitution-model constants when the whole batch shares ONE model (the common case): kernel
-    // parameters live in constant bank 0, so they reach the FP64 pipe as uniform operands without
-    // a separate host-to-device copy.  Layout as in c_model (below).
-    double model[176];
-};
-
-// per-tree layout of the per-evaluation parameter block (offsets in doubles from dyn_off)
-__host__ __device__ inline long long dyn_blv(int) { return 0; }
-__host__ __device__ inline long long dyn_U(int NN) { return NN - 1; }
-__host__ __device__ inline long long dyn_D(int NN, int K) { return NN - 1 + (long long)K * K; }
-__host__ __device__ inline long long dyn_Uinv(int NN, int K) { return NN - 1 + (long long)K * K + K; }
-__host__ __device__ inline long long dyn_mu(int NN, int K) { return NN - 1 + 2LL * K * K + K; }
-__host__ __device__ inline long long dyn_rates(int NN, int K) { return NN + 2LL * K * K + K; }
-__host__ __device__ inline long long dyn_pi(int NN, int K, int R) { return NN + 2LL * K * K + K + R; }
-__host__ __device__ inline long long dyn_slot(int NN, int K, int R) { return NN + 2LL * K * K + 2LL * K + R; }
-// branch-length prior (fused posterior epilogue, mcp_eval_posterior): 4 header doubles
-// [enabled, c0, beta, k4] and NN-1 per-branch weights w_j, for the prior written as
-//   log p(t) = c0 - beta * T + sum_j w_j log t_j + k4 log T,   T = sum_j t_j
-__host__ __device__ inline long long dyn_prior(int NN, int K, int R) { return NN + 2LL * K * K + 2LL * K + R + 1; }
-__host__ __device__ inline long long dyn_size(int NN, int K, int R) {
-    long long n = dyn_prior(NN, K, R) + 4 + (NN - 1);
-    return (n + 3) & ~3LL;  // keep every tree's block 32-byte aligned
-}
-// Branch table, one entry per (device branch, rate category), BT(K) doubles:
-//   [0, K)                    em1_i = expm1(mu * t * D_i * rate) (internal children: P = I + U diag(em1) Uinv)
-//   [K, 2K)                   de_i = D_i mu rate * exp(mu t D_i rate)  (internal children: dP/dt = U diag(de) Uinv)
-//   [2K, 2K + K*(K+1))        P columns 0..K for LEAF children: column j = P[:, j], column K = row sums
-//                             (= P * all-ones leaf); each column holds the K parent-state entries
-//   [2K + K*(K+1), 2K + 2K(K+1)) dP/dt columns, same layout
-__host__ __device__ inline int bt_size(int K) { return 2 * K + 2 * K * (K + 1); }
-
-// Model constants of the evaluation, read as CONSTANT-BANK operands (warp-uniform: no per-lane
-// register delivery, DFMA takes them directly).  One slot per distinct substitution model in the
-// batch.  Slot layout (doubles): U (K*K col-major) | Uinv (K*K col-major) | pi (K) | c[r][i] =
-// D_i * mu * rate_r (R*K).
-constexpr int MODEL_SLOT = 256;                 // doubles per slot
-constexpr int MODEL_SLOTS = 32;                 // 64 KB of constant memory
-constexpr int MAX_RATES = 16;
-__constant__ double c_model[MODEL_SLOT * MODEL_SLOTS];
-
-// --------------------------------------------------------------------------------------------
-// vector load/store helpers (K doubles per column)
-// --------------------------------------------------------------------------------------------
-// Partials: written and re-read by the SAME thread inside one kernel, so they must not go
-// through the non-coherent path; .cg keeps this streaming data out of L1.
-template <int K>
-__device__ __forceinline__ void ld_partial(const double* p, double (&v)[K]) {
-    if constexpr (K == 4) {
-        asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
-                     : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
-    } else if constexpr (K == 2) {
-        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p) : "memory");
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) v[k] = __ldcg(p + k);
-    }
-}
-template <int K>
-__device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
-    if constexpr (K == 4) {
-        asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};"
-                     :: "l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
-    } else if constexpr (K == 2) {
-        asm volatile("st.global.cg.v2.f64 [%0], {%1,%2};" :: "l"(p), "d"(v[0]), "d"(v[1]) : "memory");
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) __stcg(p + k, v[k]);
-    }
-}
-
-// Identity moves the compiler cannot see through: a value passed through them is kept in a register
-// (or spilled as one word) instead of being RE-COMPUTED at every use.  ptxas otherwise rematerialises
-// the per-thread scratch base (blockIdx * scratch_per_cta + tid * K * 8, ~13 instructions) in front of
-// every partial load/store of the walk.
-__device__ __forceinline__ unsigned char* keep_ptr(unsigned char* p) {
-    asm volatile("mov.u64 %0, %0;" : "+l"(p));
-    return p;
-}
-__device__ __forceinline__ double keep_f64(double v) {
-    asm volatile("mov.f64 %0, %0;" : "+d"(v));
-    return v;
-}
-
-// L2 prefetch of a line the thread will read a few ops later (HBM -> L2 ahead of the demand load)
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// Model view: MOFS is the slot offset into c_model; with a compile-time 0 the constant operands
-// fold into the DFMA encodings.
-// DYN = false: the single model embedded in the kernel parameters; DYN = true: slot `ofs` of c_model.
-template <int K, bool DYN>
-struct ModelT {
-    const WalkParams& p;
-    int ofs;
-    __device__ __forceinline__ double U(int s, int i) const { return DYN ? c_model[ofs + s + K * i] : p.model[s + K * i]; }
-    __device__ __forceinline__ double Ui(int i, int j) const { return DYN ? c_model[ofs + K * K + i + K * j] : p.model[K * K + i + K * j]; }
-    __device__ __forceinline__ double pi(int k) const { return DYN ? c_model[ofs + 2 * K * K + k] : p.model[2 * K * K + k]; }
-    __device__ __forceinline__ double c(int r, int i) const {
-        return DYN ? c_model[ofs + 2 * K * K + K + r * K + i] : p.model[2 * K * K + K + r * K + i];
-    }
-};
-
-// ---- eigen-space products for C columns at once (column index innermost, so one constant /
-// uniform-register operand feeds C independent DFMAs) ----
-//
-// Transitions are applied as  P L = L + U (em1 * (Uinv L)),  em1_i = expm1(mu t D_i r),  not as
-// U (e * (Uinv L)): the latter is accurate only relative to |L|_max, and a partial likelihood vector
-// routinely holds components 1e-20 of its maximum that still decide the likelihood of a site further
-// up (a mismatch selects exactly that component).  The reference multiplies by an explicit
-// non-negative P, which is component-wise accurate; adding the (accurately formed) deviation P - I
-// onto L keeps that property, costs no extra instruction (the leading multiply becomes an FMA onto
-// L), and makes identity branches exact.
-//
-// z[c] = em1 * w[c],  w[c] = Uinv L[c];  WD also returns zd[c] = de * w[c]  (the eigen-coordinates of dP L)
-template <int K, int C, bool WD, class M>
-__device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K], const double (&em1)[K], const double* de,
-                                            double (&z)[C][K], double (&zd)[C][K]) {
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        double w[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) w[c] = m.Ui(i, 0) * L[c][0];
-#pragma unroll
-        for (int j = 1; j < K; ++j)
-#pragma unroll
-            for (int c = 0; c < C; ++c) w[c] = fma(m.Ui(i, j), L[c][j], w[c]);
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            z[c][i] = em1[i] * w[c];
-            if constexpr (WD) zd[c][i] = de[i] * w[c];
-        }
-    }
-}
-// out[c] = base[c] + U z[c]
-template <int K, int C, class M>
-__device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], const double (&base)[C][K], double (&out)[C][K]) {
-#pragma unroll
-    for (int s = 0; s < K; ++s) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, 0), z[c][0], base[c][s]);
-#pragma unroll
-        for (int i = 1; i < K; ++i)
-#pragma unroll
-            for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
-    }
-}
-// out[c] = U z[c]
-template <int K, int C, class M>
-__device__ __forceinline__ void eig_expand0(const M& m, const double (&z)[C][K], double (&out)[C][K]) {
-#pragma unroll
-    for (int s = 0; s < K; ++s) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) out[c][s] = m.U(s, 0) * z[c][0];
-#pragma unroll
-        for (int i = 1; i < K; ++i)
-#pragma unroll
-            for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
-    }
-}
-// out[c] = P^T q[c] = q[c] + Uinv^T (em1 * (U^T q[c]))
-template <int K, int C, class M>
-__device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][K], const double (&em1)[K], double (&out)[C][K]) {
-    double z[C][K];
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        double w[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) w[c] = m.U(0, i) * q[c][0];
-#pragma unroll
-        for (int s = 1; s < K; ++s)
-#pragma unroll
-            for (int c = 0; c < C; ++c) w[c] = fma(m.U(s, i), q[c][s], w[c]);
-#pragma unroll
-        for (int c = 0; c < C; ++c) z[c][i] = em1[i] * w[c];
-    }
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(0, j), z[c][0], q[c][j]);
-#pragma unroll
-        for (int i = 1; i < K; ++i)
-#pragma unroll
-            for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(i, j), z[c][i], out[c][j]);
-    }
-}
-
-// Multiply a column by the exact power of two that brings its largest magnitude into [1,2);
-// returns the removed binary exponent.  Works on the exponent fields with integer ops (fp64 has no
-// native max instruction; fmax() costs ~10 instructions).  Zero / denormal / non-finite maxima are
-// left alone.
-template <int K>
-__device__ __forceinline__ int rescale_pow2(double (&v)[K]) {
-    unsigned m = (unsigned)__double2hiint(v[0]) & 0x7fffffffu;
-#pragma unroll
-    for (int k = 1; k < K; ++k) m = max(m, (unsigned)__double2hiint(v[k]) & 0x7fffffffu);
-    const int e = (int)(m >> 20);
-    if (e == 0 || e == 0x7ff) return 0;
-    const double sc = __hiloint2double((2046 - e) << 20, 0);
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] *= sc;
-    return e - 1023;
-}
-
-// 1/x for a positive, normal x: hardware seed + two Newton steps (relative error ~1e-16; the
-// quotient only scales a gradient term whose tolerance is 1e-8).
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
-    return r;
-}
-
-// lane 0 ends with sum(va) over the warp, lane 16 with sum(vb)
-__device__ __forceinline__ double warp_pair_reduce(double va, double vb, int lane) {
-    const bool upper = (lane & 16) != 0;
-    double send = upper ? va : vb;
-    double keep = upper ? vb : va;
-    double v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
-}
-
-// --------------------------------------------------------------------------------------------
-// kernel 1: branch tables for every (tree, branch, rate)
-//   e   = exp(mu t D r)
-//   P   = U diag(e) Uinv                             VectorizedFunctions.jl:116-168
-//   dP  = U diag(D r mu e) Uinv                      VectorizedFunctions.jl:89-113, 139-152
-// (P, dP columns are only read for LEAF children; same operation order as the reference.)
-// --------------------------------------------------------------------------------------------
-constexpr int KMAX_TABLE = 32;
-
-__global__ void build_branch_tables(const TreeDev* __restrict__ trees, const double* __restrict__ dyn,
-                                    double* __restrict__ btab, int K, int R) {
-    const TreeDev tr = trees[blockIdx.y];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= tr.n_br * R) return;
-    const int br = idx / R, r = idx - br * R;
-    const double* d = dyn + tr.dyn_off;
-    const double* U = d + dyn_U(tr.NN);
-    const double* D = d + dyn_D(tr.NN, K);
-    const double* Uinv = d + dyn_Uinv(tr.NN, K);
-    const double mu = d[dyn_mu(tr.NN, K)];
-    const double rate = d[dyn_rates(tr.NN, K) + r];
-    double* ev = btab + tr.btab_off + ((long long)br * R + r) * bt_size(K);
-    double* P = ev + 2 * K;
-    double* dP = P + K * (K + 1);
-    if (br >= tr.NN - 1) {  // root row (unused) and virtual branches: identity, zero derivative
-        for (int i = 0; i < K; ++i) { ev[i] = 0.0; ev[K + i] = 0.0; }   // expm1(0) and zero derivative: identity branch
-        for (int n = 0; n <= K; ++n)
-            for (int m = 0; m < K; ++m) {
-                P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0;
-                dP[n * K + m] = 0.0;
-            }
-        return;
-    }
-    const double t = d[dyn_blv(tr.NN) + br];
-    double em1[KMAX_TABLE], de[KMAX_TABLE];
-    for (int i = 0; i < K; ++i) {
-        const double x = mu * t * D[i] * rate;
-        em1[i] = expm1(x);
-        ev[i] = em1[i];
-        de[i] = D[i] * rate * mu * exp(x);
-        ev[K + i] = de[i];
-    }
-    for (int m = 0; m < K; ++m) {
-        double rs = 0.0, drs = 0.0;
-        for (int n = 0; n < K; ++n) {
-            double c = 0.0, dc = 0.0;
-            for (int k = 0; k < K; ++k) {
-                const double u = U[m + K * k], ui = Uinv[k + K * n];
-                c += (u * em1[k]) * ui;      // P - I, formed without cancellation against the identity
-                dc += (u * de[k]) * ui;
-            }
-            c += (m == n) ? 1.0 : 0.0;
-            P[n * K + m] = c;
-            dP[n * K + m] = dc;
-            rs += c;    // what P * (all-ones leaf) gives: sum_s1 1 * P[s, s1]
-            drs += dc;
-        }
-        P[K * K + m] = rs;
-        dP[K * K + m] = drs;
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// kernel 2: the fused walk.  grid = persistent CTAs, each takes a contiguous range of column
-// tiles; a tile = blockDim.x columns of one rate category of one tree.
-//
-// Per-op inputs that are uniform over the tile or byte-sized per column are staged in shared
-// memory CH ops at a time with cp.async, one chunk ahead of the compute:
-//   sdesc  3 x CH op descriptors (ring of 3: descriptors must be resident one chunk before the
-//          data they describe can be requested)
-//   se     2 x CH x 2 x 2K doubles: (em1, de) eigen-coefficient vectors of INTERNAL children
-//   scode  2 x CH x 2 x TW bytes: the state codes of LEAF children for the tile's columns
-// so the only global accesses on the per-op critical path are the thread's own partials and the
-// leaf-table gathers.  One __syncthreads per chunk.
-// --------------------------------------------------------------------------------------------
-constexpr int CH = 16;
-
-// Per-op record derived by the staging threads from the raw descriptor (schedule.hpp): everything the
-// compute threads need as ready-to-add byte offsets, so no warp repeats the uniform address math.
-//   xa / xb  LEAF child: byte offset (from the branch-table base) of the child's P columns for this
-//            tile's rate; MEM child: byte offset (from the thread's scratch base) of its stored partial
-//   post: y0 = where to store the result          pre: y0 = pre[mother] on the LIFO, y1 / y2 = where
-//                                                       pre[a] / pre[b] are pushed
-// Offsets are 32-bit: a CTA's scratch region and one tree's branch table are far below 4 GB (checked
-// on the host).
-struct __align__(16) OpRec {
-    int flags;
-    unsigned xa, xb, y0;       // first half: needed at the start of the op
-    int a_br, b_br;
-    unsigned y1, y2;           // second half: needed at its end
-};
-static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
-
-// Where a CTA accumulates its branch-gradient sums.  K <= 3: directly in its accumulator row in
-// global memory with fire-and-forget RED.ADD.F64 (the row stays in L2); a shared-memory fp64 atomic
-// add is a compare-and-swap loop (~10 instructions, 38 % retries when the 8 warps of a CTA hit the
-// same branch).  Measured (profiles/r1_walk_notes.md): 5 % faster at K = 2, but 2.5-5 % SLOWER at
-// K = 4, where the kernel sits on a register knife-edge and the extra 64-bit row pointer spills.
-__host__ __device__ constexpr bool grad_in_l2(int K) { return K <= 3; }
-
-template <int K>
-struct WalkSmem {
-    // dynamic shared memory carve-up (offsets in bytes)
-    // branch-gradient accumulator of the CTA: in shared memory for K >= 4; for K <= 3 it is the CTA's
-    // row in global memory (see grad_in_l2)
-    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) {
-        return (want_grad && !grad_in_l2(K)) ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0;
-    }
-    static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
-    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
-    static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
-    static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
-    // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
-    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
-    static __host__ __device__ size_t total(int n_br, int want_grad, int TW) {
-        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
-    }
-};
-
-// 3 resident CTAs of 256 threads per SM (<= 80 registers): the walk is latency-bound, 24 warps
-// with a few spills beat 16 warps without (profiles/r1_walk_notes.md).
-#ifndef MCP_WALK_MIN_BLOCKS
-#define MCP_WALK_MIN_BLOCKS 3
-#endif
-// Heavier per-thread state (K * columns per thread > 4 doubles per vector) gets 2 CTAs per SM
-// (<= 128 registers) instead of 3.
-#ifndef MCP_WALK_MIN_BLOCKS2
-#define MCP_WALK_MIN_BLOCKS2 2
-#endif
-// SSCR = true keeps the CTA's partials scratch in SHARED memory instead of HBM: the latency path for
-// small problems (MCMC-sized trees), where a lone warp would otherwise wait an L2 round trip for
-// every partial it has just written.
-template <int K, int CPT, bool DYN_MODEL, bool SSCR>
-#ifndef MCP_WALK_MAXT
-#define MCP_WALK_MAXT 256
-#endif
-#ifndef MCP_PREFETCH_DIST
-#define MCP_PREFETCH_DIST 0   // L2 prefetch hints for gradient-pass operands: measured slower (22.3 vs 21.0 ms), kept for experiments
-#endif
-__global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ long long s_e[8];
-    __shared__ double s_l[8];
-
-    const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int TS = TW * CPT;                          // sites per tile; column c of a thread = site0 + c*TW + tid
-    const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
-    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
-    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
-    if (tile >= tile_end) return;
-
-    double* const s_acc = reinterpret_cast<double*>(smem_raw);
-    constexpr bool GL2 = grad_in_l2(K);
-    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
-    double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
-    OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
-    double* const stab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes());
-    unsigned char* const scode = reinterpret_cast<unsigned char*>(stab) + WalkSmem<K>::tab_bytes();
-    constexpr int KK1 = K * (K + 1);                  // doubles of one leaf table (P or dP columns)
-
-    // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state]; all
-    // slot / LIFO offsets in the records are byte offsets from here
-    unsigned char* const scr = SSCR
-        ? scode + WalkSmem<K>::code_bytes(TS) + (size_t)tid * K * 8
-        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K));
-    const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
-    const unsigned slot_bytes = col_bytes * CPT;
-    const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
-    int row = p.cta_row_base[blockIdx.x];
-    const int R = p.R;
-    constexpr int BT = 2 * K + 2 * K * (K + 1);
-
-    int ti = 0;
-    while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
-
-    while (tile < tile_end) {
-        const TreeDev tr = p.trees[ti];
-        const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
-        // this CTA's gradient accumulator row for the tree (global memory, stays in L2)
-        double* const grow = p.rows + (long long)row * p.row_stride;
-        if (p.want_grad) {   // ordered before the first update by the barriers below
-            for (int i = tid; i < tr.n_br; i += TW) (GL2 ? grow : s_acc)[i] = 0.0;
-        }
-        long long e_total = 0;
-        double logsum = 0.0;
-        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
-        const int4* const post_ops = p.ops + 2 * tr.post_off;
-        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
-
-        for (; tile < tree_tile_end; ++tile) {
-            const int local = tile - tr.tile_begin;
-            const int r = local / tr.tiles_per_rate;
-            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TS;
-            bool valid[CPT];
-            double vmask[CPT];                 // 1.0 for real columns, 0.0 for the padding of a ragged tile
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                valid[c] = site0 + c * TW + tid < tr.S;
-                vmask[c] = keep_f64(valid[c] ? 1.0 : 0.0);
-            }
-            const unsigned char* const codes0 = tr.codes + site0;
-            // this tree's branch table at (branch 0, rate r); record offsets are relative to it
-            const unsigned char* const btab_b = reinterpret_cast<const unsigned char*>(p.btab + tr.btab_off + (long long)r * BT);
-            const unsigned br_bytes = (unsigned)R * BT * 8;
-
-            // ---- chunk staging (all threads of the CTA) ----
-            auto stage_desc = [&](const int4* ops, int n_ops, int c) {
-                const int base = c * CH, cnt = min(CH, n_ops - base);
-                int4* dst = sdesc + (c % 3) * (CH * 2);
-                for (int i = tid; i < cnt * 2; i += TW) cp_async16(dst + i, ops + 2 * base + i);
-            };
-            // Copies e vectors / leaf codes of chunk c and derives the per-op records (byte offsets),
-            // once per CTA instead of once per warp.  `pre` selects the pre-program field meaning.
-            auto stage_data = [&](int n_ops, int c, bool pre) {
-                const int base = c * CH, cnt = min(CH, n_ops - base);
-                const int4* d = sdesc + (c % 3) * (CH * 2);
-                double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS);
-                OpRec* rb = srec + (c & 1) * CH;
-                double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
-                const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
-                const int tab_doubles = pre ? 2 * KK1 : KK1; // P columns (+ dP columns in the gradient pass)
-                const int tpieces = (tab_doubles + 1) / 2;   // 16-byte pieces of one leaf table
-                const int epieces = K;                       // em1 and de: 2K doubles = K 16-byte pieces
-                const int per_child = pieces + tpieces > epieces ? pieces + tpieces : epieces;
-                for (int w = tid; w < cnt * 2 * per_child; w += TW) {
-                    const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
-                    const int4 o0 = d[2 * j];
-                    const int fl = d[2 * j + 1].y;
-                    const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
-                    const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
-                    const double* bsrc = reinterpret_cast<const double*>(btab_b + (unsigned)br * br_bytes);
-                    if (kind == mcp::OPK_LEAF) {
-                        if (piece < pieces) {
-                            unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TS + piece * 16;
-                            if (src >= 0) cp_async16(dstp, codes0 + (long long)src * tr.code_stride + piece * 16);
-                            else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
-                        } else if (piece < pieces + tpieces) {
-                            const int tp = piece - pieces;
-                            double* dstp = tb + (size_t)(j * 2 + ch) * 2 * KK1 + tp * 2;
-                            const double* srcp = bsrc + 2 * K + tp * 2;
-                            if constexpr ((K * 8) % 16 == 0) {
-                                cp_async16(dstp, srcp);
-                            } else {
-                                dstp[0] = __ldg(srcp);
-                                if (tp * 2 + 1 < tab_doubles) dstp[1] = __ldg(srcp + 1);
-                            }
-                        }
-                    } else if (piece < epieces) {
-                        // 2K doubles = K 16-byte pieces; entries are 16-byte aligned (bt_size is even)
-                        cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * 2 * K) + piece * 16,
-                                   reinterpret_cast<const unsigned char*>(bsrc) + piece * 16);
-                    }
-                }
-                for (int j = tid; j < cnt; j += TW) {
-                    const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
-                    const int fl = o1.y, ka = fl & 3, kb = (fl >> 2) & 3;
-                    OpRec rec;
-                    rec.flags = fl;
-                    rec.a_br = o0.y;
-                    rec.b_br = o0.w;
-                    rec.xa = ka == mcp::OPK_LEAF ? (unsigned)o0.y * br_bytes + 2 * K * 8 : (unsigned)o0.x * slot_bytes;
-                    rec.xb = kb == mcp::OPK_LEAF ? (unsigned)o0.w * br_bytes + 2 * K * 8 : (unsigned)o0.z * slot_bytes;
-                    if (pre) {
-                        rec.y0 = stack_base + (unsigned)o1.x * slot_bytes;     // pre[mother] on the LIFO
-                        rec.y1 = stack_base + (unsigned)o1.z * slot_bytes;     // where pre[a] is pushed
-                        rec.y2 = stack_base + (unsigned)o1.w * slot_bytes;     // where pre[b] is pushed
-                    } else {
-                        rec.y0 = (unsigned)o1.x * slot_bytes;                  // where the result is stored
-                        rec.y1 = 0;
-                        rec.y2 = 0;
-                    }
-                    rb[j] = rec;
-                }
-            };
-            auto prologue = [&](const int4* ops, int n_ops, bool pre) {
-                __syncthreads();                              // previous pass / tile done with the buffers
-                stage_desc(ops, n_ops, 0);
-                if (n_ops > CH) stage_desc(ops, n_ops, 1);
-                cp_async_commit();
-                cp_async_wait_all();
-                __syncthreads();
-                stage_data(n_ops, 0, pre);
-                cp_async_commit();
-            };
-            auto chunk_boundary = [&](const int4* ops, int n_ops, int c, int n_chunks, bool pre) {
-                cp_async_wait_all();
-                __syncthreads();                              // chunk c data + descriptors c, c+1 visible
-                if (c + 1 < n_chunks) stage_data(n_ops, c + 1, pre);
-                if (c + 2 < n_chunks) stage_desc(ops, n_ops, c + 2);
-                cp_async_commit();
-            };
-            auto ld_cols = [&](unsigned off, double (&v)[CPT][K]) {
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    if constexpr (SSCR) {
-                        const double* src = reinterpret_cast<const double*>(scr + off + c * col_bytes);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) v[c][k] = src[k];
-                    } else {
-                        ld_partial<K>(reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
-                    }
-                }
-            };
-            auto st_cols = [&](unsigned off, const double (&v)[CPT][K]) {
-#pragma unroll
-                for (int c = 0; c < CPT; ++c) {
-                    if constexpr (SSCR) {
-                        double* dst = reinterpret_cast<double*>(scr + off + c * col_bytes);
-#pragma unroll
-                        for (int k = 0; k < K; ++k) dst[k] = v[c][k];
-                    } else {
-                        st_partial<K>(reinterpret_cast<double*>(scr + off + c * col_bytes), v[c]);
-                    }
-                }
-            };
-
-            // ------------------------------ post pass ------------------------------
-            double cur[CPT][K];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c)
-#pragma unroll
-                for (int k = 0; k < K; ++k) cur[c][k] = 1.0;
-            int e_col[CPT];
-#pragma unroll
-            for (int c = 0; c < CPT; ++c) e_col[c] = 0;
-            {
-                const int n_post = tr.n_post, n_chunks = (n_post + CH - 1) / CH;
-                prologue(post_ops, n_post, false);
-                for (int c = 0; c < n_chunks; ++c) {
-                    chunk_boundary(post_ops, n_post, c, n_chunks, false);
-                    const OpRec* rb = srec + (c & 1) * CH;
-                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
-                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
-                    const int cnt = min(CH, n_post - c * CH);
-                    for (int j = 0; j < cnt; ++j) {
-                        const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
-                        const int flags = (int)rh.x, ka = flags & 3, kb = (flags >> 2) & 3;
-                        // stored operand (at most one per op) first: its latency overlaps the rest
-                        double Lm[CPT][K];
-                        if (ka == mcp::OPK_MEM) ld_cols(rh.y, Lm);
-                        else if (kb == mcp::OPK_MEM) ld_cols(rh.z, Lm);
-                        double Da[CPT][K], Db[CPT][K];
-                        if (ka == mcp::OPK_LEAF) {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) Da[cc][k] = t[k];
-                            }
-                        } else {
-                            double e[K], z[CPT][K];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * 2 * K + k];
-                            if (ka == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Da); }
-                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Da); }
-                        }
-                        if (kb == mcp::OPK_LEAF) {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) Db[cc][k] = t[k];
-                            }
-                        } else {
-                            double e[K], z[CPT][K];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * 2 * K + k];
-                            if (kb == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Db); }
-                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Db); }
-                        }
-#pragma unroll
-                        for (int cc = 0; cc < CPT; ++cc) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) cur[cc][k] = Da[cc][k] * Db[cc][k];
-                            e_col[cc] += rescale_pow2<K>(cur[cc]);
-                        }
-                        if (flags & mcp::POST_STORE) st_cols(rh.w, cur);
-                    }
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < CPT; ++cc) {
-                double rootv = mdl.pi(0) * cur[cc][0];
-#pragma unroll
-                for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[cc][k], rootv);
-                if (valid[cc]) {
-                    logsum += log(rootv);
-                    e_total += e_col[cc];
-                }
-            }
-
-            // ------------------------------ gradient pass ------------------------------
-            if (p.want_grad) {
-                const int n_pre = tr.n_pre, n_chunks = (n_pre + CH - 1) / CH;
-                prologue(pre_ops, n_pre, true);
-                for (int c = 0; c < n_chunks; ++c) {
-                    chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
-                    const OpRec* rb = srec + (c & 1) * CH;
-                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
-                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
-                    const int cnt = min(CH, n_pre - c * CH);
-                    for (int j = 0; j < cnt; ++j) {
-                        const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
-                        const int flags = (int)rh.x;
-                        const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
-                        if constexpr (!SSCR && MCP_PREFETCH_DIST > 0) {
-                            // the children partials of a later family were written in the post pass, long ago:
-                            // pull them from HBM into L2 now (one request per 128-byte line)
-                            if (j + MCP_PREFETCH_DIST < cnt && (lane * K * 8) % 128 == 0) {
-                                const uint4 rf = *reinterpret_cast<const uint4*>(rb + j + MCP_PREFETCH_DIST);
-                                if (((int)rf.x & 3) == mcp::OPK_MEM) {
-#pragma unroll
-                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.y + cc * col_bytes);
-                                }
-                                if ((((int)rf.x >> 2) & 3) == mcp::OPK_MEM) {
-#pragma unroll
-                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.z + cc * col_bytes);
-                                }
-                            }
-                        }
-                        const int mk = (flags >> 8) & 3;
-                        // all stored operands of the family are requested up front
-                        double pm[CPT][K], La[CPT][K], Lb[CPT][K];
-                        if (mk == mcp::PREM_STACK) ld_cols(rh.w, pm);
-                        if (ai) ld_cols(rh.y, La);
-                        if (bi) ld_cols(rh.z, Lb);
-                        if (mk == mcp::PREM_ROOT) {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                for (int k = 0; k < K; ++k) pm[cc][k] = mdl.pi(k);
-                        } else if (mk == mcp::PREM_REG) {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                for (int k = 0; k < K; ++k) pm[cc][k] = cur[cc][k];
-                        }
-                        double ea[K], ebv[K];
-                        double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
-                        if (ai) {
-                            double z[CPT][K], zd[CPT][K];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * 2 * K + k];
-                            eig_project<K, CPT, true>(mdl, La, ea, eb + (j * 2 + 0) * 2 * K + K, z, zd);
-                            eig_expand<K, CPT>(mdl, z, La, Da);
-                            eig_expand0<K, CPT>(mdl, zd, Ya);
-                        } else {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) { Da[cc][k] = t[k]; Ya[cc][k] = t[KK1 + k]; }
-                            }
-                        }
-                        if (bi) {
-                            double z[CPT][K], zd[CPT][K];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * 2 * K + k];
-                            eig_project<K, CPT, true>(mdl, Lb, ebv, eb + (j * 2 + 1) * 2 * K + K, z, zd);
-                            eig_expand<K, CPT>(mdl, z, Lb, Db);
-                            eig_expand0<K, CPT>(mdl, zd, Yb);
-                        } else {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) { Db[cc][k] = t[k]; Yb[cc][k] = t[KK1 + k]; }
-                            }
-                        }
-                        double qa[CPT][K], qb[CPT][K];
-                        double ga = 0.0, gb = 0.0;
-#pragma unroll
-                        for (int cc = 0; cc < CPT; ++cc) {
-                            double den = 0.0, na = 0.0, nb = 0.0;
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                qa[cc][k] = pm[cc][k] * Db[cc][k];
-                                qb[cc][k] = pm[cc][k] * Da[cc][k];
-                                den = fma(qa[cc][k], Da[cc][k], den);
-                                na = fma(qa[cc][k], Ya[cc][k], na);
-                                nb = fma(qb[cc][k], Yb[cc][k], nb);
-                            }
-                            const double inv = fast_rcp(den) * vmask[cc];
-                            ga = fma(na, inv, ga);
-                            gb = fma(nb, inv, gb);
-                        }
-                        const double red = warp_pair_reduce(ga, gb, lane);   // lane 0: sum of ga, lane 16: sum of gb
-                        if constexpr (GL2) {
-                            if ((lane & 15) == 0) atomicAdd(grow + ((lane >> 4) ? rb[j].b_br : rb[j].a_br), red);
-                        } else {
-                            if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
-                            else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
-                        }
-
-                        // pre[child] = P^T q, only internal children have one
-                        const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
-                        if (a_out != mcp::OUT_NONE) {
-                            double pa[CPT][K];
-                            eig_transposed<K, CPT>(mdl, qa, ea, pa);
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pa[cc]);
-                            if (a_out == mcp::OUT_KEEP) {
-#pragma unroll
-                                for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                    for (int k = 0; k < K; ++k) cur[cc][k] = pa[cc][k];
-                            } else {
-                                st_cols(rb[j].y1, pa);
-                            }
-                        }
-                        if (b_out != mcp::OUT_NONE) {
-                            double pb[CPT][K];
-                            eig_transposed<K, CPT>(mdl, qb, ebv, pb);
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pb[cc]);
-                            if (b_out == mcp::OUT_KEEP) {
-#pragma unroll
-                                for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                    for (int k = 0; k < K; ++k) cur[cc][k] = pb[cc][k];
-                            } else {
-                                st_cols(rb[j].y2, pb);
-                            }
-                        }
-                    }
-                }
-            }
-        }  // tiles of this tree
-
-        // ---- flush this CTA's sums for the tree into its accumulator row ----
-        for (int off = 16; off > 0; off >>= 1) {
-            e_total += __shfl_xor_sync(0xffffffffu, e_total, off);
-            logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
-        }
-        if (lane == 0) { s_e[warp] = e_total; s_l[warp] = logsum; }
-        __syncthreads();
-        if (tid == 0) {
-            long long es = 0;
-            double ls = 0.0;
-            for (int w = 0; w < (TW + 31) / 32; ++w) { es += s_e[w]; ls += s_l[w]; }
-            p.rows_ll[row].esum = es;
-            p.rows_ll[row].logsum = ls;
-        }
-        if constexpr (!GL2) {
-            if (p.want_grad)
-                for (int i = tid; i < tr.n_br; i += TW) grow[i] = s_acc[i];
-        }
-        __syncthreads();
-        ++row;
-        ++ti;
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// Branch-length prior epilogue (CompoundDirichlet / exponentialBL,
-// /root/reference/src/Likelihood/Prior.jl:1-57): the whole block reduces T = sum t_j and
-// W = sum w_j log t_j in a fixed order (thread-strided partial sums, then a serial sum over the
-// threads), so the value is reproducible.  s_red: 2 * blockDim.x doubles.  Returns {T, W} to
-// every thread.
-// --------------------------------------------------------------------------------------------
-struct PriorSums { double T, W; };
-__device__ inline PriorSums prior_block_sums(const double* __restrict__ blv, const double* __restrict__ w, int nb,
-                                             int tid, int nt, double* s_red) {
-    double a = 0.0, b = 0.0;
-    for (int j = tid; j < nb; j += nt) {
-        const double t = blv[j], wj = w[j];
-        a += t;
-        if (wj != 0.0) b += wj * log(t);
-    }
-    s_red[tid] = a;
-    s_red[nt + tid] = b;
-    __syncthreads();
-    PriorSums r{0.0, 0.0};
-    for (int i = 0; i < nt; ++i) { r.T += s_red[i]; r.W += s_red[nt + i]; }
-    __syncthreads();
-    return r;
-}
-// contribution of the prior to output slot j (0 = log density, j >= 1 = d/dt_j)
-__device__ inline double prior_term(const double* __restrict__ hdr, const double* __restrict__ blv,
-                                    const double* __restrict__ w, const PriorSums& ps, int j) {
-    const double c0 = hdr[1], beta = hdr[2], k4 = hdr[3];
-    if (j == 0) return c0 - beta * ps.T + ps.W + (k4 != 0.0 ? k4 * log(ps.T) : 0.0);
-    const double wj = w[j - 1];
-    return -beta + (wj != 0.0 ? wj / blv[j - 1] : 0.0) + (k4 != 0.0 ? k4 / ps.T : 0.0);
-}
-
-// --------------------------------------------------------------------------------------------
-// kernel 2c: small-tree latency path.  A tile is ONE warp wide (32 columns) but is worked on by all
-// W warps of the CTA: the level-ordered program (schedule.hpp, by_levels) lists ops of equal height
-// (post pass) / depth (gradient pass) together, the warps split each level's ops, and a
-// __syncthreads separates levels.  All partials and pre vectors of the tile live in shared memory.
-// The critical path is the tree height instead of the node count; used when the whole input is only
-// a few tiles per SM (MCMC-sized problems), where the depth-first walk runs at single-warp latency.
-// --------------------------------------------------------------------------------------------
-struct LevelSmem {
-    // byte offsets into dynamic shared memory
-    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 127) & ~(size_t)127) : 0; }
-    static __host__ __device__ size_t exp_bytes() { return 128; }
-    static __host__ __device__ size_t code_bytes(int n_rows) { return (((size_t)n_rows * 32) + 127) & ~(size_t)127; }
-    static __host__ __device__ size_t slot_bytes(int K) { return (size_t)32 * K * 8; }
-    static __host__ __device__ size_t tab_bytes(int n_br, int K) { return (((size_t)n_br * bt_size(K) * 8) + 127) & ~(size_t)127; }
-    static __host__ __device__ size_t total(int n_br, int want_grad, int n_rows, int n_slots, int n_stack, int K) {
-        return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + tab_bytes(n_br, K) +
-               (size_t)(n_slots + n_stack) * slot_bytes(K);
-    }
-};
-
-template <int K, bool DYN_MODEL>
-__global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_constant__ WalkParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ long long s_e[8];
-    __shared__ double s_l[8];
-    __shared__ double s_prior[2 * 256];   // block reduction of the branch-length prior (final reduction only)
-
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, W = NT >> 5;
-    const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
-    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
-    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
-    __shared__ unsigned s_ticket;
-
-    double* const s_acc = reinterpret_cast<double*>(smem_raw);
-    int* const s_exp = reinterpret_cast<int*>(smem_raw + LevelSmem::acc_bytes(p.max_br, p.want_grad));
-    unsigned char* const s_code = reinterpret_cast<unsigned char*>(s_exp) + LevelSmem::exp_bytes();
-    double* const s_tab = reinterpret_cast<double*>(s_code + LevelSmem::code_bytes(p.max_rows));
-    double* const s_post = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K)) + lane * K;
-    double* const s_pre = s_post + (size_t)p.n_slots * 32 * K;
-    constexpr int SLOT = 32 * K;                  // doubles per slot
-    constexpr int BT = 2 * K + 2 * K * (K + 1), KK1 = K * (K + 1);
-    int row = p.cta_row_base[blockIdx.x];
-    const int R = p.R;
-
-    int ti = 0;
-    while (tile < tile_end && ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
-
-    while (tile < tile_end) {
-        const TreeDev tr = p.trees[ti];
-        const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
-        if (p.want_grad) {
-            for (int i = tid; i < tr.n_br; i += NT) s_acc[i] = 0.0;
-        }
-        long long e_total = 0;
-        double logsum = 0.0;
-        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
-        const int4* const post_ops = p.ops + 2 * tr.post_off;
-        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
-        const int* const post_lvl = p.levels + tr.lvl_off;
-        const int* const pre_lvl = post_lvl + tr.n_post_lvl + 1;
-        int built_rate = -1;
-
-        for (; tile < tree_tile_end; ++tile) {
-            const int local = tile - tr.tile_begin;
-            const int r = local / tr.tiles_per_rate;
-            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * 32;
-            const bool valid = site0 + lane < tr.S;
-            const double* const tab_r = s_tab;                 // this tree's branch table for rate r, in shared memory
-            constexpr long long br_stride = BT;
-
-            __syncthreads();                                   // previous tile done with the shared buffers
-            if (r != built_rate) {
-                // branch table of (tree, rate r), built here instead of by a separate kernel:
-                // e = exp(t * D mu rate), P = U diag(e) Uinv, dP = U diag(D mu rate e) Uinv, plus the
-                // row-sum columns (same operation order as build_branch_tables)
-                const double* const blv = p.dyn + tr.dyn_off;
-                for (int br = tid; br < tr.n_br; br += NT) {
-                    double* ev = s_tab + (size_t)br * BT;
-                    double* P = ev + 2 * K;
-                    double* dP = P + KK1;
-                    if (br >= tr.NN - 1) {
-#pragma unroll
-                        for (int i = 0; i < K; ++i) { ev[i] = 0.0; ev[K + i] = 0.0; }
-#pragma unroll
-                        for (int n = 0; n <= K; ++n)
-#pragma unroll
-                            for (int m = 0; m < K; ++m) { P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0; dP[n * K + m] = 0.0; }
-                        continue;
-                    }
-                    const double t = __ldg(blv + br);
-                    double em1[K], de[K];
-#pragma unroll
-                    for (int i = 0; i < K; ++i) {
-                        em1[i] = expm1(t * mdl.c(r, i));
-                        de[i] = mdl.c(r, i) * exp(t * mdl.c(r, i));
-                        ev[i] = em1[i];
-                        ev[K + i] = de[i];
-                    }
-#pragma unroll
-                    for (int m = 0; m < K; ++m) {
-                        double rs = 0.0, drs = 0.0;
-#pragma unroll
-                        for (int n = 0; n < K; ++n) {
-                            double c = 0.0, dc = 0.0;
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                c += (mdl.U(m, k) * em1[k]) * mdl.Ui(k, n);
-                                dc += (mdl.U(m, k) * de[k]) * mdl.Ui(k, n);
-                            }
-                            c += (m == n) ? 1.0 : 0.0;
-                            P[n * K + m] = c;
-                            dP[n * K + m] = dc;
-                            rs += c;
-                            drs += dc;
-                        }
-                        P[K * K + m] = rs;
-                        dP[K * K + m] = drs;
-                    }
-                }
-                built_rate = r;
-            }
-            for (int i = tid; i < tr.n_rows * 32; i += NT) {   // this tile's state codes, all leaves
-                const int rw = i >> 5, l = i & 31;
-                s_code[i] = (site0 + l < tr.S) ? __ldg(tr.codes + (long long)rw * tr.code_stride + site0 + l) : (unsigned char)K;
-            }
-            if (tid < 32) s_exp[tid] = 0;
-            __syncthreads();
-
-            auto leaf_code = [&](int src) -> int { return src >= 0 ? min((int)s_code[src * 32 + lane], K) : K; };
-            auto ld_slot = [&](const double* base, int slot, double (&v)[1][K]) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) v[0][k] = base[(size_t)slot * SLOT + k];
-            };
-            auto st_slot = [&](double* base, int slot, const double (&v)[1][K]) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) base[(size_t)slot * SLOT + k] = v[0][k];
-            };
-            auto ld_vec = [&](const double* g, double (&v)[K]) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) v[k] = g[k];
-            };
-
-            // ------------------------------ post pass ------------------------------
-            for (int lv = 0; lv < tr.n_post_lvl; ++lv) {
-                const int lo = __ldg(post_lvl + lv), hi = __ldg(post_lvl + lv + 1);
-                for (int i = lo + warp; i < hi; i += W) {
-                    const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
-                    const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
-                    double Da[1][K], Db[1][K];
-                    if (ka == mcp::OPK_LEAF) {
-                        ld_vec(tab_r + o0.y * br_stride + 2 * K + leaf_code(o0.x) * K, Da[0]);
-                    } else {
-                        double L[1][K], z[1][K], e[K];
-                        ld_slot(s_post, o0.x, L);
-                        ld_vec(tab_r + o0.y * br_stride, e);
-                        eig_project<K, 1, false>(mdl, L, e, nullptr, z, z);
-                        eig_expand<K, 1>(mdl, z, L, Da);
-                    }
-                    if (kb == mcp::OPK_LEAF) {
-                        ld_vec(tab_r + o0.w * br_stride + 2 * K + leaf_code(o0.z) * K, Db[0]);
-                    } else {
-                        double L[1][K], z[1][K], e[K];
-                        ld_slot(s_post, o0.z, L);
-                        ld_vec(tab_r + o0.w * br_stride, e);
-                        eig_project<K, 1, false>(mdl, L, e, nullptr, z, z);
-                        eig_expand<K, 1>(mdl, z, L, Db);
-                    }
-                    double cur[1][K];
-#pragma unroll
-                    for (int k = 0; k < K; ++k) cur[0][k] = Da[0][k] * Db[0][k];
-                    const int ex = rescale_pow2<K>(cur[0]);
-                    if (ex != 0) atomicAdd(&s_exp[lane], ex);
-                    if (flags & mcp::POST_STORE) st_slot(s_post, o1.x, cur);
-                    if (flags & mcp::POST_ROOT) {
-                        double rootv = mdl.pi(0) * cur[0][0];
-#pragma unroll
-                        for (int k = 1; k < K; ++k) rootv = fma(mdl.pi(k), cur[0][k], rootv);
-                        if (valid) logsum += log(rootv);
-                    }
-                }
-                __syncthreads();
-            }
-            if (warp == 0 && valid) e_total += s_exp[lane];
-
-            // ------------------------------ gradient pass ------------------------------
-            if (p.want_grad) {
-                for (int lv = 0; lv < tr.n_pre_lvl; ++lv) {
-                    const int lo = __ldg(pre_lvl + lv), hi = __ldg(pre_lvl + lv + 1);
-                    for (int i = lo + warp; i < hi; i += W) {
-                        const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
-                        const int flags = o1.y;
-                        const int a_br = o0.y, b_br = o0.w;
-                        const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
-                        double pm[1][K];
-                        if (((flags >> 8) & 3) == mcp::PREM_ROOT) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) pm[0][k] = mdl.pi(k);
-                        } else {
-                            ld_slot(s_pre, o1.x, pm);
-                        }
-                        double ea[K], ebv[K];
-                        double Da[1][K], Ya[1][K], Db[1][K], Yb[1][K];
-                        if (ai) {
-                            double L[1][K], z[1][K], zd[1][K];
-                            ld_slot(s_post, o0.x, L);
-                            ld_vec(tab_r + a_br * br_stride, ea);
-                            eig_project<K, 1, true>(mdl, L, ea, tab_r + a_br * br_stride + K, z, zd);
-                            eig_expand<K, 1>(mdl, z, L, Da);
-                            eig_expand0<K, 1>(mdl, zd, Ya);
-                        } else {
-                            const double* t = tab_r + a_br * br_stride + 2 * K + leaf_code(o0.x) * K;
-                            ld_vec(t, Da[0]);
-                            ld_vec(t + KK1, Ya[0]);
-                        }
-                        if (bi) {
-                            double L[1][K], z[1][K], zd[1][K];
-                            ld_slot(s_post, o0.z, L);
-                            ld_vec(tab_r + b_br * br_stride, ebv);
-                            eig_project<K, 1, true>(mdl, L, ebv, tab_r + b_br * br_stride + K, z, zd);
-                            eig_expand<K, 1>(mdl, z, L, Db);
-                            eig_expand0<K, 1>(mdl, zd, Yb);
-                        } else {
-                            const double* t = tab_r + b_br * br_stride + 2 * K + leaf_code(o0.z) * K;
-                            ld_vec(t, Db[0]);
-                            ld_vec(t + KK1, Yb[0]);
-                        }
-                        double qa[1][K], qb[1][K];
-                        double den = 0.0, na = 0.0, nb = 0.0;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            qa[0][k] = pm[0][k] * Db[0][k];
-                            qb[0][k] = pm[0][k] * Da[0][k];
-                            den = fma(qa[0][k], Da[0][k], den);
-                            na = fma(qa[0][k], Ya[0][k], na);
-                            nb = fma(qb[0][k], Yb[0][k], nb);
-                        }
-                        const double inv = fast_rcp(den);
-                        const double red = warp_pair_reduce(valid ? na * inv : 0.0, valid ? nb * inv : 0.0, lane);
-                        if (lane == 0) atomicAdd(&s_acc[a_br], red);
-                        else if (lane == 16) atomicAdd(&s_acc[b_br], red);
-                        if (((flags >> 10) & 3) != mcp::OUT_NONE) {
-                            double pa[1][K];
-                            eig_transposed<K, 1>(mdl, qa, ea, pa);
-                            rescale_pow2<K>(pa[0]);
-                            st_slot(s_pre, o1.z, pa);
-                        }
-                        if (((flags >> 12) & 3) != mcp::OUT_NONE) {
-                            double pb[1][K];
-                            eig_transposed<K, 1>(mdl, qb, ebv, pb);
-                            rescale_pow2<K>(pb[0]);
-                            st_slot(s_pre, o1.w, pb);
-                        }
-                    }
-                    __syncthreads();
-                }
-            }
-        }  // tiles of this tree
-
-        for (int off = 16; off > 0; off >>= 1) {
-            e_total += __shfl_xor_sync(0xffffffffu, e_total, off);
-            logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
-        }
-        if (lane == 0) { s_e[warp] = e_total; s_l[warp] = logsum; }
-        __syncthreads();
-        if (tid == 0) {
-            long long es = 0;
-            double ls = 0.0;
-            for (int w = 0; w < W; ++w) { es += s_e[w]; ls += s_l[w]; }
-            p.rows_ll[row].esum = es;
-            p.rows_ll[row].logsum = ls;
-        }
-        if (p.want_grad) {
-            double* dst = p.rows + (long long)row * p.row_stride;
-            for (int i = tid; i < tr.n_br; i += NT) dst[i] = s_acc[i];
-        }
-        __syncthreads();
-        ++row;
-        ++ti;
-    }
-
-    // ---- fused final reduction: the last CTA to finish sums the accumulator rows in fixed order
-    // and writes [logL, grad] per tree to p.out (device memory, or pinned host memory for the
-    // synchronous entry points: no separate kernel, no device-to-host copy) ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
-    __syncthreads();
-    if (s_ticket == gridDim.x - 1) {
-        __threadfence();
-        // All 8 warps take part: warp w sums rows row_lo + w, row_lo + w + W, ... (lanes across the
-        // branches, so a warp reads one contiguous run per row), the per-warp partial sums meet in
-        // shared memory and are added in warp order.  Fixed order, hence reproducible; ~10x less
-        // latency than one thread per output walking all rows (rows = CTAs of the launch).
-        double* const s_fin = s_tab;               // W x NN doubles; the tile buffers are free now
-        for (int t = 0; t < p.T; ++t) {
-            const TreeDev tr = p.trees[t];
-            double* o = p.out + tr.out_off;
-            const double* d = p.dyn + tr.dyn_off;
-            const double* hdr = d + dyn_prior(tr.NN, K, R);
-            const bool prior = hdr[0] != 0.0;
-            PriorSums ps{0.0, 0.0};
-            if (prior) ps = prior_block_sums(d + dyn_blv(tr.NN), hdr + 4, tr.NN - 1, tid, NT, s_prior);
-            {
-                long long es = 0;
-                double ls = 0.0;
-                for (int rw = tr.row_lo + tid; rw < tr.row_hi; rw += NT) {
-                    es += __ldcg(&p.rows_ll[rw].esum);
-                    ls += __ldcg(&p.rows_ll[rw].logsum);
-                }
-                for (int off = 16; off > 0; off >>= 1) {
-                    es += __shfl_xor_sync(0xffffffffu, es, off);
-                    ls += __shfl_xor_sync(0xffffffffu, ls, off);
-                }
-                if (lane == 0) { s_e[warp] = es; s_l[warp] = ls; }
-            }
-            if (p.want_grad) {
-                const int nb = tr.NN - 1;
-                for (int j0 = lane; j0 < nb; j0 += 128) {
-                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                    for (int rw = tr.row_lo + warp; rw < tr.row_hi; rw += W) {
-                        const double* rp = p.rows + (long long)rw * p.row_stride + j0;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (j0 + 32 * u < nb) acc[u] += __ldcg(rp + 32 * u);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (j0 + 32 * u < nb) s_fin[warp * nb + j0 + 32 * u] = acc[u];
-                }
-            }
-            __syncthreads();
-            for (int j = tid; j < tr.NN; j += NT) {
-                double v = 0.0;
-                if (j == 0) {
-                    long long es = 0;
-                    double ls = 0.0;
-                    for (int w = 0; w < W; ++w) { es += s_e[w]; ls += s_l[w]; }
-                    v = (double)es * 0.693147180559945309417232121458 + ls;
-                } else if (p.want_grad) {
-                    for (int w = 0; w < W; ++w) v += s_fin[w * (tr.NN - 1) + (j - 1)];
-                }
-                if (prior && (j == 0 || p.want_grad)) v += prior_term(hdr, d + dyn_blv(tr.NN), hdr + 4, ps, j);
-                o[j] = v;
-            }
-            __syncthreads();                       // before the next tree reuses s_fin / s_e / s_l
-        }
-        if (tid == 0) *p.done_counter = 0;   // ready for the next launch
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// kernel 2b: generic state count (6 < K <= KMAX_GENERIC), runtime K.  Same op program, same scratch
-// layout and accumulator rows as the templated kernel, but dense-table arithmetic straight from the
-// branch table (P / dP columns are stored for every branch) and per-thread vectors in local memory.
-// Correctness path for large alphabets (e.g. 20-state protein models); not tuned.
-// --------------------------------------------------------------------------------------------
-constexpr int KMAX_GENERIC = 32;
-
-__global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams p, const int K) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ long long s_e[8];
-    __shared__ double s_l[8];
-    double* const s_acc = reinterpret_cast<double*>(smem_raw);
-
-    const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
-    const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
-    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
-    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
-    if (tile >= tile_end) return;
-
-    double* const slots = p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K;
-    const long long slot_stride = (long long)TW * K;
-    double* const stack = slots + (long long)p.n_slots * slot_stride;
-    int row = p.cta_row_base[blockIdx.x];
-    const int R = p.R;
-    const int BT = bt_size(K), KK1 = K * (K + 1);
-
-    int ti = 0;
-    while (ti < p.T - 1 && tile >= p.trees[ti].tile_begin + R * p.trees[ti].tiles_per_rate) ++ti;
-
-    // out = T L for a stored/register operand, or the code column for a leaf
-    auto down = [&](const double* __restrict__ tab, const double* L, double* out) {
-        for (int s = 0; s < K; ++s) out[s] = 0.0;
-        for (int j = 0; j < K; ++j) {
-            const double lj = L[j];
-            const double* col = tab + j * K;
-            for (int s = 0; s < K; ++s) out[s] = fma(__ldg(col + s), lj, out[s]);
-        }
-    };
-    auto rescale = [&](double* v) -> int {
-        unsigned m = 0;
-        for (int k = 0; k < K; ++k) m = max(m, (unsigned)__double2hiint(v[k]) & 0x7fffffffu);
-        const int e = (int)(m >> 20);
-        if (e == 0 || e == 0x7ff) return 0;
-        const double sc = __hiloint2double((2046 - e) << 20, 0);
-        for (int k = 0; k < K; ++k) v[k] *= sc;
-        return e - 1023;
-    };
-
-    while (tile < tile_end) {
-        const TreeDev tr = p.trees[ti];
-        const int tree_tile_end = min(tile_end, tr.tile_begin + R * tr.tiles_per_rate);
-        if (p.want_grad) {
-            for (int i = tid; i < tr.n_br; i += TW) s_acc[i] = 0.0;
-        }
-        __syncthreads();
-        long long e_total = 0;
-        double logsum = 0.0;
-        const double* const pi = p.dyn + tr.dyn_off + dyn_pi(tr.NN, K, R);
-        const int4* const post_ops = p.ops + 2 * tr.post_off;
-        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
-
-        for (; tile < tree_tile_end; ++tile) {
-            const int local = tile - tr.tile_begin;
-            const int r = local / tr.tiles_per_rate;
-            const long long site = (long long)(local - r * tr.tiles_per_rate) * TW + tid;
-            const bool valid = site < tr.S;
-            const unsigned char* const codes = tr.codes + (valid ? site : 0);
-            const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT + 2 * K;   // P columns of (branch 0, rate r)
-            const long long br_stride = (long long)R * BT;
-            auto leaf_code = [&](int src) -> int {
-                int code = (valid && src >= 0) ? (int)__ldg(codes + (long long)src * tr.code_stride) : K;
-                return min(code, K);
-            };
-
-            double cur[KMAX_GENERIC], Da[KMAX_GENERIC], Db[KMAX_GENERIC], L[KMAX_GENERIC];
-            for (int k = 0; k < K; ++k) cur[k] = 1.0;
-            int e_col = 0;
-            for (int i = 0; i < tr.n_post; ++i) {
-                const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
-                const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
-                const double* ta = tab_r + o0.y * br_stride;
-                const double* tb = tab_r + o0.w * br_stride;
-                if (ka == mcp::OPK_LEAF) {
-                    const double* col = ta + leaf_code(o0.x) * K;
-                    for (int s = 0; s < K; ++s) Da[s] = __ldg(col + s);
-                } else if (ka == mcp::OPK_REG) {
-                    down(ta, cur, Da);
-                } else {
-                    for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.x * slot_stride + k);
-                    down(ta, L, Da);
-                }
-                if (kb == mcp::OPK_LEAF) {
-                    const double* col = tb + leaf_code(o0.z) * K;
-                    for (int s = 0; s < K; ++s) Db[s] = __ldg(col + s);
-                } else if (kb == mcp::OPK_REG) {
-                    down(tb, cur, Db);
-                } else {
-                    for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.z * slot_stride + k);
-                    down(tb, L, Db);
-                }
-                for (int k = 0; k < K; ++k) cur[k] = Da[k] * Db[k];
-                e_col += rescale(cur);
-                if (flags & mcp::POST_STORE)
-                    for (int k = 0; k < K; ++k) __stcg(slots + o1.x * slot_stride + k, cur[k]);
-            }
-            {
-                double rootv = 0.0;
-                for (int k = 0; k < K; ++k) rootv = fma(__ldg(pi + k), cur[k], rootv);
-                if (valid) {
-                    logsum += log(rootv);
-                    e_total += e_col;
-                }
-            }
-
-            if (p.want_grad) {
-                double pm[KMAX_GENERIC], Ya[KMAX_GENERIC], Yb[KMAX_GENERIC];
-                for (int i = 0; i < tr.n_pre; ++i) {
-                    const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
-                    const int flags = o1.y;
-                    const int a_br = o0.y, b_br = o0.w;
-                    const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
-                    const int mk = (flags >> 8) & 3;
-                    if (mk == mcp::PREM_ROOT) { for (int k = 0; k < K; ++k) pm[k] = __ldg(pi + k); }
-                    else if (mk == mcp::PREM_REG) { for (int k = 0; k < K; ++k) pm[k] = cur[k]; }
-                    else { for (int k = 0; k < K; ++k) pm[k] = __ldcg(stack + o1.x * slot_stride + k); }
-                    const double* ta = tab_r + a_br * br_stride;
-                    const double* tb = tab_r + b_br * br_stride;
-                    if (ai) {
-                        for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.x * slot_stride + k);
-                        down(ta, L, Da);
-                        down(ta + KK1, L, Ya);
-                    } else {
-                        const double* col = ta + leaf_code(o0.x) * K;
-                        for (int s = 0; s < K; ++s) { Da[s] = __ldg(col + s); Ya[s] = __ldg(col + KK1 + s); }
-                    }
-                    if (bi) {
-                        for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.z * slot_stride + k);
-                        down(tb, L, Db);
-                        down(tb + KK1, L, Yb);
-                    } else {
-                        const double* col = tb + leaf_code(o0.z) * K;
-                        for (int s = 0; s < K; ++s) { Db[s] = __ldg(col + s); Yb[s] = __ldg(col + KK1 + s); }
-                    }
-                    double den = 0.0, na = 0.0, nb = 0.0;
-                    for (int k = 0; k < K; ++k) {
-                        const double qa = pm[k] * Db[k], qb = pm[k] * Da[k];
-                        den = fma(qa, Da[k], den);
-                        na = fma(qa, Ya[k], na);
-                        nb = fma(qb, Yb[k], nb);
-                        Ya[k] = qa;     // Ya / Yb now hold qa / qb for the transposed products
-                        Yb[k] = qb;
-                    }
-                    const double inv = 1.0 / den;
-                    const double red = warp_pair_reduce(valid ? na * inv : 0.0, valid ? nb * inv : 0.0, lane);
-                    if (lane == 0) atomicAdd(&s_acc[a_br], red);
-                    else if (lane == 16) atomicAdd(&s_acc[b_br], red);
-
-                    const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
-                    // pre[child][j] = sum_s P[s][j] q[s] = column j of the table dotted with q
-                    if (b_out != mcp::OUT_NONE) {
-                        for (int j = 0; j < K; ++j) {
-                            double acc = 0.0;
-                            for (int s = 0; s < K; ++s) acc = fma(__ldg(tb + j * K + s), Yb[s], acc);
-                            Db[j] = acc;
-                        }
-                        rescale(Db);
-                        if (b_out == mcp::OUT_PUSH)
-                            for (int k = 0; k < K; ++k) __stcg(stack + o1.w * slot_stride + k, Db[k]);
-                    }
-                    if (a_out != mcp::OUT_NONE) {
-                        for (int j = 0; j < K; ++j) {
-                            double acc = 0.0;
-                            for (int s = 0; s < K; ++s) acc = fma(__ldg(ta + j * K + s), Ya[s], acc);
-                            Da[j] = acc;
-                        }
-                        rescale(Da);
-                        if (a_out == mcp::OUT_PUSH)
-                            for (int k = 0; k < K; ++k) __stcg(stack + o1.z * slot_stride + k, Da[k]);
-                    }
-                    if (a_out == mcp::OUT_KEEP) { for (int k = 0; k < K; ++k) cur[k] = Da[k]; }
-                    else if (b_out == mcp::OUT_KEEP) { for (int k = 0; k < K; ++k) cur[k] = Db[k]; }
-                }
-            }
-        }  // tiles of this tree
-
-        for (int off = 16; off > 0; off >>= 1) {
-            e_total += __shfl_xor_sync(0xffffffffu, e_total, off);
-            logsum += __shfl_xor_sync(0xffffffffu, logsum, off);
-        }
-        if (lane == 0) { s_e[warp] = e_total; s_l[warp] = logsum; }
-        __syncthreads();
-        if (tid == 0) {
-            long long es = 0;
-            double ls = 0.0;
-            for (int w = 0; w < (TW + 31) / 32; ++w) { es += s_e[w]; ls += s_l[w]; }
-            p.rows_ll[row].esum = es;
-            p.rows_ll[row].logsum = ls;
-        }
-        if (p.want_grad) {
-            double* dst = p.rows + (long long)row * p.row_stride;
-            for (int i = tid; i < tr.n_br; i += TW) dst[i] = s_acc[i];
-        }
-        __syncthreads();
-        ++row;
-        ++ti;
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// kernel 3: fixed-order reduction of the accumulator rows -> [logL, grad] per tree
-// --------------------------------------------------------------------------------------------
-constexpr int FIN_J = 32, FIN_G = 8;   // outputs per block x row groups (blockDim = 32 x 8)
-__global__ void finalize_results(const TreeDev* __restrict__ trees, const double* __restrict__ rows,
-                                 long long row_stride, const LLRow* __restrict__ rows_ll,
-                                 double* __restrict__ out, int want_grad, const double* __restrict__ dyn, int K, int R) {
-    // Block = 32 consecutive outputs x 8 row groups: group g sums rows row_lo + g, row_lo + g + 8, ...
-    // (a warp reads 32 consecutive doubles of one row), the 8 partial sums meet in shared memory and
-    // are added in group order: fixed order, 8x shorter dependent chain than one thread per output.
-    __shared__ double s_red[2 * FIN_J * FIN_G];
-    __shared__ double s_g[FIN_G][FIN_J];
-    __shared__ long long s_es[FIN_G];
-    const TreeDev tr = trees[blockIdx.y];
-    if ((long long)blockIdx.x * FIN_J >= tr.NN) return;   // whole block idle (batch of unequal trees)
-    const int jl = threadIdx.x, g = threadIdx.y, tid = g * FIN_J + jl;
-    const double* d = dyn + tr.dyn_off;
-    const double* hdr = d + dyn_prior(tr.NN, K, R);
-    const bool prior = hdr[0] != 0.0;
-    PriorSums ps{0.0, 0.0};
-    if (prior) ps = prior_block_sums(d + dyn_blv(tr.NN), hdr + 4, tr.NN - 1, tid, FIN_J * FIN_G, s_red);
-    const int j = blockIdx.x * FIN_J + jl;
-    double v = 0.0;
-    long long es = 0;
-    if (j < tr.NN) {
-        if (j == 0) {
-            for (int rw = tr.row_lo + g; rw < tr.row_hi; rw += FIN_G) { es += rows_ll[rw].esum; v += rows_ll[rw].logsum; }
-        } else if (want_grad) {
-            for (int rw = tr.row_lo + g; rw < tr.row_hi; rw += FIN_G) v += rows[(long long)rw * row_stride + (j - 1)];
-        }
-    }
-    s_g[g][jl] = v;
-    if (j == 0) s_es[g] = es;
-    __syncthreads();
-    if (g != 0 || j >= tr.NN) return;
-    v = 0.0;
-    for (int gg = 0; gg < FIN_G; ++gg) v += s_g[gg][jl];
-    if (j == 0) {
-        es = 0;
-        for (int gg = 0; gg < FIN_G; ++gg) es += s_es[gg];
-        v += (double)es * 0.693147180559945309417232121458;
-    }
-    if (prior && (j == 0 || want_grad)) v += prior_term(hdr, d + dyn_blv(tr.NN), hdr + 4, ps, j);
-    out[tr.out_off + j] = v;
-}
 
 // --------------------------------------------------------------------------------------------
 // host side

@@ -2,7 +2,7 @@
 
 Host-side part of the hot path, restating /root/reference/src/Likelihood/SubstitutionModels.jl:
   Restriction :13-24   JC :36-50   GTR :62-74   freeK :83-102   setmatrix :106-113
-The device builds P(t) = U diag(exp(mu t D r)) Uinv from these (csrc/mcphylo_b200.cu,
+The device builds P(t) = U diag(exp(mu t D r)) Uinv from these (csrc/kernel_tables.cuh,
 kernel build_transition_tables), so only K x K work happens here.
 
 `eigen` follows what Julia's LinearAlgebra.eigen does for a real matrix: the symmetric

@@ -1,5 +1,5 @@
 """numpy emulator of the device walk program (csrc/schedule.hpp op semantics, the arithmetic of
-felsenstein_walk in csrc/mcphylo_b200.cu) — lets the host scheduler be checked without a GPU.
+felsenstein_walk in csrc/kernel_walk.cuh) — lets the host scheduler be checked without a GPU.
 All columns are processed at once as arrays; `reg` plays the per-thread register `cur`."""
 import numpy as np
 

@@ -539,3 +539,51 @@ def test_posterior_random_tree_both_kernels(oracle, level_mode):
     ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, srates, rates)
     vp, gp = _oracle_prior(oracle, prior, tree)
     _check(lp, grad, ll_o + vp, g_o + gp)
+
+
+def test_reupload_is_ordered_against_evaluations(oracle):
+    """mcp_alignment_update_codes runs on the copy stream: an evaluation enqueued BEFORE a re-upload
+    must still see the old codes, one enqueued AFTER it the new ones, without any host
+    synchronisation in between (per-alignment events)."""
+    import torch
+
+    from mcphylo_jl_b200 import capi
+
+    rng = np.random.default_rng(9)
+    tree = random_tree(120, rng)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    S = 60000                                        # big enough for the evaluation to outlast the enqueue
+    codes1, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, S, rng)
+    codes2, _ = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, S, rng)
+    assert not np.array_equal(codes1, codes2)
+    ft = mcp.flatten(tree)
+    U, D, Uinv, mu = mcp.GTR(pi, sr)
+    targs = (ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, rates, pi)
+    ctx = capi.Context(0)
+    try:
+        wave = ctx.wave_columns(4, ft.NN, True)
+        assert wave > 0 and wave % 32 == 0
+        h1 = torch.from_numpy(codes1).pin_memory()
+        h2 = torch.from_numpy(codes2).pin_memory()
+        aln = ctx.alignment_from_codes(codes1, 4, leaf_nums)
+        ref1 = ctx.eval(aln, *targs, want_grad=True)
+        out = torch.zeros((3, ft.NN), dtype=torch.float64, device="cuda:0")
+        # eval(old) | upload(new) | eval(new) | upload(old) | eval(old), all enqueued back to back
+        ctx.eval_device(aln, *targs, want_grad=True, d_out_ptr=out[0].data_ptr())
+        aln.update_codes(h2.data_ptr())
+        ctx.eval_device(aln, *targs, want_grad=True, d_out_ptr=out[1].data_ptr())
+        aln.update_codes(h1.data_ptr())
+        ctx.eval_device(aln, *targs, want_grad=True, d_out_ptr=out[2].data_ptr())
+        ctx.synchronize()
+        res = out.cpu().numpy()
+        aln2 = ctx.alignment_from_codes(codes2, 4, leaf_nums)
+        ref2 = ctx.eval(aln2, *targs, want_grad=True)
+        assert res[0, 0] == ref1[0] and res[2, 0] == ref1[0]          # logL sums are deterministic
+        assert res[1, 0] == ref2[0] and ref1[0] != ref2[0]
+        assert np.allclose(res[0, 1:], ref1[1], rtol=1e-12) and np.allclose(res[1, 1:], ref2[1], rtol=1e-12)
+        aln.close()
+        aln2.close()
+    finally:
+        ctx.close()
