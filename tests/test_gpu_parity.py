@@ -587,3 +587,55 @@ def test_reupload_is_ordered_against_evaluations(oracle):
         aln2.close()
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("K,R,S", [(2, 1, 5000), (4, 4, 700)])
+def test_rerooting_invariance_on_device(K, R, S):
+    """Pulley principle on the CUDA path (no oracle involved): shifting length across the root and
+    unrooting the tree keep logL; the two root-branch gradients are equal."""
+    from synth import reroot_variants
+
+    rng = np.random.default_rng(310 + K)
+    tree = random_tree(33, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, srates = (mcp.Restriction, np.zeros(1)) if K == 2 else (mcp.GTR, rng.uniform(0.5, 2.5, size=6))
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, S, rng, gap_frac=0.05)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+
+    def ev(t):
+        return mcp.gradlogpdf(mcp.PhyloDist(t, pi, srates, rates, model), aln)
+
+    ll, g = ev(tree)
+    a, b = tree.children
+    assert abs(g[a.num - 1] - g[b.num - 1]) <= 1e-9 * max(abs(g[a.num - 1]), 1e-3 * np.max(np.abs(g)))
+    shifted, unrooted = reroot_variants(tree)
+    assert abs(ev(shifted)[0] - ll) <= 1e-12 * abs(ll)
+    assert unrooted is not None and abs(ev(unrooted)[0] - ll) <= 1e-12 * abs(ll)
+
+
+def test_zero_length_branches_and_impossible_columns(oracle):
+    """No clamping (SURVEY.md §8a edge behaviour): a branch of length exactly 0 is evaluated as
+    P = I; a column that is impossible under the tree (two different states joined by zero-length
+    branches) gives logL = -Inf and non-finite gradient entries, as documented in DESIGN.md §1."""
+    tree = mcp.ParseNewick("(((a:0.0,b:0.0)ab:0.1,c:0.2)abc:0.05,(d:0.3,e:0.0)de:0.1);")
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    leaves = mcp.get_leaves(tree)
+    leaf_nums = np.array([n.num for n in leaves], dtype=np.int32)
+    names = [n.name for n in leaves]
+    rng = np.random.default_rng(5)
+    S = 64
+    codes = rng.integers(0, 4, size=(len(leaves), S)).astype(np.uint8)
+    codes[names.index("b")] = codes[names.index("a")]          # a == b everywhere: every column is possible
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    ll, g = mcp.gradlogpdf(pd, mcp.DeviceAlignment(codes, leaf_nums, 4))
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates)
+    assert np.isfinite(ll) and np.all(np.isfinite(g))
+    _check(ll, g, ll_o, g_o)
+    bad = codes.copy()
+    bad[names.index("b"), 7] = (bad[names.index("a"), 7] + 1) % 4   # a != b at one site, joined by t = 0
+    ll_bad, g_bad = mcp.gradlogpdf(pd, mcp.DeviceAlignment(bad, leaf_nums, 4))
+    assert ll_bad == -np.inf
+    assert not np.all(np.isfinite(g_bad))

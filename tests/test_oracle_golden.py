@@ -110,3 +110,35 @@ def test_transition_matches_expm(oracle):
             E = expm(Q * mu * t * rate)
             assert np.allclose(P[:, :, r, b], E, rtol=0, atol=1e-13)
             assert np.allclose(dP[:, :, r, b], (Q * mu * rate) @ E, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,R", [(2, 1), (4, 4)])
+def test_rerooting_invariance_and_root_branch_gradients(oracle, K, R):
+    """Independent property: for a reversible model logL depends on the two root
+    branches only through their sum, so moving length across the root or unrooting the tree leaves
+    logL unchanged, and the gradients of the two root branches are equal."""
+    from synth import random_tree, reroot_variants, simulate_codes
+
+    rng = np.random.default_rng(300 + K)
+    tree = random_tree(14, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, srates = (mcp.Restriction, np.zeros(1)) if K == 2 else (mcp.GTR, rng.uniform(0.5, 2.5, size=6))
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, 200, rng, gap_frac=0.05)
+
+    def ev(t):
+        x = oracle.codes_to_dense(codes, leaf_nums, K, mcp.flatten(t).NN)
+        return _eval(oracle, t, x, model, pi, srates, rates)
+
+    ll, g = ev(tree)
+    a, b = tree.children
+    assert g[a.num - 1] == pytest.approx(g[b.num - 1], rel=1e-9)
+    shifted, unrooted = reroot_variants(tree)
+    assert ev(shifted)[0] == pytest.approx(ll, rel=1e-12)
+    assert unrooted is not None
+    ll_u, g_u = ev(unrooted)
+    assert ll_u == pytest.approx(ll, rel=1e-12)
+    # the merged branch carries the same derivative as either root branch
+    merged = [c for c in unrooted.children if c.name == (b if a.nchild > 0 else a).name]
+    if merged:
+        assert g_u[merged[0].num - 1] == pytest.approx(g[a.num - 1], rel=1e-9)
