@@ -306,7 +306,7 @@ def run_b200(args):
 
     # ---- end to end through the public API with host buffers -------------------------------
     # PipelinedEvaluator: every step uploads the whole alignment from pinned host memory in site
-    # blocks of 2, 4, 8, ... grid waves (block b+1 crosses PCIe on the copy stream while block b is
+    # blocks of 1, 2, 4, ... grid waves (block b+1 crosses PCIe on the copy stream while block b is
     # evaluated), flattens the tree, runs the eigendecomposition, evaluates, all-reduces and reads the
     # result back.
     pipe = mcp.PipelinedEvaluator(codes, leaf_nums, w["K"], local_rank, n_blocks=args.e2e_blocks)
@@ -375,7 +375,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(NN * 8),
                     "site_blocks": [hi - lo for lo, hi in pipe.bounds],
                     "what": f"per step: alignment codes re-uploaded from pinned host memory in {len(pipe.bounds)} site "
-                            "blocks (2, 4, 8, ... grid waves) on the copy stream, each overlapped with the evaluation "
+                            "blocks (1, 2, 4, ... grid waves) on the copy stream, each overlapped with the evaluation "
                             "of the previous block; tree flattened, eigendecomposition, mcp_eval_device per block, "
                             "all-reduce, result read back"},
             "gpu_launches": int(stats["kernel_launches"] * ((args.steps + args.warmup + 1) +

@@ -78,6 +78,8 @@ int mcp_synchronize(mcp_ctx *ctx);
  * from_dense: x is the reference's own array, (K, S, NN) column-major Float64; for every leaf in
  *             leaf_nums each column must be one-hot or all ones (what datafortree produces),
  *             otherwise MCP_ERR_DATA.
+ * An alignment belongs to the context that created it (device memory, stream ordering): pass it
+ * only to calls on that context, and destroy it before the context.
  */
 int mcp_alignment_from_codes(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t S,
                              const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);

@@ -105,9 +105,9 @@ class PipelinedEvaluator:
     site axis is cut into blocks; `mcp_alignment_update_codes` puts every block's transfer on the
     context's copy stream, the evaluations follow on the compute stream and each waits only for its
     own block, so block b+1 crosses PCIe while block b is evaluated.  Block sizes are multiples of
-    one wave of the persistent grid (`mcp_wave_columns`) and grow geometrically (2, 4, 8, ... waves,
-    then the rest): the first evaluation starts after a millisecond of transfer and no launch ends
-    in a ragged wave.  Block results are summed on the device, all-reduced over the
+    one wave of the persistent grid (`mcp_wave_columns`) and grow geometrically (1, 2, 4, ... waves,
+    then the rest): the first evaluation starts after a fraction of a millisecond of transfer and no
+    launch ends in a ragged wave.  Block results are summed on the device, all-reduced over the
     process group if there is one, and read back once.
 
     `codes` is the rank's (n_leaves, S) uint8 block; pinned per-block copies are made at the first
@@ -130,12 +130,12 @@ class PipelinedEvaluator:
 
     @staticmethod
     def plan_blocks(S: int, wave_sites: int, n_blocks: int):
-        """[(lo, hi)] site ranges: 2, 4, 8, ... waves, the last block takes the rest."""
+        """[(lo, hi)] site ranges: 1, 2, 4, ... waves, the last block takes the rest."""
         wave_sites = max(1, int(wave_sites))
         waves = S // wave_sites
-        if n_blocks <= 1 or waves < 4:
+        if n_blocks <= 1 or waves < 2:
             return [(0, S)] if S > 0 else []
-        sizes, w = [], 2
+        sizes, w = [], 1
         while len(sizes) < n_blocks - 1 and sum(sizes) + w < waves:
             sizes.append(w)
             w *= 2
@@ -151,6 +151,11 @@ class PipelinedEvaluator:
         S = self.codes.shape[1]
         wave_sites = self.ctx.wave_columns(self.K, NN, True) // max(R, 1)
         self.bounds = self.plan_blocks(S, wave_sites, self.n_blocks)
+        if len(self.bounds) > 1:
+            # pin the tile width the wave size was computed for: the automatic choice narrows the
+            # tiles of inputs below two waves, which a one-wave block is by construction
+            self.ctx.set_launch(256 if self.K <= 6 else 128, 0)
+            self.ctx.set_columns_per_thread(2 if self.K <= 3 else 1)
         for lo, hi in self.bounds:
             host = torch.from_numpy(np.ascontiguousarray(self.codes[:, lo:hi])).pin_memory()
             aln = self.ctx.alignment_from_codes(host.numpy(), self.K, self.leaf_nums)
