@@ -156,6 +156,39 @@ __device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][
     }
 }
 
+// As eig_transposed, and also the branch-gradient numerator q . (dP L) formed in eigen-space:
+//   q^T U diag(de) Uinv L = sum_i (U^T q)_i * yd_i,   yd = de * (Uinv L)  (from eig_project<WD>),
+// which reuses w = U^T q and saves the expansion U yd (K*K FMAs per internal child).
+template <int K, int C, class M>
+__device__ __forceinline__ void eig_transposed_num(const M& m, const double (&q)[C][K], const double (&em1)[K],
+                                                   const double (&yd)[C][K], double (&num)[C], double (&out)[C][K]) {
+    double z[C][K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        double w[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = m.U(0, i) * q[c][0];
+#pragma unroll
+        for (int s = 1; s < K; ++s)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = fma(m.U(s, i), q[c][s], w[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            z[c][i] = em1[i] * w[c];
+            num[c] = fma(w[c], yd[c][i], num[c]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(0, j), z[c][0], q[c][j]);
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(i, j), z[c][i], out[c][j]);
+    }
+}
+
 // Multiply a column by the exact power of two that brings its largest magnitude into [1,2);
 // returns the removed binary exponent.  Works on the exponent fields with integer ops (fp64 has no
 // native max instruction; fmax() costs ~10 instructions).  Zero / denormal / non-finite maxima are

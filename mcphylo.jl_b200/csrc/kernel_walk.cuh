@@ -40,7 +40,10 @@ static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 // add is a compare-and-swap loop (~10 instructions, 38 % retries when the 8 warps of a CTA hit the
 // same branch).  Measured (profiles/r1_walk_notes.md): 5 % faster at K = 2, but 2.5-5 % SLOWER at
 // K = 4, where the kernel sits on a register knife-edge and the extra 64-bit row pointer spills.
-__host__ __device__ constexpr bool grad_in_l2(int K) { return K <= 3; }
+#ifndef MCP_GRAD_L2_MAXK
+#define MCP_GRAD_L2_MAXK 3
+#endif
+__host__ __device__ constexpr bool grad_in_l2(int K) { return K <= MCP_GRAD_L2_MAXK; }
 
 template <int K>
 struct WalkSmem {
@@ -77,6 +80,9 @@ struct WalkSmem {
 template <int K, int CPT, bool DYN_MODEL, bool SSCR>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
+#endif
+#ifndef MCP_EIGEN_NUM
+#define MCP_EIGEN_NUM 1
 #endif
 #ifndef MCP_PREFETCH_DIST
 #define MCP_PREFETCH_DIST 0   // L2 prefetch hints for gradient-pass operands: measured slower (22.3 vs 21.0 ms), kept for experiments
@@ -280,41 +286,38 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     const int cnt = min(CH, n_post - c * CH);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
-                        const int flags = (int)rh.x, ka = flags & 3, kb = (flags >> 2) & 3;
-                        // stored operand (at most one per op) first: its latency overlaps the rest
-                        double Lm[CPT][K];
-                        if (ka == mcp::OPK_MEM) ld_cols(rh.y, Lm);
-                        else if (kb == mcp::OPK_MEM) ld_cols(rh.z, Lm);
+                        const int flags = (int)rh.x, ka = flags & 3;
+                        // Canonical operand kinds (schedule.hpp): (LEAF, LEAF), (REG, LEAF), (MEM, REG).
                         double Da[CPT][K], Db[CPT][K];
-                        if (ka == mcp::OPK_LEAF) {
+                        auto leaf_cols = [&](int ch, double (&D)[CPT][K]) {
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
+                                const int code = min((int)cb[(j * 2 + ch) * TS + cc * TW], K);
+                                const double* t = tb + (j * 2 + ch) * 2 * KK1 + code * K;
 #pragma unroll
-                                for (int k = 0; k < K; ++k) Da[cc][k] = t[k];
+                                for (int k = 0; k < K; ++k) D[cc][k] = t[k];
                             }
-                        } else {
+                        };
+                        auto internal_cols = [&](int ch, const double (&L)[CPT][K], double (&D)[CPT][K]) {
                             double e[K], z[CPT][K];
 #pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 0) * 2 * K + k];
-                            if (ka == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Da); }
-                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Da); }
-                        }
-                        if (kb == mcp::OPK_LEAF) {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) Db[cc][k] = t[k];
-                            }
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
+                            eig_project<K, CPT, false>(mdl, L, e, nullptr, z, z);
+                            eig_expand<K, CPT>(mdl, z, L, D);
+                        };
+                        if (ka == mcp::OPK_MEM) {
+                            // stored operand requested first: its latency overlaps the product on the
+                            // register operand
+                            double Lm[CPT][K];
+                            ld_cols(rh.y, Lm);
+                            internal_cols(1, cur, Db);
+                            internal_cols(0, Lm, Da);
+                        } else if (ka == mcp::OPK_REG) {
+                            leaf_cols(1, Db);
+                            internal_cols(0, cur, Da);
                         } else {
-                            double e[K], z[CPT][K];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + 1) * 2 * K + k];
-                            if (kb == mcp::OPK_REG) { eig_project<K, CPT, false>(mdl, cur, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, cur, Db); }
-                            else { eig_project<K, CPT, false>(mdl, Lm, e, nullptr, z, z); eig_expand<K, CPT>(mdl, z, Lm, Db); }
+                            leaf_cols(0, Da);
+                            leaf_cols(1, Db);
                         }
 #pragma unroll
                         for (int cc = 0; cc < CPT; ++cc) {
@@ -368,72 +371,99 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             }
                         }
                         const int mk = (flags >> 8) & 3;
-                        // all stored operands of the family are requested up front
-                        double pm[CPT][K], La[CPT][K], Lb[CPT][K];
-                        if (mk == mcp::PREM_STACK) ld_cols(rh.w, pm);
+                        // Canonical family (schedule.hpp): a is the child whose pre vector stays in
+                        // registers (internal, OUT_KEEP) or a leaf; b is pushed (internal, OUT_PUSH) or a
+                        // leaf; b internal implies a internal.  pre[mother] lives in `cur`: it is either
+                        // already there (PREM_REG: kept by the op just before), popped from the LIFO, or pi.
+                        // All stored operands of the family are requested up front.
+                        double La[CPT][K], Lb[CPT][K];
+                        if (mk == mcp::PREM_STACK) ld_cols(rh.w, cur);
                         if (ai) ld_cols(rh.y, La);
                         if (bi) ld_cols(rh.z, Lb);
                         if (mk == mcp::PREM_ROOT) {
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
-                                for (int k = 0; k < K; ++k) pm[cc][k] = mdl.pi(k);
-                        } else if (mk == mcp::PREM_REG) {
+                                for (int k = 0; k < K; ++k) cur[cc][k] = mdl.pi(k);
+                        }
+                        // D = P L and Y: leaf child Y = dP L (table column); internal child Y = de * (Uinv L),
+                        // the eigen-coordinates of dP L (the numerator is then formed in eigen-space)
+                        double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
+                        auto leaf_cols = [&](int ch, double (&D)[CPT][K], double (&Y)[CPT][K]) {
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int code = min((int)cb[(j * 2 + ch) * TS + cc * TW], K);
+                                const double* t = tb + (j * 2 + ch) * 2 * KK1 + code * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) { D[cc][k] = t[k]; Y[cc][k] = t[KK1 + k]; }
+                            }
+                        };
+                        auto internal_cols = [&](int ch, const double (&L)[CPT][K], double (&D)[CPT][K], double (&Y)[CPT][K]) {
+                            double e[K], z[CPT][K];
+#pragma unroll
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
+#if MCP_EIGEN_NUM
+                            eig_project<K, CPT, true>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, Y);
+                            eig_expand<K, CPT>(mdl, z, L, D);
+#else
+                            double zd[CPT][K];
+                            eig_project<K, CPT, true>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, zd);
+                            eig_expand<K, CPT>(mdl, z, L, D);
+                            eig_expand0<K, CPT>(mdl, zd, Y);
+#endif
+                        };
+                        if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
+                        if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
+                        double qa[CPT][K], qb[CPT][K];
+                        double na[CPT], nb[CPT], inv[CPT];
+#pragma unroll
+                        for (int cc = 0; cc < CPT; ++cc) {
+                            double den = 0.0;
+                            na[cc] = 0.0;
+                            nb[cc] = 0.0;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                qa[cc][k] = cur[cc][k] * Db[cc][k];
+                                qb[cc][k] = cur[cc][k] * Da[cc][k];
+                                den = fma(qa[cc][k], Da[cc][k], den);
+                            }
+                            inv[cc] = fast_rcp(den) * vmask[cc];
+                        }
+                        // numerators q . (dP L) and the children's pre vectors P^T q (internal children only)
+                        auto num_direct = [&](const double (&q)[CPT][K], const double (&Y)[CPT][K], double (&n)[CPT]) {
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc)
 #pragma unroll
-                                for (int k = 0; k < K; ++k) pm[cc][k] = cur[cc][k];
-                        }
-                        double ea[K], ebv[K];
-                        double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
-                        if (ai) {
-                            double z[CPT][K], zd[CPT][K];
+                                for (int k = 0; k < K; ++k) n[cc] = fma(q[cc][k], Y[cc][k], n[cc]);
+                        };
+                        auto pre_child = [&](int ch, const double (&q)[CPT][K], const double (&Y)[CPT][K], double (&n)[CPT],
+                                             double (&out)[CPT][K]) {
+                            double e[K];
 #pragma unroll
-                            for (int k = 0; k < K; ++k) ea[k] = eb[(j * 2 + 0) * 2 * K + k];
-                            eig_project<K, CPT, true>(mdl, La, ea, eb + (j * 2 + 0) * 2 * K + K, z, zd);
-                            eig_expand<K, CPT>(mdl, z, La, Da);
-                            eig_expand0<K, CPT>(mdl, zd, Ya);
-                        } else {
+                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
+#if MCP_EIGEN_NUM
+                            eig_transposed_num<K, CPT>(mdl, q, e, Y, n, out);
+#else
+                            num_direct(q, Y, n);
+                            eig_transposed<K, CPT>(mdl, q, e, out);
+#endif
 #pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 0) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 0) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) { Da[cc][k] = t[k]; Ya[cc][k] = t[KK1 + k]; }
-                            }
-                        }
+                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(out[cc]);
+                        };
                         if (bi) {
-                            double z[CPT][K], zd[CPT][K];
-#pragma unroll
-                            for (int k = 0; k < K; ++k) ebv[k] = eb[(j * 2 + 1) * 2 * K + k];
-                            eig_project<K, CPT, true>(mdl, Lb, ebv, eb + (j * 2 + 1) * 2 * K + K, z, zd);
-                            eig_expand<K, CPT>(mdl, z, Lb, Db);
-                            eig_expand0<K, CPT>(mdl, zd, Yb);
+                            double pb[CPT][K];
+                            pre_child(1, qb, Yb, nb, pb);
+                            st_cols(rb[j].y2, pb);
                         } else {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + 1) * TS + cc * TW], K);
-                                const double* t = tb + (j * 2 + 1) * 2 * KK1 + code * K;
-#pragma unroll
-                                for (int k = 0; k < K; ++k) { Db[cc][k] = t[k]; Yb[cc][k] = t[KK1 + k]; }
-                            }
+                            num_direct(qb, Yb, nb);
                         }
-                        double qa[CPT][K], qb[CPT][K];
+                        if (ai) pre_child(0, qa, Ya, na, cur);   // cur (pre[mother]) is dead: qa, qb hold all that is left of it
+                        else num_direct(qa, Ya, na);
                         double ga = 0.0, gb = 0.0;
 #pragma unroll
                         for (int cc = 0; cc < CPT; ++cc) {
-                            double den = 0.0, na = 0.0, nb = 0.0;
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                qa[cc][k] = pm[cc][k] * Db[cc][k];
-                                qb[cc][k] = pm[cc][k] * Da[cc][k];
-                                den = fma(qa[cc][k], Da[cc][k], den);
-                                na = fma(qa[cc][k], Ya[cc][k], na);
-                                nb = fma(qb[cc][k], Yb[cc][k], nb);
-                            }
-                            const double inv = fast_rcp(den) * vmask[cc];
-                            ga = fma(na, inv, ga);
-                            gb = fma(nb, inv, gb);
+                            ga = fma(na[cc], inv[cc], ga);
+                            gb = fma(nb[cc], inv[cc], gb);
                         }
                         const double red = warp_pair_reduce(ga, gb, lane);   // lane 0: sum of ga, lane 16: sum of gb
                         if constexpr (GL2) {
@@ -441,37 +471,6 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         } else {
                             if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
                             else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
-                        }
-
-                        // pre[child] = P^T q, only internal children have one
-                        const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
-                        if (a_out != mcp::OUT_NONE) {
-                            double pa[CPT][K];
-                            eig_transposed<K, CPT>(mdl, qa, ea, pa);
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pa[cc]);
-                            if (a_out == mcp::OUT_KEEP) {
-#pragma unroll
-                                for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                    for (int k = 0; k < K; ++k) cur[cc][k] = pa[cc][k];
-                            } else {
-                                st_cols(rb[j].y1, pa);
-                            }
-                        }
-                        if (b_out != mcp::OUT_NONE) {
-                            double pb[CPT][K];
-                            eig_transposed<K, CPT>(mdl, qb, ebv, pb);
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(pb[cc]);
-                            if (b_out == mcp::OUT_KEEP) {
-#pragma unroll
-                                for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                    for (int k = 0; k < K; ++k) cur[cc][k] = pb[cc][k];
-                            } else {
-                                st_cols(rb[j].y2, pb);
-                            }
                         }
                     }
                 }

@@ -259,6 +259,14 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
             };
             int ka = operand(l, op.a_src, op.a_br);
             int kb = operand(r, op.b_src, op.b_br);
+            // Canonical operand order (the product Da * Db is commutative, bit for bit): the only
+            // kind pairs that occur are (LEAF, LEAF), (REG, LEAF) and (MEM, REG) -- the walk
+            // kernel branches three ways on a's kind alone.
+            if ((ka == OPK_LEAF && kb != OPK_LEAF) || (ka == OPK_REG && kb == OPK_MEM)) {
+                std::swap(ka, kb);
+                std::swap(op.a_src, op.b_src);
+                std::swap(op.a_br, op.b_br);
+            }
             op.flags = ka | (kb << 2);
             if (!want_grad && (ka == OPK_MEM || kb == OPK_MEM)) depth--;  // LIFO pop
             if (d == root) op.flags |= POST_ROOT;
@@ -304,6 +312,16 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
                 next = keep;
             } else if (ai) { a_out = OUT_KEEP; next = a; }
             else if (bi) { b_out = OUT_KEEP; next = b; }
+            // Canonical child order (the family form is symmetric in a and b): a is the child whose
+            // pre vector stays in registers (KEEP), b the pushed one or a leaf.  The kinds that occur
+            // are (LEAF, LEAF), (MEM/KEEP, LEAF) and (MEM/KEEP, MEM/PUSH).
+            if (b_out == OUT_KEEP) {
+                std::swap(ai, bi);
+                std::swap(a_out, b_out);
+                std::swap(op.a_src, op.b_src);
+                std::swap(op.a_br, op.b_br);
+                std::swap(op.a_dst, op.b_dst);
+            }
             op.flags = (ai ? OPK_MEM : OPK_LEAF) | ((bi ? OPK_MEM : OPK_LEAF) << 2) | (cur_kind << 8) |
                        (a_out << 10) | (b_out << 12);
             out.pre.push_back(op);

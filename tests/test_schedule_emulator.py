@@ -84,6 +84,16 @@ def test_structure_of_the_program():
             if kind == 2:
                 assert 0 <= src < i     # a slot is the index of an earlier op
     assert (post[-1][5] >> 5) & 1 == 1 and sum((op[5] >> 5) & 1 for op in post) == 1
+    # canonical operand order, which felsenstein_walk branches on: post ops are (LEAF, LEAF),
+    # (REG, LEAF) or (MEM, REG); pre families are (leaf, leaf), (KEEP, leaf) or (KEEP, PUSH), and a
+    # kept pre vector is consumed by the very next op (PREM_REG), everything else comes off the LIFO
+    for variant in (prog, capi.schedule_dump(ft.postorder_num, ft.parent_num, lr, False)):
+        assert {(op[5] & 3, (op[5] >> 2) & 3) for op in variant["post"]} <= {(0, 0), (1, 0), (2, 1)}
+    for i, op in enumerate(pre):
+        fl = op[5]
+        ka, kb, mk, ao, bo = fl & 3, (fl >> 2) & 3, (fl >> 8) & 3, (fl >> 10) & 3, (fl >> 12) & 3
+        assert (ka, kb, ao, bo) in {(0, 0, 0, 0), (2, 0, 1, 0), (2, 2, 1, 2)}
+        assert mk == (0 if i == 0 else (1 if ((pre[i - 1][5] >> 10) & 3) == 1 else 2))
     # LIFO depth of the gradient pass is logarithmic for any topology
     assert prog["n_stack"] <= int(np.log2(200)) + 1
     cat = mcp.ParseNewick("(" * 199 + "t000:1," + ",".join(f"t{i:03d}:1)" for i in range(1, 200)) + ";")
