@@ -72,6 +72,11 @@ struct ModelT {
     }
 };
 
+// NE = number of ACTIVE eigen-components: the host moves a null eigenvalue (every rate matrix has
+// one: its rows sum to zero) to the last position, where em1 = expm1(0) = 0 and de = 0 contribute
+// nothing, and the walk kernel is instantiated with NE = K - 1 (a quarter of the matrix-vector work
+// and of the U / Uinv constants at K = 4, half at K = 2).
+//
 // ---- eigen-space products for C columns at once (column index innermost, so one constant /
 // uniform-register operand feeds C independent DFMAs) ----
 //
@@ -84,11 +89,11 @@ struct ModelT {
 // L), and makes identity branches exact.
 //
 // z[c] = em1 * w[c],  w[c] = Uinv L[c];  WD also returns zd[c] = de * w[c]  (the eigen-coordinates of dP L)
-template <int K, int C, bool WD, class M>
+template <int K, int C, bool WD, int NE = K, class M>
 __device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K], const double (&em1)[K], const double* de,
                                             double (&z)[C][K], double (&zd)[C][K]) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
+    for (int i = 0; i < NE; ++i) {
         double w[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) w[c] = m.Ui(i, 0) * L[c][0];
@@ -104,37 +109,37 @@ __device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K],
     }
 }
 // out[c] = base[c] + U z[c]
-template <int K, int C, class M>
+template <int K, int C, int NE = K, class M>
 __device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], const double (&base)[C][K], double (&out)[C][K]) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
 #pragma unroll
         for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, 0), z[c][0], base[c][s]);
 #pragma unroll
-        for (int i = 1; i < K; ++i)
+        for (int i = 1; i < NE; ++i)
 #pragma unroll
             for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
     }
 }
 // out[c] = U z[c]
-template <int K, int C, class M>
+template <int K, int C, int NE = K, class M>
 __device__ __forceinline__ void eig_expand0(const M& m, const double (&z)[C][K], double (&out)[C][K]) {
 #pragma unroll
     for (int s = 0; s < K; ++s) {
 #pragma unroll
         for (int c = 0; c < C; ++c) out[c][s] = m.U(s, 0) * z[c][0];
 #pragma unroll
-        for (int i = 1; i < K; ++i)
+        for (int i = 1; i < NE; ++i)
 #pragma unroll
             for (int c = 0; c < C; ++c) out[c][s] = fma(m.U(s, i), z[c][i], out[c][s]);
     }
 }
 // out[c] = P^T q[c] = q[c] + Uinv^T (em1 * (U^T q[c]))
-template <int K, int C, class M>
+template <int K, int C, int NE = K, class M>
 __device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][K], const double (&em1)[K], double (&out)[C][K]) {
     double z[C][K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
+    for (int i = 0; i < NE; ++i) {
         double w[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) w[c] = m.U(0, i) * q[c][0];
@@ -150,7 +155,7 @@ __device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][
 #pragma unroll
         for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(0, j), z[c][0], q[c][j]);
 #pragma unroll
-        for (int i = 1; i < K; ++i)
+        for (int i = 1; i < NE; ++i)
 #pragma unroll
             for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(i, j), z[c][i], out[c][j]);
     }
@@ -159,12 +164,12 @@ __device__ __forceinline__ void eig_transposed(const M& m, const double (&q)[C][
 // As eig_transposed, and also the branch-gradient numerator q . (dP L) formed in eigen-space:
 //   q^T U diag(de) Uinv L = sum_i (U^T q)_i * yd_i,   yd = de * (Uinv L)  (from eig_project<WD>),
 // which reuses w = U^T q and saves the expansion U yd (K*K FMAs per internal child).
-template <int K, int C, class M>
+template <int K, int C, int NE = K, class M>
 __device__ __forceinline__ void eig_transposed_num(const M& m, const double (&q)[C][K], const double (&em1)[K],
                                                    const double (&yd)[C][K], double (&num)[C], double (&out)[C][K]) {
     double z[C][K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
+    for (int i = 0; i < NE; ++i) {
         double w[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) w[c] = m.U(0, i) * q[c][0];
@@ -183,7 +188,7 @@ __device__ __forceinline__ void eig_transposed_num(const M& m, const double (&q)
 #pragma unroll
         for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(0, j), z[c][0], q[c][j]);
 #pragma unroll
-        for (int i = 1; i < K; ++i)
+        for (int i = 1; i < NE; ++i)
 #pragma unroll
             for (int c = 0; c < C; ++c) out[c][j] = fma(m.Ui(i, j), z[c][i], out[c][j]);
     }

@@ -77,7 +77,9 @@ struct WalkSmem {
 // SSCR = true keeps the CTA's partials scratch in SHARED memory instead of HBM: the latency path for
 // small problems (MCMC-sized trees), where a lone warp would otherwise wait an L2 round trip for
 // every partial it has just written.
-template <int K, int CPT, bool DYN_MODEL, bool SSCR>
+// NE = active eigen-components (device_math.cuh): K - 1 when the host found (and moved last) a null
+// eigenvalue, the case for every rate matrix; K otherwise.
+template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
 #endif
@@ -302,8 +304,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             double e[K], z[CPT][K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
-                            eig_project<K, CPT, false>(mdl, L, e, nullptr, z, z);
-                            eig_expand<K, CPT>(mdl, z, L, D);
+                            eig_project<K, CPT, false, NE>(mdl, L, e, nullptr, z, z);
+                            eig_expand<K, CPT, NE>(mdl, z, L, D);
                         };
                         if (ka == mcp::OPK_MEM) {
                             // stored operand requested first: its latency overlaps the product on the
@@ -403,13 +405,13 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
 #if MCP_EIGEN_NUM
-                            eig_project<K, CPT, true>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, Y);
-                            eig_expand<K, CPT>(mdl, z, L, D);
+                            eig_project<K, CPT, true, NE>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, Y);
+                            eig_expand<K, CPT, NE>(mdl, z, L, D);
 #else
                             double zd[CPT][K];
-                            eig_project<K, CPT, true>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, zd);
-                            eig_expand<K, CPT>(mdl, z, L, D);
-                            eig_expand0<K, CPT>(mdl, zd, Y);
+                            eig_project<K, CPT, true, NE>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, zd);
+                            eig_expand<K, CPT, NE>(mdl, z, L, D);
+                            eig_expand0<K, CPT, NE>(mdl, zd, Y);
 #endif
                         };
                         if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
@@ -442,10 +444,10 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
 #if MCP_EIGEN_NUM
-                            eig_transposed_num<K, CPT>(mdl, q, e, Y, n, out);
+                            eig_transposed_num<K, CPT, NE>(mdl, q, e, Y, n, out);
 #else
                             num_direct(q, Y, n);
-                            eig_transposed<K, CPT>(mdl, q, e, out);
+                            eig_transposed<K, CPT, NE>(mdl, q, e, out);
 #endif
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(out[cc]);

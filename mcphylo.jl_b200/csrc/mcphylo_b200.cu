@@ -194,35 +194,45 @@ int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
     marks.push_back({ctx->device, (const void*)kern, smem});
     return 0;
 }
-template <int K, int CPT, bool DYN, bool SSCR>
+template <int K, int CPT, bool DYN, bool SSCR, int NE>
 int launch_walk_inst(mcp_ctx* ctx, const WalkParams& wp) {
-    int e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, DYN, SSCR>, ctx->smem_bytes);
+    int e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, DYN, SSCR, NE>, ctx->smem_bytes);
     if (e) return e;
-    felsenstein_walk<K, CPT, DYN, SSCR><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    felsenstein_walk<K, CPT, DYN, SSCR, NE><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
+// null_last: every model of the batch has a null eigenvalue, moved to the last position by the host
+// (true for any rate matrix) -> kernels with K - 1 active eigen-components.  Otherwise (a caller
+// passing some other decomposition) the full-K kernels, which exist in the constant-memory
+// (DYN) flavour only.
 template <int K>
-int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
-    if (ctx->smem_scratch && !dyn_model && ctx->cpt == 1) return launch_walk_inst<K, 1, false, true>(ctx, wp);
-    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true, false>(ctx, wp) : launch_walk_inst<K, 2, false, false>(ctx, wp);
-    return dyn_model ? launch_walk_inst<K, 1, true, false>(ctx, wp) : launch_walk_inst<K, 1, false, false>(ctx, wp);
+int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model, bool null_last) {
+    if (!null_last)
+        return ctx->cpt == 2 ? launch_walk_inst<K, 2, true, false, K>(ctx, wp) : launch_walk_inst<K, 1, true, false, K>(ctx, wp);
+    constexpr int NE = K - 1;
+    if (ctx->smem_scratch && !dyn_model && ctx->cpt == 1) return launch_walk_inst<K, 1, false, true, NE>(ctx, wp);
+    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true, false, NE>(ctx, wp) : launch_walk_inst<K, 2, false, false, NE>(ctx, wp);
+    return dyn_model ? launch_walk_inst<K, 1, true, false, NE>(ctx, wp) : launch_walk_inst<K, 1, false, false, NE>(ctx, wp);
 }
 template <int K, int CPT>
 int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, bool sscr, int* out) {
     int e;
+    constexpr int NE = K - 1;
     if (sscr) {
-        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, false, true>, smem))) return e;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K, 1, false, true>, block, smem));
+        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, false, true, NE>, smem))) return e;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K, 1, false, true, NE>, block, smem));
         return 0;
     }
-    // the dynamic-model variant needs a few more registers: size the persistent grid for it
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false>, smem))) return e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, false, false>, smem))) return e;
-    int o1 = 0, o2 = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true, false>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false, false>, block, smem));
-    *out = std::min(o1, o2);
+    // the variants differ by a few registers: size the persistent grid for the most demanding one
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, NE>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, false, false, NE>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, K>, smem))) return e;
+    int o1 = 0, o2 = 0, o3 = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true, false, NE>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false, false, NE>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, felsenstein_walk<K, CPT, true, false, K>, block, smem));
+    *out = std::min(o1, std::min(o2, o3));
     return 0;
 }
 template <int K>
@@ -264,6 +274,27 @@ size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
     }
 
 bool k_templated(int K) { return K >= 2 && K <= 6; }
+
+// Copies the eigen-decomposition (U, Uinv column-major K x K, D) with the eigenvalue of smallest
+// magnitude moved to the LAST position (columns of U, rows of Uinv, entries of D permuted alike:
+// U diag(f(D)) Uinv is unchanged).  Returns true when that eigenvalue is null, |D_i| <= 8 eps max|D| --
+// every rate matrix has one (rows sum to zero; LAPACK returns it as ~1e-17) -- so that its terms
+// expm1(mu t D_i r) and D_i mu r exp(.) vanish to rounding and the walk kernel may skip them.
+bool null_eigenvalue_last(const double* U, const double* D, const double* Uinv, int K, double* Uo, double* Do, double* Uinvo) {
+    int i0 = 0;
+    double dmax = 0.0;
+    for (int i = 0; i < K; ++i) {
+        if (std::fabs(D[i]) < std::fabs(D[i0])) i0 = i;
+        dmax = std::max(dmax, std::fabs(D[i]));
+    }
+    for (int i = 0; i < K; ++i) {
+        const int from = i == K - 1 ? i0 : (i < i0 ? i : i + 1);
+        Do[i] = D[from];
+        for (int s = 0; s < K; ++s) Uo[s + K * i] = U[s + K * from];
+        for (int j = 0; j < K; ++j) Uinvo[i + K * j] = Uinv[from + K * j];
+    }
+    return std::fabs(D[i0]) <= 8.0 * 2.220446049250313e-16 * dmax;
+}
 bool k_supported(int K) { return K >= 2 && K <= KMAX_GENERIC; }
 
 struct BatchArgs {
@@ -298,10 +329,10 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
         while (block > 32 && (total_cols + block - 1) / block < 6LL * ctx->sm_count) block >>= 1;
     }
     // Two columns per thread amortise the per-op overhead (descriptor decode, constant loads, warp
-    // reduction) once there is enough work to fill the GPU.  Measured: 1.2x at K = 2; at K = 4 the
-    // doubled register state costs more occupancy than it saves (profiles/r1_walk_notes.md).
+    // reduction) once there is enough work to fill the GPU.  Measured: 1.28x at K = 2, 1.06x at K = 4
+    // (cfg4: 78.2 -> 73.6 ms; 2 CTAs x 256 threads per SM at 128 registers), profiles/r1_walk_notes.md.
     int cpt = ctx->opt_cpt;
-    if (cpt <= 0) cpt = (K <= 3 && total_cols / (2LL * block) >= 12LL * ctx->sm_count) ? 2 : 1;
+    if (cpt <= 0) cpt = (K <= 4 && total_cols / (2LL * block) >= 12LL * ctx->sm_count) ? 2 : 1;
     if (!k_templated(K)) {   // generic-K kernel: one column per thread, at most 128 threads per CTA
         cpt = 1;
         if (block > 128) block = 128;
@@ -552,13 +583,13 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
 
     // per-evaluation parameters
     double* hd = (double*)ctx->h_dyn.p;
+    bool all_null_last = true;
     for (int t = 0; t < T; ++t) {
         const int NN = a.NN[t];
         double* d = hd + ctx->trees[t].dyn_off;
         std::memcpy(d + dyn_blv(NN), a.blv[t], sizeof(double) * (NN - 1));
-        std::memcpy(d + dyn_U(NN), a.U[t], sizeof(double) * K * K);
-        std::memcpy(d + dyn_D(NN, K), a.D[t], sizeof(double) * K);
-        std::memcpy(d + dyn_Uinv(NN, K), a.Uinv[t], sizeof(double) * K * K);
+        // eigen-decomposition with a null eigenvalue (if any) moved to the last position
+        all_null_last = null_eigenvalue_last(a.U[t], a.D[t], a.Uinv[t], K, d + dyn_U(NN), d + dyn_D(NN, K), d + dyn_Uinv(NN, K)) && all_null_last;
         d[dyn_mu(NN, K)] = a.mu[t];
         std::memcpy(d + dyn_rates(NN, K), a.rates[t], sizeof(double) * R);
         std::memcpy(d + dyn_pi(NN, K, R), a.pi[t], sizeof(double) * K);
@@ -612,11 +643,12 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     int n_models = 0;
     for (int t = 0; t < T && k_templated(K); ++t) {
         double cand[MODEL_SLOT];
-        std::memcpy(cand, a.U[t], sizeof(double) * K * K);
-        std::memcpy(cand + K * K, a.Uinv[t], sizeof(double) * K * K);
+        const double* dt = hd + ctx->trees[t].dyn_off;       // the permuted decomposition stored above
+        std::memcpy(cand, dt + dyn_U(a.NN[t]), sizeof(double) * K * K);
+        std::memcpy(cand + K * K, dt + dyn_Uinv(a.NN[t], K), sizeof(double) * K * K);
         std::memcpy(cand + 2 * K * K, a.pi[t], sizeof(double) * K);
         for (int r = 0; r < R; ++r)
-            for (int i = 0; i < K; ++i) cand[2 * K * K + K + r * K + i] = a.D[t][i] * a.rates[t][r] * a.mu[t];
+            for (int i = 0; i < K; ++i) cand[2 * K * K + K + r * K + i] = dt[dyn_D(a.NN[t], K) + i] * a.rates[t][r] * a.mu[t];
         int slot = -1;
         for (int m = 0; m < n_models && slot < 0; ++m)
             if (std::memcmp(hm + (size_t)m * MODEL_SLOT, cand, sizeof(double) * model_doubles) == 0) slot = m;
@@ -628,13 +660,14 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         }
         hd[ctx->trees[t].dyn_off + dyn_slot(a.NN[t], K, R)] = (double)slot;
     }
-    const bool dyn_model = n_models > 1;
+    // the walk kernels with all K eigen-components read their model from constant memory only
+    const bool dyn_model = n_models > 1 || (k_templated(K) && !all_null_last);
 
     cudaStream_t st = ctx->stream;
     mcp_stats& s = ctx->stats;
     s = mcp_stats{};
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-    if (n_models > 1) {   // several models: slots in constant memory; one model travels as a kernel parameter
+    if (dyn_model) {   // several models: slots in constant memory; one model travels as a kernel parameter
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_model, hm, sizeof(double) * MODEL_SLOT * n_models, 0, cudaMemcpyHostToDevice, st));
         s.h2d_bytes += (int64_t)(sizeof(double) * MODEL_SLOT * n_models);
     }
@@ -695,7 +728,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     if (ctx->level_mode) {
         MCP_DISPATCH_K(K, rc = launch_levels<KK>(ctx, wp, dyn_model));
     } else if (k_templated(K)) {
-        MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp, dyn_model));
+        MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp, dyn_model, all_null_last));
     } else {
         felsenstein_walk_generic<<<ctx->grid, ctx->block, ctx->smem_bytes, st>>>(wp, K);
         CUDA_TRY(ctx, cudaGetLastError());

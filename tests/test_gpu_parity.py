@@ -176,6 +176,83 @@ def test_two_columns_per_thread(oracle, K, R, S):
         ctx.set_columns_per_thread(0)
 
 
+def _shifted(model, shift):
+    """A decomposition WITHOUT a null eigenvalue: P(t) = exp(-shift mu t r) * P_model(t).  Not a
+    stochastic matrix, but a valid input of the ABI (and of the reference, which takes any U, D, Uinv)."""
+    def f(pi, srates):
+        U, D, Uinv, mu = model(pi, srates)
+        return U, np.asarray(D, float) - shift, Uinv, mu
+    return f
+
+
+@pytest.mark.parametrize("K,R,cpt", [(2, 1, 1), (2, 1, 2), (4, 4, 1), (4, 2, 2), (3, 2, 1), (6, 1, 1)])
+def test_decomposition_without_null_eigenvalue(oracle, K, R, cpt):
+    """The walk kernels skip the null eigenvalue every rate matrix has (moved last by the host);
+    any other decomposition must take the full-K kernels and still match the oracle.  Also checks
+    the eigenvalue ORDER is irrelevant (the null one first / in the middle / last)."""
+    rng = np.random.default_rng(900 + 10 * K + cpt)
+    tree = random_tree(29, rng, multifurcate=True)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    base, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, base(pi, srates), pi, rates, 333, rng, gap_frac=0.05)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+
+    def rolled(shift_pos):
+        def f(pi_, sr_):
+            U, D, Uinv, mu = base(pi_, sr_)
+            idx = np.roll(np.arange(K), shift_pos)
+            return np.asfortranarray(U[:, idx]), np.asarray(D)[idx], np.asfortranarray(Uinv[idx, :]), mu
+        return f
+
+    ctx = mcp.get_context()
+    try:
+        ctx.set_level_mode(0)
+        ctx.set_columns_per_thread(cpt)
+        ctx.set_launch(64, 0)
+        for model in (_shifted(base, 0.37), rolled(0), rolled(1), rolled(K - 1)):
+            pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+            ll, g = mcp.gradlogpdf(pd, aln)
+            ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+            _check(ll, g, ll_o, g_o)
+            _check(mcp.logpdf(pd, aln), None, ll_o, None)
+    finally:
+        ctx.set_level_mode(-1)
+        ctx.set_launch(0, 0)
+        ctx.set_columns_per_thread(0)
+
+
+def test_batch_mixing_models_with_and_without_null_eigenvalue(oracle):
+    """One batch launch, several distinct models of which one has no null eigenvalue: the whole
+    batch takes the full-K constant-memory kernels."""
+    rng = np.random.default_rng(4242)
+    K = 4
+    trees, alns, expect, pis, srs = [], [], [], [], []
+    models = [mcp.GTR, _shifted(mcp.GTR, 0.2), mcp.GTR]
+    for i, model in enumerate(models):
+        t = random_tree(15 + 4 * i, rng)
+        pi = rng.dirichlet(np.ones(K) * 5)
+        sr = rng.uniform(0.5, 2.5, size=6)
+        codes, leaf_nums = simulate_codes(t, mcp.GTR(pi, sr), pi, np.ones(1), 500, rng)
+        aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+        ll_o, g_o = _oracle_eval(oracle, t, codes, leaf_nums, K, model, pi, sr, [1.0])
+        ll, g = mcp.gradlogpdf(mcp.PhyloDist(t, pi, sr, [1.0], model), aln)
+        _check(ll, g, ll_o, g_o)
+        trees.append(t); alns.append(aln); expect.append((ll_o, g_o)); pis.append(pi); srs.append(sr)
+    # the batch entry point with per-tree models
+    from mcphylo_jl_b200.phylodist import _device_alignment
+    ctx = mcp.get_context()
+    handles, flat = [], []
+    for t, aln, m, p_, s_ in zip(trees, alns, models, pis, srs):
+        ft = mcp.flatten(t)
+        U, D, Uinv, mu = m(p_, s_)
+        handles.append(_device_alignment(aln, ft.leaf_nums, K, ctx))
+        flat.append((ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, np.ones(1), p_))
+    lls, grads = ctx.eval_batch(handles, flat, want_grad=True)
+    for ll, g, (ll_o, g_o) in zip(lls, grads, expect):
+        _check(ll, g, ll_o, g_o)
+
+
 def test_topology_cache_and_branch_updates(oracle):
     """Same topology, new branch lengths (the leapfrog pattern), then an NNI."""
     rng = np.random.default_rng(21)
