@@ -34,6 +34,31 @@ __device__ __forceinline__ void st_partial(double* p, const double (&v)[K]) {
     }
 }
 
+// Predicated load INTO the existing registers (KEEP_OLD: v keeps its value when !pred).  A plain `if (pred)
+// ld_partial(...)` makes the compiler load into temporaries and move them over under the predicate
+// (asm outputs are always fresh values): K moves per load in the innermost loop.
+// KEEP_OLD = false: v is undefined when !pred -- tells the compiler the previous contents are dead, so
+// the registers are free between the last use of v and this load.
+template <int K, bool KEEP_OLD>
+__device__ __forceinline__ void ld_partial_if(bool pred, const double* p, double (&v)[K]) {
+    if constexpr (!KEEP_OLD) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) asm volatile("" : "=d"(v[k]));
+    }
+    if constexpr (K == 4) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];\n\t}"
+                     : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]) : "l"(p), "r"((unsigned)pred) : "memory");
+    } else if constexpr (K == 2) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.cg.v2.f64 {%0,%1}, [%2];\n\t}"
+                     : "+d"(v[0]), "+d"(v[1]) : "l"(p), "r"((unsigned)pred) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cg.f64 %0, [%1];\n\t}"
+                         : "+d"(v[k]) : "l"(p + k), "r"((unsigned)pred) : "memory");
+    }
+}
+
 // Identity moves the compiler cannot see through: a value passed through them is kept in a register
 // (or spilled as one word) instead of being RE-COMPUTED at every use.  ptxas otherwise rematerialises
 // the per-thread scratch base (blockIdx * scratch_per_cta + tid * K * 8, ~13 instructions) in front of

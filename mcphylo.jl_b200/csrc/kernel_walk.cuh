@@ -83,6 +83,9 @@ template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
 #endif
+#ifndef MCP_EARLY_LOADS
+#define MCP_EARLY_LOADS (CPT == 1)   // stored operands of op j+1 are requested during op j (measured: +3 % at one column per thread; with two the pinned destination registers cost spills)
+#endif
 #ifndef MCP_EIGEN_NUM
 #define MCP_EIGEN_NUM 1
 #endif
@@ -254,6 +257,21 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     }
                 }
             };
+            // keep_old: v untouched when !pred; otherwise v is undefined then (its old contents are dead)
+            auto ld_cols_if = [&](bool pred, unsigned off, double (&v)[CPT][K], auto keep_old) {
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    if constexpr (SSCR) {
+                        const double* src = reinterpret_cast<const double*>(scr + off + c * col_bytes);
+                        if (pred) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) v[c][k] = src[k];
+                        }
+                    } else {
+                        ld_partial_if<K, decltype(keep_old)::value>(pred, reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
+                    }
+                }
+            };
             auto st_cols = [&](unsigned off, const double (&v)[CPT][K]) {
 #pragma unroll
                 for (int c = 0; c < CPT; ++c) {
@@ -286,9 +304,30 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
                     const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_post - c * CH);
+                    double Lm[CPT][K];                                              // the op's stored operand
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
                         const int flags = (int)rh.x, ka = flags & 3;
+                        // The stored operand of the NEXT op is requested as soon as Lm is free, so that its
+                        // L2 / HBM latency overlaps the rest of this op (the first op of a chunk requests
+                        // its own: the next chunk's records only become visible at the chunk barrier).
+                        if constexpr (!SSCR && MCP_PREFETCH_DIST > 0) {
+                            // a stored operand was written before the whole subtree of the other child was
+                            // walked: pull it from HBM into L2 a few ops ahead (one request per 128-byte line)
+                            if (j + MCP_PREFETCH_DIST < cnt && (lane * K * 8) % 128 == 0) {
+                                const uint2 rf = *reinterpret_cast<const uint2*>(rb + j + MCP_PREFETCH_DIST);
+                                if (((int)rf.x & 3) == mcp::OPK_MEM) {
+#pragma unroll
+                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.y + cc * col_bytes);
+                                }
+                            }
+                        }
+                        auto request_next = [&]() {
+                            if (MCP_EARLY_LOADS) {
+                                const uint2 rn = *reinterpret_cast<const uint2*>(rb + (j + 1 < cnt ? j + 1 : j));   // flags, xa
+                                ld_cols_if(j + 1 < cnt && ((int)rn.x & 3) == mcp::OPK_MEM, rn.y, Lm, std::false_type{});
+                            }
+                        };
                         // Canonical operand kinds (schedule.hpp): (LEAF, LEAF), (REG, LEAF), (MEM, REG).
                         double Da[CPT][K], Db[CPT][K];
                         auto leaf_cols = [&](int ch, double (&D)[CPT][K]) {
@@ -308,16 +347,21 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             eig_expand<K, CPT, NE>(mdl, z, L, D);
                         };
                         if (ka == mcp::OPK_MEM) {
-                            // stored operand requested first: its latency overlaps the product on the
-                            // register operand
-                            double Lm[CPT][K];
-                            ld_cols(rh.y, Lm);
-                            internal_cols(1, cur, Db);
-                            internal_cols(0, Lm, Da);
+                            ld_cols_if(!MCP_EARLY_LOADS || j == 0, rh.y, Lm, std::true_type{});
+                            if (MCP_EARLY_LOADS) {
+                                internal_cols(0, Lm, Da);
+                                request_next();
+                                internal_cols(1, cur, Db);
+                            } else {   // latency of the stored operand overlaps the product on the register operand
+                                internal_cols(1, cur, Db);
+                                internal_cols(0, Lm, Da);
+                            }
                         } else if (ka == mcp::OPK_REG) {
+                            request_next();
                             leaf_cols(1, Db);
                             internal_cols(0, cur, Da);
                         } else {
+                            request_next();
                             leaf_cols(0, Da);
                             leaf_cols(1, Db);
                         }
@@ -346,6 +390,11 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             if (p.want_grad) {
                 const int n_pre = tr.n_pre, n_chunks = (n_pre + CH - 1) / CH;
                 prologue(pre_ops, n_pre, true);
+                // the first family is the root's (PREM_ROOT, and only that one): its pre vector is pi
+#pragma unroll
+                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) cur[cc][k] = mdl.pi(k);
                 for (int c = 0; c < n_chunks; ++c) {
                     chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
                     const OpRec* rb = srec + (c & 1) * CH;
@@ -353,6 +402,19 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
                     const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_pre - c * CH);
+                    double La[CPT][K], Lb[CPT][K];                                  // the family's stored child partials
+                    // All stored operands of a family -- pre[mother] popped from the LIFO (into `cur`), the
+                    // internal children's partials -- are requested together: by the first op of a chunk for
+                    // itself, otherwise by the op before it, ahead of its warp reduction and atomics, where
+                    // nothing but `cur` is live any more (profiles/r1_walk_notes.md: 19 % of all stall samples
+                    // sat on the first use of these loads).
+                    auto request = [&](const uint4& r, bool on) {
+                        const int fl = (int)r.x;
+                        ld_cols_if(on && ((fl >> 8) & 3) == mcp::PREM_STACK, r.w, cur, std::true_type{});
+                        ld_cols_if(on && (fl & 3) == mcp::OPK_MEM, r.y, La, std::false_type{});
+                        ld_cols_if(on && ((fl >> 2) & 3) == mcp::OPK_MEM, r.z, Lb, std::false_type{});
+                    };
+                    if (MCP_EARLY_LOADS) request(*reinterpret_cast<const uint4*>(rb), true);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
                         const int flags = (int)rh.x;
@@ -372,22 +434,12 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 }
                             }
                         }
-                        const int mk = (flags >> 8) & 3;
                         // Canonical family (schedule.hpp): a is the child whose pre vector stays in
                         // registers (internal, OUT_KEEP) or a leaf; b is pushed (internal, OUT_PUSH) or a
                         // leaf; b internal implies a internal.  pre[mother] lives in `cur`: it is either
-                        // already there (PREM_REG: kept by the op just before), popped from the LIFO, or pi.
-                        // All stored operands of the family are requested up front.
-                        double La[CPT][K], Lb[CPT][K];
-                        if (mk == mcp::PREM_STACK) ld_cols(rh.w, cur);
-                        if (ai) ld_cols(rh.y, La);
-                        if (bi) ld_cols(rh.z, Lb);
-                        if (mk == mcp::PREM_ROOT) {
-#pragma unroll
-                            for (int cc = 0; cc < CPT; ++cc)
-#pragma unroll
-                                for (int k = 0; k < K; ++k) cur[cc][k] = mdl.pi(k);
-                        }
+                        // already there (PREM_REG: kept by the op just before; PREM_ROOT: pi, set before the
+                        // pass) or popped from the LIFO.
+                        if (!MCP_EARLY_LOADS) request(rh, true);
                         // D = P L and Y: leaf child Y = dP L (table column); internal child Y = de * (Uinv L),
                         // the eigen-coordinates of dP L (the numerator is then formed in eigen-space)
                         double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
@@ -461,6 +513,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         }
                         if (ai) pre_child(0, qa, Ya, na, cur);   // cur (pre[mother]) is dead: qa, qb hold all that is left of it
                         else num_direct(qa, Ya, na);
+                        if (MCP_EARLY_LOADS) request(*reinterpret_cast<const uint4*>(rb + (j + 1 < cnt ? j + 1 : j)), j + 1 < cnt);
                         double ga = 0.0, gb = 0.0;
 #pragma unroll
                         for (int cc = 0; cc < CPT; ++cc) {

@@ -30,6 +30,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "device_layout.cuh"
@@ -1063,7 +1064,7 @@ int mcp_wave_columns(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* c
     if (!k_supported(K)) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int block = ctx->opt_block > 0 ? ctx->opt_block : 256;
-    int cpt = ctx->opt_cpt > 0 ? ctx->opt_cpt : (K <= 3 ? 2 : 1);
+    int cpt = ctx->opt_cpt > 0 ? ctx->opt_cpt : (K <= 4 ? 2 : 1);   // what prepare_topology picks for large inputs
     int occ = 0, rc = 0;
     if (k_templated(K)) {
         const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad ? 1 : 0, block, cpt);

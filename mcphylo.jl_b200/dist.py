@@ -155,7 +155,7 @@ class PipelinedEvaluator:
             # pin the tile width the wave size was computed for: the automatic choice narrows the
             # tiles of inputs below two waves, which a one-wave block is by construction
             self.ctx.set_launch(256 if self.K <= 6 else 128, 0)
-            self.ctx.set_columns_per_thread(2 if self.K <= 3 else 1)
+            self.ctx.set_columns_per_thread(2 if self.K <= 4 else 1)
         for lo, hi in self.bounds:
             host = torch.from_numpy(np.ascontiguousarray(self.codes[:, lo:hi])).pin_memory()
             aln = self.ctx.alignment_from_codes(host.numpy(), self.K, self.leaf_nums)
