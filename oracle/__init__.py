@@ -5,3 +5,4 @@ import this package.  See felsenstein_oracle.c for what it restates and how it i
 """
 from .oracle import (build, codes_to_dense, felsenstein, num_threads, transition,  # noqa: F401
                      compound_dirichlet_logpdf, compound_dirichlet_gradlogpdf, exponential_bl_gradlogpdf)
+from .extended import expm_extended, felsenstein_extended  # noqa: F401

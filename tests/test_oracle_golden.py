@@ -142,3 +142,49 @@ def test_rerooting_invariance_and_root_branch_gradients(oracle, K, R):
     merged = [c for c in unrooted.children if c.name == (b if a.nchild > 0 else a).name]
     if merged:
         assert g_u[merged[0].num - 1] == pytest.approx(g[a.num - 1], rel=1e-9)
+
+
+# ---- the extended-precision arbiter (oracle/extended.py) -------------------------------------
+
+def _extended(orc, tree, codes, leaf_nums, K, model_out, rates, pi):
+    ft = mcp.flatten(tree)
+    U, D, Uinv, mu = model_out
+    ll, g = orc.felsenstein_extended(codes, leaf_nums, K, ft.postorder_num, ft.parent_num, ft.blv,
+                                     U, D, Uinv, mu, np.asarray(rates, float), np.asarray(pi, float))
+    return float(ll), g.astype(np.float64)
+
+
+def test_extended_arbiter_reproduces_the_reference_goldens(oracle):
+    tree, _, codes, leaf_nums, fx = golden_case("primates")
+    ll, _ = _extended(oracle, tree, codes, leaf_nums, 4, mcp.JC(np.asarray(fx["base_freq"]), [1.0]), [1.0], fx["base_freq"])
+    assert abs(ll - fx["logpdf"]) <= 1e-12 * abs(fx["logpdf"])
+    tree, x, codes, leaf_nums, fx = golden_case("simudata")
+    ll, g = _extended(oracle, tree, codes, leaf_nums, 4, mcp.JC(np.asarray(fx["base_freq"]), [1.0]), [1.0], fx["base_freq"])
+    assert np.max(np.abs(g - fx["grad"]) / np.abs(fx["grad"])) <= 1e-12
+    assert abs(ll - (-738.7363926174138)) <= 1e-12 * abs(ll)
+    ll_o, g_o = _eval(oracle, tree, x, mcp.JC, fx["base_freq"], [1.0], [1.0])
+    assert abs(ll - ll_o) <= 1e-13 * abs(ll) and np.max(np.abs(g - g_o) / np.abs(g_o)) <= 1e-12
+
+
+def test_reference_formula_loses_digits_on_short_branches_with_slow_rates(oracle):
+    """Why GPU parity tests carry an arbiter: on a benign case the fp64 oracle (the reference's
+    U diag(exp) Uinv arithmetic) agrees with the extended-precision evaluation to 1e-12; with a
+    slow rate category (t * r ~ 1e-8) its off-diagonal transition probabilities
+    are cancellation noise and single gradient components are off by > 1e-8 (Conditioning)."""
+    from synth import random_tree, simulate_codes
+
+    rng = np.random.default_rng(314)
+    K = 4
+    tree = random_tree(12, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model_out = mcp.GTR(pi, rng.uniform(0.5, 2.0, size=6))
+    # data simulated at rate 1 (plenty of mismatches along the branches), then evaluated with a slow category
+    codes, leaf_nums = simulate_codes(tree, model_out, pi, np.ones(1), 400, rng)
+    ft = mcp.flatten(tree)
+    x = oracle.codes_to_dense(codes, leaf_nums, K, ft.NN)
+    for rates, lo, hi in (([1.0], 0.0, 1e-12), ([1e-7, 1.0], 1e-9, 1e-4)):
+        rates = np.asarray(rates)
+        ll_o, g_o = oracle.felsenstein(x, ft.postorder_num, ft.parent_num, ft.blv, *model_out, rates, pi, True, 1)
+        ll_x, g_x = _extended(oracle, tree, codes, leaf_nums, K, model_out, rates, pi)
+        err = float(np.max(np.abs(g_o - g_x) / np.maximum(np.abs(g_x), 1e-3 * np.max(np.abs(g_x)))))
+        assert lo <= err <= hi, (rates, err)
