@@ -103,7 +103,10 @@ int mcp_alignment_destroy(mcp_ctx *ctx, mcp_alignment *aln);
  *   parent_num     NN, indexed by num: number of the mother, 0 for the root
  *   blv            NN-1, indexed by num: get_branchlength_vector(tree)
  *   U, D, Uinv, mu what d.substitution_model(base_freq, substitution_rates) returns
- *                  (K x K col-major, K, K x K col-major, scalar)
+ *                  (K x K col-major, K, K x K col-major, scalar).  Eigenvalues may come in any
+ *                  order (LAPACK's); the library works on a permuted copy with the null eigenvalue
+ *                  of a rate matrix last and skips that component in its kernels.  A
+ *                  decomposition without a null eigenvalue is accepted too (full-K kernels).
  *   rates, R       d.rates
  *   pi             d.base_freq (K)
  *   ll_out         1 double
