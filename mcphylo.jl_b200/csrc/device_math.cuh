@@ -72,9 +72,6 @@ __device__ __forceinline__ double keep_f64(double v) {
     return v;
 }
 
-// L2 prefetch of a line the thread will read a few ops later (HBM -> L2 ahead of the demand load)
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");

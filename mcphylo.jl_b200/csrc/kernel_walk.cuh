@@ -86,12 +86,6 @@ template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE>
 #ifndef MCP_EARLY_LOADS
 #define MCP_EARLY_LOADS (CPT == 1)   // stored operands of op j+1 are requested during op j (measured: +3 % at one column per thread; with two the pinned destination registers cost spills)
 #endif
-#ifndef MCP_EIGEN_NUM
-#define MCP_EIGEN_NUM 1
-#endif
-#ifndef MCP_PREFETCH_DIST
-#define MCP_PREFETCH_DIST 0   // L2 prefetch hints for gradient-pass operands: measured slower (22.3 vs 21.0 ms), kept for experiments
-#endif
 __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
@@ -311,17 +305,6 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         // The stored operand of the NEXT op is requested as soon as Lm is free, so that its
                         // L2 / HBM latency overlaps the rest of this op (the first op of a chunk requests
                         // its own: the next chunk's records only become visible at the chunk barrier).
-                        if constexpr (!SSCR && MCP_PREFETCH_DIST > 0) {
-                            // a stored operand was written before the whole subtree of the other child was
-                            // walked: pull it from HBM into L2 a few ops ahead (one request per 128-byte line)
-                            if (j + MCP_PREFETCH_DIST < cnt && (lane * K * 8) % 128 == 0) {
-                                const uint2 rf = *reinterpret_cast<const uint2*>(rb + j + MCP_PREFETCH_DIST);
-                                if (((int)rf.x & 3) == mcp::OPK_MEM) {
-#pragma unroll
-                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.y + cc * col_bytes);
-                                }
-                            }
-                        }
                         auto request_next = [&]() {
                             if (MCP_EARLY_LOADS) {
                                 const uint2 rn = *reinterpret_cast<const uint2*>(rb + (j + 1 < cnt ? j + 1 : j));   // flags, xa
@@ -419,21 +402,6 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
                         const int flags = (int)rh.x;
                         const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
-                        if constexpr (!SSCR && MCP_PREFETCH_DIST > 0) {
-                            // the children partials of a later family were written in the post pass, long ago:
-                            // pull them from HBM into L2 now (one request per 128-byte line)
-                            if (j + MCP_PREFETCH_DIST < cnt && (lane * K * 8) % 128 == 0) {
-                                const uint4 rf = *reinterpret_cast<const uint4*>(rb + j + MCP_PREFETCH_DIST);
-                                if (((int)rf.x & 3) == mcp::OPK_MEM) {
-#pragma unroll
-                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.y + cc * col_bytes);
-                                }
-                                if ((((int)rf.x >> 2) & 3) == mcp::OPK_MEM) {
-#pragma unroll
-                                    for (int cc = 0; cc < CPT; ++cc) prefetch_l2(scr + rf.z + cc * col_bytes);
-                                }
-                            }
-                        }
                         // Canonical family (schedule.hpp): a is the child whose pre vector stays in
                         // registers (internal, OUT_KEEP) or a leaf; b is pushed (internal, OUT_PUSH) or a
                         // leaf; b internal implies a internal.  pre[mother] lives in `cur`: it is either
@@ -456,15 +424,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             double e[K], z[CPT][K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
-#if MCP_EIGEN_NUM
                             eig_project<K, CPT, true, NE>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, Y);
                             eig_expand<K, CPT, NE>(mdl, z, L, D);
-#else
-                            double zd[CPT][K];
-                            eig_project<K, CPT, true, NE>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, zd);
-                            eig_expand<K, CPT, NE>(mdl, z, L, D);
-                            eig_expand0<K, CPT, NE>(mdl, zd, Y);
-#endif
                         };
                         if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
                         if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
@@ -495,12 +456,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             double e[K];
 #pragma unroll
                             for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
-#if MCP_EIGEN_NUM
                             eig_transposed_num<K, CPT, NE>(mdl, q, e, Y, n, out);
-#else
-                            num_direct(q, Y, n);
-                            eig_transposed<K, CPT, NE>(mdl, q, e, out);
-#endif
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) rescale_pow2<K>(out[cc]);
                         };
