@@ -36,14 +36,20 @@ struct __align__(16) OpRec {
 static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 
 // Where a CTA accumulates its branch-gradient sums.  K <= 3: directly in its accumulator row in
-// global memory with fire-and-forget RED.ADD.F64 (the row stays in L2); a shared-memory fp64 atomic
-// add is a compare-and-swap loop (~10 instructions, 38 % retries when the 8 warps of a CTA hit the
-// same branch).  Measured (profiles/r1_walk_notes.md): 5 % faster at K = 2, but 2.5-5 % SLOWER at
-// K = 4, where the kernel sits on a register knife-edge and the extra 64-bit row pointer spills.
+// global memory with fire-and-forget RED.ADD.F64 (the row stays in L2; 5 % faster than any
+// shared-memory scheme at K = 2).  K >= 4: in shared memory, without atomics (see WALK_PART_BYTES).
 #ifndef MCP_GRAD_L2_MAXK
 #define MCP_GRAD_L2_MAXK 3
 #endif
 __host__ __device__ constexpr bool grad_in_l2(int K) { return K <= MCP_GRAD_L2_MAXK; }
+
+// Shared-memory accumulator (K >= 4): the per-warp sums of a chunk's 2 * CH branch terms are parked here
+// and folded into the accumulator by one thread per term after the chunk barrier, in fixed warp order
+// -- no atomics (a shared fp64 atomic add is a compare-and-swap loop, ~10 instructions, 38 % retries
+// with 8 warps on one address) and a run-to-run reproducible gradient.
+//   [2 buffers][CH ops][2 children][8 warps] doubles, then [2][CH][2] branch ids
+constexpr int WALK_PART_DOUBLES = 2 * CH * 2 * 8;
+constexpr int WALK_PART_BYTES = WALK_PART_DOUBLES * 8 + 2 * CH * 2 * 4;
 
 template <int K>
 struct WalkSmem {
@@ -51,7 +57,7 @@ struct WalkSmem {
     // branch-gradient accumulator of the CTA: in shared memory for K >= 4; for K <= 3 it is the CTA's
     // row in global memory (see grad_in_l2)
     static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) {
-        return (want_grad && !grad_in_l2(K)) ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0;
+        return (want_grad && !grad_in_l2(K)) ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
     }
     static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
     static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
@@ -101,6 +107,19 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
     constexpr bool GL2 = grad_in_l2(K);
     int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
+    // parked per-warp branch sums + their branch ids sit right below the descriptors (see WALK_PART_BYTES)
+    double* const s_part = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) - WALK_PART_BYTES);
+    int* const s_pbr = reinterpret_cast<int*>(s_part + WALK_PART_DOUBLES);
+    // folds the parked sums of one chunk (buffer `buf`, `n` ops) into s_acc; call after the barrier that
+    // follows the chunk, by all threads (2 * n of them do the work; each term has its own branch)
+    auto fold_parked = [&](int buf, int n) {
+        if (tid < 2 * n) {
+            const double* pp = s_part + (buf * CH * 2 + tid) * 8;
+            double sum = pp[0];
+            for (int w = 1; w < (TW >> 5); ++w) sum += pp[w];
+            s_acc[s_pbr[buf * CH * 2 + tid]] += sum;
+        }
+    };
     double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
     OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
     double* const stab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes());
@@ -380,6 +399,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     for (int k = 0; k < K; ++k) cur[cc][k] = mdl.pi(k);
                 for (int c = 0; c < n_chunks; ++c) {
                     chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
+                    if constexpr (!GL2) {
+                        if (c > 0) fold_parked((c - 1) & 1, CH);   // the chunk before: complete since the barrier above
+                    }
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
                     const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
@@ -480,10 +502,17 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         if constexpr (GL2) {
                             if ((lane & 15) == 0) atomicAdd(grow + ((lane >> 4) ? rb[j].b_br : rb[j].a_br), red);
                         } else {
-                            if (lane == 0) atomicAdd(&s_acc[rb[j].a_br], red);
-                            else if (lane == 16) atomicAdd(&s_acc[rb[j].b_br], red);
+                            if ((lane & 15) == 0) {
+                                const int term = ((c & 1) * CH + j) * 2 + (lane >> 4);
+                                s_part[term * 8 + warp] = red;
+                                if (warp == 0) s_pbr[term] = (lane >> 4) ? rb[j].b_br : rb[j].a_br;
+                            }
                         }
                     }
+                }
+                if constexpr (!GL2) {
+                    __syncthreads();                                   // the last chunk's sums are parked
+                    fold_parked((n_chunks - 1) & 1, n_pre - (n_chunks - 1) * CH);
                 }
             }
         }  // tiles of this tree

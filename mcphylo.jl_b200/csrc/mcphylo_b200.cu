@@ -259,7 +259,7 @@ int launch_levels(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
     return 0;
 }
 size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
-    const size_t acc = (want_grad && !grad_in_l2(K)) ? (((size_t)max_br * 8 + 15) & ~(size_t)15) : 0;
+    const size_t acc = (want_grad && !grad_in_l2(K)) ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
     return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
            (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
 }
