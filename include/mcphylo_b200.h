@@ -198,6 +198,11 @@ int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);
 /* Where a CTA keeps its partial-likelihood scratch: -1 automatic (shared memory for small inputs
  * whose scratch fits, HBM otherwise), 0 always HBM, 1 shared memory whenever it fits. */
 int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
+/* Where a CTA of the walk kernel accumulates its branch-gradient sums: -1 automatic (shared memory,
+ * without atomics and bit-reproducible from run to run, for trees of up to 4096 branches; the CTA's
+ * row in global memory with RED.ADD.F64 beyond that), 0 always shared memory (fails if the tree does
+ * not fit), 1 always global memory. */
+int mcp_set_accumulator_mode(mcp_ctx *ctx, int mode);
 /* Level-parallel small-tree kernel (all warps of a CTA share one 32-column tile, one barrier per
  * tree level): -1 automatic (inputs of at most a few tiles per SM whose tree fits in shared memory),
  * 0 never, 1 whenever the tree fits. */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
-    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_level_mode",
+    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode",
     "mcp_schedule_dump",
 ]
 
@@ -70,6 +70,7 @@ def load():
     lib.mcp_set_launch.argtypes = [_vp, C.c_int, C.c_int]
     lib.mcp_set_columns_per_thread.argtypes = [_vp, C.c_int]
     lib.mcp_set_scratch_mode.argtypes = [_vp, C.c_int]
+    lib.mcp_set_accumulator_mode.argtypes = [_vp, C.c_int]
     lib.mcp_set_level_mode.argtypes = [_vp, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
@@ -178,6 +179,9 @@ class Context:
 
     def set_scratch_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_scratch_mode(self.handle, int(mode)))
+
+    def set_accumulator_mode(self, mode: int = -1):
+        self._check(self.lib.mcp_set_accumulator_mode(self.handle, int(mode)))
 
     def wave_columns(self, K: int, n_nodes: int, want_grad: bool = True) -> int:
         """Columns (sites x rates) one full wave of the persistent grid covers (mcp_wave_columns)."""

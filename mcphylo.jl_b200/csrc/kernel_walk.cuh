@@ -35,15 +35,18 @@ struct __align__(16) OpRec {
 };
 static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 
-// Where a CTA accumulates its branch-gradient sums.  K <= 3: directly in its accumulator row in
-// global memory with fire-and-forget RED.ADD.F64 (the row stays in L2; 5 % faster than any
-// shared-memory scheme at K = 2).  K >= 4: in shared memory, without atomics (see WALK_PART_BYTES).
-#ifndef MCP_GRAD_L2_MAXK
-#define MCP_GRAD_L2_MAXK 3
-#endif
-__host__ __device__ constexpr bool grad_in_l2(int K) { return K <= MCP_GRAD_L2_MAXK; }
+// Where a CTA accumulates its branch-gradient sums (template parameter ACCG, decided on the host):
+// in shared memory without atomics (below) whenever the per-branch accumulator fits next to the staging
+// buffers without costing a resident CTA -- trees of up to WALK_ACC_SHARED_MAX_NODES nodes -- else
+// (ACCG) directly in the CTA's accumulator row in global memory with fire-and-forget RED.ADD.F64 (the
+// row stays in L2; any tree size, but the sums arrive in no fixed order).  The two are separate
+// instantiations: with both paths in one kernel the K = 4 op loop spills again.
+constexpr int WALK_ACC_SHARED_MAX_NODES = 4096;
+inline bool walk_acc_global(int n_nodes, int mode /* -1 auto, 0 shared, 1 global */) {
+    return mode < 0 ? n_nodes > WALK_ACC_SHARED_MAX_NODES : mode != 0;
+}
 
-// Shared-memory accumulator (K >= 4): the per-warp sums of a chunk's 2 * CH branch terms are parked here
+// Shared-memory accumulator: the per-warp sums of a chunk's 2 * CH branch terms are parked here
 // and folded into the accumulator by one thread per term after the chunk barrier, in fixed warp order
 // -- no atomics (a shared fp64 atomic add is a compare-and-swap loop, ~10 instructions, 38 % retries
 // with 8 warps on one address) and a run-to-run reproducible gradient.
@@ -54,10 +57,10 @@ constexpr int WALK_PART_BYTES = WALK_PART_DOUBLES * 8 + 2 * CH * 2 * 4;
 template <int K>
 struct WalkSmem {
     // dynamic shared memory carve-up (offsets in bytes)
-    // branch-gradient accumulator of the CTA: in shared memory for K >= 4; for K <= 3 it is the CTA's
-    // row in global memory (see grad_in_l2)
-    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) {
-        return (want_grad && !grad_in_l2(K)) ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
+    // branch-gradient accumulator of the CTA + parked per-warp sums (shared-accumulator kernels only:
+    // callers pass want_grad && !ACCG)
+    static __host__ __device__ size_t acc_bytes(int n_br, int shared_acc) {
+        return shared_acc ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
     }
     static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
     static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
@@ -65,8 +68,8 @@ struct WalkSmem {
     static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
     // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
     static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
-    static __host__ __device__ size_t total(int n_br, int want_grad, int TW) {
-        return acc_bytes(n_br, want_grad) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
+    static __host__ __device__ size_t total(int n_br, int shared_acc, int TW) {
+        return acc_bytes(n_br, shared_acc) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
     }
 };
 
@@ -85,7 +88,7 @@ struct WalkSmem {
 // every partial it has just written.
 // NE = active eigen-components (device_math.cuh): K - 1 when the host found (and moved last) a null
 // eigenvalue, the case for every rate matrix; K otherwise.
-template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE>
+template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE, bool ACCG>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
 #endif
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     if (tile >= tile_end) return;
 
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
-    constexpr bool GL2 = grad_in_l2(K);
-    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad));
+    constexpr bool GL2 = ACCG;
+    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad && !ACCG));
     // parked per-warp branch sums + their branch ids sit right below the descriptors (see WALK_PART_BYTES)
     double* const s_part = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) - WALK_PART_BYTES);
     int* const s_pbr = reinterpret_cast<int*>(s_part + WALK_PART_DOUBLES);

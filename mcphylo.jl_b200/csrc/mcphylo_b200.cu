@@ -96,6 +96,8 @@ struct mcp_ctx {
     int max_rows = 1;
     size_t off_levels = 0;
     int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
+    int opt_acc_mode = -1;       // gradient accumulator of the walk: -1 automatic, 0 shared memory, 1 global memory (RED)
+    bool acc_global = false;     // what the current plan uses
     unsigned long long next_aln_id = 1;
 
     DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out, d_counter;
@@ -195,50 +197,62 @@ int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
     marks.push_back({ctx->device, (const void*)kern, smem});
     return 0;
 }
-template <int K, int CPT, bool DYN, bool SSCR, int NE>
+template <int K, int CPT, bool DYN, bool SSCR, int NE, bool ACCG>
 int launch_walk_inst(mcp_ctx* ctx, const WalkParams& wp) {
-    int e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, DYN, SSCR, NE>, ctx->smem_bytes);
+    int e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG>, ctx->smem_bytes);
     if (e) return e;
-    felsenstein_walk<K, CPT, DYN, SSCR, NE><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
+    felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
 // null_last: every model of the batch has a null eigenvalue, moved to the last position by the host
 // (true for any rate matrix) -> kernels with K - 1 active eigen-components.  Otherwise (a caller
-// passing some other decomposition) the full-K kernels, which exist in the constant-memory
-// (DYN) flavour only.
+// passing some other decomposition) the full-K kernels.  Those, and the kernels that accumulate the
+// gradient in global memory (ctx->acc_global: very large trees), exist in the constant-memory (DYN)
+// flavour only -- and the latter with one column per thread only, which prepare_topology arranges.
 template <int K>
 int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model, bool null_last) {
-    if (!null_last)
-        return ctx->cpt == 2 ? launch_walk_inst<K, 2, true, false, K>(ctx, wp) : launch_walk_inst<K, 1, true, false, K>(ctx, wp);
     constexpr int NE = K - 1;
-    if (ctx->smem_scratch && !dyn_model && ctx->cpt == 1) return launch_walk_inst<K, 1, false, true, NE>(ctx, wp);
-    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true, false, NE>(ctx, wp) : launch_walk_inst<K, 2, false, false, NE>(ctx, wp);
-    return dyn_model ? launch_walk_inst<K, 1, true, false, NE>(ctx, wp) : launch_walk_inst<K, 1, false, false, NE>(ctx, wp);
+    if (ctx->acc_global)
+        return null_last ? launch_walk_inst<K, 1, true, false, NE, true>(ctx, wp) : launch_walk_inst<K, 1, true, false, K, true>(ctx, wp);
+    if (!null_last)
+        return ctx->cpt == 2 ? launch_walk_inst<K, 2, true, false, K, false>(ctx, wp) : launch_walk_inst<K, 1, true, false, K, false>(ctx, wp);
+    if (ctx->smem_scratch && !dyn_model && ctx->cpt == 1) return launch_walk_inst<K, 1, false, true, NE, false>(ctx, wp);
+    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true, false, NE, false>(ctx, wp) : launch_walk_inst<K, 2, false, false, NE, false>(ctx, wp);
+    return dyn_model ? launch_walk_inst<K, 1, true, false, NE, false>(ctx, wp) : launch_walk_inst<K, 1, false, false, NE, false>(ctx, wp);
 }
 template <int K, int CPT>
-int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, bool sscr, int* out) {
+int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, bool sscr, bool acc_global, int* out) {
     int e;
     constexpr int NE = K - 1;
+    if (acc_global) {
+        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, true, false, K, true>, smem))) return e;
+        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, true, false, NE, true>, smem))) return e;
+        int o1 = 0, o2 = 0;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, 1, true, false, K, true>, block, smem));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, 1, true, false, NE, true>, block, smem));
+        *out = std::min(o1, o2);
+        return 0;
+    }
     if (sscr) {
-        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, false, true, NE>, smem))) return e;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K, 1, false, true, NE>, block, smem));
+        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, false, true, NE, false>, smem))) return e;
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K, 1, false, true, NE, false>, block, smem));
         return 0;
     }
     // the variants differ by a few registers: size the persistent grid for the most demanding one
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, NE>, smem))) return e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, false, false, NE>, smem))) return e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, K>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, NE, false>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, false, false, NE, false>, smem))) return e;
+    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, K, false>, smem))) return e;
     int o1 = 0, o2 = 0, o3 = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true, false, NE>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false, false, NE>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, felsenstein_walk<K, CPT, true, false, K>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true, false, NE, false>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false, false, NE, false>, block, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, felsenstein_walk<K, CPT, true, false, K, false>, block, smem));
     *out = std::min(o1, std::min(o2, o3));
     return 0;
 }
 template <int K>
-int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, bool sscr, int* out) {
-    return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, false, out) : occupancy_inst<K, 1>(ctx, block, smem, sscr, out);
+int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, bool sscr, bool acc_global, int* out) {
+    return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, false, acc_global, out) : occupancy_inst<K, 1>(ctx, block, smem, sscr, acc_global, out);
 }
 template <int K>
 int occupancy_levels(mcp_ctx* ctx, int block, size_t smem, int* out) {
@@ -258,8 +272,8 @@ int launch_levels(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
     CUDA_TRY(ctx, cudaGetLastError());
     return 0;
 }
-size_t walk_smem_bytes(int K, int max_br, int want_grad, int block, int cpt) {
-    const size_t acc = (want_grad && !grad_in_l2(K)) ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
+size_t walk_smem_bytes(int K, int max_br, int shared_acc, int block, int cpt) {
+    const size_t acc = shared_acc ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
     return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
            (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
 }
@@ -334,6 +348,12 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     // (cfg4: 78.2 -> 73.6 ms; 2 CTAs x 256 threads per SM at 128 registers), profiles/r1_walk_notes.md.
     int cpt = ctx->opt_cpt;
     if (cpt <= 0) cpt = (K <= 4 && total_cols / (2LL * block) >= 12LL * ctx->sm_count) ? 2 : 1;
+    // Very large trees: the per-branch accumulator no longer fits in shared memory next to the staging
+    // buffers; those kernels exist with one column per thread only (launch_walk).
+    int max_nn = 0;
+    for (int t = 0; t < T; ++t) max_nn = std::max(max_nn, (int)a.NN[t]);
+    const bool acc_global = a.want_grad && k_templated(K) && walk_acc_global(max_nn, ctx->opt_acc_mode);
+    if (acc_global) cpt = 1;
     if (!k_templated(K)) {   // generic-K kernel: one column per thread, at most 128 threads per CTA
         cpt = 1;
         if (block > 128) block = 128;
@@ -443,15 +463,16 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     ctx->total_out = out_off;
     ctx->total_dyn = dyn_off;
     ctx->total_btab = btab_off;
+    ctx->acc_global = acc_global && !level_mode;
     ctx->smem_bytes = level_mode ? LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K)
-                      : k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad ? 1 : 0, block, cpt)
+                      : k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad && !acc_global ? 1 : 0, block, cpt)
                                        : (a.want_grad ? (size_t)max_br * sizeof(double) : 0);
     // Small problems: keep the partials scratch in shared memory (latency path).  Automatic when the
     // whole input is a handful of tiles per SM and the scratch of one CTA fits next to the staging
     // buffers.
     {
         const size_t scr_bytes = (size_t)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8;
-        const bool fits = !level_mode && k_templated(K) && cpt == 1 && ctx->smem_bytes + scr_bytes <= 96 * 1024;
+        const bool fits = !level_mode && !acc_global && k_templated(K) && cpt == 1 && ctx->smem_bytes + scr_bytes <= 96 * 1024;
         ctx->smem_scratch = fits && (ctx->opt_smem_scratch == 1 ||
                                      (ctx->opt_smem_scratch < 0 && ctx->n_tiles <= 4 * ctx->sm_count));
         if (ctx->smem_scratch) ctx->smem_bytes += scr_bytes;
@@ -464,7 +485,7 @@ int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
     if (level_mode) {
         MCP_DISPATCH_K(K, rc = occupancy_levels<KK>(ctx, block, ctx->smem_bytes, &occ));
     } else if (k_templated(K)) {
-        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, ctx->smem_scratch, &occ));
+        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, ctx->smem_scratch, ctx->acc_global, &occ));
     } else {
         if ((rc = ensure_smem_attr(ctx, felsenstein_walk_generic, ctx->smem_bytes))) return rc;
         CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, felsenstein_walk_generic, block, ctx->smem_bytes));
@@ -662,7 +683,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         hd[ctx->trees[t].dyn_off + dyn_slot(a.NN[t], K, R)] = (double)slot;
     }
     // the walk kernels with all K eigen-components read their model from constant memory only
-    const bool dyn_model = n_models > 1 || (k_templated(K) && !all_null_last);
+    const bool dyn_model = n_models > 1 || (k_templated(K) && (!all_null_last || ctx->acc_global));
 
     cudaStream_t st = ctx->stream;
     mcp_stats& s = ctx->stats;
@@ -928,6 +949,14 @@ int mcp_set_scratch_mode(mcp_ctx* ctx, int mode) {
     return 0;
 }
 
+int mcp_set_accumulator_mode(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "accumulator mode must be -1 (automatic), 0 (shared memory) or 1 (global memory)");
+    ctx->opt_acc_mode = mode;
+    ctx->sig.clear();
+    return 0;
+}
+
 int mcp_set_level_mode(mcp_ctx* ctx, int mode) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "level mode must be -1 (automatic), 0 (off) or 1 (whenever the tree fits)");
@@ -1067,8 +1096,10 @@ int mcp_wave_columns(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* c
     int cpt = ctx->opt_cpt > 0 ? ctx->opt_cpt : (K <= 4 ? 2 : 1);   // what prepare_topology picks for large inputs
     int occ = 0, rc = 0;
     if (k_templated(K)) {
-        const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad ? 1 : 0, block, cpt);
-        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, smem, false, &occ));
+        const bool acc_global = want_grad && walk_acc_global(n_nodes, ctx->opt_acc_mode);
+        if (acc_global) cpt = 1;
+        const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad && !acc_global ? 1 : 0, block, cpt);
+        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, smem, false, acc_global, &occ));
         if (rc) return rc;
     } else {
         cpt = 1;

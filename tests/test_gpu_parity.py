@@ -716,3 +716,60 @@ def test_zero_length_branches_and_impossible_columns(oracle):
     ll_bad, g_bad = mcp.gradlogpdf(pd, mcp.DeviceAlignment(bad, leaf_nums, 4))
     assert ll_bad == -np.inf
     assert not np.all(np.isfinite(g_bad))
+
+
+@pytest.mark.parametrize("K,cpt", [(2, 2), (3, 1), (4, 1), (4, 2), (5, 1)])
+def test_gradient_is_bit_reproducible(K, cpt):
+    """The walk accumulates the branch sums without atomics (per-warp sums parked per chunk, folded in
+    fixed order): repeated evaluations return identical bits, logL and every gradient component."""
+    rng = np.random.default_rng(600 + K)
+    tree = random_tree(60, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, 5000, rng, gap_frac=0.02)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_level_mode(0)
+        ctx.set_columns_per_thread(cpt)
+        runs = [mcp.gradlogpdf(pd, aln) for _ in range(4)]
+    finally:
+        ctx.set_level_mode(-1)
+        ctx.set_columns_per_thread(0)
+    assert all(r[0] == runs[0][0] for r in runs)
+    assert all(np.array_equal(r[1], runs[0][1]) for r in runs)
+
+
+@pytest.mark.parametrize("K,R,null_eig", [(2, 1, True), (4, 4, True), (4, 2, False), (6, 1, True)])
+def test_gradient_accumulator_in_global_memory(oracle, K, R, null_eig):
+    """Trees beyond 4096 nodes accumulate the branch sums in the CTA's row in global memory (RED.ADD.F64)
+    instead of shared memory; the mode can be forced, which is how a small tree gets to test it."""
+    rng = np.random.default_rng(800 + K + R)
+    tree = random_tree(45, rng, multifurcate=True)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    base, pi, srates = _model(K, pi, rng)
+    model = base if null_eig else _shifted(base, 0.25)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, base(pi, srates), pi, rates, 1300, rng, gap_frac=0.05)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_level_mode(0)
+        results = []
+        for mode in (1, 0):
+            ctx.set_accumulator_mode(mode)
+            for cpt in (1, 2):          # two columns per thread falls back to one in global mode
+                ctx.set_columns_per_thread(cpt)
+                ll, g = mcp.gradlogpdf(pd, aln)
+                _check(ll, g, ll_o, g_o)
+                _check(mcp.logpdf(pd, aln), None, ll_o, None)
+                results.append((ll, g))
+        assert all(r[0] == results[0][0] for r in results[:2])       # logL is order-independent of the accumulator
+    finally:
+        ctx.set_accumulator_mode(-1)
+        ctx.set_level_mode(-1)
+        ctx.set_columns_per_thread(0)
