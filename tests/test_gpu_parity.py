@@ -773,3 +773,28 @@ def test_gradient_accumulator_in_global_memory(oracle, K, R, null_eig):
         ctx.set_accumulator_mode(-1)
         ctx.set_level_mode(-1)
         ctx.set_columns_per_thread(0)
+
+
+def test_tree_beyond_the_shared_accumulator(oracle):
+    """2100 taxa = 4199 nodes: the automatic choice moves the gradient accumulator to global memory
+    (and would otherwise need 34 KB of shared memory per CTA for it)."""
+    rng = np.random.default_rng(2100)
+    K = 4
+    tree = random_tree(2100, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    srates = rng.uniform(0.5, 2.5, size=6)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 2)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, srates), pi, rates, 96, rng, gap_frac=0.02)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, mcp.GTR)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll, g = mcp.gradlogpdf(pd, aln)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, mcp.GTR, pi, srates, rates)
+    _check(ll, g, ll_o, g_o)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_accumulator_mode(0)        # forced shared memory still works at this size
+        ll2, g2 = mcp.gradlogpdf(pd, aln)
+        _check(ll2, g2, ll_o, g_o)
+        assert ll2 == ll
+    finally:
+        ctx.set_accumulator_mode(-1)
