@@ -222,6 +222,16 @@ int mcp_schedule_dump(int NN, const int32_t *postorder_num, const int32_t *paren
                       const int32_t *leaf_row, int want_grad, int32_t *post_ops, int cap_post,
                       int32_t *pre_ops, int cap_pre, int32_t *info);
 
+/*
+ * Host-only: the reordering every evaluation applies to the caller's eigen-decomposition before it
+ * is uploaded -- the eigenvalue of smallest magnitude moved to the last position (columns of U,
+ * entries of D, rows of Uinv permuted alike, so U diag(f(D)) Uinv is unchanged).  Returns 1 in
+ * *null_last when that eigenvalue is null (<= 8 eps max|D|), i.e. when the kernels skip it.
+ * U, Uinv, U_out, Uinv_out are K x K column-major; D, D_out hold K doubles.
+ */
+int mcp_model_reorder(int K, const double *U, const double *D, const double *Uinv,
+                      double *U_out, double *D_out, double *Uinv_out, int *null_last);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ SYMBOLS = [
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
     "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode",
-    "mcp_schedule_dump",
+    "mcp_schedule_dump", "mcp_model_reorder",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     lib.mcp_wave_columns.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.mcp_schedule_dump.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]
+    lib.mcp_model_reorder.argtypes = [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int)]
     for name in SYMBOLS:
         if name != "mcp_last_error":
             getattr(lib, name).restype = C.c_int
@@ -284,6 +285,24 @@ class Context:
         if want_grad:
             return ll, [g[:int(n) - 1] for g, n in zip(grads, NN)]
         return ll, None
+
+
+def model_reorder(U, D, Uinv):
+    """Host-only view of the eigen-decomposition as the kernels see it (mcp_model_reorder):
+    returns (U, D, Uinv, null_last)."""
+    lib = load()
+    U = np.asfortranarray(U, dtype=np.float64)
+    Uinv = np.asfortranarray(Uinv, dtype=np.float64)
+    D = _f64(D)
+    K = D.size
+    assert U.shape == (K, K) and Uinv.shape == (K, K)
+    Uo, Uio, Do = np.zeros((K, K), order="F"), np.zeros((K, K), order="F"), np.zeros(K)
+    flag = C.c_int(0)
+    rc = lib.mcp_model_reorder(K, U.ctypes.data, D.ctypes.data, Uinv.ctypes.data, Uo.ctypes.data, Do.ctypes.data,
+                               Uio.ctypes.data, C.byref(flag))
+    if rc:
+        raise McpError(rc, lib.mcp_last_error(None).decode())
+    return Uo, Do, Uio, bool(flag.value)
 
 
 def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool, by_levels: bool = False):

@@ -14,10 +14,11 @@
 // chunk-wise staging of per-op inputs (descriptors, leaf codes, branch data) in shared memory.
 // Partials live in a CTA-private scratch region laid out [slot][column][thread][state] so that a
 // warp's access is one contiguous run of 32*K doubles (256-bit vector ld/st per thread at K = 4).
-// fp64 throughout.  Transitions are applied in eigen-space, P L = U (e * (Uinv L)), with U / Uinv as
-// constant-bank operands.  Rescaling uses exact powers of two (exponent extraction) instead of the
-// reference's divide-by-max + log per node; the integer exponent sum is exact and
-// logL = ln2 * sum(exponents) + sum(log(pi . L_root)).
+// fp64 throughout.  Transitions are applied in eigen-space, P L = L + U (expm1(.) * (Uinv L)), with
+// U / Uinv as constant-bank operands and the null eigenvalue of the rate matrix skipped.  Rescaling
+// uses exact powers of two (exponent extraction) instead of the reference's divide-by-max + log per
+// node; the integer exponent sum is exact and logL = ln2 * sum(exponents) + sum(log(pi . L_root)).
+// Branch-gradient sums are accumulated without atomics, in a fixed order (reproducible bit for bit).
 #include "../../include/mcphylo_b200.h"
 #include "schedule.hpp"
 
@@ -1125,6 +1126,15 @@ int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {
     } else {
         cudaGetLastError();
     }
+    return 0;
+}
+
+int mcp_model_reorder(int K, const double* U, const double* D, const double* Uinv, double* U_out, double* D_out,
+                      double* Uinv_out, int* null_last) {
+    if (!U || !D || !Uinv || !U_out || !D_out || !Uinv_out || !null_last)
+        return fail(nullptr, MCP_ERR_ARG, "mcp_model_reorder: null argument");
+    if (!k_supported(K)) return fail(nullptr, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
+    *null_last = null_eigenvalue_last(U, D, Uinv, K, U_out, D_out, Uinv_out) ? 1 : 0;
     return 0;
 }
 

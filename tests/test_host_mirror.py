@@ -122,3 +122,27 @@ def test_nexus_and_csv_parsers_agree(tmp_path):
     bad.write_text("not nexus\n")
     with pytest.raises(mcp.FileSyntaxError):
         mcp.ParseNexus(str(bad))
+
+
+def test_model_reorder_moves_the_null_eigenvalue_last():
+    """Host logic of the C library (no GPU): every evaluation works on a copy of the caller's
+    eigen-decomposition with the null eigenvalue last; the product U diag(f(D)) Uinv is unchanged."""
+    from mcphylo_jl_b200 import capi
+
+    rng = np.random.default_rng(5)
+    pi = rng.dirichlet(np.ones(4) * 5)
+    U, D, Uinv, mu = mcp.GTR(pi, rng.uniform(0.5, 2.0, size=6))
+    for shift in range(4):
+        idx = np.roll(np.arange(4), shift)
+        Uo, Do, Uio, null_last = capi.model_reorder(U[:, idx], D[idx], Uinv[idx, :])
+        assert null_last and abs(Do[3]) <= 1e-14 * np.max(np.abs(Do)) and np.all(np.abs(Do[:3]) > 1e-3)
+        assert np.allclose(Uo @ np.diag(np.exp(0.3 * Do)) @ Uio, U @ np.diag(np.exp(0.3 * D)) @ Uinv, rtol=0, atol=1e-15)
+        # the other components keep their relative order
+        keep = [i for i in idx if abs(D[i]) > 1e-3]
+        assert np.array_equal(Do[:3], D[keep])
+    # Restriction: D = [-1, 0] is already in place; a decomposition without a null eigenvalue is flagged
+    U2, D2, Uinv2, _ = mcp.Restriction(np.array([0.3, 0.7]), [])
+    assert capi.model_reorder(U2, D2, Uinv2)[3]
+    Uo, Do, Uio, null_last = capi.model_reorder(U, D - 0.4, Uinv)
+    assert not null_last and sorted(Do) == sorted(D - 0.4)
+    assert np.argmin(np.abs(Do)) == 3
