@@ -15,10 +15,16 @@ def _rescale(v):
     return v * np.ldexp(1.0, -e)[None, :], e
 
 
-def run_program(prog, codes, K, P, dP, pi, n_real_branches):
+def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
     """prog: capi.schedule_dump output.  codes (rows, S) uint8.  P, dP: (K, K, R, NB) Fortran
     arrays [s_parent, s_child, r, branch] for the REAL branches.  Returns (ll, grad_dev) with
-    grad_dev indexed by device branch id."""
+    grad_dev indexed by device branch id.
+
+    eigen = dict(U, D, Uinv, mu, blv, rates, NE) switches INTERNAL children to the walk kernel's own
+    arithmetic (csrc/device_math.cuh): P L = L + U (em1 * (Uinv L)) and P^T q = q + Uinv^T (em1 * (U^T q))
+    over the first NE eigen-components only (the host has moved the null eigenvalue last,
+    capi.model_reorder), and the gradient numerator in eigen-space, sum_i (U^T q)_i de_i (Uinv L)_i.
+    Leaf children keep using the P / dP table columns, as on the device."""
     R = P.shape[2]
     S = codes.shape[1]
     nd = prog["n_dnodes"]
@@ -34,6 +40,16 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches):
         c = np.full(S, K) if row < 0 else np.minimum(codes[row].astype(int), K)
         return ext[:, c]
 
+    if eigen is not None:
+        NE = eigen["NE"]
+        Ue, Uie = np.asarray(eigen["U"])[:, :NE], np.asarray(eigen["Uinv"])[:NE, :]
+
+        def eig_vecs(br, r):
+            if br >= n_real_branches:            # virtual identity branch
+                return np.zeros(NE), np.zeros(NE)
+            x = eigen["mu"] * eigen["blv"][br] * np.asarray(eigen["D"])[:NE] * eigen["rates"][r]
+            return np.expm1(x), np.asarray(eigen["D"])[:NE] * eigen["mu"] * eigen["rates"][r] * np.exp(x)
+
     ll = 0.0
     grad = np.zeros(nd)
     for r in range(R):
@@ -48,6 +64,9 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches):
                 if kind == OPK_LEAF:
                     return leaf_down(Pm, src)
                 L = reg if kind == OPK_REG else slots[src]
+                if eigen is not None:
+                    em1, _ = eig_vecs(br, r)
+                    return L + Ue @ (em1[:, None] * (Uie @ L))
                 return Pm @ L
             Da = down(flags & 3, a_src, a_br)
             Db = down((flags >> 2) & 3, b_src, b_br)
@@ -67,18 +86,27 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches):
                 Pm, dPm = tables(br, r)
                 if internal:
                     L = slots[src]
+                    if eigen is not None:    # Y = eigen-coordinates of dP L
+                        em1, de = eig_vecs(br, r)
+                        w = Uie @ L
+                        return L + Ue @ (em1[:, None] * w), de[:, None] * w, Pm
                     return Pm @ L, dPm @ L, Pm
                 return leaf_down(Pm, src), leaf_down(dPm, src), Pm
             Da, Ya, Pa = child((flags & 3) == OPK_MEM, a_src, a_br)
             Db, Yb, Pb = child(((flags >> 2) & 3) == OPK_MEM, b_src, b_br)
             qa, qb = pm * Db, pm * Da
             den = (qa * Da).sum(axis=0)
-            grad[a_br] += ((qa * Ya).sum(axis=0) / den).sum()
-            grad[b_br] += ((qb * Yb).sum(axis=0) / den).sum()
-            for out, dst, Pm, q in (((flags >> 10) & 3, a_dst, Pa, qa), ((flags >> 12) & 3, b_dst, Pb, qb)):
+            for internal, br, q, Y in (((flags & 3) == OPK_MEM, a_br, qa, Ya), (((flags >> 2) & 3) == OPK_MEM, b_br, qb, Yb)):
+                num = ((Ue.T @ q) * Y).sum(axis=0) if (eigen is not None and internal) else (q * Y).sum(axis=0)
+                grad[br] += (num / den).sum()
+            for out, dst, Pm, q, br in (((flags >> 10) & 3, a_dst, Pa, qa, a_br), ((flags >> 12) & 3, b_dst, Pb, qb, b_br)):
                 if out == OUT_NONE:
                     continue
-                v, _ = _rescale(Pm.T @ q)
+                if eigen is not None:
+                    em1, _ = eig_vecs(br, r)
+                    v, _ = _rescale(q + Uie.T @ (em1[:, None] * (Ue.T @ q)))
+                else:
+                    v, _ = _rescale(Pm.T @ q)
                 if out == OUT_KEEP:
                     reg = v
                 else:

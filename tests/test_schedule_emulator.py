@@ -143,3 +143,30 @@ def test_level_ordered_program(oracle, n_taxa, K, seed):
     # no REG / KEEP in this variant
     assert all((op[5] & 3) != 1 and ((op[5] >> 2) & 3) != 1 for op in prog["post"])
     assert all(((op[5] >> 10) & 3) != 1 and ((op[5] >> 12) & 3) != 1 and ((op[5] >> 8) & 3) != 1 for op in prog["pre"])
+
+
+@pytest.mark.parametrize("n_taxa,K,R,seed,drop_null", [(17, 2, 1, 2, True), (40, 4, 4, 3, True), (25, 4, 2, 5, False),
+                                                       (30, 6, 2, 6, True)])
+def test_walk_kernel_arithmetic_in_eigen_space(oracle, n_taxa, K, R, seed, drop_null):
+    """The arithmetic of felsenstein_walk (csrc/device_math.cuh) emulated in numpy: transitions applied as
+    L + U (expm1 * (Uinv L)) over the K-1 non-null eigen-components of the reordered decomposition
+    (capi.model_reorder = what every evaluation uploads), numerator q.(dP L) formed in eigen-space.
+    Reproduces the oracle; with all K components (drop_null False) likewise."""
+    rng = np.random.default_rng(700 + seed)
+    tree = random_tree(n_taxa, rng, multifurcate=(seed % 2 == 1), unary=(seed == 3))
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model = mcp.Restriction(pi, []) if K == 2 else (mcp.GTR(pi, rng.uniform(0.5, 2.0, size=6)) if K == 4 else mcp.JC(pi, []))
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model, pi, rates, 41, rng, gap_frac=0.1)
+    ft = mcp.flatten(tree)
+    x = oracle.codes_to_dense(codes, leaf_nums, K, ft.NN)
+    U, D, Uinv, mu = model
+    ll_o, g_o = oracle.felsenstein(x, ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, rates, pi, True, 1)
+    Ur, Dr, Uir, null_last = capi.model_reorder(U, D, Uinv)
+    assert null_last
+    P, dP = oracle.transition(U, D, Uinv, mu, np.asarray(rates, float), ft.blv, want_dP=True)
+    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, _leaf_row(ft, leaf_nums), True)
+    eigen = dict(U=Ur, D=Dr, Uinv=Uir, mu=mu, blv=ft.blv, rates=np.asarray(rates, float), NE=K - 1 if drop_null else K)
+    ll, g = run_program(prog, codes, K, P, dP, np.asarray(pi, float), ft.NN - 1, eigen=eigen)
+    assert abs(ll - ll_o) <= 1e-11 * abs(ll_o)
+    assert np.allclose(g[:ft.NN - 1], g_o, rtol=1e-9, atol=1e-9)
