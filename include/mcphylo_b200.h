@@ -30,16 +30,17 @@
 #ifndef MCPHYLO_B200_H
 #define MCPHYLO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define MCP_ABI_VERSION 1
+#define MCP_ABI_VERSION 2
 
-typedef struct mcp_ctx mcp_ctx;             /* one per (process, GPU) */
-typedef struct mcp_alignment mcp_alignment; /* leaf data resident on the GPU */
+typedef struct mcp_ctx mcp_ctx;             /* one per (process, GPU) -- or per (process, set of GPUs), mcp_create_multi */
+typedef struct mcp_alignment mcp_alignment; /* leaf data resident on the GPU(s) of its context */
 
 typedef enum mcp_status {
     MCP_OK = 0,
@@ -58,6 +59,52 @@ const char *mcp_last_error(const mcp_ctx *ctx);
 /* Binds a context to CUDA device `device`, creates its stream and staging buffers. */
 int mcp_create(mcp_ctx **out, int device);
 int mcp_destroy(mcp_ctx *ctx);
+
+/*
+ * Multi-GPU, one host process (what a Julia session is): ONE context that owns n_dev GPUs of the box.
+ * Every entry point below takes such a context exactly like a single-device one:
+ *   - mcp_alignment_from_codes / _from_dense split the SITE axis: device g of G holds the contiguous
+ *     columns [g*ceil(S/G), min(S, (g+1)*ceil(S/G))) of every leaf row (mcp_shard_bounds), for all nodes
+ *     and rate categories; tree, branch tables and model are replicated.
+ *   - mcp_eval / mcp_eval_posterior / mcp_eval_batch / mcp_eval_streamed run the fused walk on every
+ *     device at once (one host thread and one stream per device) and sum the per-device vectors
+ *     [logL, grad[1..NN-1]] -- the ONLY exchange of the path -- by
+ *       MCP_REDUCE_NCCL  one grouped ncclAllReduce(count = NN, ncclDouble, ncclSum) on the devices'
+ *                        evaluation streams (communicators from ncclCommInitAll; NCCL is resolved at run
+ *                        time with dlopen("libnccl.so.2"), or the library MCPHYLO_B200_NCCL names),
+ *       MCP_REDUCE_PEER  no library: every device's final-reduction kernel stores its vector straight
+ *                        into a gather buffer on device 0 over NVLink peer access, and one small kernel
+ *                        on device 0 adds the G vectors in device order into pinned host memory
+ *                        (bit-reproducible; also works with the same device listed more than once),
+ *       MCP_REDUCE_HOST  each device copies its vector to pinned host memory, the host adds them in
+ *                        device order (bit-reproducible; the comparison SURVEY.md 8e allows),
+ *       MCP_REDUCE_AUTO  NCCL when it can be loaded and the devices are distinct, else PEER, else HOST.
+ *     A branch-length prior (mcp_eval_posterior) is added once, not per device.
+ *   - the tuning knobs apply to every device; mcp_get_stats reports the slowest device's times and
+ *     summed bytes / launches, mcp_get_stats_member one device's.
+ *   - mcp_eval_device and mcp_set_stream are single-device calls and fail with MCP_ERR_UNSUPPORTED.
+ * This is the entry a reference-side `gradlogpdf(d::PhyloDist, x)`
+ * (/root/reference/src/distributions/Phylodist.jl:124-138) binds to reach 2-8 GPUs through `ccall`.
+ */
+enum mcp_reduce_mode { MCP_REDUCE_AUTO = 0, MCP_REDUCE_NCCL = 1, MCP_REDUCE_PEER = 2, MCP_REDUCE_HOST = 3 };
+int mcp_create_multi(mcp_ctx **out, int n_dev, const int *dev_ids, int reduce_mode);
+/* Devices behind a context (1 for mcp_create / mcp_create_rank) and the reduction it resolved to. */
+int mcp_device_count(const mcp_ctx *ctx);
+int mcp_reduce_mode(const mcp_ctx *ctx);
+/* The site range [*lo, *hi) shard `shard` of `n_shards` owns (the rule mcp_create_multi applies). */
+int mcp_shard_bounds(int64_t S, int n_shards, int shard, int64_t *lo, int64_t *hi);
+
+/*
+ * Multi-GPU, one host process PER GPU (MPI-style launchers, torchrun): rank 0 obtains a 128-byte NCCL
+ * unique id, the launcher's own channel carries it to the other ranks, and every rank creates a context on
+ * its device.  The rank passes ITS shard of the alignment (mcp_shard_bounds) to mcp_alignment_from_codes;
+ * mcp_eval / mcp_eval_posterior / mcp_eval_batch then all-reduce [logL, grad] over the ranks on the
+ * evaluation stream (ncclAllReduce, communicator from ncclCommInitRank) before the result is read back,
+ * so every rank returns the full-alignment result.  Collective: all ranks must make the same calls in
+ * the same order.  A branch-length prior is added by rank 0 only.
+ */
+int mcp_nccl_unique_id(void *id128);
+int mcp_create_rank(mcp_ctx **out, int device, int n_ranks, int rank, const void *id128);
 
 /* Optional: run on a caller-provided cudaStream_t (cast to void*) instead of the context's own
  * non-blocking stream.  NULL selects the CUDA default stream (that is what e.g. torch's default
@@ -78,8 +125,8 @@ int mcp_synchronize(mcp_ctx *ctx);
  * from_dense: x is the reference's own array, (K, S, NN) column-major Float64; for every leaf in
  *             leaf_nums each column must be one-hot or all ones (what datafortree produces),
  *             otherwise MCP_ERR_DATA.
- * An alignment belongs to the context that created it (device memory, stream ordering): pass it
- * only to calls on that context, and destroy it before the context.
+ * An alignment belongs to the context that created it (device memory, stream ordering): passing it to
+ * a call on another context fails with MCP_ERR_ARG; destroy it before the context.
  */
 int mcp_alignment_from_codes(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t S,
                              const int32_t *leaf_nums, int n_leaves, mcp_alignment **out);
@@ -151,6 +198,27 @@ int mcp_eval_device(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_
                     int want_grad, double *d_out);
 
 /*
+ * One evaluation of an alignment that lives in HOST memory and is not kept on the device: `codes` is the
+ * (n_leaves, S) row-major array mcp_alignment_from_codes takes.  Each device's site range is cut into a few
+ * blocks (a small first one, then doubling); block b+1 crosses PCIe on the copy stream while block b is
+ * evaluated, the block results are added on the device in block order, reduced over the devices of a
+ * multi-device context as in mcp_eval, and read back once.  Device buffers and plans persist between
+ * calls with the same (K, S, leaf_nums, NN, R, want_grad), so repeated calls only pay transfer + kernels.
+ * Use page-locked memory for `codes` (mcp_host_register pins an existing array in place) -- pageable
+ * memory works but is staged by the driver and does not overlap.
+ * mcp_stream_blocks reports the blocks of one device after a call: up to `cap` pairs [lo, hi) into lo_hi,
+ * returns their number.
+ */
+int mcp_eval_streamed(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t S, const int32_t *leaf_nums,
+                      int n_leaves, int NN, const int32_t *postorder_num, const int32_t *parent_num,
+                      const double *blv, const double *U, const double *D, const double *Uinv, double mu,
+                      const double *rates, int R, const double *pi, int want_grad, double *ll_out,
+                      double *grad_out);
+int mcp_stream_blocks(const mcp_ctx *ctx, int member, int64_t *lo_hi, int cap);
+int mcp_host_register(void *p, size_t bytes);
+int mcp_host_unregister(void *p);
+
+/*
  * T independent evaluations in one launch (MultiplePhyloDist; also proposal/chain batches).
  * Every per-tree argument of mcp_eval becomes an array of T entries.  K and R are shared.
  *   ll_out    T doubles
@@ -178,8 +246,11 @@ typedef struct mcp_stats {
     int32_t tiles;             /* column tiles processed */
     int32_t schedule_rebuilt;  /* 1 if the topology differed from the cached one */
     int64_t scratch_bytes;     /* device scratch currently held for partials */
+    int32_t columns_per_thread;/* walk kernel: alignment columns per thread (1 or 2) */
+    int32_t reserved;
 } mcp_stats;
 int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
+int mcp_get_stats_member(const mcp_ctx *ctx, int member, mcp_stats *out);
 
 /*
  * Columns (sites x rate categories) that ONE full wave of the persistent walk grid covers for a large
@@ -190,8 +261,10 @@ int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
  */
 int mcp_wave_columns(mcp_ctx *ctx, int K, int n_nodes, int want_grad, int64_t *columns);
 
-/* Tuning knobs: block = threads per CTA (= columns per tile; 0 = automatic),
- * ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
+/* Tuning knobs: block = threads per CTA (a multiple of 32 up to 256; a tile is block x columns-per-thread
+ * alignment columns wide; 0 = automatic: narrow tiles for small inputs, and for inputs that fill the GPU
+ * the width in {256, 224, 192, 160, 128} x {2, 1} columns per thread whose last round of tiles wastes
+ * least), ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
 int mcp_set_launch(mcp_ctx *ctx, int block, int ctas_per_sm);
 /* Alignment columns walked by one thread: 1, 2, or 0 = automatic (2 once the GPU is full). */
 int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);

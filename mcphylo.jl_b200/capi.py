@@ -19,6 +19,9 @@ _lib = None
 SYMBOLS = [
     "mcp_abi_version", "mcp_last_error", "mcp_create", "mcp_destroy", "mcp_set_stream",
     "mcp_use_own_stream", "mcp_synchronize",
+    "mcp_create_multi", "mcp_device_count", "mcp_reduce_mode", "mcp_shard_bounds", "mcp_nccl_unique_id",
+    "mcp_create_rank", "mcp_eval_streamed", "mcp_stream_blocks", "mcp_host_register", "mcp_host_unregister",
+    "mcp_get_stats_member",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
@@ -37,7 +40,7 @@ class Stats(C.Structure):
     _fields_ = [("walk_ms", C.c_double), ("device_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32), ("grid", C.c_int32),
                 ("block", C.c_int32), ("tiles", C.c_int32), ("schedule_rebuilt", C.c_int32),
-                ("scratch_bytes", C.c_int64)]
+                ("scratch_bytes", C.c_int64), ("columns_per_thread", C.c_int32), ("reserved", C.c_int32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -82,13 +85,24 @@ def load():
     lib.mcp_eval_posterior.argtypes = eval_args[:-1] + [C.c_int, _vp, _dp, _vp]
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    lib.mcp_get_stats_member.argtypes = [_vp, C.c_int, C.POINTER(Stats)]
+    lib.mcp_create_multi.argtypes = [C.POINTER(_vp), C.c_int, _vp, C.c_int]
+    lib.mcp_device_count.argtypes = [_vp]
+    lib.mcp_reduce_mode.argtypes = [_vp]
+    lib.mcp_shard_bounds.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.mcp_nccl_unique_id.argtypes = [_vp]
+    lib.mcp_create_rank.argtypes = [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp]
+    lib.mcp_eval_streamed.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int] + eval_args[2:] + [_dp, _vp]
+    lib.mcp_stream_blocks.argtypes = [_vp, C.c_int, _vp, C.c_int]
+    lib.mcp_host_register.argtypes = [_vp, C.c_size_t]
+    lib.mcp_host_unregister.argtypes = [_vp]
     lib.mcp_wave_columns.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.mcp_schedule_dump.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp]
     lib.mcp_model_reorder.argtypes = [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int)]
     for name in SYMBOLS:
         if name != "mcp_last_error":
             getattr(lib, name).restype = C.c_int
-    if lib.mcp_abi_version() != 1:
+    if lib.mcp_abi_version() != 2:
         raise ImportError("libmcphylo_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
@@ -131,17 +145,59 @@ class Alignment:
             pass
 
 
-class Context:
-    """One mcp_ctx: a (process, GPU) pair."""
+REDUCE_AUTO, REDUCE_NCCL, REDUCE_PEER, REDUCE_HOST = 0, 1, 2, 3
+REDUCE_NAMES = {REDUCE_AUTO: "auto", REDUCE_NCCL: "nccl", REDUCE_PEER: "peer", REDUCE_HOST: "host"}
 
-    def __init__(self, device: int = 0):
+
+def shard_bounds(S: int, n_shards: int, shard: int):
+    """The site range [lo, hi) a shard owns (mcp_shard_bounds; host-only)."""
+    lo, hi = C.c_int64(), C.c_int64()
+    rc = load().mcp_shard_bounds(int(S), int(n_shards), int(shard), C.byref(lo), C.byref(hi))
+    if rc:
+        raise McpError(rc, load().mcp_last_error(None).decode())
+    return lo.value, hi.value
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id for mcp_create_rank (rank 0 makes it, the launcher's channel shares it)."""
+    buf = C.create_string_buffer(128)
+    rc = load().mcp_nccl_unique_id(buf)
+    if rc:
+        raise McpError(rc, load().mcp_last_error(None).decode())
+    return buf.raw
+
+
+class Context:
+    """One mcp_ctx: a (process, GPU) pair; `devices=[...]` makes it a (process, set of GPUs) context
+    (mcp_create_multi: site-sharded alignments, one all-reduce of [logL, grad] per evaluation), and
+    `rank=(n_ranks, rank, unique_id)` one rank of a multi-process group (mcp_create_rank)."""
+
+    def __init__(self, device: int = 0, devices: Optional[Sequence[int]] = None, reduce: int = REDUCE_AUTO,
+                 rank: Optional[tuple] = None):
         self.lib = load()
         h = _vp()
-        rc = self.lib.mcp_create(C.byref(h), int(device))
+        if devices is not None:
+            ids = _i32(list(devices))
+            rc = self.lib.mcp_create_multi(C.byref(h), int(ids.size), ids.ctypes.data, int(reduce))
+            device = int(ids[0])
+        elif rank is not None:
+            n_ranks, r, uid = rank
+            assert len(uid) == 128
+            rc = self.lib.mcp_create_rank(C.byref(h), int(device), int(n_ranks), int(r), C.c_char_p(uid))
+        else:
+            rc = self.lib.mcp_create(C.byref(h), int(device))
         if rc:
             raise McpError(rc, self.lib.mcp_last_error(None).decode())
         self.handle = h
         self.device = device
+
+    @property
+    def device_count(self) -> int:
+        return int(self.lib.mcp_device_count(self.handle))
+
+    @property
+    def reduce_mode(self) -> int:
+        return int(self.lib.mcp_reduce_mode(self.handle))
 
     def _check(self, rc: int):
         if rc:
@@ -190,10 +246,19 @@ class Context:
         self._check(self.lib.mcp_wave_columns(self.handle, int(K), int(n_nodes), int(want_grad), C.byref(out)))
         return out.value
 
-    def stats(self) -> dict:
+    def stats(self, member: Optional[int] = None) -> dict:
         s = Stats()
-        self._check(self.lib.mcp_get_stats(self.handle, C.byref(s)))
+        if member is None:
+            self._check(self.lib.mcp_get_stats(self.handle, C.byref(s)))
+        else:
+            self._check(self.lib.mcp_get_stats_member(self.handle, int(member), C.byref(s)))
         return s.asdict()
+
+    def stream_blocks(self, member: int = 0):
+        """Site blocks [lo, hi) one device used in the last mcp_eval_streamed call."""
+        buf = np.zeros((16, 2), dtype=np.int64)
+        n = self.lib.mcp_stream_blocks(self.handle, int(member), buf.ctypes.data, 16)
+        return [(int(a), int(b)) for a, b in buf[:max(n, 0)]]
 
     # ---- leaf data -------------------------------------------------------------------
     def alignment_from_codes(self, codes, K: int, leaf_nums) -> Alignment:
@@ -251,6 +316,22 @@ class Context:
                                                 int(prior_kind), pp.ctypes.data, C.byref(lp),
                                                 grad.ctypes.data if want_grad else None))
         return lp.value, (grad[:NN - 1] if want_grad else None)
+
+    def eval_streamed(self, codes_ptr: int, K: int, S: int, leaf_nums, postorder_num, parent_num, blv, U, D, Uinv, mu,
+                      rates, pi, want_grad: bool = True):
+        """One evaluation of a HOST-resident (n_leaves, S) uint8 alignment at `codes_ptr` (pinned memory
+        recommended), uploaded block by block under the evaluation (mcp_eval_streamed)."""
+        po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
+        leaf_nums = _i32(leaf_nums)
+        NN = po.size
+        ll = C.c_double()
+        grad = np.zeros(max(NN - 1, 1), dtype=np.float64) if want_grad else None
+        self._check(self.lib.mcp_eval_streamed(self.handle, _vp(codes_ptr), int(K), int(S), leaf_nums.ctypes.data,
+                                               leaf_nums.size, NN, po.ctypes.data, pa.ctypes.data, blv.ctypes.data,
+                                               U.ctypes.data, D.ctypes.data, Uinv.ctypes.data, float(mu),
+                                               rates.ctypes.data, rates.size, pi.ctypes.data, int(want_grad),
+                                               C.byref(ll), grad.ctypes.data if want_grad else None))
+        return ll.value, (grad[:NN - 1] if want_grad else None)
 
     def eval_device(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
                     want_grad: bool, d_out_ptr: int):

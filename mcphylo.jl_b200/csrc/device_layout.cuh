@@ -1,8 +1,9 @@
 // device_layout.cuh — device-side data layout: tree / walk parameter blocks, per-evaluation parameter layout, branch-table layout, model constants.
-// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+// Part of libmcphylo_b200.so; shared by the host translation unit and the per-K kernel translation units
+// (named namespace: these types cross translation-unit boundaries through kernel_api.hpp).
 #pragma once
 
-namespace {
+namespace mcpdev {
 
 using mcp::PostOp;
 using mcp::PreOp;
@@ -89,6 +90,7 @@ __host__ __device__ inline int bt_size(int K) { return 2 * K + 2 * K * (K + 1); 
 constexpr int MODEL_SLOT = 256;                 // doubles per slot
 constexpr int MODEL_SLOTS = 32;                 // 64 KB of constant memory
 constexpr int MAX_RATES = 16;
-__constant__ double c_model[MODEL_SLOT * MODEL_SLOTS];
+constexpr int KMAX_GENERIC = 32;                // largest state count of the runtime-K kernel
 
-}  // namespace
+}  // namespace mcpdev
+using namespace mcpdev;

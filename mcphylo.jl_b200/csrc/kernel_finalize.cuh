@@ -51,3 +51,21 @@ __global__ void finalize_results(const TreeDev* __restrict__ trees, const double
 }
 
 }  // namespace
+
+namespace {
+
+// --------------------------------------------------------------------------------------------
+// Fixed-order sum of n result vectors of `len` doubles, `stride` doubles apart:  out[j] = sum_i in[i][j].
+// Used for the site blocks of a streamed alignment and, on a multi-device context in PEER mode, for
+// the per-device parts the other GPUs have written into device 0's gather buffer over NVLink (`out` may
+// be pinned host memory: the result then needs no separate copy).
+// --------------------------------------------------------------------------------------------
+__global__ void sum_rows(const double* __restrict__ in, long long stride, int n, long long len, double* __restrict__ out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= len) return;
+    double v = in[j];
+    for (int i = 1; i < n; ++i) v += in[(long long)i * stride + j];
+    out[j] = v;
+}
+
+}  // namespace

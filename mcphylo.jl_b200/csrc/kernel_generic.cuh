@@ -10,8 +10,6 @@ namespace {
 // branch table (P / dP columns are stored for every branch) and per-thread vectors in local memory.
 // Correctness path for large alphabets (e.g. 20-state protein models); not tuned.
 // --------------------------------------------------------------------------------------------
-constexpr int KMAX_GENERIC = 32;
-
 __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams p, const int K) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];

@@ -1,5 +1,5 @@
 // kernel_levels.cuh — kernel 2a: level-parallel small-tree kernel (tables + walk + final reduction in one launch).
-// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+// Part of libmcphylo_b200.so; instantiated per state count K in walk_k*.cu (walk_inst.cuh).
 #pragma once
 
 namespace {
@@ -12,19 +12,6 @@ namespace {
 // The critical path is the tree height instead of the node count; used when the whole input is only
 // a few tiles per SM (MCMC-sized problems), where the depth-first walk runs at single-warp latency.
 // --------------------------------------------------------------------------------------------
-struct LevelSmem {
-    // byte offsets into dynamic shared memory
-    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 127) & ~(size_t)127) : 0; }
-    static __host__ __device__ size_t exp_bytes() { return 128; }
-    static __host__ __device__ size_t code_bytes(int n_rows) { return (((size_t)n_rows * 32) + 127) & ~(size_t)127; }
-    static __host__ __device__ size_t slot_bytes(int K) { return (size_t)32 * K * 8; }
-    static __host__ __device__ size_t tab_bytes(int n_br, int K) { return (((size_t)n_br * bt_size(K) * 8) + 127) & ~(size_t)127; }
-    static __host__ __device__ size_t total(int n_br, int want_grad, int n_rows, int n_slots, int n_stack, int K) {
-        return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + tab_bytes(n_br, K) +
-               (size_t)(n_slots + n_stack) * slot_bytes(K);
-    }
-};
-
 template <int K, bool DYN_MODEL>
 __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

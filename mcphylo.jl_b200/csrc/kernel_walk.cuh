@@ -1,5 +1,5 @@
 // kernel_walk.cuh — kernel 2: the persistent fused walk (post pass + gradient pass), one thread per column.
-// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+// Part of libmcphylo_b200.so; instantiated per state count K in walk_k*.cu (walk_inst.cuh).
 #pragma once
 
 namespace {
@@ -17,8 +17,6 @@ namespace {
 // so the only global accesses on the per-op critical path are the thread's own partials and the
 // leaf-table gathers.  One __syncthreads per chunk.
 // --------------------------------------------------------------------------------------------
-constexpr int CH = 16;
-
 // Per-op record derived by the staging threads from the raw descriptor (schedule.hpp): everything the
 // compute threads need as ready-to-add byte offsets, so no warp repeats the uniform address math.
 //   xa / xb  LEAF child: byte offset (from the branch-table base) of the child's P columns for this
@@ -34,44 +32,6 @@ struct __align__(16) OpRec {
     unsigned y1, y2;           // second half: needed at its end
 };
 static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
-
-// Where a CTA accumulates its branch-gradient sums (template parameter ACCG, decided on the host):
-// in shared memory without atomics (below) whenever the per-branch accumulator fits next to the staging
-// buffers without costing a resident CTA -- trees of up to WALK_ACC_SHARED_MAX_NODES nodes -- else
-// (ACCG) directly in the CTA's accumulator row in global memory with fire-and-forget RED.ADD.F64 (the
-// row stays in L2; any tree size, but the sums arrive in no fixed order).  The two are separate
-// instantiations: with both paths in one kernel the K = 4 op loop spills again.
-constexpr int WALK_ACC_SHARED_MAX_NODES = 4096;
-inline bool walk_acc_global(int n_nodes, int mode /* -1 auto, 0 shared, 1 global */) {
-    return mode < 0 ? n_nodes > WALK_ACC_SHARED_MAX_NODES : mode != 0;
-}
-
-// Shared-memory accumulator: the per-warp sums of a chunk's 2 * CH branch terms are parked here
-// and folded into the accumulator by one thread per term after the chunk barrier, in fixed warp order
-// -- no atomics (a shared fp64 atomic add is a compare-and-swap loop, ~10 instructions, 38 % retries
-// with 8 warps on one address) and a run-to-run reproducible gradient.
-//   [2 buffers][CH ops][2 children][8 warps] doubles, then [2][CH][2] branch ids
-constexpr int WALK_PART_DOUBLES = 2 * CH * 2 * 8;
-constexpr int WALK_PART_BYTES = WALK_PART_DOUBLES * 8 + 2 * CH * 2 * 4;
-
-template <int K>
-struct WalkSmem {
-    // dynamic shared memory carve-up (offsets in bytes)
-    // branch-gradient accumulator of the CTA + parked per-warp sums (shared-accumulator kernels only:
-    // callers pass want_grad && !ACCG)
-    static __host__ __device__ size_t acc_bytes(int n_br, int shared_acc) {
-        return shared_acc ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
-    }
-    static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
-    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
-    static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
-    static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
-    // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
-    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
-    static __host__ __device__ size_t total(int n_br, int shared_acc, int TW) {
-        return acc_bytes(n_br, shared_acc) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
-    }
-};
 
 // 3 resident CTAs of 256 threads per SM (<= 80 registers): the walk is latency-bound, 24 warps
 // with a few spills beat 16 warps without (profiles/r1_walk_notes.md).

@@ -1,4 +1,4 @@
-// mcphylo_b200.cu — libmcphylo_b200.so: C ABI (include/mcphylo_b200.h) + sm_100a kernels.
+// mcphylo_b200.cu — libmcphylo_b200.so: C ABI (include/mcphylo_b200.h), host side.
 //
 // Replaces, for one PhyloDist evaluation, the reference's
 //   my_repeat + parallel_transition_prob + FelsensteinFunction (post-order pruning with per-column
@@ -19,277 +19,18 @@
 // uses exact powers of two (exponent extraction) instead of the reference's divide-by-max + log per
 // node; the integer exponent sum is exact and logL = ln2 * sum(exponents) + sum(log(pi . L_root)).
 // Branch-gradient sums are accumulated without atomics, in a fixed order (reproducible bit for bit).
-#include "../../include/mcphylo_b200.h"
-#include "schedule.hpp"
+//
+// Source map: the walk kernels are compiled per state count in walk_k2.cu .. walk_k6.cu and
+// walk_generic.cu and reached through kernel_api.hpp; this unit holds the planner (planner.hpp), the
+// evaluation driver, the multi-GPU group (site shards + one all-reduce of [logL, gradient]) and the
+// small kernels around the walk (branch tables, final reductions).
+#include "planner.hpp"
 
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <mutex>
-#include <string>
-#include <type_traits>
-#include <vector>
-
-#include "device_layout.cuh"
-#include "device_math.cuh"
 #include "kernel_tables.cuh"
-#include "kernel_walk.cuh"
 #include "epilogue_prior.cuh"
-#include "kernel_levels.cuh"
-#include "kernel_generic.cuh"
 #include "kernel_finalize.cuh"
 
 namespace {
-
-// --------------------------------------------------------------------------------------------
-// host side
-// --------------------------------------------------------------------------------------------
-thread_local std::string g_error;
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-struct PinBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-}  // namespace
-
-struct mcp_alignment {
-    int K = 0;
-    long long S = 0, stride = 0;
-    int n_leaves = 0;
-    unsigned char* d_codes = nullptr;
-    std::vector<int32_t> leaf_nums;
-    unsigned long long id = 0;
-    // Re-uploads (mcp_alignment_update_codes) run on the context's copy stream so that they overlap
-    // evaluations of OTHER alignments; these order them against the evaluations of THIS one.
-    cudaEvent_t ev_uploaded = nullptr;
-    cudaEvent_t ev_read_done = nullptr;      // recorded after every walk that read d_codes, once `streamed`
-    mutable bool upload_pending = false;     // an upload has been enqueued that no evaluation has waited for yet
-    mutable bool read_since_upload = false;  // an evaluation reading d_codes was enqueued after the last upload
-    mutable bool streamed = false;           // has been re-uploaded at least once: evaluations record ev_read_done
-};
-
-struct mcp_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t copy_stream = nullptr;     // alignment re-uploads (overlap with evaluations)
-    cudaEvent_t ev_walk_done = nullptr;     // the walk kernel of the last evaluation has finished reading the codes
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_staged = nullptr;   // the pinned staging buffers of the last evaluation have been consumed
-    bool staged_pending = false;
-    std::string error;
-    bool pending_async = false;
-    int opt_block = 0, opt_ctas_per_sm = 0, opt_cpt = 0;
-    int cpt = 1;   // columns per thread of the cached launch
-    bool smem_scratch = false;   // partials scratch in shared memory (small-problem latency path)
-    bool level_mode = false;     // level-parallel small-tree kernel
-    int opt_levels = -1;         // -1 automatic, 0 never, 1 whenever it fits
-    int sig_levels = -1;
-    int max_rows = 1;
-    size_t off_levels = 0;
-    int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
-    int opt_acc_mode = -1;       // gradient accumulator of the walk: -1 automatic, 0 shared memory, 1 global memory (RED)
-    bool acc_global = false;     // what the current plan uses
-    unsigned long long next_aln_id = 1;
-
-    DevBuf d_topo, d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out, d_counter;
-    PinBuf h_topo, h_dyn, h_out, h_model;
-
-    // cached topology
-    struct TreeSig {
-        unsigned long long aln_id;
-        int NN;
-        std::vector<int32_t> po, pa;
-    };
-    std::vector<TreeSig> sig;
-    int sig_want_grad = -1, sig_block = 0, sig_K = 0, sig_R = 0, sig_cpt = 0;
-    // derived launch state kept with the cached topology
-    std::vector<TreeDev> trees;
-    std::vector<Schedule> scheds;
-    size_t topo_bytes = 0, off_trees = 0, off_ops = 0, off_rowbase = 0;
-    int n_tiles = 0, grid = 0, block = 0, n_rows = 0, n_slots = 0, n_stack = 0, max_br = 0;
-    long long total_out = 0, total_dyn = 0, total_btab = 0, scratch_per_cta = 0, row_stride = 0;
-    size_t smem_bytes = 0;
-
-    mcp_stats stats{};
-};
-
-namespace {
-
-int fail(mcp_ctx* ctx, int code, const char* fmt, ...) {
-    char buf[1024];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (ctx) ctx->error = buf;
-    else g_error = buf;
-    return code;
-}
-
-#define CUDA_TRY(ctx, expr)                                                                      \
-    do {                                                                                         \
-        cudaError_t _e = (expr);                                                                 \
-        if (_e != cudaSuccess)                                                                   \
-            return fail(ctx, MCP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
-                        __FILE__, __LINE__);                                                     \
-    } while (0)
-
-int ensure_dev(mcp_ctx* ctx, DevBuf& b, size_t bytes) {
-    if (bytes <= b.cap) return 0;
-    if (ctx->pending_async) {
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->pending_async = false;
-    }
-    if (b.p) CUDA_TRY(ctx, cudaFree(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        want = bytes;
-        e = cudaMalloc(&b.p, want);
-    }
-    if (e != cudaSuccess) {
-        b.p = nullptr;
-        return fail(ctx, MCP_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
-    }
-    b.cap = want;
-    return 0;
-}
-int ensure_pin(mcp_ctx* ctx, PinBuf& b, size_t bytes) {
-    if (bytes <= b.cap) return 0;
-    if (b.p) CUDA_TRY(ctx, cudaFreeHost(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-    size_t want = bytes + bytes / 4 + 4096;
-    CUDA_TRY(ctx, cudaMallocHost(&b.p, want));
-    b.cap = want;
-    return 0;
-}
-
-// cudaFuncSetAttribute is only needed when a kernel's dynamic shared memory grows.  The attribute
-// belongs to the (device, function) pair and is shared by every context of the process, so the
-// high-water marks are process-global and only ever raised.
-template <class Kern>
-int ensure_smem_attr(mcp_ctx* ctx, Kern kern, size_t smem) {
-    struct Mark { int device; const void* fn; size_t bytes; };
-    static std::mutex mu;
-    static std::vector<Mark> marks;
-    std::lock_guard<std::mutex> lock(mu);
-    for (auto& m : marks)
-        if (m.device == ctx->device && m.fn == (const void*)kern) {
-            if (m.bytes >= smem) return 0;
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            m.bytes = smem;
-            return 0;
-        }
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    marks.push_back({ctx->device, (const void*)kern, smem});
-    return 0;
-}
-template <int K, int CPT, bool DYN, bool SSCR, int NE, bool ACCG>
-int launch_walk_inst(mcp_ctx* ctx, const WalkParams& wp) {
-    int e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG>, ctx->smem_bytes);
-    if (e) return e;
-    felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
-    CUDA_TRY(ctx, cudaGetLastError());
-    return 0;
-}
-// null_last: every model of the batch has a null eigenvalue, moved to the last position by the host
-// (true for any rate matrix) -> kernels with K - 1 active eigen-components.  Otherwise (a caller
-// passing some other decomposition) the full-K kernels.  Those, and the kernels that accumulate the
-// gradient in global memory (ctx->acc_global: very large trees), exist in the constant-memory (DYN)
-// flavour only -- and the latter with one column per thread only, which prepare_topology arranges.
-template <int K>
-int launch_walk(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model, bool null_last) {
-    constexpr int NE = K - 1;
-    if (ctx->acc_global)
-        return null_last ? launch_walk_inst<K, 1, true, false, NE, true>(ctx, wp) : launch_walk_inst<K, 1, true, false, K, true>(ctx, wp);
-    if (!null_last)
-        return ctx->cpt == 2 ? launch_walk_inst<K, 2, true, false, K, false>(ctx, wp) : launch_walk_inst<K, 1, true, false, K, false>(ctx, wp);
-    if (ctx->smem_scratch && !dyn_model && ctx->cpt == 1) return launch_walk_inst<K, 1, false, true, NE, false>(ctx, wp);
-    if (ctx->cpt == 2) return dyn_model ? launch_walk_inst<K, 2, true, false, NE, false>(ctx, wp) : launch_walk_inst<K, 2, false, false, NE, false>(ctx, wp);
-    return dyn_model ? launch_walk_inst<K, 1, true, false, NE, false>(ctx, wp) : launch_walk_inst<K, 1, false, false, NE, false>(ctx, wp);
-}
-template <int K, int CPT>
-int occupancy_inst(mcp_ctx* ctx, int block, size_t smem, bool sscr, bool acc_global, int* out) {
-    int e;
-    constexpr int NE = K - 1;
-    if (acc_global) {
-        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, true, false, K, true>, smem))) return e;
-        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, true, false, NE, true>, smem))) return e;
-        int o1 = 0, o2 = 0;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, 1, true, false, K, true>, block, smem));
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, 1, true, false, NE, true>, block, smem));
-        *out = std::min(o1, o2);
-        return 0;
-    }
-    if (sscr) {
-        if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, 1, false, true, NE, false>, smem))) return e;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk<K, 1, false, true, NE, false>, block, smem));
-        return 0;
-    }
-    // the variants differ by a few registers: size the persistent grid for the most demanding one
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, NE, false>, smem))) return e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, false, false, NE, false>, smem))) return e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk<K, CPT, true, false, K, false>, smem))) return e;
-    int o1 = 0, o2 = 0, o3 = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk<K, CPT, true, false, NE, false>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk<K, CPT, false, false, NE, false>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, felsenstein_walk<K, CPT, true, false, K, false>, block, smem));
-    *out = std::min(o1, std::min(o2, o3));
-    return 0;
-}
-template <int K>
-int occupancy_for(mcp_ctx* ctx, int block, int cpt, size_t smem, bool sscr, bool acc_global, int* out) {
-    return cpt == 2 ? occupancy_inst<K, 2>(ctx, block, smem, false, acc_global, out) : occupancy_inst<K, 1>(ctx, block, smem, sscr, acc_global, out);
-}
-template <int K>
-int occupancy_levels(mcp_ctx* ctx, int block, size_t smem, int* out) {
-    int e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk_levels<K, true>, smem))) return e;
-    if ((e = ensure_smem_attr(ctx, felsenstein_walk_levels<K, false>, smem))) return e;
-    int o1 = 0, o2 = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk_levels<K, true>, block, smem));
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk_levels<K, false>, block, smem));
-    *out = std::min(o1, o2);
-    return 0;
-}
-template <int K>
-int launch_levels(mcp_ctx* ctx, const WalkParams& wp, bool dyn_model) {
-    if (dyn_model) felsenstein_walk_levels<K, true><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
-    else felsenstein_walk_levels<K, false><<<ctx->grid, ctx->block, ctx->smem_bytes, ctx->stream>>>(wp);
-    CUDA_TRY(ctx, cudaGetLastError());
-    return 0;
-}
-size_t walk_smem_bytes(int K, int max_br, int shared_acc, int block, int cpt) {
-    const size_t acc = shared_acc ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
-    return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
-           (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
-}
-
-#define MCP_DISPATCH_K(K, CALL)                      \
-    switch (K) {                                     \
-        case 2: { constexpr int KK = 2; CALL; break; } \
-        case 3: { constexpr int KK = 3; CALL; break; } \
-        case 4: { constexpr int KK = 4; CALL; break; } \
-        case 5: { constexpr int KK = 5; CALL; break; } \
-        case 6: { constexpr int KK = 6; CALL; break; } \
-        default: rc = MCP_ERR_UNSUPPORTED;           \
-    }
-
-bool k_templated(int K) { return K >= 2 && K <= 6; }
 
 // Copies the eigen-decomposition (U, Uinv column-major K x K, D) with the eigenvalue of smallest
 // magnitude moved to the LAST position (columns of U, rows of Uinv, entries of D permuted alike:
@@ -311,453 +52,271 @@ bool null_eigenvalue_last(const double* U, const double* D, const double* Uinv, 
     }
     return std::fabs(D[i0]) <= 8.0 * 2.220446049250313e-16 * dmax;
 }
-bool k_supported(int K) { return K >= 2 && K <= KMAX_GENERIC; }
 
-struct BatchArgs {
-    int T;
-    const mcp_alignment* const* alns;
-    const int32_t* NN;
-    const int32_t* const* po;
-    const int32_t* const* pa;
-    const double* const* blv;
-    const double* const* U;
-    const double* const* D;
-    const double* const* Uinv;
-    const double* mu;
-    const double* const* rates;
-    int R;
-    const double* const* pi;
-    int want_grad;
-    // optional branch-length prior (mcp_eval_posterior); applies to every tree of the batch
-    int prior_kind = MCP_PRIOR_NONE;
-    const double* prior_params = nullptr;
+// Several contexts of one process may share a GPU (chains in threads, a streaming context next to a
+// resident one).  The constant-memory model slots of a kernel translation unit are per device, so a
+// context that is about to overwrite them waits (on its stream) for the last kernel of any other context
+// that read them; the bookkeeping is guarded by a mutex, the waiting happens on the device.
+struct ModelSlotGuard {
+    std::mutex mu;
+    struct Entry { int device; const void* unit; cudaEvent_t ev; mcp_ctx* last; };
+    std::vector<Entry> entries;
+    Entry* find(int device, const void* unit) {
+        for (auto& e : entries)
+            if (e.device == device && e.unit == unit) return &e;
+        return nullptr;
+    }
 };
+ModelSlotGuard g_slots;
 
-// (Re)build schedules, tile/row assignment and the topology upload if anything structural changed.
-int prepare_topology(mcp_ctx* ctx, const BatchArgs& a, int K, bool* rebuilt) {
-    const int T = a.T, R = a.R;
-    // choose the tile width first: it is part of the signature
-    long long total_cols = 0;
-    for (int t = 0; t < T; ++t) total_cols += a.alns[t]->S * R;
-    int block = ctx->opt_block;
-    if (block <= 0) {
-        block = 256;
-        while (block > 32 && (total_cols + block - 1) / block < 6LL * ctx->sm_count) block >>= 1;
-    }
-    // Two columns per thread amortise the per-op overhead (descriptor decode, constant loads, warp
-    // reduction) once there is enough work to fill the GPU.  Measured: 1.28x at K = 2, 1.06x at K = 4
-    // (cfg4: 78.2 -> 73.6 ms; 2 CTAs x 256 threads per SM at 128 registers), profiles/r1_walk_notes.md.
-    int cpt = ctx->opt_cpt;
-    if (cpt <= 0) cpt = (K <= 4 && total_cols / (2LL * block) >= 12LL * ctx->sm_count) ? 2 : 1;
-    // Very large trees: the per-branch accumulator no longer fits in shared memory next to the staging
-    // buffers; those kernels exist with one column per thread only (launch_walk).
-    int max_nn = 0;
-    for (int t = 0; t < T; ++t) max_nn = std::max(max_nn, (int)a.NN[t]);
-    const bool acc_global = a.want_grad && k_templated(K) && walk_acc_global(max_nn, ctx->opt_acc_mode);
-    if (acc_global) cpt = 1;
-    if (!k_templated(K)) {   // generic-K kernel: one column per thread, at most 128 threads per CTA
-        cpt = 1;
-        if (block > 128) block = 128;
-    }
-    // Small inputs (a few one-warp tiles per SM): level-parallel kernel, a tile is 32 columns wide
-    // and is worked on by all 8 warps of a 256-thread CTA.
-    const bool try_levels = k_templated(K) && ctx->opt_levels != 0 &&
-                            (ctx->opt_levels == 1 || (ctx->opt_block == 0 && total_cols <= 32LL * 4 * ctx->sm_count));
-    bool same = (int)ctx->sig.size() == T && ctx->sig_want_grad == a.want_grad && ctx->sig_block == block &&
-                ctx->sig_K == K && ctx->sig_R == R && ctx->sig_cpt == cpt && ctx->sig_levels == (int)try_levels;
-    for (int t = 0; same && t < T; ++t) {
-        const auto& s = ctx->sig[t];
-        same = s.aln_id == a.alns[t]->id && s.NN == a.NN[t] &&
-               std::memcmp(s.po.data(), a.po[t], sizeof(int32_t) * a.NN[t]) == 0 &&
-               std::memcmp(s.pa.data(), a.pa[t], sizeof(int32_t) * a.NN[t]) == 0;
-    }
-    *rebuilt = !same;
-    if (same) return 0;
-
-    ctx->sig.clear();
-    long long n_ops = 0, out_off = 0, dyn_off = 0, btab_off = 0, n_lvl_ints = 0;
-    int tile_cursor = 0, n_slots = 1, n_stack = 1, max_br = 1, max_rows = 1;
-    std::vector<int32_t> leaf_row;
-    bool level_mode = try_levels;
-    auto build_all = [&](bool by_levels, int tile_w) -> int {
-    ctx->sig.clear();
-    ctx->scheds.assign(T, Schedule());
-    ctx->trees.assign(T, TreeDev());
-    n_ops = out_off = dyn_off = btab_off = n_lvl_ints = 0;
-    tile_cursor = 0; n_slots = 1; n_stack = 1; max_br = 1; max_rows = 1;
-    for (int t = 0; t < T; ++t) {
-        const mcp_alignment* al = a.alns[t];
-        const int NN = a.NN[t];
-        if (NN < 2) return fail(ctx, MCP_ERR_ARG, "tree %d: NN must be >= 2", t);
-        leaf_row.assign(NN, -1);
-        for (int i = 0; i < al->n_leaves; ++i) {
-            int num = al->leaf_nums[i];
-            if (num >= 1 && num <= NN) leaf_row[num - 1] = i;
+// Branch-length prior -> the form  c0 - beta*T + sum_j w_j log t_j + k4 log T  (topology-only constants);
+// sums over the branch lengths and the gradient are formed on the device in the final reduction.
+// pr = [enabled, c0, beta, k4, w_1 .. w_{NN-1}].  Returns an error message or null.
+const char* fill_prior(int kind, const double* params, int NN, const int32_t* pa, double* pr) {
+    pr[0] = 0.0;
+    if (kind == MCP_PRIOR_NONE) return nullptr;
+    if (!params) return "branch-length prior without parameters";
+    double* w = pr + 4;
+    if (kind == MCP_PRIOR_EXPONENTIAL) {
+        const double scale = params[0];
+        if (!(scale > 0.0)) return "exponentialBL: scale must be positive";
+        pr[1] = -(double)(NN - 1) * std::log(scale);
+        pr[2] = 1.0 / scale;
+        pr[3] = 0.0;
+        for (int j = 0; j < NN - 1; ++j) w[j] = 0.0;
+    } else if (kind == MCP_PRIOR_COMPOUND_DIRICHLET) {
+        const double alpha = params[0], aa = params[1], beta = params[2], c = params[3];
+        if (!(alpha > 0.0 && aa > 0.0 && beta > 0.0 && c > 0.0)) return "CompoundDirichlet: alpha, a, beta, c must be positive";
+        // internal_external: 1 = the branch leads to an internal node, 0 = to a leaf (Prior.jl:15-23)
+        std::vector<char> internal(NN, 0);
+        for (int j = 0; j < NN; ++j) {
+            const int m = pa[j];
+            if (m >= 1 && m <= NN) internal[m - 1] = 1;
         }
-        std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, ctx->scheds[t], by_levels);
-        if (!err.empty()) return fail(ctx, MCP_ERR_ARG, "tree %d: %s", t, err.c_str());
-        const Schedule& sc = ctx->scheds[t];
-        TreeDev& td = ctx->trees[t];
-        td.post_off = n_ops;
-        n_ops += (long long)sc.post.size();
-        td.pre_off = n_ops;
-        n_ops += (long long)sc.pre.size();
-        td.n_post = (int)sc.post.size();
-        td.n_pre = (int)sc.pre.size();
-        td.NN = NN;
-        td.n_br = sc.n_dnodes;
-        td.codes = al->d_codes;
-        td.S = al->S;
-        td.code_stride = al->stride;
-        td.out_off = out_off;
-        out_off += NN;
-        td.dyn_off = dyn_off;
-        dyn_off += dyn_size(NN, K, R);
-        td.btab_off = btab_off;
-        btab_off += (long long)sc.n_dnodes * R * bt_size(K);
-        td.tiles_per_rate = (int)((al->S + (long long)tile_w - 1) / (long long)tile_w);
-        td.n_rows = al->n_leaves;
-        td.lvl_off = (int)n_lvl_ints;
-        td.n_post_lvl = sc.post_levels.empty() ? 0 : (int)sc.post_levels.size() - 1;
-        td.n_pre_lvl = sc.pre_levels.empty() ? 0 : (int)sc.pre_levels.size() - 1;
-        n_lvl_ints += (long long)sc.post_levels.size() + (long long)sc.pre_levels.size();
-        max_rows = std::max(max_rows, al->n_leaves);
-        td.tile_begin = tile_cursor;
-        long long nt = (long long)td.tiles_per_rate * R;
-        if (tile_cursor + nt > 0x7fffffffLL) return fail(ctx, MCP_ERR_ARG, "too many column tiles");
-        tile_cursor += (int)nt;
-        n_slots = std::max(n_slots, sc.n_slots);
-        n_stack = std::max(n_stack, sc.n_stack);
-        max_br = std::max(max_br, sc.n_dnodes);
-        mcp_ctx::TreeSig sg;
-        sg.aln_id = al->id;
-        sg.NN = NN;
-        sg.po.assign(a.po[t], a.po[t] + NN);
-        sg.pa.assign(a.pa[t], a.pa[t] + NN);
-        ctx->sig.push_back(std::move(sg));
-    }
-    return 0;
-    };  // build_all
-    int be = 0;
-    if (level_mode) {
-        if ((be = build_all(true, 32))) { ctx->sig.clear(); return be; }
-        const size_t need = LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K);
-        if (need > 160 * 1024) level_mode = false;     // tree too large for the shared-memory path
-    }
-    if (!level_mode && (be = build_all(false, block * cpt))) { ctx->sig.clear(); return be; }
-    const int sig_block = block, sig_cpt = cpt;
-    if (level_mode) { block = 256; cpt = 1; }
-    ctx->level_mode = level_mode;
-    ctx->sig_levels = (int)try_levels;
-    ctx->max_rows = max_rows;
-    ctx->sig_want_grad = a.want_grad;
-    ctx->sig_block = sig_block;
-    ctx->sig_cpt = sig_cpt;
-    ctx->cpt = cpt;
-    ctx->sig_K = K;
-    ctx->sig_R = R;
-    ctx->n_tiles = tile_cursor;
-    ctx->block = block;
-    ctx->n_slots = n_slots;
-    ctx->n_stack = a.want_grad ? n_stack : 0;
-    ctx->max_br = max_br;
-    ctx->total_out = out_off;
-    ctx->total_dyn = dyn_off;
-    ctx->total_btab = btab_off;
-    ctx->acc_global = acc_global && !level_mode;
-    ctx->smem_bytes = level_mode ? LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K)
-                      : k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad && !acc_global ? 1 : 0, block, cpt)
-                                       : (a.want_grad ? (size_t)max_br * sizeof(double) : 0);
-    // Small problems: keep the partials scratch in shared memory (latency path).  Automatic when the
-    // whole input is a handful of tiles per SM and the scratch of one CTA fits next to the staging
-    // buffers.
-    {
-        const size_t scr_bytes = (size_t)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8;
-        const bool fits = !level_mode && !acc_global && k_templated(K) && cpt == 1 && ctx->smem_bytes + scr_bytes <= 96 * 1024;
-        ctx->smem_scratch = fits && (ctx->opt_smem_scratch == 1 ||
-                                     (ctx->opt_smem_scratch < 0 && ctx->n_tiles <= 4 * ctx->sm_count));
-        if (ctx->smem_scratch) ctx->smem_bytes += scr_bytes;
-    }
-    if (ctx->smem_bytes > 200 * 1024)
-        return fail(ctx, MCP_ERR_UNSUPPORTED, "tree with %d nodes exceeds the shared-memory gradient accumulator", max_br);
-
-    // persistent grid
-    int occ = 0, rc = 0;
-    if (level_mode) {
-        MCP_DISPATCH_K(K, rc = occupancy_levels<KK>(ctx, block, ctx->smem_bytes, &occ));
-    } else if (k_templated(K)) {
-        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, ctx->smem_bytes, ctx->smem_scratch, ctx->acc_global, &occ));
+        double nterm = 0.0;
+        for (int j = 0; j < NN - 1; ++j) {
+            w[j] = internal[j] ? aa * c - 1.0 : aa - 1.0;
+            if (!internal[j]) nterm += 1.0;
+        }
+        const double n_int = nterm - 3.0;
+        pr[1] = alpha * std::log(beta) - std::lgamma(alpha) - std::lgamma(aa) - std::lgamma(c) + std::lgamma(aa + c);
+        pr[2] = beta;
+        pr[3] = alpha - aa * nterm - aa * c * n_int;
     } else {
-        if ((rc = ensure_smem_attr(ctx, felsenstein_walk_generic, ctx->smem_bytes))) return rc;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, felsenstein_walk_generic, block, ctx->smem_bytes));
+        return "unknown branch-length prior kind";
     }
-    if (rc) return rc == MCP_ERR_UNSUPPORTED ? fail(ctx, rc, "no kernel compiled for K = %d states", K) : rc;
-    if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d, smem %zu)", block, ctx->smem_bytes);
-    if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
-    ctx->grid = (int)std::min<long long>((long long)ctx->n_tiles, (long long)occ * ctx->sm_count);
-    if (ctx->grid < 1) ctx->grid = 1;
-    {   // very large trees: fewer persistent CTAs rather than a scratch allocation that cannot succeed
-        size_t free_b = 0, total_b = 0;
-        const double per_cta = level_mode ? 0.0 : (double)(ctx->n_slots + ctx->n_stack) * block * cpt * K * 8.0;
-        if (per_cta * ctx->grid <= (double)ctx->d_scratch.cap) {
-            // fits the scratch already held: nothing to allocate, no need to ask the driver
-            // (cudaMemGetInfo costs milliseconds on a GPU with many live allocations)
-        } else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_cta > 0) {
-            const double budget = 0.6 * ((double)free_b + (double)ctx->d_scratch.cap);
-            if (per_cta * ctx->grid > budget) ctx->grid = (int)std::max(1.0, std::floor(budget / per_cta));
-        } else {
-            cudaGetLastError();
-        }
-    }
-
-    // accumulator rows: one per (CTA, tree) pair in CTA order (also tree order)
-    std::vector<int32_t> row_base(ctx->grid, 0);
-    {
-        const int q = ctx->n_tiles / ctx->grid, rem = ctx->n_tiles % ctx->grid;
-        int row = 0, ti = 0;
-        for (int t = 0; t < T; ++t) ctx->trees[t].row_lo = ctx->trees[t].row_hi = 0;
-        std::vector<char> seen(T, 0);
-        for (int c = 0; c < ctx->grid; ++c) {
-            int t0 = c * q + std::min(c, rem), t1 = t0 + q + (c < rem ? 1 : 0);
-            row_base[c] = row;
-            int tile = t0;
-            while (ti < T - 1 && tile >= ctx->trees[ti].tile_begin + R * ctx->trees[ti].tiles_per_rate) ++ti;
-            int tj = ti;
-            while (tile < t1) {
-                int tend = std::min(t1, ctx->trees[tj].tile_begin + R * ctx->trees[tj].tiles_per_rate);
-                if (!seen[tj]) { ctx->trees[tj].row_lo = row; seen[tj] = 1; }
-                ++row;
-                ctx->trees[tj].row_hi = row;
-                tile = tend;
-                ++tj;
-            }
-        }
-        ctx->n_rows = row;
-    }
-    ctx->row_stride = (max_br + 3) & ~3;
-    if ((!level_mode && (double)(ctx->n_slots + n_stack + 1) * block * cpt * K * 8.0 >= 4.0e9) || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
-        return fail(ctx, MCP_ERR_UNSUPPORTED, "tree too large for 32-bit scratch offsets (%d nodes)", max_br);
-    ctx->scratch_per_cta = level_mode ? 4 : (long long)(ctx->n_slots + ctx->n_stack) * block * cpt * K;
-
-    // topology upload: [TreeDev x T][ops][row_base]
-    ctx->off_trees = 0;
-    ctx->off_ops = (sizeof(TreeDev) * T + 31) & ~(size_t)31;
-    ctx->off_rowbase = ctx->off_ops + (size_t)n_ops * 32;
-    ctx->off_levels = ctx->off_rowbase + sizeof(int32_t) * ctx->grid;
-    ctx->topo_bytes = ctx->off_levels + sizeof(int32_t) * (size_t)std::max<long long>(n_lvl_ints, 1);
-    int e;
-    if ((e = ensure_pin(ctx, ctx->h_topo, ctx->topo_bytes))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_topo, ctx->topo_bytes))) return e;
-    char* h = (char*)ctx->h_topo.p;
-    std::memcpy(h + ctx->off_trees, ctx->trees.data(), sizeof(TreeDev) * T);
-    char* ho = h + ctx->off_ops;
-    for (int t = 0; t < T; ++t) {
-        const Schedule& sc = ctx->scheds[t];
-        std::memcpy(ho, sc.post.data(), sc.post.size() * 32);
-        ho += sc.post.size() * 32;
-        std::memcpy(ho, sc.pre.data(), sc.pre.size() * 32);
-        ho += sc.pre.size() * 32;
-    }
-    std::memcpy(h + ctx->off_rowbase, row_base.data(), sizeof(int32_t) * ctx->grid);
-    {
-        int32_t* hl = (int32_t*)(h + ctx->off_levels);
-        for (int t = 0; t < T; ++t) {
-            const Schedule& sc = ctx->scheds[t];
-            for (int32_t v : sc.post_levels) *hl++ = v;
-            for (int32_t v : sc.pre_levels) *hl++ = v;
-        }
-    }
-    return 0;
+    pr[0] = 1.0;
+    return nullptr;
 }
 
-int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_out, double* const* grad_out) {
-    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+int validate_batch(mcp_ctx* ctx, const BatchArgs& a, int* K_out) {
     if (a.T < 1) return fail(ctx, MCP_ERR_ARG, "batch must hold at least one tree");
     if (a.R < 1) return fail(ctx, MCP_ERR_ARG, "need at least one rate category");
+    if (a.R > MAX_RATES) return fail(ctx, MCP_ERR_UNSUPPORTED, "more than %d rate categories", MAX_RATES);
     for (int t = 0; t < a.T; ++t) {
         if (!a.alns[t] || !a.po[t] || !a.pa[t] || !a.blv[t] || !a.U[t] || !a.D[t] || !a.Uinv[t] || !a.rates[t] || !a.pi[t])
             return fail(ctx, MCP_ERR_ARG, "tree %d: null argument", t);
         if (a.alns[t]->K != a.alns[0]->K) return fail(ctx, MCP_ERR_ARG, "all alignments of a batch must share K");
+        if (a.alns[t]->owner != ctx) return fail(ctx, MCP_ERR_ARG, "tree %d: the alignment belongs to another context", t);
     }
-    const int K = a.alns[0]->K, R = a.R, T = a.T;
+    const int K = a.alns[0]->K;
     if (!k_supported(K)) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (ctx->staged_pending) {  // the previous (asynchronous) evaluation may still be reading the staging buffers
-        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_staged));
-        ctx->staged_pending = false;
+    if (k_templated(K) && 2 * K * K + K + a.R * K > MODEL_SLOT)
+        return fail(ctx, MCP_ERR_UNSUPPORTED, "model with K=%d, R=%d does not fit a constant slot", K, a.R);
+    if (a.prior_kind != MCP_PRIOR_NONE) {   // parameter errors surface before anything is planned or enqueued
+        if (a.prior_kind != MCP_PRIOR_EXPONENTIAL && a.prior_kind != MCP_PRIOR_COMPOUND_DIRICHLET)
+            return fail(ctx, MCP_ERR_ARG, "unknown branch-length prior kind %d", a.prior_kind);
+        if (!a.prior_params) return fail(ctx, MCP_ERR_ARG, "branch-length prior without parameters");
+        const int np = a.prior_kind == MCP_PRIOR_EXPONENTIAL ? 1 : 4;
+        for (int i = 0; i < np; ++i)
+            if (!(a.prior_params[i] > 0.0))
+                return fail(ctx, MCP_ERR_ARG, a.prior_kind == MCP_PRIOR_EXPONENTIAL ? "exponentialBL: scale must be positive"
+                                                                                    : "CompoundDirichlet: alpha, a, beta, c must be positive");
     }
+    *K_out = K;
+    return 0;
+}
+
+// One evaluation on ONE device.  d_out_user != null: the result [logL, grad] per tree is left there
+// (device-addressable memory: this GPU, a peer GPU, or pinned host memory) and nothing is synchronised;
+// otherwise the call returns the results in ll_out / grad_out.
+int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_out, double* const* grad_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    int K = 0, e;
+    if ((e = validate_batch(ctx, a, &K))) return e;
+    const int R = a.R, T = a.T;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Plan* plp = nullptr;
     bool rebuilt = false;
-    int e = prepare_topology(ctx, a, K, &rebuilt);
-    if (e) { ctx->sig.clear(); return e; }
+    if ((e = get_plan(ctx, a, K, &plp, &rebuilt))) return e;
+    Plan& pl = *plp;
+    ctx->last_plan = plp;
+    const KernelTable* kt = kernels_for(K);
 
     // buffers
-    if ((e = ensure_pin(ctx, ctx->h_dyn, sizeof(double) * ctx->total_dyn))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_dyn, sizeof(double) * ctx->total_dyn))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_btab, sizeof(double) * ctx->total_btab))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_scratch, sizeof(double) * ctx->scratch_per_cta * ctx->grid))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_rows, sizeof(double) * ctx->row_stride * ctx->n_rows))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_rows_ll, sizeof(LLRow) * ctx->n_rows))) return e;
+    const int slot = ctx->stage_next;
+    ctx->stage_next = (slot + 1) % MCP_STAGE_SLOTS;
+    if (ctx->staged_pending[slot]) {   // an earlier asynchronous evaluation may still be reading this staging slot
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_staged[slot]));
+        ctx->staged_pending[slot] = false;
+    }
+    if ((e = ensure_pin(ctx, ctx->h_dyn[slot], sizeof(double) * pl.total_dyn))) return e;
+    if ((e = ensure_pin(ctx, ctx->h_model[slot], sizeof(double) * MODEL_SLOT * MODEL_SLOTS))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_dyn, sizeof(double) * pl.total_dyn))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_btab, sizeof(double) * pl.total_btab))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_scratch, sizeof(double) * pl.scratch_per_cta * pl.grid))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_rows, sizeof(double) * pl.row_stride * pl.n_rows))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_rows_ll, sizeof(LLRow) * pl.n_rows))) return e;
+    const bool fused = pl.level_mode;   // small-tree kernel: tables, walk and final reduction in ONE launch
+    const bool via_comm = !d_out_user && ctx->rank_comm != nullptr;
     double* d_out = d_out_user;
     if (!d_out) {
-        if ((e = ensure_dev(ctx, ctx->d_out, sizeof(double) * ctx->total_out))) return e;
-        if ((e = ensure_pin(ctx, ctx->h_out, sizeof(double) * ctx->total_out))) return e;
+        if ((e = ensure_dev(ctx, ctx->d_out, sizeof(double) * pl.total_out))) return e;
+        if ((e = ensure_pin(ctx, ctx->h_out, sizeof(double) * pl.total_out))) return e;
         d_out = (double*)ctx->d_out.p;
+    }
+    if (fused && !ctx->d_counter.p) {
+        if ((e = ensure_dev(ctx, ctx->d_counter, 256))) return e;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, ctx->stream));
     }
 
     // per-evaluation parameters
-    double* hd = (double*)ctx->h_dyn.p;
+    double* hd = (double*)ctx->h_dyn[slot].p;
     bool all_null_last = true;
+    const bool prior_here = a.prior_kind != MCP_PRIOR_NONE && (ctx->rank_comm == nullptr || ctx->rank == 0);
     for (int t = 0; t < T; ++t) {
         const int NN = a.NN[t];
-        double* d = hd + ctx->trees[t].dyn_off;
+        double* d = hd + pl.trees[t].dyn_off;
         std::memcpy(d + dyn_blv(NN), a.blv[t], sizeof(double) * (NN - 1));
         // eigen-decomposition with a null eigenvalue (if any) moved to the last position
         all_null_last = null_eigenvalue_last(a.U[t], a.D[t], a.Uinv[t], K, d + dyn_U(NN), d + dyn_D(NN, K), d + dyn_Uinv(NN, K)) && all_null_last;
         d[dyn_mu(NN, K)] = a.mu[t];
         std::memcpy(d + dyn_rates(NN, K), a.rates[t], sizeof(double) * R);
         std::memcpy(d + dyn_pi(NN, K, R), a.pi[t], sizeof(double) * K);
-        double* pr = d + dyn_prior(NN, K, R);
-        pr[0] = 0.0;
-        if (a.prior_kind != MCP_PRIOR_NONE) {
-            // The prior is brought to the form  c0 - beta*T + sum_j w_j log t_j + k4 log T  on the host
-            // (topology-only constants); sums over the branch lengths and the gradient are formed
-            // on the device in the final reduction.
-            if (!a.prior_params) return fail(ctx, MCP_ERR_ARG, "branch-length prior without parameters");
-            double* w = pr + 4;
-            if (a.prior_kind == MCP_PRIOR_EXPONENTIAL) {
-                const double scale = a.prior_params[0];
-                if (!(scale > 0.0)) return fail(ctx, MCP_ERR_ARG, "exponentialBL: scale must be positive");
-                pr[1] = -(double)(NN - 1) * std::log(scale);
-                pr[2] = 1.0 / scale;
-                pr[3] = 0.0;
-                for (int j = 0; j < NN - 1; ++j) w[j] = 0.0;
-            } else if (a.prior_kind == MCP_PRIOR_COMPOUND_DIRICHLET) {
-                const double alpha = a.prior_params[0], aa = a.prior_params[1], beta = a.prior_params[2], c = a.prior_params[3];
-                if (!(alpha > 0.0 && aa > 0.0 && beta > 0.0 && c > 0.0))
-                    return fail(ctx, MCP_ERR_ARG, "CompoundDirichlet: alpha, a, beta, c must be positive");
-                // internal_external: 1 = the branch leads to an internal node, 0 = to a leaf (Prior.jl:15-23)
-                std::vector<char> internal(NN, 0);
-                for (int j = 0; j < NN; ++j) {
-                    const int m = a.pa[t][j];
-                    if (m >= 1 && m <= NN) internal[m - 1] = 1;
-                }
-                double nterm = 0.0;
-                for (int j = 0; j < NN - 1; ++j) {
-                    w[j] = internal[j] ? aa * c - 1.0 : aa - 1.0;
-                    if (!internal[j]) nterm += 1.0;
-                }
-                const double n_int = nterm - 3.0;
-                pr[1] = alpha * std::log(beta) - std::lgamma(alpha) - std::lgamma(aa) - std::lgamma(c) + std::lgamma(aa + c);
-                pr[2] = beta;
-                pr[3] = alpha - aa * nterm - aa * c * n_int;
-            } else {
-                return fail(ctx, MCP_ERR_ARG, "unknown branch-length prior kind %d", a.prior_kind);
-            }
-            pr[0] = 1.0;
-        }
+        const char* perr = fill_prior(prior_here ? a.prior_kind : MCP_PRIOR_NONE, a.prior_params, NN, a.pa[t], d + dyn_prior(NN, K, R));
+        if (perr) return fail(ctx, MCP_ERR_ARG, "%s", perr);
     }
 
-    // substitution-model constants -> constant memory, one slot per distinct model of the batch
-    if (R > MAX_RATES) return fail(ctx, MCP_ERR_UNSUPPORTED, "more than %d rate categories", MAX_RATES);
+    // substitution-model constants: one slot per distinct model of the batch
     const int model_doubles = k_templated(K) ? 2 * K * K + K + R * K : 0;
-    if (model_doubles > MODEL_SLOT) return fail(ctx, MCP_ERR_UNSUPPORTED, "model with K=%d, R=%d does not fit a constant slot", K, R);
-    if ((e = ensure_pin(ctx, ctx->h_model, sizeof(double) * MODEL_SLOT * MODEL_SLOTS))) return e;
-    double* hm = (double*)ctx->h_model.p;
+    double* hm = (double*)ctx->h_model[slot].p;
     int n_models = 0;
     for (int t = 0; t < T && k_templated(K); ++t) {
         double cand[MODEL_SLOT];
-        const double* dt = hd + ctx->trees[t].dyn_off;       // the permuted decomposition stored above
+        const double* dt = hd + pl.trees[t].dyn_off;       // the permuted decomposition stored above
         std::memcpy(cand, dt + dyn_U(a.NN[t]), sizeof(double) * K * K);
         std::memcpy(cand + K * K, dt + dyn_Uinv(a.NN[t], K), sizeof(double) * K * K);
         std::memcpy(cand + 2 * K * K, a.pi[t], sizeof(double) * K);
         for (int r = 0; r < R; ++r)
             for (int i = 0; i < K; ++i) cand[2 * K * K + K + r * K + i] = dt[dyn_D(a.NN[t], K) + i] * a.rates[t][r] * a.mu[t];
-        int slot = -1;
-        for (int m = 0; m < n_models && slot < 0; ++m)
-            if (std::memcmp(hm + (size_t)m * MODEL_SLOT, cand, sizeof(double) * model_doubles) == 0) slot = m;
-        if (slot < 0) {
+        int ms = -1;
+        for (int m = 0; m < n_models && ms < 0; ++m)
+            if (std::memcmp(hm + (size_t)m * MODEL_SLOT, cand, sizeof(double) * model_doubles) == 0) ms = m;
+        if (ms < 0) {
             if (n_models == MODEL_SLOTS)
                 return fail(ctx, MCP_ERR_UNSUPPORTED, "more than %d distinct substitution models in one batch", MODEL_SLOTS);
-            slot = n_models++;
-            std::memcpy(hm + (size_t)slot * MODEL_SLOT, cand, sizeof(double) * model_doubles);
+            ms = n_models++;
+            std::memcpy(hm + (size_t)ms * MODEL_SLOT, cand, sizeof(double) * model_doubles);
         }
-        hd[ctx->trees[t].dyn_off + dyn_slot(a.NN[t], K, R)] = (double)slot;
+        hd[pl.trees[t].dyn_off + dyn_slot(a.NN[t], K, R)] = (double)ms;
     }
     // the walk kernels with all K eigen-components read their model from constant memory only
-    const bool dyn_model = n_models > 1 || (k_templated(K) && (!all_null_last || ctx->acc_global));
+    const bool dyn_model = n_models > 1 || (k_templated(K) && (!all_null_last || pl.acc_global));
 
+    // ---- everything below only enqueues; from the first enqueue on, an error leaves the plan marked
+    // "not uploaded" so that a retry re-sends the topology block instead of trusting a half-done one ----
     cudaStream_t st = ctx->stream;
     mcp_stats& s = ctx->stats;
     s = mcp_stats{};
+    struct UploadGuard {
+        Plan& pl; bool ok = false; bool was;
+        explicit UploadGuard(Plan& p) : pl(p), was(p.uploaded) {}
+        ~UploadGuard() { if (!ok) pl.uploaded = false; }
+    } guard(pl);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     if (dyn_model) {   // several models: slots in constant memory; one model travels as a kernel parameter
-        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(c_model, hm, sizeof(double) * MODEL_SLOT * n_models, 0, cudaMemcpyHostToDevice, st));
+        std::lock_guard<std::mutex> lock(g_slots.mu);
+        ModelSlotGuard::Entry* en = g_slots.find(ctx->device, kt);
+        if (en && en->last != ctx) CUDA_TRY(ctx, cudaStreamWaitEvent(st, en->ev, 0));
+        cudaError_t ce = kt->upload_model(hm, sizeof(double) * MODEL_SLOT * n_models, st);
+        if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(ce));
         s.h2d_bytes += (int64_t)(sizeof(double) * MODEL_SLOT * n_models);
     }
-    if (rebuilt) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_topo.p, ctx->h_topo.p, ctx->topo_bytes, cudaMemcpyHostToDevice, st));
-        s.h2d_bytes += (int64_t)ctx->topo_bytes;
+    if (!pl.uploaded) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(pl.d_topo.p, pl.h_topo.p, pl.topo_bytes, cudaMemcpyHostToDevice, st));
+        s.h2d_bytes += (int64_t)pl.topo_bytes;
+        pl.uploaded = true;
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(double) * ctx->total_dyn, cudaMemcpyHostToDevice, st));
-    s.h2d_bytes += (int64_t)(sizeof(double) * ctx->total_dyn);
-
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged, st));
-    ctx->staged_pending = true;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(double) * pl.total_dyn, cudaMemcpyHostToDevice, st));
+    s.h2d_bytes += (int64_t)(sizeof(double) * pl.total_dyn);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged[slot], st));
+    ctx->staged_pending[slot] = true;
     for (int t = 0; t < T; ++t)   // re-uploads of these alignments that are still in flight on the copy stream
         if (a.alns[t]->upload_pending) {
             CUDA_TRY(ctx, cudaStreamWaitEvent(st, a.alns[t]->ev_uploaded, 0));
             a.alns[t]->upload_pending = false;
         }
 
-    const TreeDev* d_trees = (const TreeDev*)((char*)ctx->d_topo.p + ctx->off_trees);
-    const bool fused = ctx->level_mode;   // small-tree kernel: tables, walk and final reduction in ONE launch
-    if (fused && !ctx->d_counter.p) {
-        if ((e = ensure_dev(ctx, ctx->d_counter, 256))) return e;
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counter.p, 0, 256, st));
-    }
+    const TreeDev* d_trees = (const TreeDev*)((char*)pl.d_topo.p + pl.off_trees);
     if (!fused) {
-        dim3 grid((ctx->max_br * R + 127) / 128, T);
+        dim3 grid((pl.max_br * R + 127) / 128, T);
         build_branch_tables<<<grid, 128, 0, st>>>(d_trees, (const double*)ctx->d_dyn.p, (double*)ctx->d_btab.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     WalkParams wp;
     wp.trees = d_trees;
-    wp.ops = (const int4*)((char*)ctx->d_topo.p + ctx->off_ops);
+    wp.ops = (const int4*)((char*)pl.d_topo.p + pl.off_ops);
     wp.btab = (const double*)ctx->d_btab.p;
     wp.dyn = (const double*)ctx->d_dyn.p;
     wp.scratch = (double*)ctx->d_scratch.p;
-    wp.scratch_per_cta = ctx->scratch_per_cta;
+    wp.scratch_per_cta = pl.scratch_per_cta;
     wp.rows = (double*)ctx->d_rows.p;
     wp.rows_ll = (LLRow*)ctx->d_rows_ll.p;
-    wp.cta_row_base = (const int*)((char*)ctx->d_topo.p + ctx->off_rowbase);
-    wp.levels = (const int*)((char*)ctx->d_topo.p + ctx->off_levels);
+    wp.cta_row_base = (const int*)((char*)pl.d_topo.p + pl.off_rowbase);
+    wp.levels = (const int*)((char*)pl.d_topo.p + pl.off_levels);
     // pinned host memory is device-addressable (unified addressing): the fused kernel writes results there
-    wp.out = d_out_user ? d_out_user : (double*)ctx->h_out.p;
+    wp.out = d_out_user ? d_out_user : via_comm ? d_out : (double*)ctx->h_out.p;
     wp.done_counter = (unsigned int*)ctx->d_counter.p;
-    wp.row_stride = ctx->row_stride;
-    wp.n_slots = ctx->n_slots;
-    wp.n_stack = ctx->n_stack;
-    wp.n_tiles = ctx->n_tiles;
+    wp.row_stride = pl.row_stride;
+    wp.n_slots = pl.n_slots;
+    wp.n_stack = pl.n_stack;
+    wp.n_tiles = pl.n_tiles;
     wp.T = T;
     wp.R = R;
     wp.want_grad = a.want_grad ? 1 : 0;
-    wp.max_br = ctx->max_br;
-    wp.max_rows = ctx->max_rows;
+    wp.max_br = pl.max_br;
+    wp.max_rows = pl.max_rows;
     static_assert(sizeof(wp.model) / sizeof(double) >= 2 * 6 * 6 + 6 + MAX_RATES * 6, "model parameter block too small");
     std::memset(wp.model, 0, sizeof wp.model);
     if (n_models == 1) std::memcpy(wp.model, hm, sizeof(double) * model_doubles);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
-    int rc = 0;
-    if (ctx->level_mode) {
-        MCP_DISPATCH_K(K, rc = launch_levels<KK>(ctx, wp, dyn_model));
-    } else if (k_templated(K)) {
-        MCP_DISPATCH_K(K, rc = launch_walk<KK>(ctx, wp, dyn_model, all_null_last));
-    } else {
-        felsenstein_walk_generic<<<ctx->grid, ctx->block, ctx->smem_bytes, st>>>(wp, K);
-        CUDA_TRY(ctx, cudaGetLastError());
+    LaunchCfg lc;
+    lc.device = ctx->device;
+    lc.K = K;
+    lc.grid = pl.grid;
+    lc.block = pl.block;
+    lc.cpt = pl.cpt;
+    lc.smem = pl.smem_bytes;
+    lc.stream = st;
+    lc.smem_scratch = pl.smem_scratch;
+    lc.acc_global = pl.acc_global;
+    {
+        cudaError_t ce = pl.level_mode ? kt->launch_levels(lc, wp, dyn_model) : kt->launch_walk(lc, wp, dyn_model, all_null_last);
+        if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(ce));
     }
-    if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (dyn_model) {   // the next writer of this unit's model slots on this device waits for this kernel
+        std::lock_guard<std::mutex> lock(g_slots.mu);
+        ModelSlotGuard::Entry* en = g_slots.find(ctx->device, kt);
+        if (!en) {
+            cudaEvent_t ev = nullptr;
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            g_slots.entries.push_back({ctx->device, kt, ev, ctx});
+            en = &g_slots.entries.back();
+        }
+        CUDA_TRY(ctx, cudaEventRecord(en->ev, st));
+        en->last = ctx;
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_done, st));
     for (int t = 0; t < T; ++t) {
         a.alns[t]->read_since_upload = true;
@@ -767,48 +326,60 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         int maxNN = 0;
         for (int t = 0; t < T; ++t) maxNN = std::max(maxNN, a.NN[t]);
         dim3 grid((maxNN + FIN_J - 1) / FIN_J, T);
-        finalize_results<<<grid, dim3(FIN_J, FIN_G), 0, st>>>(d_trees, (const double*)ctx->d_rows.p, ctx->row_stride,
+        finalize_results<<<grid, dim3(FIN_J, FIN_G), 0, st>>>(d_trees, (const double*)ctx->d_rows.p, pl.row_stride,
                                                (const LLRow*)ctx->d_rows_ll.p, d_out, wp.want_grad,
                                                (const double*)ctx->d_dyn.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
     s.kernel_launches = fused ? 1 : 3;
-    s.grid = ctx->grid;
-    s.block = ctx->block;
-    s.tiles = ctx->n_tiles;
+    s.grid = pl.grid;
+    s.block = pl.block;
+    s.tiles = pl.n_tiles;
+    s.columns_per_thread = pl.cpt;
     s.schedule_rebuilt = rebuilt ? 1 : 0;
     s.scratch_bytes = (int64_t)ctx->d_scratch.cap;
+    guard.ok = true;
     if (d_out_user) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
         ctx->pending_async = true;
         return 0;
     }
-    if (!fused) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * ctx->total_out, cudaMemcpyDeviceToHost, st));
-    s.d2h_bytes = (int64_t)(sizeof(double) * ctx->total_out);
+    if (via_comm) {   // one rank of a multi-process group: sum [logL, grad] over the ranks, then read it back
+        const mcpnccl::Api& nc = mcpnccl::api();
+        mcpnccl::result_t nr = nc.AllReduce(d_out, d_out, (size_t)pl.total_out, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, st);
+        if (nr) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce failed: %s", nc.GetErrorString(nr));
+    }
+    if (!fused || via_comm) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * pl.total_out, cudaMemcpyDeviceToHost, st));
+    s.d2h_bytes = (int64_t)(sizeof(double) * pl.total_out);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    ctx->staged_pending = false;
+    for (bool& p : ctx->staged_pending) p = false;
     ctx->pending_async = false;
     const double* ho = (const double*)ctx->h_out.p;
     for (int t = 0; t < T; ++t) {
-        const double* o = ho + ctx->trees[t].out_off;
+        const double* o = ho + pl.trees[t].out_off;
         if (ll_out) ll_out[t] = o[0];
         if (a.want_grad && grad_out && grad_out[t]) std::memcpy(grad_out[t], o + 1, sizeof(double) * (a.NN[t] - 1));
     }
     return 0;
 }
 
-int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, const int32_t* leaf_nums,
+int make_alignment(mcp_ctx* ctx, const unsigned char* codes, size_t src_pitch, int K, long long S, const int32_t* leaf_nums,
                    int n_leaves, mcp_alignment** out) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     mcp_alignment* al = new mcp_alignment();
     al->K = K;
     al->S = S;
-    al->stride = (S + 1023) & ~1023LL;   // a tile (<= 256 threads x 4 columns) never reads past a row
+    al->owner = ctx;
+    al->stride = (S + 1023) & ~1023LL;
     if (al->stride == 0) al->stride = 1024;
     al->n_leaves = n_leaves;
     al->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
     al->id = ctx->next_aln_id++;
-    size_t bytes = (size_t)al->stride * (size_t)std::max(n_leaves, 1);
+    // One tile of slack behind the last row: a tile whose width does not divide the row stride (widths are
+    // multiples of 32, up to 512 columns) may stage codes past the end of a row; the values are masked, the
+    // read must stay inside the allocation.
+    size_t bytes = (size_t)al->stride * (size_t)std::max(n_leaves, 1) + 1024;
     cudaError_t e = cudaMalloc((void**)&al->d_codes, bytes);
     if (e != cudaSuccess) {
         delete al;
@@ -819,7 +390,7 @@ int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S,
     // non-blocking stream that does not wait for the default stream.
     e = cudaMemsetAsync(al->d_codes, K, bytes, ctx->stream);
     if (e == cudaSuccess && S > 0 && n_leaves > 0)
-        e = cudaMemcpy2DAsync(al->d_codes, (size_t)al->stride, codes, (size_t)S, (size_t)S, (size_t)n_leaves,
+        e = cudaMemcpy2DAsync(al->d_codes, (size_t)al->stride, codes, src_pitch, (size_t)S, (size_t)n_leaves,
                               cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&al->ev_uploaded, cudaEventDisableTiming);
@@ -835,20 +406,372 @@ int make_alignment(mcp_ctx* ctx, const unsigned char* codes, int K, long long S,
     return 0;
 }
 
-}  // namespace
+int update_codes_one(mcp_ctx* ctx, mcp_alignment* aln, const unsigned char* codes, size_t src_pitch) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // On the copy stream: the transfer overlaps whatever the evaluation stream is doing (the
+    // evaluation of another site block, typically).  It must not overtake an evaluation that still
+    // reads this buffer, and the next evaluation of this alignment waits for it (eval_impl).
+    if (aln->read_since_upload) {
+        // first re-upload: only the context-wide "last walk finished" event exists (conservative);
+        // afterwards every evaluation of this alignment records the alignment's own event
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, aln->streamed ? aln->ev_read_done : ctx->ev_walk_done, 0));
+        aln->read_since_upload = false;
+    }
+    aln->streamed = true;
+    if (aln->S > 0)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(aln->d_codes, (size_t)aln->stride, codes, src_pitch, (size_t)aln->S,
+                                        (size_t)aln->n_leaves, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(aln->ev_uploaded, ctx->copy_stream));
+    aln->upload_pending = true;
+    ctx->pending_async = true;   // only consulted before buffers are freed / the stream is changed
+    return 0;
+}
+
+void destroy_alignment_one(mcp_ctx* ctx, mcp_alignment* aln) {
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        ctx->pending_async = false;
+        invalidate_plans(ctx, aln->id);
+    }
+    if (aln->ev_uploaded) cudaEventDestroy(aln->ev_uploaded);
+    if (aln->ev_read_done) cudaEventDestroy(aln->ev_read_done);
+    if (aln->d_codes) cudaFree(aln->d_codes);
+    delete aln;
+}
+
+int dense_to_codes(mcp_ctx* ctx, const double* x, int K, int64_t S, int NN, const int32_t* leaf_nums, int n_leaves,
+                   std::vector<unsigned char>& codes) {
+    codes.resize((size_t)n_leaves * (size_t)S);
+    for (int l = 0; l < n_leaves; ++l) {
+        const int num = leaf_nums[l];
+        if (num < 1 || num > NN) return fail(ctx, MCP_ERR_ARG, "leaf number %d out of range", num);
+        const double* slab = x + (size_t)K * (size_t)S * (size_t)(num - 1);
+        for (int64_t s = 0; s < S; ++s) {
+            const double* col = slab + (size_t)K * s;
+            int ones = 0, zeros = 0, first = -1;
+            for (int k = 0; k < K; ++k) {
+                if (col[k] == 1.0) { ++ones; if (first < 0) first = k; }
+                else if (col[k] == 0.0) ++zeros;
+            }
+            unsigned char c;
+            if (ones == K) c = (unsigned char)K;
+            else if (ones == 1 && zeros == K - 1) c = (unsigned char)first;
+            else
+                return fail(ctx, MCP_ERR_DATA, "leaf %d, site %lld: column is neither one-hot nor all ones", num, (long long)s + 1);
+            codes[(size_t)l * S + s] = c;
+        }
+    }
+    return 0;
+}
+
+void shard_range(long long S, int G, int g, long long* lo, long long* hi) {
+    const long long per = (S + G - 1) / G;
+    *lo = std::min(S, (long long)g * per);
+    *hi = std::min(S, *lo + per);
+}
 
 // --------------------------------------------------------------------------------------------
-// C ABI
+// multi-device groups
 // --------------------------------------------------------------------------------------------
-extern "C" {
+// Runs fn(g) for every member of a group, member g > 0 on its own persistent host thread (MemberPool).
+// Returns the first non-zero result.
+int for_each_member(mcp_ctx* ctx, const std::function<int(int)>& fn) {
+    const int G = (int)ctx->members.size();
+    std::vector<int> serial_rc;
+    const std::vector<int>* rc = &serial_rc;
+    if (G == 1 || !ctx->pool) {
+        serial_rc.resize(G);
+        for (int g = 0; g < G; ++g) serial_rc[g] = fn(g);
+    } else {
+        ctx->pool->run(fn);
+        rc = &ctx->pool->rc;
+    }
+    for (int g = 0; g < G; ++g)
+        if ((*rc)[g]) {
+            ctx->error = "device " + std::to_string(ctx->members[g]->device) + ": " + ctx->members[g]->error;
+            return (*rc)[g];
+        }
+    return 0;
+}
 
-int mcp_abi_version(void) { return MCP_ABI_VERSION; }
+// Sums the members' result vectors (`len` doubles each; member g's lives at part[g], see group_targets)
+// and returns the sum in pinned host memory (*h_result).
+int group_reduce(mcp_ctx* ctx, const std::vector<double*>& part, long long len, const double** h_result) {
+    const int G = (int)ctx->members.size();
+    mcp_ctx* m0 = ctx->members[0];
+    int e;
+    CUDA_TRY(ctx, cudaSetDevice(m0->device));
+    if ((e = ensure_pin(m0, m0->h_out, sizeof(double) * len))) { ctx->error = m0->error; return e; }
+    if (ctx->reduce_mode == MCP_REDUCE_NCCL) {
+        const mcpnccl::Api& nc = mcpnccl::api();
+        mcpnccl::result_t nr = nc.GroupStart();
+        for (int g = 0; g < G && !nr; ++g)
+            nr = nc.AllReduce(part[g], part[g], (size_t)len, mcpnccl::kFloat64, mcpnccl::kSum, ctx->comms[g], ctx->members[g]->stream);
+        mcpnccl::result_t ne = nc.GroupEnd();
+        if (nr || ne) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce failed: %s", nc.GetErrorString(nr ? nr : ne));
+        CUDA_TRY(ctx, cudaSetDevice(m0->device));
+        CUDA_TRY(ctx, cudaMemcpyAsync(m0->h_out.p, part[0], sizeof(double) * len, cudaMemcpyDeviceToHost, m0->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(m0->stream));
+        m0->pending_async = false;
+    } else if (ctx->reduce_mode == MCP_REDUCE_PEER) {
+        // every member has written its part into device 0's gather buffer (NVLink peer stores issued by its
+        // own final-reduction kernel); device 0 waits for them and adds the parts in member order
+        for (int g = 1; g < G; ++g) {
+            CUDA_TRY(ctx, cudaSetDevice(ctx->members[g]->device));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_member[g], ctx->members[g]->stream));
+        }
+        CUDA_TRY(ctx, cudaSetDevice(m0->device));
+        for (int g = 1; g < G; ++g) CUDA_TRY(ctx, cudaStreamWaitEvent(m0->stream, ctx->ev_member[g], 0));
+        sum_rows<<<(unsigned)((len + 255) / 256), 256, 0, m0->stream>>>(part[0], len, G, len, (double*)m0->h_out.p);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaStreamSynchronize(m0->stream));
+        for (mcp_ctx* m : ctx->members) m->pending_async = false;
+    } else {   // MCP_REDUCE_HOST
+        for (int g = 0; g < G; ++g) {
+            mcp_ctx* m = ctx->members[g];
+            CUDA_TRY(ctx, cudaSetDevice(m->device));
+            if ((e = ensure_pin(m, ctx->h_member_out[g], sizeof(double) * len))) { ctx->error = m->error; return e; }
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_member_out[g].p, part[g], sizeof(double) * len, cudaMemcpyDeviceToHost, m->stream));
+        }
+        for (int g = 0; g < G; ++g) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->members[g]->stream));
+            ctx->members[g]->pending_async = false;
+        }
+        double* o = (double*)m0->h_out.p;
+        std::memcpy(o, ctx->h_member_out[0].p, sizeof(double) * len);
+        for (int g = 1; g < G; ++g) {
+            const double* pg = (const double*)ctx->h_member_out[g].p;
+            for (long long j = 0; j < len; ++j) o[j] += pg[j];
+        }
+    }
+    // parameter staging slots are free again wherever the member's stream is known to have drained
+    for (mcp_ctx* m : ctx->members)
+        if (m == m0 || ctx->reduce_mode != MCP_REDUCE_NCCL)
+            for (bool& p : m->staged_pending) p = false;
+    *h_result = (const double*)m0->h_out.p;
+    return 0;
+}
 
-const char* mcp_last_error(const mcp_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+// Where each member leaves its [logL, grad] part of `len` doubles.  PEER: rows of one buffer on device 0
+// (the other members reach it through peer access); NCCL / HOST: a buffer on the member's own device.
+int group_targets(mcp_ctx* ctx, long long len, std::vector<double*>& part) {
+    const int G = (int)ctx->members.size();
+    part.assign(G, nullptr);
+    int e;
+    if (ctx->reduce_mode == MCP_REDUCE_PEER) {
+        mcp_ctx* m0 = ctx->members[0];
+        CUDA_TRY(ctx, cudaSetDevice(m0->device));
+        if (sizeof(double) * len * G > ctx->d_gather.cap) {   // growing it: nobody may still be writing into the old one
+            for (mcp_ctx* m : ctx->members) {
+                cudaSetDevice(m->device);
+                cudaStreamSynchronize(m->stream);
+            }
+            CUDA_TRY(ctx, cudaSetDevice(m0->device));
+        }
+        if ((e = ensure_dev(m0, ctx->d_gather, sizeof(double) * len * G))) { ctx->error = m0->error; return e; }
+        for (int g = 0; g < G; ++g) part[g] = (double*)ctx->d_gather.p + (long long)g * len;
+    } else {
+        for (int g = 0; g < G; ++g) {
+            mcp_ctx* m = ctx->members[g];
+            CUDA_TRY(ctx, cudaSetDevice(m->device));
+            if ((e = ensure_dev(m, m->d_out, sizeof(double) * len))) { ctx->error = m->error; return e; }
+            part[g] = (double*)m->d_out.p;
+        }
+    }
+    return 0;
+}
 
-int mcp_create(mcp_ctx** out, int device) {
-    if (!out) return fail(nullptr, MCP_ERR_ARG, "mcp_create: null output pointer");
-    *out = nullptr;
+void unpack_results(const BatchArgs& a, const double* h, double* ll_out, double* const* grad_out) {
+    long long off = 0;
+    for (int t = 0; t < a.T; ++t) {
+        if (ll_out) ll_out[t] = h[off];
+        if (a.want_grad && grad_out && grad_out[t]) std::memcpy(grad_out[t], h + off + 1, sizeof(double) * (a.NN[t] - 1));
+        off += a.NN[t];
+    }
+}
+
+int group_eval(mcp_ctx* ctx, const BatchArgs& a, double* ll_out, double* const* grad_out) {
+    const int G = (int)ctx->members.size();
+    int K = 0, e;
+    if ((e = validate_batch(ctx, a, &K))) return e;
+    long long len = 0;
+    for (int t = 0; t < a.T; ++t) {
+        if ((int)a.alns[t]->shards.size() != G) return fail(ctx, MCP_ERR_ARG, "tree %d: alignment was not created on this multi-device context", t);
+        len += a.NN[t];
+    }
+    std::vector<double*> part;
+    if ((e = group_targets(ctx, len, part))) return e;
+    e = for_each_member(ctx, [&](int g) -> int {
+        std::vector<const mcp_alignment*> alns(a.T);
+        for (int t = 0; t < a.T; ++t) alns[t] = a.alns[t]->shards[g];
+        BatchArgs ag = a;
+        ag.alns = alns.data();
+        if (g > 0) ag.prior_kind = MCP_PRIOR_NONE;   // the prior is added once, by member 0
+        return eval_impl(ctx->members[g], ag, part[g], nullptr, nullptr);
+    });
+    if (e) return e;
+    const double* h = nullptr;
+    if ((e = group_reduce(ctx, part, len, &h))) return e;
+    unpack_results(a, h, ll_out, grad_out);
+    return 0;
+}
+
+int eval_any(mcp_ctx* ctx, const BatchArgs& a, double* ll_out, double* const* grad_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    return ctx->members.empty() ? eval_impl(ctx, a, nullptr, ll_out, grad_out) : group_eval(ctx, a, ll_out, grad_out);
+}
+
+// --------------------------------------------------------------------------------------------
+// streamed evaluation: alignment in host memory, uploaded block by block under the evaluation
+// --------------------------------------------------------------------------------------------
+// Site blocks of one device's range [lo, hi): a small first block so that the first kernel starts after a
+// fraction of a millisecond of transfer, then doubling (every later transfer hides under the evaluation of
+// the block before it, which takes 3-4x longer than the transfer), the last block takes the rest.
+void plan_stream_blocks(long long lo, long long hi, long long wave_sites, std::vector<std::pair<long long, long long>>& out) {
+    out.clear();
+    const long long n = hi - lo;
+    if (n <= 0) return;
+    long long first = std::min(wave_sites, std::max<long long>(n / 8, 4096));
+    first = (first + 511) & ~511LL;
+    if (n < 4 * first) { out.push_back({lo, hi}); return; }
+    long long at = lo, sz = first;
+    while ((int)out.size() < 5 && hi - at > 3 * sz) {
+        out.push_back({at, at + sz});
+        at += sz;
+        sz *= 2;
+    }
+    out.push_back({at, hi});
+}
+
+int wave_columns_impl(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* columns) {
+    const KernelTable* kt = kernels_for(K);
+    if (!kt) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int block = ctx->opt_block > 0 ? ctx->opt_block : 256;
+    int cpt = ctx->opt_cpt > 0 ? ctx->opt_cpt : (K <= 4 ? 2 : 1);   // what the planner picks for large inputs
+    int occ = 0, e;
+    if (k_templated(K)) {
+        const bool acc_global = want_grad && walk_acc_global(n_nodes, ctx->opt_acc_mode);
+        if (acc_global) cpt = 1;
+        const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad && !acc_global ? 1 : 0, block, cpt);
+        if ((e = walk_occupancy(ctx, kt, K, block, cpt, smem, false, acc_global, false, &occ))) return e;
+    } else {
+        cpt = 1;
+        block = std::min(block, 128);
+        if ((e = walk_occupancy(ctx, kt, K, block, cpt, generic_smem_bytes(std::max(n_nodes, 1), want_grad), false, false, false, &occ))) return e;
+    }
+    if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d)", block);
+    if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
+    *columns = (int64_t)occ * ctx->sm_count * block * cpt;
+    return 0;
+}
+
+void drop_stream_set(mcp_ctx* m) {
+    if (!m->stream_set) return;
+    for (auto& b : m->stream_set->blocks) destroy_alignment_one(m, b.aln);
+    m->stream_set.reset();
+}
+
+// (Re)creates the block alignments of member `m` for the host alignment described by the arguments.
+int ensure_stream_set(mcp_ctx* m, const unsigned char* codes, int K, long long S, const int32_t* leaf_nums, int n_leaves,
+                      long long lo, long long hi, int NN, int R, int want_grad) {
+    StreamSet* ss = m->stream_set.get();
+    if (ss && ss->K == K && ss->S == S && ss->n_leaves == n_leaves && ss->R == R && ss->NN == NN && ss->want_grad == want_grad &&
+        std::memcmp(ss->leaf_nums.data(), leaf_nums, sizeof(int32_t) * n_leaves) == 0)
+        return 0;
+    drop_stream_set(m);
+    std::unique_ptr<StreamSet> ns(new StreamSet());
+    ns->K = K; ns->S = S; ns->n_leaves = n_leaves; ns->R = R; ns->NN = NN; ns->want_grad = want_grad;
+    ns->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
+    int64_t wave = 0;
+    int e;
+    if ((e = wave_columns_impl(m, K, NN, want_grad, &wave))) return e;
+    std::vector<std::pair<long long, long long>> bounds;
+    plan_stream_blocks(lo, hi, std::max<long long>(1, wave / std::max(R, 1)), bounds);
+    if (bounds.empty()) bounds.push_back({lo, lo});   // an empty range still yields a (zero) result vector
+    for (auto& b : bounds) {
+        mcp_alignment* al = nullptr;
+        if ((e = make_alignment(m, codes + b.first, (size_t)S, K, b.second - b.first, leaf_nums, n_leaves, &al))) {
+            for (auto& bb : ns->blocks) destroy_alignment_one(m, bb.aln);
+            return e;
+        }
+        ns->blocks.push_back({al, b.first, b.second});
+    }
+    m->stream_set = std::move(ns);
+    return 0;
+}
+
+int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, const int32_t* leaf_nums, int n_leaves,
+                  int NN, const int32_t* po, const int32_t* pa, const double* blv, const double* U, const double* D,
+                  const double* Uinv, double mu, const double* rates, int R, const double* pi, int want_grad,
+                  double* ll_out, double* grad_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!codes || !leaf_nums || !po || !pa || !blv || !U || !D || !Uinv || !rates || !pi)
+        return fail(ctx, MCP_ERR_ARG, "mcp_eval_streamed: null argument");
+    if (K < 1 || K > 254 || S < 0 || n_leaves < 1 || NN < 2) return fail(ctx, MCP_ERR_ARG, "mcp_eval_streamed: bad K/S/n_leaves/NN");
+    if (ctx->rank_comm) return fail(ctx, MCP_ERR_UNSUPPORTED, "mcp_eval_streamed is not available on a rank context");
+    const bool multi = !ctx->members.empty();
+    std::vector<mcp_ctx*> single{ctx};
+    const std::vector<mcp_ctx*>& mem = multi ? ctx->members : single;
+    const int G = (int)mem.size();
+    const long long len = NN;
+    int e;
+    std::vector<double*> part;
+    if (multi) {
+        if ((e = group_targets(ctx, len, part))) return e;
+    } else {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        if ((e = ensure_dev(ctx, ctx->d_out, sizeof(double) * len))) return e;
+        if ((e = ensure_pin(ctx, ctx->h_out, sizeof(double) * len))) return e;
+        part.assign(1, (double*)ctx->d_out.p);
+    }
+    auto run_member = [&](int g) -> int {
+        mcp_ctx* m = mem[g];
+        long long lo, hi;
+        shard_range(S, G, g, &lo, &hi);
+        int er;
+        if ((er = ensure_stream_set(m, codes, K, S, leaf_nums, n_leaves, lo, hi, NN, R, want_grad))) return er;
+        StreamSet& ss = *m->stream_set;
+        const int B = (int)ss.blocks.size();
+        if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, MCP_ERR_CUDA, "cudaSetDevice failed");
+        if ((er = ensure_dev(m, m->d_part, sizeof(double) * len * B))) return er;
+        // Issue order matters: host-to-device transfers are served first-in first-out, and every
+        // evaluation starts with a small parameter upload of its own.  Transfer b, evaluation b,
+        // transfer b+1, ...: the parameters of evaluation b queue right behind the block they need
+        // anyway, and transfer b+1 then runs under the kernels of evaluation b.
+        for (int b = 0; b < B; ++b) {
+            mcp_alignment* al = ss.blocks[b].aln;
+            if ((er = update_codes_one(m, al, codes + ss.blocks[b].lo, (size_t)S))) return er;
+            const mcp_alignment* alp = al;
+            BatchArgs ab{1, &alp, &NN, &po, &pa, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
+            double* dst = B == 1 ? part[g] : (double*)m->d_part.p + (long long)b * len;
+            if ((er = eval_impl(m, ab, dst, nullptr, nullptr))) return er;
+        }
+        if (B > 1) {
+            sum_rows<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>((const double*)m->d_part.p, len, B, len, part[g]);
+            if (cudaGetLastError() != cudaSuccess) return fail(m, MCP_ERR_CUDA, "sum_rows launch failed");
+        }
+        return 0;
+    };
+    const double* h = nullptr;
+    if (multi) {
+        if ((e = for_each_member(ctx, run_member))) return e;
+        if ((e = group_reduce(ctx, part, len, &h))) return e;
+    } else {
+        if ((e = run_member(0))) return e;
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, part[0], sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (bool& p : ctx->staged_pending) p = false;
+        h = (const double*)ctx->h_out.p;
+    }
+    if (ll_out) *ll_out = h[0];
+    if (want_grad && grad_out) std::memcpy(grad_out, h + 1, sizeof(double) * (NN - 1));
+    return 0;
+}
+
+int create_single(mcp_ctx** out, int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -870,8 +793,9 @@ int mcp_create(mcp_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; e == cudaSuccess && i < 4; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming);
+    for (int i = 0; e == cudaSuccess && i < MCP_STAGE_SLOTS; ++i) e = cudaEventCreateWithFlags(&ctx->ev_staged[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_walk_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         std::string msg = cudaGetErrorString(e);
@@ -883,27 +807,219 @@ int mcp_create(mcp_ctx** out, int device) {
     return 0;
 }
 
-int mcp_destroy(mcp_ctx* ctx) {
-    if (!ctx) return 0;
+void destroy_single(mcp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    for (DevBuf* b : {&ctx->d_topo, &ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter})
-        if (b->p) cudaFree(b->p);
-    for (PinBuf* b : {&ctx->h_topo, &ctx->h_dyn, &ctx->h_out, &ctx->h_model})
-        if (b->p) cudaFreeHost(b->p);
+    drop_stream_set(ctx);
+    if (ctx->rank_comm) mcpnccl::api().CommDestroy(ctx->rank_comm);
+    for (DevBuf* b : {&ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter, &ctx->d_part})
+        free_dev(*b);
+    free_pin(ctx->h_out);
+    for (int i = 0; i < MCP_STAGE_SLOTS; ++i) {
+        free_pin(ctx->h_dyn[i]);
+        free_pin(ctx->h_model[i]);
+        if (ctx->ev_staged[i]) cudaEventDestroy(ctx->ev_staged[i]);
+    }
+    for (auto& pl : ctx->plans) {
+        free_dev(pl->d_topo);
+        free_pin(pl->h_topo);
+    }
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
-    if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
     if (ctx->ev_walk_done) cudaEventDestroy(ctx->ev_walk_done);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    {   // this context may be remembered as the last user of a unit's constant model slots
+        std::lock_guard<std::mutex> lock(g_slots.mu);
+        for (auto& en : g_slots.entries)
+            if (en.last == ctx) en.last = nullptr;
+    }
     delete ctx;
+}
+
+template <class F>
+int for_members_or_self(mcp_ctx* ctx, F f) {
+    if (ctx->members.empty()) return f(ctx);
+    for (mcp_ctx* m : ctx->members) {
+        int e = f(m);
+        if (e) { ctx->error = m->error; return e; }
+    }
+    return 0;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------------
+extern "C" {
+
+int mcp_abi_version(void) { return MCP_ABI_VERSION; }
+
+const char* mcp_last_error(const mcp_ctx* ctx) { return ctx ? ctx->error.c_str() : g_error.c_str(); }
+
+int mcp_create(mcp_ctx** out, int device) {
+    if (!out) return fail(nullptr, MCP_ERR_ARG, "mcp_create: null output pointer");
+    *out = nullptr;
+    return create_single(out, device);
+}
+
+int mcp_create_multi(mcp_ctx** out, int n_dev, const int* dev_ids, int reduce_mode) {
+    if (!out) return fail(nullptr, MCP_ERR_ARG, "mcp_create_multi: null output pointer");
+    *out = nullptr;
+    if (n_dev < 1 || n_dev > 64 || !dev_ids) return fail(nullptr, MCP_ERR_ARG, "mcp_create_multi: need 1..64 device ids");
+    if (reduce_mode < MCP_REDUCE_AUTO || reduce_mode > MCP_REDUCE_HOST) return fail(nullptr, MCP_ERR_ARG, "mcp_create_multi: unknown reduce mode %d", reduce_mode);
+    bool distinct = true;
+    for (int i = 0; i < n_dev; ++i)
+        for (int j = 0; j < i; ++j) distinct = distinct && dev_ids[i] != dev_ids[j];
+    std::unique_ptr<mcp_ctx> grp(new mcp_ctx());
+    auto cleanup = [&]() {
+        for (mcp_ctx* m : grp->members) destroy_single(m);
+        grp->members.clear();
+    };
+    for (int i = 0; i < n_dev; ++i) {
+        mcp_ctx* m = nullptr;
+        int e = create_single(&m, dev_ids[i]);
+        if (e) { cleanup(); return e; }
+        grp->members.push_back(m);
+    }
+    grp->device = dev_ids[0];
+    grp->sm_count = grp->members[0]->sm_count;
+    // peer access towards device 0 (PEER reduction; harmless otherwise)
+    bool peer_ok = true;
+    for (int i = 1; i < n_dev; ++i) {
+        if (dev_ids[i] == dev_ids[0]) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dev_ids[i], dev_ids[0]);
+        if (!can) { peer_ok = false; continue; }
+        cudaSetDevice(dev_ids[i]);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(dev_ids[0], 0);
+        if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) peer_ok = false;
+        cudaGetLastError();
+    }
+    std::string why;
+    int mode = reduce_mode;
+    if (mode == MCP_REDUCE_AUTO) {
+        // the [logL, gradient] all-reduce over NVLink is NCCL's whenever it can be: distinct devices and a
+        // loadable library; otherwise peer stores into device 0, otherwise a sum on the host
+        mode = (n_dev > 1 && distinct && mcpnccl::api(&why).ok()) ? MCP_REDUCE_NCCL : peer_ok ? MCP_REDUCE_PEER : MCP_REDUCE_HOST;
+    }
+    if (mode == MCP_REDUCE_NCCL) {
+        if (!distinct) { cleanup(); return fail(nullptr, MCP_ERR_ARG, "mcp_create_multi: the NCCL reduction needs distinct devices"); }
+        const mcpnccl::Api& nc = mcpnccl::api(&why);
+        if (!nc.ok()) { cleanup(); return fail(nullptr, MCP_ERR_UNSUPPORTED, "mcp_create_multi: NCCL is not available (%s)", why.c_str()); }
+        grp->comms.assign(n_dev, nullptr);
+        mcpnccl::result_t nr = nc.CommInitAll(grp->comms.data(), n_dev, dev_ids);
+        if (nr) {
+            grp->comms.clear();
+            cleanup();
+            return fail(nullptr, MCP_ERR_CUDA, "ncclCommInitAll failed: %s", nc.GetErrorString(nr));
+        }
+    } else if (mode == MCP_REDUCE_PEER) {
+        if (!peer_ok) { cleanup(); return fail(nullptr, MCP_ERR_UNSUPPORTED, "mcp_create_multi: peer access to device %d is not available", dev_ids[0]); }
+        grp->ev_member.assign(n_dev, nullptr);
+        for (int i = 1; i < n_dev; ++i) {
+            cudaSetDevice(dev_ids[i]);
+            if (cudaEventCreateWithFlags(&grp->ev_member[i], cudaEventDisableTiming) != cudaSuccess) {
+                cleanup();
+                return fail(nullptr, MCP_ERR_CUDA, "event creation failed");
+            }
+        }
+    } else {
+        grp->h_member_out.assign(n_dev, PinBuf());
+    }
+    grp->reduce_mode = mode;
+    if (n_dev > 1 && !std::getenv("MCPHYLO_B200_SERIAL_GROUP")) grp->pool.reset(new MemberPool(n_dev));
+    *out = grp.release();
+    return 0;
+}
+
+int mcp_nccl_unique_id(void* id128) {
+    if (!id128) return fail(nullptr, MCP_ERR_ARG, "mcp_nccl_unique_id: null argument");
+    std::string why;
+    const mcpnccl::Api& nc = mcpnccl::api(&why);
+    if (!nc.ok()) return fail(nullptr, MCP_ERR_UNSUPPORTED, "NCCL is not available (%s)", why.c_str());
+    mcpnccl::unique_id id;
+    mcpnccl::result_t nr = nc.GetUniqueId(&id);
+    if (nr) return fail(nullptr, MCP_ERR_CUDA, "ncclGetUniqueId failed: %s", nc.GetErrorString(nr));
+    std::memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+int mcp_create_rank(mcp_ctx** out, int device, int n_ranks, int rank, const void* id128) {
+    if (!out) return fail(nullptr, MCP_ERR_ARG, "mcp_create_rank: null output pointer");
+    *out = nullptr;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id128) return fail(nullptr, MCP_ERR_ARG, "mcp_create_rank: bad rank / id");
+    std::string why;
+    const mcpnccl::Api& nc = mcpnccl::api(&why);
+    if (!nc.ok()) return fail(nullptr, MCP_ERR_UNSUPPORTED, "NCCL is not available (%s)", why.c_str());
+    mcp_ctx* ctx = nullptr;
+    int e = create_single(&ctx, device);
+    if (e) return e;
+    mcpnccl::unique_id id;
+    std::memcpy(&id, id128, sizeof id);
+    mcpnccl::result_t nr = nc.CommInitRank(&ctx->rank_comm, n_ranks, id, rank);
+    if (nr) {
+        ctx->rank_comm = nullptr;
+        destroy_single(ctx);
+        return fail(nullptr, MCP_ERR_CUDA, "ncclCommInitRank failed: %s", nc.GetErrorString(nr));
+    }
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    *out = ctx;
+    return 0;
+}
+
+int mcp_device_count(const mcp_ctx* ctx) { return !ctx ? 0 : ctx->members.empty() ? 1 : (int)ctx->members.size(); }
+
+int mcp_reduce_mode(const mcp_ctx* ctx) {
+    if (!ctx) return MCP_REDUCE_AUTO;
+    if (ctx->rank_comm) return MCP_REDUCE_NCCL;
+    return ctx->members.empty() ? MCP_REDUCE_AUTO : ctx->reduce_mode;
+}
+
+int mcp_shard_bounds(int64_t S, int n_shards, int shard, int64_t* lo, int64_t* hi) {
+    if (S < 0 || n_shards < 1 || shard < 0 || shard >= n_shards || !lo || !hi) return fail(nullptr, MCP_ERR_ARG, "mcp_shard_bounds: bad argument");
+    long long l, h;
+    shard_range(S, n_shards, shard, &l, &h);
+    *lo = l;
+    *hi = h;
+    return 0;
+}
+
+int mcp_destroy(mcp_ctx* ctx) {
+    if (!ctx) return 0;
+    if (!ctx->members.empty()) {
+        for (mcp_ctx* m : ctx->members) {
+            cudaSetDevice(m->device);
+            cudaStreamSynchronize(m->stream);
+        }
+        if (!ctx->comms.empty()) {
+            const mcpnccl::Api& nc = mcpnccl::api();
+            for (auto c : ctx->comms)
+                if (c) nc.CommDestroy(c);
+        }
+        for (auto ev : ctx->ev_member)
+            if (ev) cudaEventDestroy(ev);
+        for (auto& b : ctx->h_member_out) free_pin(b);
+        if (ctx->d_gather.p) {
+            cudaSetDevice(ctx->members[0]->device);
+            free_dev(ctx->d_gather);
+        }
+        ctx->pool.reset();
+        for (mcp_ctx* m : ctx->members) destroy_single(m);
+        delete ctx;
+        return 0;
+    }
+    destroy_single(ctx);
     return 0;
 }
 
 int mcp_set_stream(mcp_ctx* ctx, void* cuda_stream) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!ctx->members.empty()) return fail(ctx, MCP_ERR_UNSUPPORTED, "mcp_set_stream: a multi-device context runs on its own streams");
     if (ctx->pending_async) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->pending_async = false;
@@ -914,15 +1030,18 @@ int mcp_set_stream(mcp_ctx* ctx, void* cuda_stream) {
 
 int mcp_synchronize(mcp_ctx* ctx) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    ctx->pending_async = false;
-    return 0;
+    return for_members_or_self(ctx, [](mcp_ctx* m) -> int {
+        CUDA_TRY(m, cudaSetDevice(m->device));
+        CUDA_TRY(m, cudaStreamSynchronize(m->stream));
+        CUDA_TRY(m, cudaStreamSynchronize(m->copy_stream));
+        m->pending_async = false;
+        return 0;
+    });
 }
 
 int mcp_use_own_stream(mcp_ctx* ctx) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!ctx->members.empty()) return 0;
     if (ctx->pending_async) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->pending_async = false;
@@ -936,41 +1055,79 @@ int mcp_set_launch(mcp_ctx* ctx, int block, int ctas_per_sm) {
     if (block != 0 && (block < 32 || block > 256 || (block & 31)))
         return fail(ctx, MCP_ERR_ARG, "block must be 0 or a multiple of 32 in [32, 256]");
     if (ctas_per_sm < 0) return fail(ctx, MCP_ERR_ARG, "ctas_per_sm must be >= 0");
-    ctx->opt_block = block;
-    ctx->opt_ctas_per_sm = ctas_per_sm;
-    ctx->sig.clear();
-    return 0;
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_block = block;
+        m->opt_ctas_per_sm = ctas_per_sm;
+        invalidate_plans(m);
+        return 0;
+    });
 }
 
 int mcp_set_scratch_mode(mcp_ctx* ctx, int mode) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "scratch mode must be -1 (automatic), 0 (HBM) or 1 (shared memory when it fits)");
-    ctx->opt_smem_scratch = mode;
-    ctx->sig.clear();
-    return 0;
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_smem_scratch = mode;
+        invalidate_plans(m);
+        return 0;
+    });
 }
 
 int mcp_set_accumulator_mode(mcp_ctx* ctx, int mode) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "accumulator mode must be -1 (automatic), 0 (shared memory) or 1 (global memory)");
-    ctx->opt_acc_mode = mode;
-    ctx->sig.clear();
-    return 0;
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_acc_mode = mode;
+        invalidate_plans(m);
+        return 0;
+    });
 }
 
 int mcp_set_level_mode(mcp_ctx* ctx, int mode) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "level mode must be -1 (automatic), 0 (off) or 1 (whenever the tree fits)");
-    ctx->opt_levels = mode;
-    ctx->sig.clear();
-    return 0;
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_levels = mode;
+        invalidate_plans(m);
+        return 0;
+    });
 }
 
 int mcp_set_columns_per_thread(mcp_ctx* ctx, int cpt) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (cpt != 0 && cpt != 1 && cpt != 2) return fail(ctx, MCP_ERR_ARG, "columns per thread must be 0 (automatic), 1 or 2");
-    ctx->opt_cpt = cpt;
-    ctx->sig.clear();
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_cpt = cpt;
+        invalidate_plans(m);
+        return 0;
+    });
+}
+
+static int alignment_from_codes_any(mcp_ctx* ctx, const uint8_t* codes, int K, int64_t S, const int32_t* leaf_nums,
+                                    int n_leaves, mcp_alignment** out) {
+    if (ctx->members.empty()) return make_alignment(ctx, codes, (size_t)S, K, S, leaf_nums, n_leaves, out);
+    const int G = (int)ctx->members.size();
+    std::unique_ptr<mcp_alignment> al(new mcp_alignment());
+    al->K = K;
+    al->S = S;
+    al->n_leaves = n_leaves;
+    al->owner = ctx;
+    al->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
+    al->id = ctx->next_aln_id++;
+    for (int g = 0; g < G; ++g) {
+        long long lo, hi;
+        shard_range(S, G, g, &lo, &hi);
+        mcp_alignment* sh = nullptr;
+        int e = make_alignment(ctx->members[g], codes + lo, (size_t)S, K, hi - lo, leaf_nums, n_leaves, &sh);
+        if (e) {
+            ctx->error = ctx->members[g]->error;
+            for (int j = 0; j < g; ++j) destroy_alignment_one(ctx->members[j], al->shards[j]);
+            return e;
+        }
+        al->shards.push_back(sh);
+        al->shard_lo.push_back(lo);
+    }
+    *out = al.release();
     return 0;
 }
 
@@ -979,8 +1136,7 @@ int mcp_alignment_from_codes(mcp_ctx* ctx, const uint8_t* codes, int K, int64_t 
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!out || !codes || !leaf_nums) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_codes: null argument");
     if (K < 1 || K > 254 || S < 0 || n_leaves < 1) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_codes: bad K/S/n_leaves");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return make_alignment(ctx, codes, K, S, leaf_nums, n_leaves, out);
+    return alignment_from_codes_any(ctx, codes, K, S, leaf_nums, n_leaves, out);
 }
 
 int mcp_alignment_from_dense(mcp_ctx* ctx, const double* x, int K, int64_t S, int NN, const int32_t* leaf_nums,
@@ -988,66 +1144,34 @@ int mcp_alignment_from_dense(mcp_ctx* ctx, const double* x, int K, int64_t S, in
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!out || !x || !leaf_nums) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_dense: null argument");
     if (K < 1 || K > 254 || S < 0 || n_leaves < 1 || NN < n_leaves) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_from_dense: bad sizes");
-    std::vector<unsigned char> codes((size_t)n_leaves * (size_t)S);
-    for (int l = 0; l < n_leaves; ++l) {
-        const int num = leaf_nums[l];
-        if (num < 1 || num > NN) return fail(ctx, MCP_ERR_ARG, "leaf number %d out of range", num);
-        const double* slab = x + (size_t)K * (size_t)S * (size_t)(num - 1);
-        for (int64_t s = 0; s < S; ++s) {
-            const double* col = slab + (size_t)K * s;
-            int ones = 0, zeros = 0, first = -1;
-            for (int k = 0; k < K; ++k) {
-                if (col[k] == 1.0) { ++ones; if (first < 0) first = k; }
-                else if (col[k] == 0.0) ++zeros;
-            }
-            unsigned char c;
-            if (ones == K) c = (unsigned char)K;
-            else if (ones == 1 && zeros == K - 1) c = (unsigned char)first;
-            else
-                return fail(ctx, MCP_ERR_DATA, "leaf %d, site %lld: column is neither one-hot nor all ones", num, (long long)s + 1);
-            codes[(size_t)l * S + s] = c;
-        }
-    }
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return make_alignment(ctx, codes.data(), K, S, leaf_nums, n_leaves, out);
+    std::vector<unsigned char> codes;
+    int e = dense_to_codes(ctx, x, K, S, NN, leaf_nums, n_leaves, codes);
+    if (e) return e;
+    static const unsigned char none = 0;
+    return alignment_from_codes_any(ctx, codes.empty() ? &none : codes.data(), K, S, leaf_nums, n_leaves, out);
 }
 
 int mcp_alignment_update_codes(mcp_ctx* ctx, mcp_alignment* aln, const uint8_t* codes) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!aln || !codes) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_update_codes: null argument");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    // On the copy stream: the transfer overlaps whatever the evaluation stream is doing (the
-    // evaluation of another site block, typically).  It must not overtake an evaluation that still
-    // reads this buffer, and the next evaluation of this alignment waits for it (eval_impl).
-    if (aln->read_since_upload) {
-        // first re-upload: only the context-wide "last walk finished" event exists (conservative);
-        // afterwards every evaluation of this alignment records the alignment's own event
-        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, aln->streamed ? aln->ev_read_done : ctx->ev_walk_done, 0));
-        aln->read_since_upload = false;
+    if (aln->owner != ctx) return fail(ctx, MCP_ERR_ARG, "mcp_alignment_update_codes: the alignment belongs to another context");
+    if (ctx->members.empty()) return update_codes_one(ctx, aln, codes, (size_t)aln->S);
+    for (size_t g = 0; g < aln->shards.size(); ++g) {
+        int e = update_codes_one(ctx->members[g], aln->shards[g], codes + aln->shard_lo[g], (size_t)aln->S);
+        if (e) { ctx->error = ctx->members[g]->error; return e; }
     }
-    aln->streamed = true;
-    if (aln->S > 0)
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(aln->d_codes, (size_t)aln->stride, codes, (size_t)aln->S, (size_t)aln->S,
-                                        (size_t)aln->n_leaves, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CUDA_TRY(ctx, cudaEventRecord(aln->ev_uploaded, ctx->copy_stream));
-    aln->upload_pending = true;
-    ctx->pending_async = true;   // only consulted before buffers are freed / the stream is changed
     return 0;
 }
 
 int mcp_alignment_destroy(mcp_ctx* ctx, mcp_alignment* aln) {
     if (!aln) return 0;
-    if (ctx) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-        ctx->pending_async = false;
-        ctx->sig.clear();
+    if (!aln->shards.empty()) {
+        for (size_t g = 0; g < aln->shards.size(); ++g)
+            destroy_alignment_one(ctx && g < ctx->members.size() ? ctx->members[g] : nullptr, aln->shards[g]);
+        delete aln;
+        return 0;
     }
-    if (aln->ev_uploaded) cudaEventDestroy(aln->ev_uploaded);
-    if (aln->ev_read_done) cudaEventDestroy(aln->ev_read_done);
-    if (aln->d_codes) cudaFree(aln->d_codes);
-    delete aln;
+    destroy_alignment_one(ctx, aln);
     return 0;
 }
 
@@ -1056,7 +1180,7 @@ int mcp_eval(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* post
              int R, const double* pi, int want_grad, double* ll_out, double* grad_out) {
     BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
     double* g = grad_out;
-    return eval_impl(ctx, a, nullptr, ll_out, &g);
+    return eval_any(ctx, a, ll_out, &g);
 }
 
 int mcp_eval_posterior(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
@@ -1067,13 +1191,15 @@ int mcp_eval_posterior(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int
     a.prior_kind = prior_kind;
     a.prior_params = prior_params;
     double* g = grad_out;
-    return eval_impl(ctx, a, nullptr, lp_out, &g);
+    return eval_any(ctx, a, lp_out, &g);
 }
 
 int mcp_eval_device(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
                     const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
                     double mu, const double* rates, int R, const double* pi, int want_grad, double* d_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!d_out) return fail(ctx, MCP_ERR_ARG, "mcp_eval_device: null device output pointer");
+    if (!ctx->members.empty()) return fail(ctx, MCP_ERR_UNSUPPORTED, "mcp_eval_device: not available on a multi-device context (use mcp_eval)");
     BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
     return eval_impl(ctx, a, d_out, nullptr, nullptr);
 }
@@ -1086,37 +1212,59 @@ int mcp_eval_batch(mcp_ctx* ctx, int T, const mcp_alignment* const* alns, const 
     if (!alns || !NN || !postorder_num || !parent_num || !blv || !U || !D || !Uinv || !mu || !rates || !pi)
         return fail(ctx, MCP_ERR_ARG, "mcp_eval_batch: null argument array");
     BatchArgs a{T, alns, NN, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, R, pi, want_grad};
-    return eval_impl(ctx, a, nullptr, ll_out, grad_out);
+    return eval_any(ctx, a, ll_out, grad_out);
+}
+
+int mcp_eval_streamed(mcp_ctx* ctx, const uint8_t* codes, int K, int64_t S, const int32_t* leaf_nums, int n_leaves,
+                      int NN, const int32_t* postorder_num, const int32_t* parent_num, const double* blv, const double* U,
+                      const double* D, const double* Uinv, double mu, const double* rates, int R, const double* pi,
+                      int want_grad, double* ll_out, double* grad_out) {
+    return eval_streamed(ctx, codes, K, S, leaf_nums, n_leaves, NN, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, R,
+                         pi, want_grad, ll_out, grad_out);
+}
+
+int mcp_stream_blocks(const mcp_ctx* ctx, int member, int64_t* lo_hi, int cap) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    const mcp_ctx* m = ctx->members.empty() ? ctx : (member >= 0 && member < (int)ctx->members.size() ? ctx->members[member] : nullptr);
+    if (!m || !m->stream_set) return 0;
+    int n = 0;
+    for (auto& b : m->stream_set->blocks) {
+        if (lo_hi && n < cap) { lo_hi[2 * n] = b.lo; lo_hi[2 * n + 1] = b.hi; }
+        ++n;
+    }
+    return n;
+}
+
+int mcp_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(nullptr, MCP_ERR_ARG, "mcp_host_register: null argument");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, MCP_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int mcp_host_unregister(void* p) {
+    if (!p) return 0;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, MCP_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
 }
 
 int mcp_wave_columns(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* columns) {
     if (!ctx || !columns) return fail(ctx, MCP_ERR_ARG, "mcp_wave_columns: null argument");
     if (!k_supported(K)) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    int block = ctx->opt_block > 0 ? ctx->opt_block : 256;
-    int cpt = ctx->opt_cpt > 0 ? ctx->opt_cpt : (K <= 4 ? 2 : 1);   // what prepare_topology picks for large inputs
-    int occ = 0, rc = 0;
-    if (k_templated(K)) {
-        const bool acc_global = want_grad && walk_acc_global(n_nodes, ctx->opt_acc_mode);
-        if (acc_global) cpt = 1;
-        const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad && !acc_global ? 1 : 0, block, cpt);
-        MCP_DISPATCH_K(K, rc = occupancy_for<KK>(ctx, block, cpt, smem, false, acc_global, &occ));
-        if (rc) return rc;
-    } else {
-        cpt = 1;
-        block = std::min(block, 128);
-        const size_t smem = want_grad ? (size_t)std::max(n_nodes, 1) * sizeof(double) : 0;
-        if ((rc = ensure_smem_attr(ctx, felsenstein_walk_generic, smem))) return rc;
-        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, felsenstein_walk_generic, block, smem));
-    }
-    if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d)", block);
-    if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
-    *columns = (int64_t)occ * ctx->sm_count * block * cpt;
-    return 0;
+    mcp_ctx* m = ctx->members.empty() ? ctx : ctx->members[0];
+    int e = wave_columns_impl(m, K, n_nodes, want_grad, columns);
+    if (e && m != ctx) ctx->error = m->error;
+    return e;
 }
 
-int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {
-    if (!ctx || !out) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats: null argument");
+static void read_stats(const mcp_ctx* ctx, mcp_stats* out) {
     *out = ctx->stats;
     // event times are read lazily: they exist once the stream has passed the last event
     float ms = 0.f;
@@ -1126,6 +1274,45 @@ int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {
     } else {
         cudaGetLastError();
     }
+}
+
+int mcp_get_stats(const mcp_ctx* ctx, mcp_stats* out) {
+    if (!ctx || !out) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats: null argument");
+    if (ctx->members.empty()) {
+        read_stats(ctx, out);
+        return 0;
+    }
+    // multi-device: times are the slowest member's, bytes and launches are summed, the shape is member 0's
+    mcp_stats acc{};
+    for (size_t g = 0; g < ctx->members.size(); ++g) {
+        mcp_stats s;
+        cudaSetDevice(ctx->members[g]->device);
+        read_stats(ctx->members[g], &s);
+        if (g == 0) acc = s;
+        else {
+            acc.walk_ms = std::max(acc.walk_ms, s.walk_ms);
+            acc.device_ms = std::max(acc.device_ms, s.device_ms);
+            acc.h2d_bytes += s.h2d_bytes;
+            acc.d2h_bytes += s.d2h_bytes;
+            acc.kernel_launches += s.kernel_launches;
+            acc.tiles += s.tiles;
+            acc.scratch_bytes += s.scratch_bytes;
+        }
+    }
+    *out = acc;
+    return 0;
+}
+
+int mcp_get_stats_member(const mcp_ctx* ctx, int member, mcp_stats* out) {
+    if (!ctx || !out) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats_member: null argument");
+    if (ctx->members.empty()) {
+        if (member != 0) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats_member: member out of range");
+        read_stats(ctx, out);
+        return 0;
+    }
+    if (member < 0 || member >= (int)ctx->members.size()) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats_member: member out of range");
+    cudaSetDevice(ctx->members[member]->device);
+    read_stats(ctx->members[member], out);
     return 0;
 }
 
@@ -1141,7 +1328,7 @@ int mcp_model_reorder(int K, const double* U, const double* D, const double* Uin
 int mcp_schedule_dump(int NN, const int32_t* postorder_num, const int32_t* parent_num, const int32_t* leaf_row,
                       int want_grad, int32_t* post_ops, int cap_post, int32_t* pre_ops, int cap_pre, int32_t* info) {
     if (!postorder_num || !parent_num || !leaf_row || !info) return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: null argument");
-    Schedule sc;
+    mcp::Schedule sc;
     const bool by_levels = (want_grad & 2) != 0;   // bit 1 of want_grad selects the level-ordered program
     want_grad &= 1;
     std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, want_grad != 0, sc, by_levels);

@@ -1,0 +1,62 @@
+// smem_layout.cuh — shared-memory carve-ups of the walk kernels and the constants the host needs to
+// size a launch (chunk length, accumulator placement).  Shared by the host translation unit and the
+// kernel translation units.
+#pragma once
+
+namespace mcpdev {
+
+constexpr int CH = 16;
+
+// Where a CTA accumulates its branch-gradient sums (template parameter ACCG, decided on the host):
+// in shared memory without atomics (below) whenever the per-branch accumulator fits next to the staging
+// buffers without costing a resident CTA -- trees of up to WALK_ACC_SHARED_MAX_NODES nodes -- else
+// (ACCG) directly in the CTA's accumulator row in global memory with fire-and-forget RED.ADD.F64 (the
+// row stays in L2; any tree size, but the sums arrive in no fixed order).  The two are separate
+// instantiations: with both paths in one kernel the K = 4 op loop spills again.
+constexpr int WALK_ACC_SHARED_MAX_NODES = 4096;
+inline bool walk_acc_global(int n_nodes, int mode /* -1 auto, 0 shared, 1 global */) {
+    return mode < 0 ? n_nodes > WALK_ACC_SHARED_MAX_NODES : mode != 0;
+}
+
+// Shared-memory accumulator: the per-warp sums of a chunk's 2 * CH branch terms are parked here
+// and folded into the accumulator by one thread per term after the chunk barrier, in fixed warp order
+// -- no atomics (a shared fp64 atomic add is a compare-and-swap loop, ~10 instructions, 38 % retries
+// with 8 warps on one address) and a run-to-run reproducible gradient.
+//   [2 buffers][CH ops][2 children][8 warps] doubles, then [2][CH][2] branch ids
+constexpr int WALK_PART_DOUBLES = 2 * CH * 2 * 8;
+constexpr int WALK_PART_BYTES = WALK_PART_DOUBLES * 8 + 2 * CH * 2 * 4;
+
+template <int K>
+struct WalkSmem {
+    // dynamic shared memory carve-up (offsets in bytes)
+    // branch-gradient accumulator of the CTA + parked per-warp sums (shared-accumulator kernels only:
+    // callers pass want_grad && !ACCG)
+    static __host__ __device__ size_t acc_bytes(int n_br, int shared_acc) {
+        return shared_acc ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
+    }
+    static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
+    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
+    static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
+    static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
+    // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
+    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
+    static __host__ __device__ size_t total(int n_br, int shared_acc, int TW) {
+        return acc_bytes(n_br, shared_acc) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
+    }
+};
+
+struct LevelSmem {
+    // byte offsets into dynamic shared memory
+    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 127) & ~(size_t)127) : 0; }
+    static __host__ __device__ size_t exp_bytes() { return 128; }
+    static __host__ __device__ size_t code_bytes(int n_rows) { return (((size_t)n_rows * 32) + 127) & ~(size_t)127; }
+    static __host__ __device__ size_t slot_bytes(int K) { return (size_t)32 * K * 8; }
+    static __host__ __device__ size_t tab_bytes(int n_br, int K) { return (((size_t)n_br * bt_size(K) * 8) + 127) & ~(size_t)127; }
+    static __host__ __device__ size_t total(int n_br, int want_grad, int n_rows, int n_slots, int n_stack, int K) {
+        return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + tab_bytes(n_br, K) +
+               (size_t)(n_slots + n_stack) * slot_bytes(K);
+    }
+};
+
+}  // namespace mcpdev
+using namespace mcpdev;

@@ -57,9 +57,11 @@ def get_context(device: Optional[int] = None) -> capi.Context:
     that distributions stay serialisable (SURVEY.md §5 checkpoint/resume)."""
     if device is None:
         device = _default_device
+    if isinstance(device, (list, tuple)):       # several GPUs behind one context (mcp_create_multi)
+        device = tuple(int(d) for d in device)
     ctx = _contexts.get(device)
     if ctx is None:
-        ctx = capi.Context(device)
+        ctx = capi.Context(devices=device) if isinstance(device, tuple) else capi.Context(device)
         _contexts[device] = ctx
     return ctx
 
@@ -67,9 +69,10 @@ def get_context(device: Optional[int] = None) -> capi.Context:
 _default_device = 0
 
 
-def set_default_device(device: int) -> None:
+def set_default_device(device) -> None:
+    """An int, or a list of device ids: every logpdf / gradlogpdf then shards the site axis over them."""
     global _default_device
-    _default_device = int(device)
+    _default_device = tuple(int(d) for d in device) if isinstance(device, (list, tuple)) else int(device)
 
 
 def release_device_cache() -> None:
@@ -84,19 +87,22 @@ def release_device_cache() -> None:
 
 def _device_alignment(x, leaf_nums: np.ndarray, K: int, ctx: capi.Context) -> capi.Alignment:
     if isinstance(x, DeviceAlignment):
-        h = x._handles.get(ctx.device)
-        if h is None or h.handle is None:
+        h = x._handles.get(id(ctx))        # an alignment belongs to the context that created it
+        if h is None or h.handle is None or h.ctx is not ctx:
             if x.K != K:
                 raise DimensionMismatch(f"alignment has {x.K} states, distribution has {K}")
             h = ctx.alignment_from_codes(x.codes, x.K, x.leaf_nums)
-            x._handles[ctx.device] = h
+            x._handles[id(ctx)] = h
         return h
     x = np.asarray(x)
     if x.ndim != 3:
         raise DimensionMismatch("x must be a (K, S, NN) array")
-    key = (id(x), ctx.device)
+    # Rows are mapped through leaf_nums when the alignment is created, so the ORDER in which a topology
+    # lists its leaves is irrelevant (an NNI permutes get_leaves): only the set has to match.
+    key = (id(x), id(ctx))
     hit = _dense_cache.get(key)
-    if hit is not None and hit[0]() is x and hit[1].handle is not None and np.array_equal(hit[2], leaf_nums):
+    if hit is not None and hit[0]() is x and hit[1].handle is not None and hit[1].ctx is ctx and \
+            np.array_equal(hit[2], np.sort(leaf_nums)):
         return hit[1]
     if x.shape[0] != K:
         raise DimensionMismatch(f"x has {x.shape[0]} states, distribution has {K}")
@@ -105,7 +111,7 @@ def _device_alignment(x, leaf_nums: np.ndarray, K: int, ctx: capi.Context) -> ca
         ref = weakref.ref(x, lambda _r, k=key: _dense_cache.pop(k, None))
     except TypeError:
         ref = (lambda v: (lambda: v))(x)
-    _dense_cache[key] = (ref, aln, leaf_nums.copy())
+    _dense_cache[key] = (ref, aln, np.sort(leaf_nums))
     return aln
 
 

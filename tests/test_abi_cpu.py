@@ -19,7 +19,7 @@ def test_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert capi.load().mcp_abi_version() == 1
+    assert capi.load().mcp_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():
@@ -36,7 +36,7 @@ def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, "mcphylo.jl_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".hpp", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 with open(os.path.join(dirpath, f)) as fh:
                     src = fh.read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), f
