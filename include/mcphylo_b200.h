@@ -215,6 +215,10 @@ int mcp_eval_streamed(mcp_ctx *ctx, const uint8_t *codes, int K, int64_t S, cons
                       const double *rates, int R, const double *pi, int want_grad, double *ll_out,
                       double *grad_out);
 int mcp_stream_blocks(const mcp_ctx *ctx, int member, int64_t *lo_hi, int cap);
+/* Device timeline of the last mcp_eval_streamed call on one device, 5 doubles per block (milliseconds since
+ * the first transfer began): transfer begin, transfer end, evaluation enqueued, walk kernel begin, walk
+ * kernel end.  Returns the number of blocks written (at most cap_blocks). */
+int mcp_stream_timeline(const mcp_ctx *ctx, int member, double *ms, int cap_blocks);
 int mcp_host_register(void *p, size_t bytes);
 int mcp_host_unregister(void *p);
 
@@ -251,6 +255,12 @@ typedef struct mcp_stats {
 } mcp_stats;
 int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
 int mcp_get_stats_member(const mcp_ctx *ctx, int member, mcp_stats *out);
+/* Device-side stopwatch over any number of calls: mcp_timer_start records a CUDA event on the evaluation
+ * stream of every device of the context, mcp_timer_stop records a second one, waits for it and returns
+ * the elapsed milliseconds (the slowest device's).  The context's streams are its own, so a caller's
+ * events (torch.cuda.Event, ...) would not see this work. */
+int mcp_timer_start(mcp_ctx *ctx);
+int mcp_timer_stop(mcp_ctx *ctx, double *ms_out);
 
 /*
  * Columns (sites x rate categories) that ONE full wave of the persistent walk grid covers for a large
@@ -262,9 +272,8 @@ int mcp_get_stats_member(const mcp_ctx *ctx, int member, mcp_stats *out);
 int mcp_wave_columns(mcp_ctx *ctx, int K, int n_nodes, int want_grad, int64_t *columns);
 
 /* Tuning knobs: block = threads per CTA (a multiple of 32 up to 256; a tile is block x columns-per-thread
- * alignment columns wide; 0 = automatic: narrow tiles for small inputs, and for inputs that fill the GPU
- * the width in {256, 224, 192, 160, 128} x {2, 1} columns per thread whose last round of tiles wastes
- * least), ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
+ * alignment columns wide; 0 = automatic: 256, the measured optimum at every input size, narrowed only for
+ * alignments of fewer than 256 sites), ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
 int mcp_set_launch(mcp_ctx *ctx, int block, int ctas_per_sm);
 /* Alignment columns walked by one thread: 1, 2, or 0 = automatic (2 once the GPU is full). */
 int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);

@@ -20,8 +20,8 @@ SYMBOLS = [
     "mcp_abi_version", "mcp_last_error", "mcp_create", "mcp_destroy", "mcp_set_stream",
     "mcp_use_own_stream", "mcp_synchronize",
     "mcp_create_multi", "mcp_device_count", "mcp_reduce_mode", "mcp_shard_bounds", "mcp_nccl_unique_id",
-    "mcp_create_rank", "mcp_eval_streamed", "mcp_stream_blocks", "mcp_host_register", "mcp_host_unregister",
-    "mcp_get_stats_member",
+    "mcp_create_rank", "mcp_eval_streamed", "mcp_stream_blocks", "mcp_stream_timeline", "mcp_host_register", "mcp_host_unregister",
+    "mcp_get_stats_member", "mcp_timer_start", "mcp_timer_stop",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
@@ -86,6 +86,8 @@ def load():
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     lib.mcp_get_stats_member.argtypes = [_vp, C.c_int, C.POINTER(Stats)]
+    lib.mcp_timer_start.argtypes = [_vp]
+    lib.mcp_timer_stop.argtypes = [_vp, _dp]
     lib.mcp_create_multi.argtypes = [C.POINTER(_vp), C.c_int, _vp, C.c_int]
     lib.mcp_device_count.argtypes = [_vp]
     lib.mcp_reduce_mode.argtypes = [_vp]
@@ -94,6 +96,7 @@ def load():
     lib.mcp_create_rank.argtypes = [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp]
     lib.mcp_eval_streamed.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int] + eval_args[2:] + [_dp, _vp]
     lib.mcp_stream_blocks.argtypes = [_vp, C.c_int, _vp, C.c_int]
+    lib.mcp_stream_timeline.argtypes = [_vp, C.c_int, _vp, C.c_int]
     lib.mcp_host_register.argtypes = [_vp, C.c_size_t]
     lib.mcp_host_unregister.argtypes = [_vp]
     lib.mcp_wave_columns.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
@@ -254,6 +257,22 @@ class Context:
             self._check(self.lib.mcp_get_stats_member(self.handle, int(member), C.byref(s)))
         return s.asdict()
 
+    def stream_timeline(self, member: int = 0):
+        """Per block of the last mcp_eval_streamed call: ms since the first transfer began of
+        [transfer begin, transfer end, evaluation enqueued, walk begin, walk end]."""
+        buf = np.zeros((16, 5), dtype=np.float64)
+        n = self.lib.mcp_stream_timeline(self.handle, int(member), buf.ctypes.data, 16)
+        return buf[:max(n, 0)].round(3).tolist()
+
+    def timer_start(self):
+        self._check(self.lib.mcp_timer_start(self.handle))
+
+    def timer_stop(self) -> float:
+        """Milliseconds of device time since timer_start (CUDA events on the context's streams)."""
+        ms = C.c_double()
+        self._check(self.lib.mcp_timer_stop(self.handle, C.byref(ms)))
+        return ms.value
+
     def stream_blocks(self, member: int = 0):
         """Site blocks [lo, hi) one device used in the last mcp_eval_streamed call."""
         buf = np.zeros((16, 2), dtype=np.int64)
@@ -366,6 +385,39 @@ class Context:
         if want_grad:
             return ll, [g[:int(n) - 1] for g, n in zip(grads, NN)]
         return ll, None
+
+
+class PreparedBatch:
+    """mcp_eval_batch (T >= 1 trees) with every argument array packed ONCE: what a compiled host (the
+    Julia glue keeps its arrays between leapfrog steps) pays per call is the C call itself, not Python's
+    array conversions.  `set_blv(t, blv)` overwrites tree t's branch lengths in place."""
+
+    def __init__(self, ctx: "Context", alns: Sequence[Alignment], trees: Sequence[tuple], want_grad: bool = True):
+        self.ctx, self.T, self.want_grad = ctx, len(alns), bool(want_grad)
+        assert self.T == len(trees) and self.T >= 1
+        self._alns = list(alns)
+        self._packed = [Context._pack(t[0], t[1], np.array(t[2], dtype=np.float64), t[3], t[4], t[5], t[7], t[8]) for t in trees]
+        self.R = self._packed[0][6].size
+        assert all(p[6].size == self.R for p in self._packed)
+        self.NN = _i32([p[0].size for p in self._packed])
+        self._mu = _f64([t[6] for t in trees])
+        T = self.T
+        self._ptrs = [(C.c_void_p * T)(*[p[i].ctypes.data for p in self._packed]) for i in range(8)]
+        self._aln_ptrs = (C.c_void_p * T)(*[a.handle.value for a in alns])
+        self.ll = np.zeros(T, dtype=np.float64)
+        self.grads = [np.zeros(max(int(n) - 1, 1), dtype=np.float64) for n in self.NN]
+        self._gptrs = (C.c_void_p * T)(*[g.ctypes.data for g in self.grads]) if want_grad else None
+
+    def set_blv(self, t: int, blv):
+        self._packed[t][2][:] = blv
+
+    def eval(self):
+        """Returns (ll[T], [grad_t]) -- views of buffers that the next call overwrites."""
+        c, p = self.ctx, self._ptrs
+        c._check(c.lib.mcp_eval_batch(c.handle, self.T, self._aln_ptrs, self.NN.ctypes.data, p[0], p[1], p[2], p[3],
+                                      p[4], p[5], self._mu.ctypes.data, p[6], self.R, p[7], int(self.want_grad),
+                                      self.ll.ctypes.data, self._gptrs))
+        return self.ll, ([g[:int(n) - 1] for g, n in zip(self.grads, self.NN)] if self.want_grad else None)
 
 
 def model_reorder(U, D, Uinv):

@@ -89,7 +89,9 @@ struct StreamSet {
     int K = 0, n_leaves = 0, R = 0, NN = 0, want_grad = -1;
     long long S = 0;
     std::vector<int32_t> leaf_nums;
-    struct Block { mcp_alignment* aln; long long lo, hi; };
+    // ev: device timeline of the block in the last call -- transfer begin / end (copy stream), evaluation
+    // enqueued / walk begin / walk end (evaluation stream); read by mcp_stream_timeline
+    struct Block { mcp_alignment* aln; long long lo, hi; cudaEvent_t ev[5] = {}; };
     std::vector<Block> blocks;      // of this device's site range, in evaluation order
 };
 
@@ -158,6 +160,8 @@ struct mcp_ctx {
     cudaEvent_t ev_walk_done = nullptr;     // the walk kernel of the last evaluation has finished reading the codes
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_done = nullptr;          // everything enqueued by the last evaluation has finished
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;   // mcp_timer_start / mcp_timer_stop
+    cudaEvent_t ev_walk_begin = nullptr, ev_walk_end = nullptr;   // borrowed per-block events (mcp_eval_streamed timeline)
     std::string error;
     bool pending_async = false;
     int opt_block = 0, opt_ctas_per_sm = 0, opt_cpt = 0;

@@ -242,12 +242,20 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(ce));
         s.h2d_bytes += (int64_t)(sizeof(double) * MODEL_SLOT * n_models);
     }
+    // host -> device through a kernel that reads the pinned staging buffers (see stage_from_host): the copy
+    // engine stays free for bulk alignment transfers and cannot delay an evaluation behind them
+    auto stage = [&](const void* h, void* d, size_t bytes) -> cudaError_t {
+        const long long n16 = (long long)((bytes + 15) / 16);
+        const unsigned blocks = (unsigned)std::min<long long>((n16 + 255) / 256, 4LL * ctx->sm_count);
+        stage_from_host<<<std::max(blocks, 1u), 256, 0, st>>>((const uint4*)h, (uint4*)d, n16);
+        return cudaGetLastError();
+    };
     if (!pl.uploaded) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(pl.d_topo.p, pl.h_topo.p, pl.topo_bytes, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, stage(pl.h_topo.p, pl.d_topo.p, pl.topo_bytes));
         s.h2d_bytes += (int64_t)pl.topo_bytes;
         pl.uploaded = true;
     }
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_dyn.p, hd, sizeof(double) * pl.total_dyn, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, stage(hd, ctx->d_dyn.p, sizeof(double) * pl.total_dyn));
     s.h2d_bytes += (int64_t)(sizeof(double) * pl.total_dyn);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged[slot], st));
     ctx->staged_pending[slot] = true;
@@ -290,6 +298,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     std::memset(wp.model, 0, sizeof wp.model);
     if (n_models == 1) std::memcpy(wp.model, hm, sizeof(double) * model_doubles);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (ctx->ev_walk_begin) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_begin, st));
     LaunchCfg lc;
     lc.device = ctx->device;
     lc.K = K;
@@ -305,6 +314,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (ctx->ev_walk_end) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_end, st));
     if (dyn_model) {   // the next writer of this unit's model slots on this device waits for this kernel
         std::lock_guard<std::mutex> lock(g_slots.mu);
         ModelSlotGuard::Entry* en = g_slots.find(ctx->device, kt);
@@ -331,7 +341,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
                                                (const double*)ctx->d_dyn.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    s.kernel_launches = fused ? 1 : 3;
+    s.kernel_launches = (fused ? 1 : 3) + 1 + (rebuilt ? 1 : 0);   // + parameter staging (+ topology staging)
     s.grid = pl.grid;
     s.block = pl.block;
     s.tiles = pl.n_tiles;
@@ -626,21 +636,31 @@ int eval_any(mcp_ctx* ctx, const BatchArgs& a, double* ll_out, double* const* gr
 // --------------------------------------------------------------------------------------------
 // streamed evaluation: alignment in host memory, uploaded block by block under the evaluation
 // --------------------------------------------------------------------------------------------
-// Site blocks of one device's range [lo, hi): a small first block so that the first kernel starts after a
-// fraction of a millisecond of transfer, then doubling (every later transfer hides under the evaluation of
-// the block before it, which takes 3-4x longer than the transfer), the last block takes the rest.
+// Site blocks of one device's range [lo, hi).  The transfer of block b+1 runs under the evaluation of block b,
+// so it stays hidden as long as  size(b+1) * t_upload <= size(b) * t_eval  per site.  For cfg4 (1000 taxa, K = 4,
+// Gamma-4) a site costs ~38 ns to upload (1000 bytes at ~26 GB/s) and ~74 ns to evaluate on one GPU, i.e. blocks
+// may grow by at most ~1.9x: they grow by 1.5x, in whole waves of the persistent grid once the range is long
+// enough (no ragged last round), the first block is one wave at most (its transfer is the only one exposed) and
+// the last block takes the rest while that is under 1.8x its predecessor.
 void plan_stream_blocks(long long lo, long long hi, long long wave_sites, std::vector<std::pair<long long, long long>>& out) {
     out.clear();
     const long long n = hi - lo;
     if (n <= 0) return;
-    long long first = std::min(wave_sites, std::max<long long>(n / 8, 4096));
-    first = (first + 511) & ~511LL;
-    if (n < 4 * first) { out.push_back({lo, hi}); return; }
-    long long at = lo, sz = first;
-    while ((int)out.size() < 5 && hi - at > 3 * sz) {
+    wave_sites = std::max<long long>(wave_sites, 512);
+    const bool whole_waves = n >= 8 * wave_sites;
+    long long sz = whole_waves ? wave_sites : std::min(wave_sites, std::max<long long>((n / 4 + 511) & ~511LL, 4096));
+    long long at = lo;
+    while ((int)out.size() < 15 && (double)(hi - at - sz) > 1.8 * (double)sz) {
         out.push_back({at, at + sz});
         at += sz;
-        sz *= 2;
+        long long next = sz + sz / 2;
+        if (whole_waves) next = std::max(sz + wave_sites, next / wave_sites * wave_sites);
+        else next = (next + 511) & ~511LL;
+        sz = next;
+    }
+    if ((double)(hi - at) > 1.8 * (double)sz && (int)out.size() < 15) {
+        out.push_back({at, at + sz});
+        at += sz;
     }
     out.push_back({at, hi});
 }
@@ -670,7 +690,11 @@ int wave_columns_impl(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* 
 
 void drop_stream_set(mcp_ctx* m) {
     if (!m->stream_set) return;
-    for (auto& b : m->stream_set->blocks) destroy_alignment_one(m, b.aln);
+    for (auto& b : m->stream_set->blocks) {
+        destroy_alignment_one(m, b.aln);
+        for (cudaEvent_t ev : b.ev)
+            if (ev) cudaEventDestroy(ev);
+    }
     m->stream_set.reset();
 }
 
@@ -697,7 +721,12 @@ int ensure_stream_set(mcp_ctx* m, const unsigned char* codes, int K, long long S
             for (auto& bb : ns->blocks) destroy_alignment_one(m, bb.aln);
             return e;
         }
-        ns->blocks.push_back({al, b.first, b.second});
+        StreamSet::Block blk;
+        blk.aln = al;
+        blk.lo = b.first;
+        blk.hi = b.second;
+        for (cudaEvent_t& ev : blk.ev) cudaEventCreate(&ev);
+        ns->blocks.push_back(blk);
     }
     m->stream_set = std::move(ns);
     return 0;
@@ -711,7 +740,6 @@ int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, 
     if (!codes || !leaf_nums || !po || !pa || !blv || !U || !D || !Uinv || !rates || !pi)
         return fail(ctx, MCP_ERR_ARG, "mcp_eval_streamed: null argument");
     if (K < 1 || K > 254 || S < 0 || n_leaves < 1 || NN < 2) return fail(ctx, MCP_ERR_ARG, "mcp_eval_streamed: bad K/S/n_leaves/NN");
-    if (ctx->rank_comm) return fail(ctx, MCP_ERR_UNSUPPORTED, "mcp_eval_streamed is not available on a rank context");
     const bool multi = !ctx->members.empty();
     std::vector<mcp_ctx*> single{ctx};
     const std::vector<mcp_ctx*>& mem = multi ? ctx->members : single;
@@ -741,13 +769,33 @@ int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, 
         // evaluation starts with a small parameter upload of its own.  Transfer b, evaluation b,
         // transfer b+1, ...: the parameters of evaluation b queue right behind the block they need
         // anyway, and transfer b+1 then runs under the kernels of evaluation b.
+        // experiments only (tools/e2e_probe.py): "noupload" re-uses the device copies of the previous call,
+        // "serial" finishes every transfer before the first evaluation starts
+        const char* probe = std::getenv("MCPHYLO_B200_STREAM_PROBE");
+        const bool no_upload = probe && !std::strcmp(probe, "noupload") && ss.blocks[0].aln->streamed;
+        const bool serial = probe && !std::strcmp(probe, "serial");
+        if (serial) {
+            for (int b = 0; b < B; ++b)
+                if ((er = update_codes_one(m, ss.blocks[b].aln, codes + ss.blocks[b].lo, (size_t)S))) return er;
+            cudaStreamSynchronize(m->copy_stream);
+        }
         for (int b = 0; b < B; ++b) {
-            mcp_alignment* al = ss.blocks[b].aln;
-            if ((er = update_codes_one(m, al, codes + ss.blocks[b].lo, (size_t)S))) return er;
+            StreamSet::Block& blk = ss.blocks[b];
+            mcp_alignment* al = blk.aln;
+            if (!no_upload && !serial) {
+                cudaEventRecord(blk.ev[0], m->copy_stream);
+                if ((er = update_codes_one(m, al, codes + blk.lo, (size_t)S))) return er;
+                cudaEventRecord(blk.ev[1], m->copy_stream);
+            }
             const mcp_alignment* alp = al;
             BatchArgs ab{1, &alp, &NN, &po, &pa, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
             double* dst = B == 1 ? part[g] : (double*)m->d_part.p + (long long)b * len;
-            if ((er = eval_impl(m, ab, dst, nullptr, nullptr))) return er;
+            cudaEventRecord(blk.ev[2], m->stream);
+            m->ev_walk_begin = blk.ev[3];
+            m->ev_walk_end = blk.ev[4];
+            er = eval_impl(m, ab, dst, nullptr, nullptr);
+            m->ev_walk_begin = m->ev_walk_end = nullptr;
+            if (er) return er;
         }
         if (B > 1) {
             sum_rows<<<(unsigned)((len + 255) / 256), 256, 0, m->stream>>>((const double*)m->d_part.p, len, B, len, part[g]);
@@ -761,6 +809,11 @@ int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, 
         if ((e = group_reduce(ctx, part, len, &h))) return e;
     } else {
         if ((e = run_member(0))) return e;
+        if (ctx->rank_comm) {   // one rank of a multi-process group: S, codes describe this rank's shard
+            const mcpnccl::Api& nc = mcpnccl::api();
+            mcpnccl::result_t nr = nc.AllReduce(part[0], part[0], (size_t)len, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, ctx->stream);
+            if (nr) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce failed: %s", nc.GetErrorString(nr));
+        }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, part[0], sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         for (bool& p : ctx->staged_pending) p = false;
@@ -829,6 +882,8 @@ void destroy_single(mcp_ctx* ctx) {
         if (ev) cudaEventDestroy(ev);
     if (ctx->ev_walk_done) cudaEventDestroy(ctx->ev_walk_done);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+    if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     {   // this context may be remembered as the last user of a unit's constant model slots
@@ -1235,6 +1290,26 @@ int mcp_stream_blocks(const mcp_ctx* ctx, int member, int64_t* lo_hi, int cap) {
     return n;
 }
 
+int mcp_stream_timeline(const mcp_ctx* ctx, int member, double* ms, int cap_blocks) {
+    if (!ctx || !ms) return fail(nullptr, MCP_ERR_ARG, "mcp_stream_timeline: null argument");
+    const mcp_ctx* m = ctx->members.empty() ? ctx : (member >= 0 && member < (int)ctx->members.size() ? ctx->members[member] : nullptr);
+    if (!m || !m->stream_set || m->stream_set->blocks.empty()) return 0;
+    cudaSetDevice(m->device);
+    const auto& blocks = m->stream_set->blocks;
+    cudaEvent_t origin = blocks[0].ev[0];
+    int n = 0;
+    for (const auto& b : blocks) {
+        if (n >= cap_blocks) break;
+        for (int i = 0; i < 5; ++i) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, origin, b.ev[i]) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+            ms[5 * n + i] = t;
+        }
+        ++n;
+    }
+    return n;
+}
+
 int mcp_host_register(void* p, size_t bytes) {
     if (!p || !bytes) return fail(nullptr, MCP_ERR_ARG, "mcp_host_register: null argument");
     cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
@@ -1313,6 +1388,39 @@ int mcp_get_stats_member(const mcp_ctx* ctx, int member, mcp_stats* out) {
     if (member < 0 || member >= (int)ctx->members.size()) return fail(nullptr, MCP_ERR_ARG, "mcp_get_stats_member: member out of range");
     cudaSetDevice(ctx->members[member]->device);
     read_stats(ctx->members[member], out);
+    return 0;
+}
+
+int mcp_timer_start(mcp_ctx* ctx) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    return for_members_or_self(ctx, [](mcp_ctx* m) -> int {
+        CUDA_TRY(m, cudaSetDevice(m->device));
+        if (!m->ev_t0) {
+            CUDA_TRY(m, cudaEventCreate(&m->ev_t0));
+            CUDA_TRY(m, cudaEventCreate(&m->ev_t1));
+        }
+        CUDA_TRY(m, cudaStreamSynchronize(m->copy_stream));
+        CUDA_TRY(m, cudaEventRecord(m->ev_t0, m->stream));
+        return 0;
+    });
+}
+
+int mcp_timer_stop(mcp_ctx* ctx, double* ms_out) {
+    if (!ctx || !ms_out) return fail(ctx, MCP_ERR_ARG, "mcp_timer_stop: null argument");
+    double worst = 0.0;
+    int e = for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        if (!m->ev_t0) return fail(m, MCP_ERR_ARG, "mcp_timer_stop without mcp_timer_start");
+        CUDA_TRY(m, cudaSetDevice(m->device));
+        CUDA_TRY(m, cudaStreamSynchronize(m->copy_stream));
+        CUDA_TRY(m, cudaEventRecord(m->ev_t1, m->stream));
+        CUDA_TRY(m, cudaEventSynchronize(m->ev_t1));
+        float ms = 0.f;
+        CUDA_TRY(m, cudaEventElapsedTime(&ms, m->ev_t0, m->ev_t1));
+        worst = std::max(worst, (double)ms);
+        return 0;
+    });
+    if (e) return e;
+    *ms_out = worst;
     return 0;
 }
 

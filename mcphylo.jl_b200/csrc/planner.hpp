@@ -104,64 +104,42 @@ long long tiles_for(const BatchArgs& a, int tile_w) {
     return n;
 }
 
-// Launch shape of the depth-first walk.  Small inputs: the tile narrows until every SM has a few tiles.
-// Large inputs (the GPU is full either way): the persistent grid walks ceil(tiles / grid) rounds of
-// tiles, and what the last, partly filled round wastes depends on how the tile width divides the input --
-// e.g. a 125 k-site shard of cfg4 is 3.3 rounds of 512-column tiles on 296 CTAs but 3.97 rounds of
-// 448-column tiles.  Candidate shapes are costed as rounds x columns in flight per round / relative
-// throughput of the shape (two columns per thread amortise the per-op overhead: 1.28x at K = 2, 1.06x at
-// K = 4, profiles/r1_walk_notes.md; fewer resident warps hide less latency), the last round discounted
-// because a half-empty machine finishes its tiles faster.
+// Launch shape of the depth-first walk.  Measured on cfg4 shards of 15 k .. 250 k sites for every tile width
+// in {64 .. 256} x {1, 2} columns per thread (profiles/r2_shape_sweep.json):
+//   - the widest tile (256 threads) wins at every size, also when it leaves SMs without a CTA: the cost of a
+//     tile is dominated by per-CTA work that does not shrink with the tile (chunk staging, barriers), and a
+//     15 k-site input costs one tile time (1.5 ms for a 1999-node tree) whatever the width -- 64-wide tiles
+//     take 2x longer;
+//   - a partly filled last round of tiles costs nothing measurable (3.3 rounds run at the per-site cost of
+//     26 rounds: CTAs drift apart and the stragglers speed up as the SMs empty), so no width is ever chosen
+//     to "fill the last round";
+//   - two columns per thread win as soon as one column per thread would need more than two CTAs per SM.
+// Hence: 256 threads, narrowed only for inputs of fewer than 256 columns; two columns per thread (K <= 4)
+// when the input has more than 2 x SMs tiles of 256 columns.
 int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, int K, int max_br, bool acc_global,
                       WalkShape* out) {
     const int R = a.R;
-    long long total_cols = 0;
-    for (int t = 0; t < a.T; ++t) total_cols += a.alns[t]->S * R;
+    long long total_cols = 0, widest = 0;
+    for (int t = 0; t < a.T; ++t) {
+        total_cols += a.alns[t]->S * R;
+        widest = std::max<long long>(widest, a.alns[t]->S);
+    }
     const bool templated = k_templated(K);
     const int shared_acc = a.want_grad && !acc_global ? 1 : 0;
-    auto smem_of = [&](int b, int c) {
-        return templated ? walk_smem_bytes(K, max_br, shared_acc, b, c) : generic_smem_bytes(max_br, a.want_grad);
-    };
     int block = ctx->opt_block;
     if (block <= 0) {
-        block = 256;
-        while (block > 32 && (total_cols + block - 1) / block < 6LL * ctx->sm_count) block >>= 1;
+        block = templated ? 256 : 128;      // runtime-K kernel: at most 128 threads per CTA
+        while (block > 32 && widest <= block / 2) block >>= 1;
     }
+    if (!templated && block > 128) block = 128;
     int cpt = ctx->opt_cpt;
     const bool cpt2_ok = templated && K <= 4 && !acc_global;
-    const bool large = total_cols / (2LL * 256) >= 12LL * ctx->sm_count;
-    if (cpt <= 0) cpt = cpt2_ok && total_cols / (2LL * block) >= 12LL * ctx->sm_count ? 2 : 1;
+    if (cpt <= 0) cpt = cpt2_ok && tiles_for(a, block) > 2LL * ctx->sm_count ? 2 : 1;
     if (!cpt2_ok) cpt = 1;
-    if (!templated && block > 128) block = 128;   // runtime-K kernel: at most 128 threads per CTA
+    const size_t smem = templated ? walk_smem_bytes(K, max_br, shared_acc, block, cpt) : generic_smem_bytes(max_br, a.want_grad);
     int e, occ = 0;
-    if (ctx->opt_block > 0 || ctx->opt_cpt > 0 || !templated || !large || std::getenv("MCPHYLO_B200_NO_SHAPE_SEARCH")) {
-        if ((e = walk_occupancy(ctx, kt, K, block, cpt, smem_of(block, cpt), false, acc_global, false, &occ))) return e;
-        *out = {block, cpt, occ};
-        return 0;
-    }
-    const double base1 = K <= 2 ? 0.78 : K == 3 ? 0.86 : 0.94;   // throughput of one column per thread relative to two
-    double best = 0.0;
-    WalkShape pick{};
-    static const int widths[] = {256, 224, 192, 160, 128};
-    for (int c = cpt2_ok ? 2 : 1; c >= 1; --c)
-        for (int b : widths) {
-            int o = 0;
-            if ((e = walk_occupancy(ctx, kt, K, b, c, smem_of(b, c), false, acc_global, false, &o))) return e;
-            if (o < 1) continue;
-            if (ctx->opt_ctas_per_sm > 0) o = std::min(o, ctx->opt_ctas_per_sm);
-            const long long grid = (long long)o * ctx->sm_count, tiles = tiles_for(a, b * c);
-            const long long full = tiles / grid, rest = tiles - full * grid;
-            const double last = rest ? 0.6 + 0.4 * (double)rest / (double)grid : 0.0;
-            const double warps = o * b / 32.0, want = c == 2 ? 16.0 : 24.0;
-            const double thr = (c == 2 ? 1.0 : base1) * std::sqrt(std::min(1.0, warps / want));
-            const double cost = ((double)full + last) * (double)(b * c) * o / thr;
-            if (pick.occ == 0 || cost < best * (b == 256 ? 1.0 : 0.995)) {   // ties go to the wider tile
-                best = cost;
-                pick = {b, c, o};
-            }
-        }
-    if (pick.occ == 0) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM for any tile width");
-    *out = pick;
+    if ((e = walk_occupancy(ctx, kt, K, block, cpt, smem, false, acc_global, false, &occ))) return e;
+    *out = {block, cpt, occ};
     return 0;
 }
 
