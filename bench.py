@@ -607,16 +607,16 @@ def run_b200(args):
     barrier()
     torch.cuda.synchronize()
     sampler.start()
-    t_wall = time.perf_counter()
     ctx.timer_start()
+    t_wall = time.perf_counter()
     for i in range(args.steps):
         ll, grad = ctx.eval(aln, *prepared[i], want_grad=True)
         st = ctx.stats()
         walk_ms.append(st["walk_ms"])
         launches += st["kernel_launches"]
+    t_wall = (time.perf_counter() - t_wall) * 1e3
     ms_total = ctx.timer_stop()
     torch.cuda.synchronize()
-    t_wall = (time.perf_counter() - t_wall) * 1e3
     barrier()
     sampler.stop()
     stats = ctx.stats()
@@ -639,16 +639,17 @@ def run_b200(args):
     barrier()
     torch.cuda.synchronize()
     sampler.start()
-    t_e2e_wall = time.perf_counter()
     ctx.timer_start()
+    t_e2e_wall = time.perf_counter()
     for i in range(args.steps):
         ll_e, grad_e = e2e_step(i)
+    t_e2e_wall = (time.perf_counter() - t_e2e_wall) * 1e3
     ms_e2e = ctx.timer_stop()
     torch.cuda.synchronize()
-    t_e2e_wall = (time.perf_counter() - t_e2e_wall) * 1e3
     barrier()
     sampler.stop()
     blocks = [ctx.stream_blocks(g) for g in range(ctx.device_count)]
+    timeline = [ctx.stream_timeline(g) for g in range(ctx.device_count)]
     e2e_launches = args.steps * sum(3 * len(b) + (1 if len(b) > 1 else 0) for b in blocks)
 
     if world > 1 and not group_mode:
@@ -683,6 +684,9 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(w["S"] * w["n_taxa"] + stats["h2d_bytes"]),
                     "d2h_bytes_per_step": int(NN * 8),
                     "site_blocks_per_gpu": [[b - a for a, b in bl] for bl in blocks],
+                    "last_step_timeline_ms_gpu0": timeline[0],
+                    "timeline_what": "per site block on GPU 0: transfer begin, transfer end, evaluation enqueued, walk "
+                                     "begin, walk end (CUDA events, ms since the first transfer of the step began)",
                     "what": "per step through mcp_eval_streamed: alignment codes re-uploaded from pinned host memory, each "
                             "GPU's site range in blocks (a small first block, then doubling) on the copy stream, block b+1 "
                             "in flight while block b is evaluated; tree flattened and eigendecomposition on the host; block "

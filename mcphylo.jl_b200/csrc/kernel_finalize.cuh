@@ -74,7 +74,7 @@ __global__ void sum_rows(const double* __restrict__ in, long long stride, int n,
 // A cudaMemcpyAsync on the evaluation stream shares the host-to-device copy engine with the bulk alignment
 // transfers of mcp_eval_streamed, and the engine does not serve streams in issue order: measured on B200, the
 // 16 KB parameter copy of the first site block waited for four later bulk transfers (11 ms) before its
-// kernel could start (profiles/r2_e2e_timeline_before.json).  n16 = number of 16-byte words.
+// kernel could start (profiles/r2_e2e_timeline.json).  n16 = number of 16-byte words.
 // --------------------------------------------------------------------------------------------
 __global__ void stage_from_host(const uint4* __restrict__ h_src, uint4* __restrict__ d_dst, long long n16) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
