@@ -650,7 +650,9 @@ def run_b200(args):
     sampler.stop()
     blocks = [ctx.stream_blocks(g) for g in range(ctx.device_count)]
     timeline = [ctx.stream_timeline(g) for g in range(ctx.device_count)]
-    e2e_launches = args.steps * sum(3 * len(b) + (1 if len(b) > 1 else 0) for b in blocks)
+    # per GPU and launch over a site range: parameter staging + branch tables + walk + final reduction; one more
+    # kernel adds the block results when a range was evaluated in several launches
+    e2e_launches = args.steps * sum(4 * len(b) + (1 if len(b) > 1 else 0) for b in blocks)
 
     if world > 1 and not group_mode:
         t = torch.tensor([ms_total, ms_e2e, t_wall, t_e2e_wall], dtype=torch.float64)
@@ -687,10 +689,11 @@ def run_b200(args):
                     "last_step_timeline_ms_gpu0": timeline[0],
                     "timeline_what": "per site block on GPU 0: transfer begin, transfer end, evaluation enqueued, walk "
                                      "begin, walk end (CUDA events, ms since the first transfer of the step began)",
-                    "what": "per step through mcp_eval_streamed: alignment codes re-uploaded from pinned host memory, each "
-                            "GPU's site range in blocks (a small first block, then doubling) on the copy stream, block b+1 "
-                            "in flight while block b is evaluated; tree flattened and eigendecomposition on the host; block "
-                            "results added on the device, reduced over the GPUs, read back"},
+                    "what": "per step through mcp_eval_streamed: alignment codes re-uploaded from pinned host memory on the "
+                            "copy stream of every GPU in transfer units of 2 k .. 64 k sites, each followed by its ready flags; "
+                            "ONE walk launch per GPU starts before the data has arrived, takes tiles by atomic ticket in site "
+                            "order and waits per tile for the flags; tree flattened and eigendecomposition on the host; "
+                            "results reduced over the GPUs, read back"},
             "ms_per_step_host_wall": t_wall / args.steps,
             "gpu_launches": int(launches + e2e_launches),
             "gpu_launches_timed": int(launches),

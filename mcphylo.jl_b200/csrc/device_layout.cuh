@@ -52,6 +52,16 @@ struct WalkParams {
     int n_tiles, T, R, want_grad;
     int max_br;
     int max_rows;               // largest number of leaf rows in the batch
+    // Streamed evaluation (mcp_eval_streamed, one tree): the walk is launched BEFORE the alignment has arrived.
+    // Tiles are handed out by an atomic ticket in site order (all rate categories of a site tile are
+    // consecutive tickets), and a CTA starts a tile once the copy stream has marked the tile's sites as
+    // landed: ready_flags[site >> ready_shift] == ready_epoch.  All null for a resident alignment
+    // (static contiguous tile ranges, rate-major tile order).
+    const unsigned* ready_flags;
+    unsigned* ticket;
+    unsigned* error_flag;       // set when a tile's data did not arrive within the spin limit
+    unsigned ready_epoch;
+    int ready_shift;
     // Substitution-model constants when the whole batch shares ONE model (the common case): kernel
     // parameters live in constant bank 0, so they reach the FP64 pipe as uniform operands without
     // a separate host-to-device copy.  Layout as in c_model (below).

@@ -93,6 +93,24 @@ struct StreamSet {
     // enqueued / walk begin / walk end (evaluation stream); read by mcp_stream_timeline
     struct Block { mcp_alignment* aln; long long lo, hi; cudaEvent_t ev[5] = {}; };
     std::vector<Block> blocks;      // of this device's site range, in evaluation order
+    // Fused mode (one walk launch over the whole range, started before the data has arrived; tiles wait
+    // for per-site-group ready flags the copy stream sets): blocks holds the single whole-range alignment.
+    bool fused = false;
+    std::vector<std::pair<long long, long long>> chunks;   // transfer units, sites relative to the range start
+    DevBuf d_ctl;                   // [0] tile ticket, [1] error flag, [STREAM_CTL_WORDS ..) ready flag per site group
+    PinBuf h_epoch, h_err;          // epoch words the flag copies read; error word read back
+    unsigned epoch = 0;
+};
+constexpr int STREAM_GROUP_SHIFT = 11;   // ready-flag granularity: 2048 sites
+constexpr int STREAM_CTL_WORDS = 64;     // ticket / error words, padded to their own 256 bytes
+
+// What eval_impl passes to the walk kernel for a streamed evaluation.
+struct StreamFlags {
+    const unsigned* flags;
+    unsigned* ticket;
+    unsigned* error;
+    unsigned epoch;
+    int shift;
 };
 
 // Host threads of a multi-device context: member g > 0 is driven by its own persistent thread (member 0
@@ -182,6 +200,7 @@ struct mcp_ctx {
     std::vector<std::unique_ptr<Plan>> plans;
     Plan* last_plan = nullptr;
     std::unique_ptr<StreamSet> stream_set;
+    const StreamFlags* sf = nullptr;        // set by mcp_eval_streamed around its fused launch
 
     // ---- more than one device behind this handle (mcp_create_multi) ----
     std::vector<mcp_ctx*> members;          // one single-device context per device; empty for a plain context

@@ -62,10 +62,28 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 
     const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int TS = TW * CPT;                          // sites per tile; column c of a thread = site0 + c*TW + tid
+    // Tiles: a static contiguous range per CTA, or (streamed evaluation, one tree) an atomic ticket per tile
+    // so that CTAs whose data arrives early simply do more of the work.
+    __shared__ int s_ticket;
+    const bool dynamic_tiles = p.ticket != nullptr;
+    auto next_ticket = [&]() -> int {
+        __syncthreads();                                  // everybody has read the previous ticket
+        if (tid == 0) s_ticket = (int)min(atomicAdd(p.ticket, 1u), 0x7fffffffu);
+        __syncthreads();
+        return s_ticket;
+    };
     const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
-    int tile = blockIdx.x * q + min((int)blockIdx.x, rem);
-    const int tile_end = tile + q + ((int)blockIdx.x < rem ? 1 : 0);
-    if (tile >= tile_end) return;
+    int tile = dynamic_tiles ? next_ticket() : blockIdx.x * q + min((int)blockIdx.x, rem);
+    const int tile_end = dynamic_tiles ? p.n_tiles : tile + q + ((int)blockIdx.x < rem ? 1 : 0);
+    if (tile >= tile_end) {
+        if (dynamic_tiles) {   // this CTA got no tile: its accumulator row must still read as zero
+            const int row0 = p.cta_row_base[blockIdx.x];
+            if (tid == 0) { p.rows_ll[row0].esum = 0; p.rows_ll[row0].logsum = 0.0; }
+            if (p.want_grad)
+                for (int i = tid; i < p.max_br; i += TW) p.rows[(long long)row0 * p.row_stride + i] = 0.0;
+        }
+        return;
+    }
 
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
     constexpr bool GL2 = ACCG;
@@ -118,10 +136,24 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
         const int4* const post_ops = p.ops + 2 * tr.post_off;
         const int4* const pre_ops = p.ops + 2 * tr.pre_off;
 
-        for (; tile < tree_tile_end; ++tile) {
+        for (; tile < tree_tile_end; tile = dynamic_tiles ? next_ticket() : tile + 1) {
             const int local = tile - tr.tile_begin;
-            const int r = local / tr.tiles_per_rate;
-            const long long site0 = (long long)(local - r * tr.tiles_per_rate) * TS;
+            // resident: rate-major tile order; streamed: site-major (tickets follow the arrival of the sites)
+            const int r = dynamic_tiles ? local % R : local / tr.tiles_per_rate;
+            const long long site0 = (long long)(dynamic_tiles ? local / R : local - r * tr.tiles_per_rate) * TS;
+            if (p.ready_flags != nullptr && tid == 0) {
+                // wait until the copy stream has marked the last site of this tile as landed (sites arrive in
+                // order); the other threads wait at the barrier that opens the post pass
+                const long long last = min(site0 + TS, tr.S) - 1;
+                const unsigned* flag = p.ready_flags + (last >> p.ready_shift);
+                unsigned seen, spins = 0;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                    if (seen == p.ready_epoch) break;
+                    __nanosleep(200);
+                    if (++spins > (1u << 24)) { atomicExch(p.error_flag, 1u); break; }   // ~4 s: give up, the host reports it
+                }
+            }
             bool valid[CPT];
             double vmask[CPT];                 // 1.0 for real columns, 0.0 for the padding of a ragged tile
 #pragma unroll

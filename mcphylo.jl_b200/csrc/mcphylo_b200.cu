@@ -259,7 +259,12 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     s.h2d_bytes += (int64_t)(sizeof(double) * pl.total_dyn);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged[slot], st));
     ctx->staged_pending[slot] = true;
-    for (int t = 0; t < T; ++t)   // re-uploads of these alignments that are still in flight on the copy stream
+    if (ctx->sf) {
+        if (pl.level_mode || pl.acc_global || !k_templated(K) || T != 1)
+            return fail(ctx, MCP_ERR_ARG, "internal: streamed launch planned for a kernel without ready flags");
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->sf->ticket, 0, sizeof(unsigned) * STREAM_CTL_WORDS, st));
+    }
+    for (int t = 0; t < T && !ctx->sf; ++t)   // re-uploads of these alignments that are still in flight on the copy stream
         if (a.alns[t]->upload_pending) {
             CUDA_TRY(ctx, cudaStreamWaitEvent(st, a.alns[t]->ev_uploaded, 0));
             a.alns[t]->upload_pending = false;
@@ -294,6 +299,11 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.want_grad = a.want_grad ? 1 : 0;
     wp.max_br = pl.max_br;
     wp.max_rows = pl.max_rows;
+    wp.ready_flags = ctx->sf ? ctx->sf->flags : nullptr;
+    wp.ticket = ctx->sf ? ctx->sf->ticket : nullptr;
+    wp.error_flag = ctx->sf ? ctx->sf->error : nullptr;
+    wp.ready_epoch = ctx->sf ? ctx->sf->epoch : 0u;
+    wp.ready_shift = ctx->sf ? ctx->sf->shift : 0;
     static_assert(sizeof(wp.model) / sizeof(double) >= 2 * 6 * 6 + 6 + MAX_RATES * 6, "model parameter block too small");
     std::memset(wp.model, 0, sizeof wp.model);
     if (n_models == 1) std::memcpy(wp.model, hm, sizeof(double) * model_doubles);
@@ -695,30 +705,63 @@ void drop_stream_set(mcp_ctx* m) {
         for (cudaEvent_t ev : b.ev)
             if (ev) cudaEventDestroy(ev);
     }
+    free_dev(m->stream_set->d_ctl);
+    free_pin(m->stream_set->h_epoch);
+    free_pin(m->stream_set->h_err);
     m->stream_set.reset();
 }
 
 // (Re)creates the block alignments of member `m` for the host alignment described by the arguments.
+// Transfer units of the fused mode, in sites relative to the range start: small first units so that the first
+// tiles can start after a few hundred microseconds, doubling up to a cap; every boundary is a multiple of the
+// ready-flag granularity.
+void plan_stream_chunks(long long n, std::vector<std::pair<long long, long long>>& out) {
+    out.clear();
+    const long long g = 1LL << STREAM_GROUP_SHIFT;
+    const long long cap = std::min<long long>(65536, std::max<long long>(16384, ((n / 48 + g - 1) / g) * g));
+    long long at = 0, sz = g;
+    while (at < n) {
+        const long long end = std::min(n, at + sz);
+        out.push_back({at, end});
+        at = end;
+        sz = std::min(cap, sz * 2);
+    }
+}
+
 int ensure_stream_set(mcp_ctx* m, const unsigned char* codes, int K, long long S, const int32_t* leaf_nums, int n_leaves,
-                      long long lo, long long hi, int NN, int R, int want_grad) {
+                      long long lo, long long hi, int NN, int R, int want_grad, bool fused) {
     StreamSet* ss = m->stream_set.get();
     if (ss && ss->K == K && ss->S == S && ss->n_leaves == n_leaves && ss->R == R && ss->NN == NN && ss->want_grad == want_grad &&
-        std::memcmp(ss->leaf_nums.data(), leaf_nums, sizeof(int32_t) * n_leaves) == 0)
+        ss->fused == fused && std::memcmp(ss->leaf_nums.data(), leaf_nums, sizeof(int32_t) * n_leaves) == 0)
         return 0;
     drop_stream_set(m);
     std::unique_ptr<StreamSet> ns(new StreamSet());
     ns->K = K; ns->S = S; ns->n_leaves = n_leaves; ns->R = R; ns->NN = NN; ns->want_grad = want_grad;
+    ns->fused = fused;
     ns->leaf_nums.assign(leaf_nums, leaf_nums + n_leaves);
     int64_t wave = 0;
     int e;
     if ((e = wave_columns_impl(m, K, NN, want_grad, &wave))) return e;
     std::vector<std::pair<long long, long long>> bounds;
-    plan_stream_blocks(lo, hi, std::max<long long>(1, wave / std::max(R, 1)), bounds);
+    if (fused) {
+        bounds.push_back({lo, hi});
+        plan_stream_chunks(hi - lo, ns->chunks);
+        const size_t n_groups = (size_t)((hi - lo + (1LL << STREAM_GROUP_SHIFT) - 1) >> STREAM_GROUP_SHIFT);
+        if ((e = ensure_dev(m, ns->d_ctl, sizeof(unsigned) * (STREAM_CTL_WORDS + n_groups)))) return e;
+        if ((e = ensure_pin(m, ns->h_epoch, sizeof(unsigned) * n_groups))) { free_dev(ns->d_ctl); return e; }
+        if ((e = ensure_pin(m, ns->h_err, 64))) { free_dev(ns->d_ctl); free_pin(ns->h_epoch); return e; }
+        cudaMemsetAsync(ns->d_ctl.p, 0, sizeof(unsigned) * (STREAM_CTL_WORDS + n_groups), m->stream);
+    } else {
+        plan_stream_blocks(lo, hi, std::max<long long>(1, wave / std::max(R, 1)), bounds);
+    }
     if (bounds.empty()) bounds.push_back({lo, lo});   // an empty range still yields a (zero) result vector
     for (auto& b : bounds) {
         mcp_alignment* al = nullptr;
         if ((e = make_alignment(m, codes + b.first, (size_t)S, K, b.second - b.first, leaf_nums, n_leaves, &al))) {
             for (auto& bb : ns->blocks) destroy_alignment_one(m, bb.aln);
+            free_dev(ns->d_ctl);
+            free_pin(ns->h_epoch);
+            free_pin(ns->h_err);
             return e;
         }
         StreamSet::Block blk;
@@ -760,11 +803,70 @@ int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, 
         long long lo, hi;
         shard_range(S, G, g, &lo, &hi);
         int er;
-        if ((er = ensure_stream_set(m, codes, K, S, leaf_nums, n_leaves, lo, hi, NN, R, want_grad))) return er;
+        // One launch over the whole range with per-tile ready flags whenever the walk kernel that will run has
+        // them (templated K, shared-memory accumulator, an input beyond the small-tree kernel's reach);
+        // otherwise -- and with MCPHYLO_B200_STREAM_BLOCKS set, for comparison -- one launch per site block.
+        const bool fused = k_templated(K) && !std::getenv("MCPHYLO_B200_STREAM_BLOCKS") && m->opt_levels != 1 &&
+                           (hi - lo) * (long long)R > 2LL * 32 * 4 * m->sm_count &&
+                           !(want_grad && walk_acc_global(NN, m->opt_acc_mode));
+        if ((er = ensure_stream_set(m, codes, K, S, leaf_nums, n_leaves, lo, hi, NN, R, want_grad, fused))) return er;
         StreamSet& ss = *m->stream_set;
         const int B = (int)ss.blocks.size();
         if (cudaSetDevice(m->device) != cudaSuccess) return fail(m, MCP_ERR_CUDA, "cudaSetDevice failed");
         if ((er = ensure_dev(m, m->d_part, sizeof(double) * len * B))) return er;
+        if (fused) {
+            StreamSet::Block& blk = ss.blocks[0];
+            mcp_alignment* al = blk.aln;
+            if (++ss.epoch == 0) ss.epoch = 1;
+            const size_t n_groups = (size_t)((hi - lo + (1LL << STREAM_GROUP_SHIFT) - 1) >> STREAM_GROUP_SHIFT);
+            unsigned* he = (unsigned*)ss.h_epoch.p;
+            for (size_t i = 0; i < n_groups; ++i) he[i] = ss.epoch;
+            unsigned* ctl = (unsigned*)ss.d_ctl.p;
+            if (al->read_since_upload) {   // the previous evaluation of this buffer must have finished reading it
+                if (cudaStreamWaitEvent(m->copy_stream, al->streamed ? al->ev_read_done : m->ev_walk_done, 0) != cudaSuccess)
+                    return fail(m, MCP_ERR_CUDA, "cudaStreamWaitEvent failed");
+                al->read_since_upload = false;
+            }
+            al->streamed = true;
+            al->upload_pending = false;
+            m->pending_async = true;
+            cudaEventRecord(blk.ev[0], m->copy_stream);
+            auto send = [&](size_t c) -> int {
+                const long long c0 = ss.chunks[c].first, c1 = ss.chunks[c].second;
+                if (cudaMemcpy2DAsync(al->d_codes + c0, (size_t)al->stride, codes + lo + c0, (size_t)S, (size_t)(c1 - c0),
+                                      (size_t)al->n_leaves, cudaMemcpyHostToDevice, m->copy_stream) != cudaSuccess)
+                    return fail(m, MCP_ERR_CUDA, "alignment transfer failed: %s", cudaGetErrorString(cudaGetLastError()));
+                const size_t g0 = (size_t)(c0 >> STREAM_GROUP_SHIFT), g1 = (size_t)((c1 + (1LL << STREAM_GROUP_SHIFT) - 1) >> STREAM_GROUP_SHIFT);
+                // same stream, hence after the sites themselves: mark their groups as landed
+                if (cudaMemcpyAsync(ctl + STREAM_CTL_WORDS + g0, he + g0, sizeof(unsigned) * (g1 - g0), cudaMemcpyHostToDevice,
+                                    m->copy_stream) != cudaSuccess)
+                    return fail(m, MCP_ERR_CUDA, "ready-flag transfer failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return 0;
+            };
+            // the first few units go out before the kernels are enqueued, the rest right after: the walk must
+            // not sit behind a long run of host-side enqueue calls, nor the transfers behind the launch
+            const size_t n_first = std::min<size_t>(3, ss.chunks.size());
+            for (size_t c = 0; c < n_first; ++c)
+                if ((er = send(c))) return er;
+            StreamFlags sf{ctl + STREAM_CTL_WORDS, ctl, ctl + 1, ss.epoch, STREAM_GROUP_SHIFT};
+            const mcp_alignment* alp = al;
+            BatchArgs ab{1, &alp, &NN, &po, &pa, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, want_grad};
+            cudaEventRecord(blk.ev[2], m->stream);
+            m->sf = &sf;
+            m->ev_walk_begin = blk.ev[3];
+            m->ev_walk_end = blk.ev[4];
+            er = eval_impl(m, ab, part[g], nullptr, nullptr);
+            m->sf = nullptr;
+            m->ev_walk_begin = m->ev_walk_end = nullptr;
+            // whatever happened, every unit must be sent: a launched walk waits for all of them
+            int er2 = 0;
+            for (size_t c = n_first; c < ss.chunks.size() && !er2; ++c) er2 = send(c);
+            cudaEventRecord(blk.ev[1], m->copy_stream);
+            if (er || er2) return er ? er : er2;
+            if (cudaMemcpyAsync(ss.h_err.p, ctl + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, m->stream) != cudaSuccess)
+                return fail(m, MCP_ERR_CUDA, "cudaMemcpyAsync failed");
+            return 0;
+        }
         // Issue order matters: host-to-device transfers are served first-in first-out, and every
         // evaluation starts with a small parameter upload of its own.  Transfer b, evaluation b,
         // transfer b+1, ...: the parameters of evaluation b queue right behind the block they need
@@ -819,6 +921,13 @@ int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, 
         for (bool& p : ctx->staged_pending) p = false;
         h = (const double*)ctx->h_out.p;
     }
+    for (mcp_ctx* m : mem)
+        if (m->stream_set && m->stream_set->fused) {
+            cudaSetDevice(m->device);
+            CUDA_TRY(ctx, cudaStreamSynchronize(m->stream));
+            if (*(const unsigned*)m->stream_set->h_err.p != 0)
+                return fail(ctx, MCP_ERR_CUDA, "mcp_eval_streamed: device %d gave up waiting for alignment data (transfer stalled)", m->device);
+        }
     if (ll_out) *ll_out = h[0];
     if (want_grad && grad_out) std::memcpy(grad_out, h + 1, sizeof(double) * (NN - 1));
     return 0;

@@ -158,12 +158,17 @@ def test_two_gpus_vs_oracle(oracle, reduce):
         ctx.close()
 
 
+@pytest.mark.parametrize("mode", ["fused", "blocks"])
 @pytest.mark.parametrize("devices", [None, [0, 0, 0]])
 @pytest.mark.parametrize("S", [700, 40000])
-def test_streamed_evaluation_vs_oracle(oracle, devices, S):
-    """mcp_eval_streamed: the alignment stays in (pinned) host memory and is uploaded block by block;
-    repeated calls with new branch lengths and with CHANGED codes give the oracle's values."""
+def test_streamed_evaluation_vs_oracle(oracle, monkeypatch, devices, S, mode):
+    """mcp_eval_streamed: the alignment stays in (pinned) host memory and is uploaded during the call --
+    one walk launch whose tiles wait for ready flags ("fused", the default for inputs beyond the small-tree
+    kernel), or one launch per site block ("blocks"); repeated calls with new branch lengths and with
+    CHANGED codes give the oracle's values."""
     import torch
+    if mode == "blocks":
+        monkeypatch.setenv("MCPHYLO_B200_STREAM_BLOCKS", "1")
     n_taxa = 24 if S > 1000 else 50
     tree, pi, model, srates, rates, codes, leaf_nums = _case(n_taxa, 4, 2, S, 404)
     ctx = capi.Context(devices=devices, reduce=capi.REDUCE_PEER) if devices else capi.Context(0)
@@ -176,7 +181,10 @@ def test_streamed_evaluation_vs_oracle(oracle, devices, S):
         blocks = ctx.stream_blocks(0)
         assert blocks and blocks[0][0] == 0 and all(b[1] > b[0] for b in blocks)
         if S >= 40000 and not devices:
-            assert len(blocks) >= 3            # pipelined: small first block, then doubling
+            # blocks: small first block, then growing; fused: the whole range is one launch
+            assert len(blocks) >= 3 if mode == "blocks" else len(blocks) == 1
+            tl = ctx.stream_timeline(0)
+            assert len(tl) == len(blocks) and all(t[1] >= t[0] >= 0 and t[4] >= t[3] >= 0 for t in tl)
         # new data in the same host buffer + new branch lengths: nothing stale may be reused
         codes2 = codes.copy()
         codes2[:, ::3] = (codes2[:, ::3] + 1) % 4
