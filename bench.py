@@ -113,7 +113,8 @@ def walk_bytes(tree, S, K, R, want_grad=True):
     program: per column and K-vector (K*8 bytes) one store per stored post result, one load
     per stored post operand, one load per stored child partial in the gradient pass, one store + one load
     per pre vector that goes through the LIFO; leaf codes once per rate category and pass.  Second children
-    and kept pre vectors never leave registers.  Part of this traffic (LIFO entries, partials re-read soon
+    and kept pre vectors never leave registers; cherries (both children leaves) are recomputed from their
+    codes in the gradient pass instead of being stored and re-read.  Part of this traffic (LIFO entries, partials re-read soon
     after they were written) is served by L2 and never reaches DRAM: `traffic` is the measured remainder."""
     import mcphylo_jl_b200 as mcp
     from mcphylo_jl_b200 import capi
@@ -121,7 +122,7 @@ def walk_bytes(tree, S, K, R, want_grad=True):
     ft = mcp.flatten(tree)
     leaf_row = np.full(ft.NN, -1, dtype=np.int32)
     leaf_row[ft.leaf_nums - 1] = np.arange(ft.leaf_nums.size)
-    sd = capi.schedule_dump(ft.postorder_num, ft.parent_num, leaf_row, want_grad)
+    sd = capi.schedule_dump(ft.postorder_num, ft.parent_num, leaf_row, want_grad, cherries=K <= 6)
     post, pre = sd["post"], sd["pre"]
     flags = post[:, 5]
     n_store = int(np.sum((flags & 16) != 0))
@@ -134,7 +135,7 @@ def walk_bytes(tree, S, K, R, want_grad=True):
         n_pop = int(np.sum(((pf >> 8) & 3) == 2))
         n_push = int(np.sum(((pf >> 10) & 3) == 2) + np.sum(((pf >> 12) & 3) == 2))
         vec += n_mem_pre + n_pop + n_push
-        n_leaf_reads += int(np.sum((pf & 3) == 0) + np.sum(((pf >> 2) & 3) == 0))
+        n_leaf_reads += int(np.sum((pf & 3) == 0) + np.sum(((pf >> 2) & 3) == 0) + 2 * np.sum((pf & 3) == 3))
     return int(S * R * K * 8 * vec + S * R * n_leaf_reads)
 
 

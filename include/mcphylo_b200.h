@@ -285,6 +285,14 @@ int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
  * row in global memory with RED.ADD.F64 beyond that), 0 always shared memory (fails if the tree does
  * not fit), 1 always global memory. */
 int mcp_set_accumulator_mode(mcp_ctx *ctx, int mode);
+/* Gradient pass, K <= 6: an internal node whose two children are leaves (a "cherry") is recomputed from the
+ * two leaf codes instead of being stored by the post pass and re-read (bit-identical; a third of the stored
+ * partials of a random binary tree).  -1 automatic (on), 0 off (every partial stored), 1 on. */
+int mcp_set_cherry_mode(mcp_ctx *ctx, int mode);
+/* How the persistent CTAs of the walk share the column tiles of a RESIDENT single-tree evaluation: 0 a static
+ * contiguous range per CTA, rate-major; 1 an atomic ticket per tile, site-major (what mcp_eval_streamed always
+ * uses); -1 automatic.  Results are identical up to the order of the per-CTA sums. */
+int mcp_set_tile_order(mcp_ctx *ctx, int mode);
 /* Level-parallel small-tree kernel (all warps of a CTA share one 32-column tile, one barrier per
  * tree level): -1 automatic (inputs of at most a few tiles per SM whose tree fits in shared memory),
  * 0 never, 1 whenever the tree fits. */
@@ -298,7 +306,8 @@ int mcp_set_level_mode(mcp_ctx *ctx, int mode);
  *   info[0]=n_post info[1]=n_pre info[2]=n_slots info[3]=n_stack info[4]=n_dnodes
  *   info[5]=post levels info[6]=pre levels (info must hold 8 ints)
  * want_grad: bit 0 = gradient program wanted, bit 1 = emit the level-ordered variant used by the
- * small-tree kernel instead of the depth-first one.
+ * small-tree kernel instead of the depth-first one, bit 2 = cherries recomputed in the gradient pass
+ * (OPK_CHERRY children, csrc/schedule.hpp); info[7] = number of such children.
  */
 int mcp_schedule_dump(int NN, const int32_t *postorder_num, const int32_t *parent_num,
                       const int32_t *leaf_row, int want_grad, int32_t *post_ops, int cap_post,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
-    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode",
+    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode",
     "mcp_schedule_dump", "mcp_model_reorder",
 ]
 
@@ -75,6 +75,8 @@ def load():
     lib.mcp_set_scratch_mode.argtypes = [_vp, C.c_int]
     lib.mcp_set_accumulator_mode.argtypes = [_vp, C.c_int]
     lib.mcp_set_level_mode.argtypes = [_vp, C.c_int]
+    lib.mcp_set_tile_order.argtypes = [_vp, C.c_int]
+    lib.mcp_set_cherry_mode.argtypes = [_vp, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
@@ -236,6 +238,12 @@ class Context:
 
     def set_level_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_level_mode(self.handle, int(mode)))
+
+    def set_cherry_mode(self, mode: int = -1):
+        self._check(self.lib.mcp_set_cherry_mode(self.handle, int(mode)))
+
+    def set_tile_order(self, mode: int = -1):
+        self._check(self.lib.mcp_set_tile_order(self.handle, int(mode)))
 
     def set_scratch_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_scratch_mode(self.handle, int(mode)))
@@ -438,7 +446,7 @@ def model_reorder(U, D, Uinv):
     return Uo, Do, Uio, bool(flag.value)
 
 
-def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool, by_levels: bool = False):
+def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool, by_levels: bool = False, cherries: bool = False):
     """Host-only view of the device walk program (no GPU needed)."""
     lib = load()
     po, pa, lr = _i32(postorder_num), _i32(parent_num), _i32(leaf_row)
@@ -447,10 +455,10 @@ def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool, by_level
     post = np.zeros((cap, 8), dtype=np.int32)
     pre = np.zeros((cap, 8), dtype=np.int32)
     info = np.zeros(8, dtype=np.int32)
-    rc = lib.mcp_schedule_dump(NN, po.ctypes.data, pa.ctypes.data, lr.ctypes.data, int(bool(want_grad)) | (2 if by_levels else 0),
+    rc = lib.mcp_schedule_dump(NN, po.ctypes.data, pa.ctypes.data, lr.ctypes.data, int(bool(want_grad)) | (2 if by_levels else 0) | (4 if cherries else 0),
                                post.ctypes.data, cap, pre.ctypes.data, cap, info.ctypes.data)
     if rc:
         raise McpError(rc, lib.mcp_last_error(None).decode())
     return {"post": post[:info[0]].copy(), "pre": pre[:info[1]].copy(), "n_slots": int(info[2]),
             "n_stack": int(info[3]), "n_dnodes": int(info[4]), "post_levels": int(info[5]),
-            "pre_levels": int(info[6])}
+            "pre_levels": int(info[6]), "n_cherries": int(info[7])}

@@ -186,9 +186,11 @@ struct mcp_ctx {
     int opt_levels = -1;         // -1 automatic, 0 never, 1 whenever it fits
     int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
     int opt_acc_mode = -1;       // gradient accumulator of the walk: -1 automatic, 0 shared memory, 1 global memory (RED)
+    int opt_cherry = -1;         // gradient pass recomputes cherries from their leaves (-1 / 1) or re-reads stored copies (0)
+    int opt_dynamic = -1;        // resident single-tree walk: tiles by atomic ticket in site order (1) or static ranges (0)
     unsigned long long next_aln_id = 1, clock = 0;
 
-    DevBuf d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out, d_counter, d_part;
+    DevBuf d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out, d_counter, d_part, d_ticket;
     PinBuf h_out;
     // parameter staging ring: an evaluation fills slot `stage_next`, the copy to the device is
     // asynchronous, and the slot is reused only after its event has passed

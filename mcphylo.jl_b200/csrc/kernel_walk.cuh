@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state]; all
     // slot / LIFO offsets in the records are byte offsets from here
     unsigned char* const scr = SSCR
-        ? scode + WalkSmem<K>::code_bytes(TS) + (size_t)tid * K * 8
+        ? scode + WalkSmem<K>::code_bytes(TS, 2) + (size_t)tid * K * 8
         : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K));
     const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
     const unsigned slot_bytes = col_bytes * CPT;
@@ -138,9 +138,11 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 
         for (; tile < tree_tile_end; tile = dynamic_tiles ? next_ticket() : tile + 1) {
             const int local = tile - tr.tile_begin;
-            // resident: rate-major tile order; streamed: site-major (tickets follow the arrival of the sites)
-            const int r = dynamic_tiles ? local % R : local / tr.tiles_per_rate;
-            const long long site0 = (long long)(dynamic_tiles ? local / R : local - r * tr.tiles_per_rate) * TS;
+            // Site-major tile order: the R rate categories of one site range are consecutive tiles, so a CTA (or
+            // its neighbours) re-reads that range's codes from L2 while they are hot, and the tickets of a
+            // streamed evaluation follow the arrival of the sites.
+            const int stile = local / R, r = local - stile * R;
+            const long long site0 = (long long)stile * TS;
             if (p.ready_flags != nullptr && tid == 0) {
                 // wait until the copy stream has marked the last site of this tile as landed (sites arrive in
                 // order); the other threads wait at the barrier that opens the post pass
@@ -172,47 +174,64 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 int4* dst = sdesc + (c % 3) * (CH * 2);
                 for (int i = tid; i < cnt * 2; i += TW) cp_async16(dst + i, ops + 2 * base + i);
             };
-            // Copies e vectors / leaf codes of chunk c and derives the per-op records (byte offsets),
-            // once per CTA instead of once per warp.  `pre` selects the pre-program field meaning.
+            // Copies e vectors / leaf codes / leaf tables of chunk c and derives the per-op records (byte
+            // offsets), once per CTA instead of once per warp.  `pre` selects the pre-program field meaning.
+            // Work split: one (op, child) pair per warp at a time, the lanes share the pair's 16-byte pieces --
+            // the operand kind is warp-uniform and every kind fetches exactly what it needs:
+            //   LEAF    its code row segment + the branch's P (gradient pass: and dP) columns
+            //   CHERRY  (gradient pass) the code rows and P columns of BOTH leaves below it + its own (em1, de)
+            //   REG/MEM (em1, de) of the branch
             auto stage_data = [&](int n_ops, int c, bool pre) {
                 const int base = c * CH, cnt = min(CH, n_ops - base);
                 const int4* d = sdesc + (c % 3) * (CH * 2);
                 double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS);
+                const int crows = pre ? 2 : 1;               // code rows per child slot
+                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * 2 * TS);
                 OpRec* rb = srec + (c & 1) * CH;
                 double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                 const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
-                const int tab_doubles = pre ? 2 * KK1 : KK1; // P columns (+ dP columns in the gradient pass)
-                const int tpieces = (tab_doubles + 1) / 2;   // 16-byte pieces of one leaf table
-                const int epieces = K;                       // em1 and de: 2K doubles = K 16-byte pieces
-                const int per_child = pieces + tpieces > epieces ? pieces + tpieces : epieces;
-                for (int w = tid; w < cnt * 2 * per_child; w += TW) {
-                    const int piece = w % per_child, jc = w / per_child, j = jc >> 1, ch = jc & 1;
-                    const int4 o0 = d[2 * j];
-                    const int fl = d[2 * j + 1].y;
+                const int tpieces = KK1 / 2;                 // 16-byte pieces of one leaf table (K (K + 1) is even)
+                auto copy_codes = [&](unsigned char* dstrow, int row) {
+                    for (int piece = lane; piece < pieces; piece += 32) {
+                        unsigned char* dstp = dstrow + piece * 16;
+                        if (row >= 0) cp_async16(dstp, codes0 + (long long)row * tr.code_stride + piece * 16);
+                        else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
+                    }
+                };
+                auto copy_table = [&](double* dst, const double* src, int n_tab) {   // n_tab tables of KK1 doubles
+                    for (int tp = lane; tp < n_tab * tpieces; tp += 32) {
+                        if constexpr ((K * 8) % 16 == 0) {
+                            cp_async16(dst + tp * 2, src + tp * 2);
+                        } else {
+                            dst[tp * 2] = __ldg(src + tp * 2);
+                            dst[tp * 2 + 1] = __ldg(src + tp * 2 + 1);
+                        }
+                    }
+                };
+                for (int jc = warp; jc < cnt * 2; jc += (TW >> 5)) {
+                    const int j = jc >> 1, ch = jc & 1;
+                    const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
+                    const int fl = o1.y;
                     const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
                     const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
                     const double* bsrc = reinterpret_cast<const double*>(btab_b + (unsigned)br * br_bytes);
+                    unsigned char* crow = cb + (size_t)(j * 2 + ch) * crows * TS;
+                    double* tdst = tb + (size_t)(j * 2 + ch) * 2 * KK1;
                     if (kind == mcp::OPK_LEAF) {
-                        if (piece < pieces) {
-                            unsigned char* dstp = cb + (size_t)(j * 2 + ch) * TS + piece * 16;
-                            if (src >= 0) cp_async16(dstp, codes0 + (long long)src * tr.code_stride + piece * 16);
-                            else *reinterpret_cast<uint4*>(dstp) = make_uint4(0x01010101u * K, 0x01010101u * K, 0x01010101u * K, 0x01010101u * K);
-                        } else if (piece < pieces + tpieces) {
-                            const int tp = piece - pieces;
-                            double* dstp = tb + (size_t)(j * 2 + ch) * 2 * KK1 + tp * 2;
-                            const double* srcp = bsrc + 2 * K + tp * 2;
-                            if constexpr ((K * 8) % 16 == 0) {
-                                cp_async16(dstp, srcp);
-                            } else {
-                                dstp[0] = __ldg(srcp);
-                                if (tp * 2 + 1 < tab_doubles) dstp[1] = __ldg(srcp + 1);
-                            }
+                        copy_codes(crow, src);
+                        copy_table(tdst, bsrc + 2 * K, pre ? 2 : 1);
+                    } else {
+                        if (pre && kind == mcp::OPK_CHERRY) {    // child a only: leaves in a_src, their branches in a_dst
+                            const int bx = o1.z & 0xffff, by = (o1.z >> 16) & 0xffff;
+                            copy_codes(crow, src & 0xffff);
+                            copy_codes(crow + TS, (src >> 16) & 0xffff);
+                            copy_table(tdst, reinterpret_cast<const double*>(btab_b + (unsigned)bx * br_bytes) + 2 * K, 1);
+                            copy_table(tdst + KK1, reinterpret_cast<const double*>(btab_b + (unsigned)by * br_bytes) + 2 * K, 1);
                         }
-                    } else if (piece < epieces) {
-                        // 2K doubles = K 16-byte pieces; entries are 16-byte aligned (bt_size is even)
-                        cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * 2 * K) + piece * 16,
-                                   reinterpret_cast<const unsigned char*>(bsrc) + piece * 16);
+                        // (em1, de): 2K doubles = K 16-byte pieces; entries are 16-byte aligned (bt_size is even)
+                        if (lane < K)
+                            cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2 + ch) * 2 * K) + lane * 16,
+                                       reinterpret_cast<const unsigned char*>(bsrc) + lane * 16);
                     }
                 }
                 for (int j = tid; j < cnt; j += TW) {
@@ -309,7 +328,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     chunk_boundary(post_ops, n_post, c, n_chunks, false);
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * 2 * TS) + tid;
                     const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_post - c * CH);
                     double Lm[CPT][K];                                              // the op's stored operand
@@ -399,7 +418,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     }
                     const OpRec* rb = srec + (c & 1) * CH;
                     const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * TS) + tid;
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * 2 * TS) + tid;
                     const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
                     const int cnt = min(CH, n_pre - c * CH);
                     double La[CPT][K], Lb[CPT][K];                                  // the family's stored child partials
@@ -418,7 +437,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
                         const int flags = (int)rh.x;
-                        const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
+                        const bool ai = (flags & 3) != mcp::OPK_LEAF, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
                         // Canonical family (schedule.hpp): a is the child whose pre vector stays in
                         // registers (internal, OUT_KEEP) or a leaf; b is pushed (internal, OUT_PUSH) or a
                         // leaf; b internal implies a internal.  pre[mother] lives in `cur`: it is either
@@ -431,7 +450,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         auto leaf_cols = [&](int ch, double (&D)[CPT][K], double (&Y)[CPT][K]) {
 #pragma unroll
                             for (int cc = 0; cc < CPT; ++cc) {
-                                const int code = min((int)cb[(j * 2 + ch) * TS + cc * TW], K);
+                                const int code = min((int)cb[(j * 2 + ch) * 2 * TS + cc * TW], K);
                                 const double* t = tb + (j * 2 + ch) * 2 * KK1 + code * K;
 #pragma unroll
                                 for (int k = 0; k < K; ++k) { D[cc][k] = t[k]; Y[cc][k] = t[KK1 + k]; }
@@ -444,6 +463,20 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             eig_project<K, CPT, true, NE>(mdl, L, e, eb + (j * 2 + ch) * 2 * K + K, z, Y);
                             eig_expand<K, CPT, NE>(mdl, z, L, D);
                         };
+                        if ((flags & 3) == mcp::OPK_CHERRY) {
+                            // a is a cherry: its post result is rebuilt from the two leaves below it -- the same
+                            // products and the same power-of-two rescaling as in the post pass, hence the same bits
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) {
+                                const int cx = min((int)cb[(j * 2) * 2 * TS + cc * TW], K);
+                                const int cy = min((int)cb[((j * 2) * 2 + 1) * TS + cc * TW], K);
+                                const double* tx = tb + (j * 2) * 2 * KK1 + cx * K;
+                                const double* ty = tb + (j * 2) * 2 * KK1 + KK1 + cy * K;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) La[cc][k] = tx[k] * ty[k];
+                                rescale_pow2<K>(La[cc]);
+                            }
+                        }
                         if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
                         if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
                         double qa[CPT][K], qb[CPT][K];

@@ -259,6 +259,12 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     s.h2d_bytes += (int64_t)(sizeof(double) * pl.total_dyn);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged[slot], st));
     ctx->staged_pending[slot] = true;
+    // resident alignment, one tree: tiles by atomic ticket (site-major order) instead of static ranges
+    const bool dyn_tiles = !ctx->sf && ctx->opt_dynamic == 1 && !pl.level_mode && !pl.acc_global && k_templated(K) && T == 1;
+    if (dyn_tiles) {
+        if ((e = ensure_dev(ctx, ctx->d_ticket, sizeof(unsigned) * STREAM_CTL_WORDS))) return e;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(unsigned) * STREAM_CTL_WORDS, st));
+    }
     if (ctx->sf) {
         if (pl.level_mode || pl.acc_global || !k_templated(K) || T != 1)
             return fail(ctx, MCP_ERR_ARG, "internal: streamed launch planned for a kernel without ready flags");
@@ -300,7 +306,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.max_br = pl.max_br;
     wp.max_rows = pl.max_rows;
     wp.ready_flags = ctx->sf ? ctx->sf->flags : nullptr;
-    wp.ticket = ctx->sf ? ctx->sf->ticket : nullptr;
+    wp.ticket = ctx->sf ? ctx->sf->ticket : dyn_tiles ? (unsigned*)ctx->d_ticket.p : nullptr;
     wp.error_flag = ctx->sf ? ctx->sf->error : nullptr;
     wp.ready_epoch = ctx->sf ? ctx->sf->epoch : 0u;
     wp.ready_shift = ctx->sf ? ctx->sf->shift : 0;
@@ -975,7 +981,7 @@ void destroy_single(mcp_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     drop_stream_set(ctx);
     if (ctx->rank_comm) mcpnccl::api().CommDestroy(ctx->rank_comm);
-    for (DevBuf* b : {&ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter, &ctx->d_part})
+    for (DevBuf* b : {&ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter, &ctx->d_part, &ctx->d_ticket})
         free_dev(*b);
     free_pin(ctx->h_out);
     for (int i = 0; i < MCP_STAGE_SLOTS; ++i) {
@@ -1243,6 +1249,25 @@ int mcp_set_accumulator_mode(mcp_ctx* ctx, int mode) {
     return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
         m->opt_acc_mode = mode;
         invalidate_plans(m);
+        return 0;
+    });
+}
+
+int mcp_set_cherry_mode(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "cherry mode must be -1 (automatic), 0 (stored) or 1 (recomputed)");
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_cherry = mode;
+        invalidate_plans(m);
+        return 0;
+    });
+}
+
+int mcp_set_tile_order(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "tile order must be -1 (automatic), 0 (static ranges) or 1 (atomic tickets)");
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_dynamic = mode;
         return 0;
     });
 }
@@ -1547,8 +1572,9 @@ int mcp_schedule_dump(int NN, const int32_t* postorder_num, const int32_t* paren
     if (!postorder_num || !parent_num || !leaf_row || !info) return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: null argument");
     mcp::Schedule sc;
     const bool by_levels = (want_grad & 2) != 0;   // bit 1 of want_grad selects the level-ordered program
+    const bool cherries = (want_grad & 4) != 0;    // bit 2: cherries recomputed in the gradient pass (K <= 6 walk kernels)
     want_grad &= 1;
-    std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, want_grad != 0, sc, by_levels);
+    std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, want_grad != 0, sc, by_levels, cherries && !by_levels);
     if (!err.empty()) return fail(nullptr, MCP_ERR_ARG, "%s", err.c_str());
     info[0] = (int32_t)sc.post.size();
     info[1] = (int32_t)sc.pre.size();
@@ -1557,6 +1583,7 @@ int mcp_schedule_dump(int NN, const int32_t* postorder_num, const int32_t* paren
     info[4] = sc.n_dnodes;
     info[5] = (int32_t)(sc.post_levels.empty() ? 0 : sc.post_levels.size() - 1);
     info[6] = (int32_t)(sc.pre_levels.empty() ? 0 : sc.pre_levels.size() - 1);
+    info[7] = sc.n_cherries;
     if ((int)sc.post.size() > cap_post || (int)sc.pre.size() > cap_pre)
         return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_dump: output arrays too small");
     if (post_ops) std::memcpy(post_ops, sc.post.data(), sc.post.size() * 32);

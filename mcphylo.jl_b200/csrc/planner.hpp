@@ -32,7 +32,7 @@ const KernelTable* kernels_for(int K) {
 size_t walk_smem_bytes(int K, int max_br, int shared_acc, int block, int cpt) {
     const size_t acc = shared_acc ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
     return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
-           (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * block * cpt;
+           (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * 2 * block * cpt;   // = WalkSmem<K>::total
 }
 size_t generic_smem_bytes(int max_br, int want_grad) { return want_grad ? (size_t)max_br * sizeof(double) : 0; }
 
@@ -207,7 +207,8 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
                 int num = al->leaf_nums[i];
                 if (num >= 1 && num <= NN) leaf_row[num - 1] = i;
             }
-            std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, pl.scheds[t], by_levels);
+            std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, pl.scheds[t], by_levels,
+                                                  !by_levels && k_templated(K) && ctx->opt_cherry != 0);
             if (!err.empty()) return fail(ctx, MCP_ERR_ARG, "tree %d: %s", t, err.c_str());
             const mcp::Schedule& sc = pl.scheds[t];
             TreeDev& td = pl.trees[t];

@@ -35,10 +35,20 @@
 
 namespace mcp {
 
-enum : int { OPK_LEAF = 0, OPK_REG = 1, OPK_MEM = 2 };          // post operand kinds
+enum : int { OPK_LEAF = 0, OPK_REG = 1, OPK_MEM = 2, OPK_CHERRY = 3 };   // operand kinds (CHERRY: pre program only)
 enum : int { PREM_ROOT = 0, PREM_REG = 1, PREM_STACK = 2 };     // where pre[mother] comes from
 enum : int { OUT_NONE = 0, OUT_KEEP = 1, OUT_PUSH = 2 };        // what happens to pre[child]
 
+// CHERRY (pre program, child a only): the child is an internal node whose two children are both real
+// leaves x, y.  Its post result L = rescale(P_x[:, code_x] * P_y[:, code_y]) is two table look-ups and K
+// multiplies, so the gradient pass RECOMPUTES it from the codes instead of re-reading a stored copy, and the
+// post pass does not store it: in a random binary tree a third of the internal nodes are cherries, i.e. a
+// third of the stored partials and of their re-reads (64 of ~190 bytes per column and node at K = 4).
+//   a_src = row_x | row_y << 16   (alignment rows)     a_dst = br_x | br_y << 16   (branch-table rows)
+//   a_br stays the cherry's own branch.  Same arithmetic in the same order as the post op, hence the same
+//   bits.  Only emitted when allow_cherry is set (depth-first walk kernels for K <= 6), for a cherry that is
+//   the kept child of its family and whose post result the post pass itself does not re-read.
+//
 // Both op types are 8 x int32 with a common head so that the kernel's staging code can treat
 // them alike:
 //   word 0..3  a_src, a_br, b_src, b_br   child operands: LEAF -> alignment row (-1 = all ones),
@@ -73,6 +83,7 @@ struct Schedule {
     int n_slots = 0;    // post result slots needed per column
     int n_stack = 0;    // pre LIFO depth needed per column
     int n_real_branches = 0;  // NN-1
+    int n_cherries = 0;       // pre-program children recomputed from their two leaves instead of re-read
     // level-ordered variant only: ops [levels[l], levels[l+1]) are mutually independent
     std::vector<int32_t> post_levels, pre_levels;
 };
@@ -85,7 +96,8 @@ struct Schedule {
 // parallel on different warps; every operand goes through a slot (no REG / KEEP), post result of
 // internal node i lives in post slot i, its pre vector in pre ("LIFO") slot i.
 inline std::string build_schedule(int NN, const int32_t* postorder_num, const int32_t* parent_num,
-                                  const int32_t* leaf_row, bool want_grad, Schedule& out, bool by_levels = false) {
+                                  const int32_t* leaf_row, bool want_grad, Schedule& out, bool by_levels = false,
+                                  bool allow_cherry = false) {
     if (NN < 2) return "tree must have at least two nodes";
     if (postorder_num[NN - 1] != NN) return "root must come last in post-order and carry num == NN";
     std::vector<int> pos(NN, -1);
@@ -222,6 +234,7 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
         return "";
     }
 
+    std::vector<char> post_reread(ND, 0);   // the post pass itself re-reads this node's stored result
     // ---- POST program: larger subtree first --------------------------------------------------
     {
         std::vector<std::pair<int, int>> st;
@@ -255,6 +268,7 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
                 if (is_leaf(c)) { src = dn[c].row; return OPK_LEAF; }
                 if (c == last_emitted) { src = 0; return OPK_REG; }
                 src = want_grad ? slot_of[c] : out.post[slot_of[c]].dst;
+                post_reread[c] = 1;
                 return OPK_MEM;
             };
             int ka = operand(l, op.a_src, op.a_br);
@@ -322,8 +336,19 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
                 std::swap(op.a_br, op.b_br);
                 std::swap(op.a_dst, op.b_dst);
             }
-            op.flags = (ai ? OPK_MEM : OPK_LEAF) | ((bi ? OPK_MEM : OPK_LEAF) << 2) | (cur_kind << 8) |
-                       (a_out << 10) | (b_out << 12);
+            int a_kind = ai ? OPK_MEM : OPK_LEAF;
+            if (allow_cherry && ai && a_out == OUT_KEEP && ND < 65536) {
+                const int c = op.a_br, x = dn[c].left, y = dn[c].right;
+                if (is_leaf(x) && is_leaf(y) && dn[x].row >= 0 && dn[y].row >= 0 && dn[x].row < 65536 && dn[y].row < 65536 &&
+                    !post_reread[c]) {
+                    a_kind = OPK_CHERRY;
+                    op.a_src = dn[x].row | (dn[y].row << 16);
+                    op.a_dst = x | (y << 16);
+                    out.post[slot_of[c]].flags &= ~POST_STORE;      // nobody reads the stored copy any more
+                    ++out.n_cherries;
+                }
+            }
+            op.flags = a_kind | ((bi ? OPK_MEM : OPK_LEAF) << 2) | (cur_kind << 8) | (a_out << 10) | (b_out << 12);
             out.pre.push_back(op);
             if (next >= 0) { cur = next; cur_kind = PREM_REG; cur_src = 0; }
             else if (!pending.empty()) {

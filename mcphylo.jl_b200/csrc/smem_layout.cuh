@@ -36,12 +36,14 @@ struct WalkSmem {
     }
     static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
     static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
-    static __host__ __device__ size_t code_bytes(int TW) { return (size_t)2 * CH * 2 * TW; }
+    // state codes of leaf children: [2 buffers][CH ops][2 children][rows][tile sites]; a child slot holds two
+    // rows (a cherry child of the gradient pass stages the rows of both leaves below it)
+    static __host__ __device__ size_t code_bytes(int TS, int rows) { return (size_t)2 * CH * 2 * rows * TS; }
     static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
     // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
     static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
-    static __host__ __device__ size_t total(int n_br, int shared_acc, int TW) {
-        return acc_bytes(n_br, shared_acc) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TW);
+    static __host__ __device__ size_t total(int n_br, int shared_acc, int TS) {
+        return acc_bytes(n_br, shared_acc) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TS, 2);
     }
 };
 

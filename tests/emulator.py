@@ -3,7 +3,7 @@ felsenstein_walk in csrc/kernel_walk.cuh) — lets the host scheduler be checked
 All columns are processed at once as arrays; `reg` plays the per-thread register `cur`."""
 import numpy as np
 
-OPK_LEAF, OPK_REG, OPK_MEM = 0, 1, 2
+OPK_LEAF, OPK_REG, OPK_MEM, OPK_CHERRY = 0, 1, 2, 3
 PREM_ROOT, PREM_REG, PREM_STACK = 0, 1, 2
 OUT_NONE, OUT_KEEP, OUT_PUSH = 0, 1, 2
 
@@ -82,21 +82,27 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
             mk = (flags >> 8) & 3
             pm = np.repeat(pi[:, None], S, axis=1) if mk == PREM_ROOT else (reg if mk == PREM_REG else stack[m_src])
 
-            def child(internal, src, br):
+            def child(kind, src, br, dst):
                 Pm, dPm = tables(br, r)
+                internal = kind != OPK_LEAF
                 if internal:
-                    L = slots[src]
+                    if kind == OPK_CHERRY:     # rebuilt from the two leaves below it, as the post pass built it
+                        Lx = leaf_down(tables(dst & 0xffff, r)[0], src & 0xffff)
+                        Ly = leaf_down(tables((dst >> 16) & 0xffff, r)[0], (src >> 16) & 0xffff)
+                        L, _ = _rescale(Lx * Ly)
+                    else:
+                        L = slots[src]
                     if eigen is not None:    # Y = eigen-coordinates of dP L
                         em1, de = eig_vecs(br, r)
                         w = Uie @ L
                         return L + Ue @ (em1[:, None] * w), de[:, None] * w, Pm
                     return Pm @ L, dPm @ L, Pm
                 return leaf_down(Pm, src), leaf_down(dPm, src), Pm
-            Da, Ya, Pa = child((flags & 3) == OPK_MEM, a_src, a_br)
-            Db, Yb, Pb = child(((flags >> 2) & 3) == OPK_MEM, b_src, b_br)
+            Da, Ya, Pa = child(flags & 3, a_src, a_br, a_dst)
+            Db, Yb, Pb = child((flags >> 2) & 3, b_src, b_br, b_dst)
             qa, qb = pm * Db, pm * Da
             den = (qa * Da).sum(axis=0)
-            for internal, br, q, Y in (((flags & 3) == OPK_MEM, a_br, qa, Ya), (((flags >> 2) & 3) == OPK_MEM, b_br, qb, Yb)):
+            for internal, br, q, Y in (((flags & 3) != OPK_LEAF, a_br, qa, Ya), (((flags >> 2) & 3) != OPK_LEAF, b_br, qb, Yb)):
                 num = ((Ue.T @ q) * Y).sum(axis=0) if (eigen is not None and internal) else (q * Y).sum(axis=0)
                 grad[br] += (num / den).sum()
             for out, dst, Pm, q, br in (((flags >> 10) & 3, a_dst, Pa, qa, a_br), ((flags >> 12) & 3, b_dst, Pb, qb, b_br)):

@@ -18,11 +18,11 @@ def _leaf_row(ft, leaf_nums):
     return lr
 
 
-def _emulate(oracle, tree, codes, leaf_nums, model_out, rates, pi, want_grad=True):
+def _emulate(oracle, tree, codes, leaf_nums, model_out, rates, pi, want_grad=True, cherries=False):
     ft = mcp.flatten(tree)
     U, D, Uinv, mu = model_out
     P, dP = oracle.transition(U, D, Uinv, mu, np.asarray(rates, float), ft.blv, want_dP=True)
-    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, _leaf_row(ft, leaf_nums), want_grad)
+    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, _leaf_row(ft, leaf_nums), want_grad, cherries=cherries)
     ll, g = run_program(prog, codes, len(D), P, dP, np.asarray(pi, float), ft.NN - 1)
     return ll, g[:ft.NN - 1], prog, ft
 
@@ -58,6 +58,14 @@ def test_random_trees_match_oracle(oracle, n_taxa, K, R, seed):
     ll, g, prog, _ = _emulate(oracle, tree, codes, leaf_nums, model, rates, pi)
     assert abs(ll - ll_o) <= 1e-11 * abs(ll_o)
     assert np.allclose(g, g_o, rtol=1e-9, atol=1e-9)
+    # cherries recomputed in the gradient pass instead of stored: same values, fewer stored partials
+    ll_c, g_c, prog_c, _ = _emulate(oracle, tree, codes, leaf_nums, model, rates, pi, cherries=True)
+    assert ll_c == ll and np.array_equal(g_c, g)
+    stored = lambda pr: int(np.sum((pr["post"][:, 5] & 16) != 0))
+    assert stored(prog_c) == stored(prog) - prog_c["n_cherries"]
+    assert prog_c["n_cherries"] == int(np.sum((prog_c["pre"][:, 5] & 3) == 3)) and prog["n_cherries"] == 0
+    if n_taxa >= 17:
+        assert prog_c["n_cherries"] >= 1
     # logL-only program (LIFO slots) gives the same value
     ll2, _, prog2, _ = _emulate(oracle, tree, codes, leaf_nums, model, rates, pi, want_grad=False)
     assert abs(ll2 - ll_o) <= 1e-11 * abs(ll_o)
