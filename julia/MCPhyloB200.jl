@@ -9,6 +9,8 @@
 # tested on the GPU (tests/test_gpu_parity.py), see INTEGRATION.md.
 #
 # Usage:  using MCPhylo; include("MCPhyloB200.jl"); MCPhyloB200.enable!("/path/to/libmcphylo_b200.so")
+#         ENV["MCPHYLO_B200_DEVICES"] = "0,1,2,3,4,5,6,7" before the first evaluation shards every alignment
+#         over the 8 GPUs of the box (one context, mcp_create_multi); nothing else changes.
 module MCPhyloB200
 
 using MCPhylo
@@ -19,32 +21,78 @@ const LIB = Ref{String}("libmcphylo_b200")
 # The handle is process-local and created lazily; it is never stored in a PhyloDist / Model, so
 # serialised chains (src/output/fileio.jl:15-35) stay loadable.
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
-# One resident device alignment per data array object (the observed node's value is the same
-# Array for the life of a chain, src/model/dependent.jl:344-358).
-const ALIGNMENTS = IdDict{Any,Ptr{Cvoid}}()
+# One resident device alignment per data array OBJECT (the observed node's value is the same Array for
+# the life of a chain, src/model/dependent.jl:344-358).  Keyed by objectid and NOT holding the array:
+# `mcmc` deep-copies the model -- and with it the data -- on every call (src/model/mcmc.jl:115), so a
+# table with strong references would pin one more host array and one more device alignment per run.
+# A finalizer on the array queues its device alignment for destruction; the queue is drained at the
+# start of the next evaluation (finalizers must not re-enter the library in the middle of a call).
+const ALIGNMENTS = Dict{UInt,Ptr{Cvoid}}()
+const SLABS = Dict{Tuple{UInt,Int},Array{Float64,3}}()      # MultiplePhyloDist: per-tree slabs of a 4-d array
+const RELEASED = Ptr{Cvoid}[]
+const RELEASED_LOCK = Threads.SpinLock()
 
 last_error(ctx) = unsafe_string(ccall((:mcp_last_error, LIB[]), Cstring, (Ptr{Cvoid},), ctx))
 check(rc::Cint, ctx = CTX[]) = rc == 0 ? nothing : error("libmcphylo_b200 ($rc): " * last_error(ctx))
 
-function context(device::Integer = parse(Int, get(ENV, "MCPHYLO_B200_DEVICE", "0")))
+"""
+    context()
+
+The process-wide library context, created on first use.  One GPU: `MCPHYLO_B200_DEVICE=3` (default 0).
+Several GPUs of the box behind the SAME calls: `MCPHYLO_B200_DEVICES=0,1,2,3,4,5,6,7` -- the alignment's
+site axis is split across them and every `logpdf` / `gradlogpdf` ends in one all-reduce of
+`[logL, gradient]` (`mcp_create_multi`; `MCPHYLO_B200_REDUCE` = auto | nccl | peer | host).
+"""
+function context()
     if CTX[] == C_NULL
         out = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:mcp_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Cint), out, device)
+        if haskey(ENV, "MCPHYLO_B200_DEVICES")
+            ids = Cint[parse(Cint, strip(t)) for t in split(ENV["MCPHYLO_B200_DEVICES"], ",")]
+            mode = Cint(findfirst(==(lowercase(get(ENV, "MCPHYLO_B200_REDUCE", "auto"))), ["auto", "nccl", "peer", "host"]) - 1)
+            rc = ccall((:mcp_create_multi, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}, Cint), out, length(ids), ids, mode)
+        else
+            rc = ccall((:mcp_create, LIB[]), Cint, (Ref{Ptr{Cvoid}}, Cint), out, parse(Cint, get(ENV, "MCPHYLO_B200_DEVICE", "0")))
+        end
         rc == 0 || error("libmcphylo_b200 ($rc): " * last_error(C_NULL))   # no CPU fallback
         CTX[] = out[]
     end
     CTX[]
 end
 
-function alignment(x::Array{Float64,3}, leaf_nums::Vector{Int32})
-    get!(ALIGNMENTS, x) do
-        K, S, NN = size(x)
-        out = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ccall((:mcp_alignment_from_dense, LIB[]), Cint,
-                    (Ptr{Cvoid}, Ptr{Float64}, Cint, Int64, Cint, Ptr{Int32}, Cint, Ref{Ptr{Cvoid}}),
-                    context(), x, K, S, NN, leaf_nums, length(leaf_nums), out))
-        out[]
+# device alignments whose host arrays have been collected
+function drain_released()
+    isempty(RELEASED) && return
+    lock(RELEASED_LOCK)
+    handles = copy(RELEASED); empty!(RELEASED)
+    unlock(RELEASED_LOCK)
+    CTX[] == C_NULL && return
+    for h in handles
+        ccall((:mcp_alignment_destroy, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], h)
     end
+end
+
+function release_later(x)
+    key = objectid(x)
+    h = pop!(ALIGNMENTS, key, C_NULL)
+    for k in [k for k in keys(SLABS) if k[1] == key]       # slabs cut from a 4-d array die with it
+        release_later(pop!(SLABS, k))
+    end
+    h == C_NULL && return
+    lock(RELEASED_LOCK); push!(RELEASED, h); unlock(RELEASED_LOCK)
+end
+
+function alignment(x::Array{Float64,3}, leaf_nums::Vector{Int32})
+    drain_released()
+    h = get(ALIGNMENTS, objectid(x), C_NULL)
+    h != C_NULL && return h
+    K, S, NN = size(x)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mcp_alignment_from_dense, LIB[]), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Cint, Int64, Cint, Ptr{Int32}, Cint, Ref{Ptr{Cvoid}}),
+                context(), x, K, S, NN, leaf_nums, length(leaf_nums), out))
+    ALIGNMENTS[objectid(x)] = out[]
+    finalizer(release_later, x)
+    out[]
 end
 
 # Tree -> flat arrays, using MCPhyloTree's own accessors so the numbering rule is never re-derived.
@@ -103,7 +151,8 @@ function evaluate(d::MultiplePhyloDist, x::Array{Float64,4}, want_grad::Bool)
     T = length(d.DistCollector)
     flat = [flatten(pd.tree) for pd in d.DistCollector]
     models = [pd.substitution_model(pd.base_freq, pd.substitution_rates) for pd in d.DistCollector]
-    slabs = [get!(() -> x[:, :, 1:d.size_array[t], t], SLABS, (x, t)) for t in 1:T]
+    slabs = [get!(() -> x[:, :, 1:d.size_array[t], t], SLABS, (objectid(x), t)) for t in 1:T]
+    isempty(SLABS) || haskey(ALIGNMENTS, objectid(x)) || (ALIGNMENTS[objectid(x)] = C_NULL; finalizer(release_later, x))
     alns = Ptr{Cvoid}[alignment(slabs[t], flat[t][5]) for t in 1:T]
     NN = Int32[f[1] for f in flat]
     blv = [Vector{Float64}(f[4]) for f in flat]
@@ -124,7 +173,6 @@ function evaluate(d::MultiplePhyloDist, x::Array{Float64,4}, want_grad::Bool)
     end
     ll, grads
 end
-const SLABS = IdDict{Any,Any}()
 
 """Route the four PhyloDist methods through the GPU library (method redefinition)."""
 function enable!(libpath::AbstractString = LIB[])
@@ -158,9 +206,12 @@ function enable!(libpath::AbstractString = LIB[])
     nothing
 end
 
+"""Frees every device alignment and the context (also safe to call between `mcmc` runs: everything is
+re-created on demand)."""
 function shutdown!()
+    drain_released()
     for (_, a) in ALIGNMENTS
-        ccall((:mcp_alignment_destroy, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], a)
+        a == C_NULL || ccall((:mcp_alignment_destroy, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), CTX[], a)
     end
     empty!(ALIGNMENTS); empty!(SLABS)
     CTX[] == C_NULL || ccall((:mcp_destroy, LIB[]), Cint, (Ptr{Cvoid},), CTX[])

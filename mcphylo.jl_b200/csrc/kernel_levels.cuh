@@ -17,7 +17,6 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
-    __shared__ double s_prior[2 * 256];   // block reduction of the branch-length prior (final reduction only)
 
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, W = NT >> 5;
     const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
@@ -31,6 +30,11 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     double* const s_tab = reinterpret_cast<double*>(s_code + LevelSmem::code_bytes(p.max_rows));
     double* const s_post = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K)) + lane * K;
     double* const s_pre = s_post + (size_t)p.n_slots * 32 * K;
+    // the tree's op program and level offsets, copied once per (CTA, tree): read from global memory they put
+    // two dependent L2 round trips (level bounds, then the descriptors) on the critical path of EVERY level
+    int4* const s_ops = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K) +
+                                                LevelSmem::slots_bytes(p.n_slots, p.n_stack, K));
+    int* const s_lvl = reinterpret_cast<int*>(s_ops + 4 * (size_t)p.max_br);
     constexpr int SLOT = 32 * K;                  // doubles per slot
     constexpr int BT = 2 * K + 2 * K * (K + 1), KK1 = K * (K + 1);
     int row = p.cta_row_base[blockIdx.x];
@@ -48,9 +52,13 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
         long long e_total = 0;
         double logsum = 0.0;
         const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
-        const int4* const post_ops = p.ops + 2 * tr.post_off;
-        const int4* const pre_ops = p.ops + 2 * tr.pre_off;
-        const int* const post_lvl = p.levels + tr.lvl_off;
+        // post program, then pre program (contiguous in the topology block); likewise the level offsets
+        __syncthreads();                                       // the previous tree's program is no longer in use
+        for (int i = tid; i < 2 * (tr.n_post + tr.n_pre); i += NT) s_ops[i] = __ldg(p.ops + 2 * tr.post_off + i);
+        for (int i = tid; i < tr.n_post_lvl + tr.n_pre_lvl + 2; i += NT) s_lvl[i] = __ldg(p.levels + tr.lvl_off + i);
+        const int4* const post_ops = s_ops;
+        const int4* const pre_ops = s_ops + 2 * tr.n_post;
+        const int* const post_lvl = s_lvl;
         const int* const pre_lvl = post_lvl + tr.n_post_lvl + 1;
         int built_rate = -1;
 
@@ -136,9 +144,9 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
 
             // ------------------------------ post pass ------------------------------
             for (int lv = 0; lv < tr.n_post_lvl; ++lv) {
-                const int lo = __ldg(post_lvl + lv), hi = __ldg(post_lvl + lv + 1);
+                const int lo = post_lvl[lv], hi = post_lvl[lv + 1];
                 for (int i = lo + warp; i < hi; i += W) {
-                    const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
+                    const int4 o0 = post_ops[2 * i], o1 = post_ops[2 * i + 1];
                     const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
                     double Da[1][K], Db[1][K];
                     if (ka == mcp::OPK_LEAF) {
@@ -179,9 +187,9 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
             // ------------------------------ gradient pass ------------------------------
             if (p.want_grad) {
                 for (int lv = 0; lv < tr.n_pre_lvl; ++lv) {
-                    const int lo = __ldg(pre_lvl + lv), hi = __ldg(pre_lvl + lv + 1);
+                    const int lo = pre_lvl[lv], hi = pre_lvl[lv + 1];
                     for (int i = lo + warp; i < hi; i += W) {
-                        const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
+                        const int4 o0 = pre_ops[2 * i], o1 = pre_ops[2 * i + 1];
                         const int flags = o1.y;
                         const int a_br = o0.y, b_br = o0.w;
                         const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
@@ -286,6 +294,8 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
         // shared memory and are added in warp order.  Fixed order, hence reproducible; ~10x less
         // latency than one thread per output walking all rows (rows = CTAs of the launch).
         double* const s_fin = s_tab;               // W x NN doubles; the tile buffers are free now
+        // block reduction of the branch-length prior: 2 x 256 doubles in the (idle) slot region
+        double* const s_prior = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K));
         for (int t = 0; t < p.T; ++t) {
             const TreeDev tr = p.trees[t];
             double* o = p.out + tr.out_off;
@@ -311,11 +321,23 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                 const int nb = tr.NN - 1;
                 for (int j0 = lane; j0 < nb; j0 += 128) {
                     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                    for (int rw = tr.row_lo + warp; rw < tr.row_hi; rw += W) {
-                        const double* rp = p.rows + (long long)rw * p.row_stride + j0;
+                    // 8 rows are requested before the first is added (same order of additions): one L2 round
+                    // trip per 8 rows instead of one per row -- the walk of the row list used to be 40 % of a
+                    // cfg2 evaluation
+                    for (int rw0 = tr.row_lo + warp; rw0 < tr.row_hi; rw0 += 8 * W) {
+                        double v[8][4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (j0 + 32 * u < nb) acc[u] += __ldcg(rp + 32 * u);
+                        for (int b = 0; b < 8; ++b) {
+                            const int rw = rw0 + b * W;
+                            const double* rp = p.rows + (long long)rw * p.row_stride + j0;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) v[b][u] = (rw < tr.row_hi && j0 + 32 * u < nb) ? __ldcg(rp + 32 * u) : 0.0;
+                        }
+#pragma unroll
+                        for (int b = 0; b < 8; ++b)
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (rw0 + b * W < tr.row_hi) acc[u] += v[b][u];
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
                     if (seen == p.ready_epoch) break;
                     __nanosleep(200);
-                    if (++spins > (1u << 24)) { atomicExch(p.error_flag, 1u); break; }   // ~4 s: give up, the host reports it
+                    if (++spins > (1u << 22)) { atomicExch(p.error_flag, 1u); break; }   // seconds: give up, the host reports it
                 }
             }
             bool valid[CPT];

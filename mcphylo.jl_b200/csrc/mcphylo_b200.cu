@@ -849,9 +849,11 @@ int eval_streamed(mcp_ctx* ctx, const unsigned char* codes, int K, long long S, 
                     return fail(m, MCP_ERR_CUDA, "ready-flag transfer failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return 0;
             };
-            // the first few units go out before the kernels are enqueued, the rest right after: the walk must
-            // not sit behind a long run of host-side enqueue calls, nor the transfers behind the launch
-            const size_t n_first = std::min<size_t>(3, ss.chunks.size());
+            // Every unit is enqueued BEFORE the walk is launched (a few microseconds of host time per unit, during
+            // which the first units are already crossing PCIe): a launch that blocks the host until the kernel
+            // has finished -- profilers, compute-sanitizer, CUDA_LAUNCH_BLOCKING -- then still finds its data
+            // on the way instead of spinning until the time-out.
+            const size_t n_first = ss.chunks.size();
             for (size_t c = 0; c < n_first; ++c)
                 if ((er = send(c))) return er;
             StreamFlags sf{ctl + STREAM_CTL_WORDS, ctl, ctl + 1, ss.epoch, STREAM_GROUP_SHIFT};

@@ -54,9 +54,16 @@ struct LevelSmem {
     static __host__ __device__ size_t code_bytes(int n_rows) { return (((size_t)n_rows * 32) + 127) & ~(size_t)127; }
     static __host__ __device__ size_t slot_bytes(int K) { return (size_t)32 * K * 8; }
     static __host__ __device__ size_t tab_bytes(int n_br, int K) { return (((size_t)n_br * bt_size(K) * 8) + 127) & ~(size_t)127; }
+    // post + pre slots; the region doubles as the 4 KB scratch of the prior's block reduction at the very end
+    static __host__ __device__ size_t slots_bytes(int n_slots, int n_stack, int K) {
+        const size_t b = (size_t)(n_slots + n_stack) * slot_bytes(K);
+        return b < 4096 ? 4096 : b;
+    }
+    // op program (post + pre: at most 2 ops of 32 bytes per device node) and level offsets of the tree
+    static __host__ __device__ size_t prog_bytes(int n_br) { return (size_t)n_br * 64 + (((size_t)(2 * n_br + 4) * 4 + 15) & ~(size_t)15); }
     static __host__ __device__ size_t total(int n_br, int want_grad, int n_rows, int n_slots, int n_stack, int K) {
         return acc_bytes(n_br, want_grad) + exp_bytes() + code_bytes(n_rows) + tab_bytes(n_br, K) +
-               (size_t)(n_slots + n_stack) * slot_bytes(K);
+               slots_bytes(n_slots, n_stack, K) + prog_bytes(n_br);
     }
 };
 

@@ -316,9 +316,122 @@ def test_finite_differences_on_device():
         assert abs((vals[0] - vals[1]) / 2e-6 - g[b]) <= 2e-6 * max(1.0, abs(g[b]))
 
 
+@pytest.mark.parametrize("block,cpt,ctas", [(256, 2, 0), (256, 1, 3), (128, 2, 0)])
+def test_cfg4_tree_oracle_window_at_bench_launch_shapes(oracle, block, cpt, ctas):
+    """BASELINE config 4's own tree (1000 taxa, bench.py seeds, GTR + Gamma-4) on a 512-site window of its
+    alignment, against the oracle, with the launch shapes the timed runs use forced: two columns per thread
+    on 256-thread CTAs (every GPU count since round 2), round 1's 8-GPU shape (one column per thread, 3 CTAs
+    per SM, grid 444), and a narrower tile.  The dense oracle needs 3 x 130 MB for this."""
+    import bench
+    w = bench.make_workload("cfg4", 512)
+    codes, leaf_nums = bench.make_codes(w, 0, 512)
+    assert codes.shape == (1000, 512)
+    ctx = mcp.get_context()
+    ctx.set_launch(block, ctas)
+    ctx.set_columns_per_thread(cpt)
+    ctx.set_level_mode(0)
+    ctx.set_scratch_mode(0)
+    try:
+        pd = mcp.PhyloDist(w["tree"], w["pi"], w["srates"], w["rates"], w["model"])
+        aln = mcp.DeviceAlignment(codes, leaf_nums, 4)
+        ll, g = mcp.gradlogpdf(pd, aln)
+        st = ctx.stats()
+        assert st["block"] == block and st["columns_per_thread"] == cpt
+        ll_only = mcp.logpdf(pd, aln)
+    finally:
+        ctx.set_launch(0, 0)
+        ctx.set_columns_per_thread(0)
+        ctx.set_level_mode(-1)
+        ctx.set_scratch_mode(-1)
+    ll_o, g_o = _oracle_eval(oracle, w["tree"], codes, leaf_nums, 4, w["model"], w["pi"], w["srates"], w["rates"])
+    assert g.shape == (1998,)
+    _check(ll, g, ll_o, g_o)
+    _check(ll_only, None, ll_o, None)
+
+
+def test_cfg5_shape_batch_oracle_window(oracle):
+    """BASELINE config 5's shape -- 256 independent 100-taxon trees (bench.py seeds 5000 + i), binary sites,
+    ONE mcp_eval_batch launch -- on a 256-site window per tree, every tree against the oracle
+    (the MultiplePhyloDist path, /root/reference/src/distributions/Phylodist.jl:281-297)."""
+    from mcphylo_jl_b200 import capi
+    from mcphylo_jl_b200.phylodist import _tree_args
+    import bench
+    T, n_taxa, S = 256, 100, 256
+    pi = bench.RESTRICTION_PI
+    model_out = mcp.Restriction(pi, [])
+    ctx = capi.Context(0)
+    try:
+        alns, targs, cases = [], [], []
+        for i in range(T):
+            tree = mcp.random_tree(n_taxa, np.random.default_rng(5000 + i))
+            rng = np.random.default_rng(1005 * 1000 + i)
+            codes, leaf_nums = mcp.simulate_codes(tree, model_out, pi, np.ones(1), S, rng, gap_frac=0.01)
+            alns.append(ctx.alignment_from_codes(codes, 2, leaf_nums))
+            targs.append(_tree_args(mcp.PhyloDist(tree, pi, [0.0], [1.0], mcp.Restriction))[1])
+            cases.append((tree, codes, leaf_nums))
+        prep = capi.PreparedBatch(ctx, alns, targs, want_grad=True)
+        ll, grads = prep.eval()
+        ll, grads = ll.copy(), [g.copy() for g in grads]                   # eval() returns views of reused buffers
+        st = ctx.stats()
+        assert st["kernel_launches"] == 3 + 1 + st["schedule_rebuilt"]      # all 256 trees in one walk launch
+        for i, (tree, codes, leaf_nums) in enumerate(cases):
+            ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0])
+            _check(ll[i], grads[i], ll_o, g_o)
+        # logL only, and a second call with new branch lengths on the cached plan
+        for t, (tree, _, _) in enumerate(cases):
+            prep.set_blv(t, mcp.get_branchlength_vector(tree) * 1.1)
+        ll2, _ = prep.eval()
+        assert ctx.stats()["schedule_rebuilt"] == 0 and np.all(ll2 != ll)
+        tree, codes, leaf_nums = cases[17]
+        mcp.set_branchlength_vector(tree, mcp.get_branchlength_vector(tree) * 1.1)
+        ll_o, _ = _oracle_eval(oracle, tree, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0])
+        _check(ll2[17], None, ll_o, None)
+        for a in alns:
+            a.close()
+    finally:
+        ctx.close()
+
+
+def test_nni_pair_in_one_batched_launch(oracle):
+    """The PNUTS caller pattern (/root/reference/src/samplers/tree_hamiltonian/refraction.jl:2-31,62-69):
+    a gradient on the current tree, then the log-likelihoods of the tree before and after an NNI.  The two
+    logpdf calls of an NNI attempt go out as ONE mcp_eval_batch launch (T = 2, same alignment), and the
+    sequence gradient / pair / gradient on the accepted tree matches the oracle at cfg2 shape."""
+    import copy
+    from mcphylo_jl_b200 import capi
+    from mcphylo_jl_b200.phylodist import _tree_args
+    rng = np.random.default_rng(20242)
+    tree = random_tree(50, rng)
+    pi = np.array([0.3, 0.7])
+    codes, leaf_nums = simulate_codes(tree, mcp.Restriction(pi, []), pi, np.ones(1), 10000, rng, gap_frac=0.01)
+    ctx = capi.Context(0)
+    try:
+        aln = ctx.alignment_from_codes(codes, 2, leaf_nums)
+        inner = [n for n in mcp.post_order(tree) if n.nchild == 2 and not n.root]
+        for attempt in range(3):
+            ta = _tree_args(mcp.PhyloDist(tree, pi, [0.0], [1.0], mcp.Restriction))[1]
+            ll, g = ctx.eval(aln, *ta, want_grad=True)
+            _check(ll, g, *_oracle_eval(oracle, tree, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0]))
+            proposal = copy.deepcopy(tree)
+            target = [n for n in mcp.post_order(proposal) if n.num == inner[(7 * attempt + 3) % len(inner)].num][0]
+            assert mcp.NNI(proposal, target, lor=bool(attempt % 2)) == 1
+            tb = _tree_args(mcp.PhyloDist(proposal, pi, [0.0], [1.0], mcp.Restriction))[1]
+            pair, none = ctx.eval_batch([aln, aln], [ta, tb], want_grad=False)
+            assert none is None and ctx.stats()["kernel_launches"] <= 4 + ctx.stats()["schedule_rebuilt"]   # one call, one walk
+            assert pair[0] == ll or abs(pair[0] - ll) <= 1e-12 * abs(ll)
+            ll_b, _ = _oracle_eval(oracle, proposal, codes, leaf_nums, 2, mcp.Restriction, pi, [0.0], [1.0], want_grad=False)
+            _check(pair[1], None, ll_b, None)
+            tree = proposal                                   # "accept": the next gradient runs on the new topology
+            inner = [n for n in mcp.post_order(tree) if n.nchild == 2 and not n.root]
+        aln.close()
+    finally:
+        ctx.close()
+
+
 def test_large_properties_without_oracle():
-    """Sizes the dense oracle cannot hold: additivity over site blocks (the multi-GPU sharding
-    identity), invariance to the launch shape, and rate-category additivity."""
+    """1000 taxa x 20 000 sites (more than the dense oracle is asked to hold in a test; the oracle-window
+    tests above cover this tree size): additivity over site blocks (the multi-GPU sharding identity),
+    rate-category additivity, and the logL-only path."""
     rng = np.random.default_rng(20244)
     n_taxa, S = 1000, 20000
     tree = random_tree(n_taxa, rng)
