@@ -13,7 +13,8 @@ namespace {
 // a few tiles per SM (MCMC-sized problems), where the depth-first walk runs at single-warp latency.
 // --------------------------------------------------------------------------------------------
 template <int K, bool DYN_MODEL>
-__global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_constant__ WalkParams p) {
+// 3 CTAs per SM (<= 85 registers): an MCMC-sized input is one tile per CTA, and all of them should be resident at once
+__global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
@@ -29,7 +30,9 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
     unsigned char* const s_code = reinterpret_cast<unsigned char*>(s_exp) + LevelSmem::exp_bytes();
     double* const s_tab = reinterpret_cast<double*>(s_code + LevelSmem::code_bytes(p.max_rows));
     double* const s_post = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K)) + lane * K;
-    double* const s_pre = s_post + (size_t)p.n_slots * 32 * K;
+    // pre[i] takes over the slot of post[i]: a family's op reads the children's post partials into registers
+    // before it writes their pre vectors, and nothing reads post[i] after its mother's op -- half the slots
+    double* const s_pre = s_post;
     // the tree's op program and level offsets, copied once per (CTA, tree): read from global memory they put
     // two dependent L2 round trips (level bounds, then the descriptors) on the critical path of EVERY level
     int4* const s_ops = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K) +
@@ -321,20 +324,20 @@ __global__ void __launch_bounds__(256) felsenstein_walk_levels(const __grid_cons
                 const int nb = tr.NN - 1;
                 for (int j0 = lane; j0 < nb; j0 += 128) {
                     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                    // 8 rows are requested before the first is added (same order of additions): one L2 round
-                    // trip per 8 rows instead of one per row -- the walk of the row list used to be 40 % of a
+                    // 4 rows are requested before the first is added (same order of additions): one L2 round
+                    // trip per 4 rows instead of one per row -- the walk of the row list used to be 40 % of a
                     // cfg2 evaluation
-                    for (int rw0 = tr.row_lo + warp; rw0 < tr.row_hi; rw0 += 8 * W) {
-                        double v[8][4];
+                    for (int rw0 = tr.row_lo + warp; rw0 < tr.row_hi; rw0 += 4 * W) {
+                        double v[4][4];
 #pragma unroll
-                        for (int b = 0; b < 8; ++b) {
+                        for (int b = 0; b < 4; ++b) {
                             const int rw = rw0 + b * W;
                             const double* rp = p.rows + (long long)rw * p.row_stride + j0;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) v[b][u] = (rw < tr.row_hi && j0 + 32 * u < nb) ? __ldcg(rp + 32 * u) : 0.0;
                         }
 #pragma unroll
-                        for (int b = 0; b < 8; ++b)
+                        for (int b = 0; b < 4; ++b)
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
                                 if (rw0 + b * W < tr.row_hi) acc[u] += v[b][u];

@@ -113,9 +113,12 @@ long long tiles_for(const BatchArgs& a, int tile_w) {
 //   - a partly filled last round of tiles costs nothing measurable (3.3 rounds run at the per-site cost of
 //     26 rounds: CTAs drift apart and the stragglers speed up as the SMs empty), so no width is ever chosen
 //     to "fill the last round";
-//   - two columns per thread win as soon as one column per thread would need more than two CTAs per SM.
-// Hence: 256 threads, narrowed only for inputs of fewer than 256 columns; two columns per thread (K <= 4)
-// when the input has more than 2 x SMs tiles of 256 columns.
+//   - two columns per thread win as soon as one column per thread would need more than two CTAs per SM --
+//     for K = 2 always (1.28x, round 1), for K = 3, 4 only on large trees: cfg4's 1999-node tree gains 2-6 %,
+//     cfg3's 399-node tree LOSES 5 % (1.52 vs 1.60 ms, profiles/r2_shape_sweep_cfg3.json; its smaller
+//     accumulator leaves room for 24 resident warps at one column per thread).
+// Hence: 256 threads, narrowed only for inputs of fewer than 256 columns; two columns per thread when the input
+// has more than 2 x SMs tiles of 256 columns and (K = 2, or K <= 4 and a tree of at least 1000 nodes).
 int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, int K, int max_br, bool acc_global,
                       WalkShape* out) {
     const int R = a.R;
@@ -134,7 +137,9 @@ int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, i
     if (!templated && block > 128) block = 128;
     int cpt = ctx->opt_cpt;
     const bool cpt2_ok = templated && K <= 4 && !acc_global;
-    if (cpt <= 0) cpt = cpt2_ok && tiles_for(a, block) > 2LL * ctx->sm_count ? 2 : 1;
+    int max_nn = 0;
+    for (int t = 0; t < a.T; ++t) max_nn = std::max(max_nn, (int)a.NN[t]);
+    if (cpt <= 0) cpt = cpt2_ok && tiles_for(a, block) > 2LL * ctx->sm_count && (K == 2 || max_nn >= 1000) ? 2 : 1;
     if (!cpt2_ok) cpt = 1;
     const size_t smem = templated ? walk_smem_bytes(K, max_br, shared_acc, block, cpt) : generic_smem_bytes(max_br, a.want_grad);
     int e, occ = 0;
@@ -244,7 +249,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     int e;
     if (level_mode) {
         if ((e = build_all(true))) return e;
-        const size_t need = LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K);
+        const size_t need = LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, 0, K);
         if (need > 160 * 1024) level_mode = false;     // tree too large for the shared-memory path
     }
     if (!level_mode && (e = build_all(false))) return e;
@@ -255,7 +260,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     if (level_mode) {
         block = 256;
         cpt = 1;
-        smem = LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, a.want_grad ? n_stack : 0, K);
+        smem = LevelSmem::total(max_br, a.want_grad ? 1 : 0, max_rows, n_slots, 0, K);   // pre vectors reuse the post slots
         if ((e = walk_occupancy(ctx, kt, K, block, cpt, smem, false, false, true, &occ))) return e;
     } else {
         WalkShape ws;
@@ -285,7 +290,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     pl.n_tiles = tile_cursor;
     pl.block = block;
     pl.n_slots = n_slots;
-    pl.n_stack = a.want_grad ? n_stack : 0;
+    pl.n_stack = a.want_grad && !level_mode ? n_stack : 0;
     pl.max_br = max_br;
     pl.total_out = out_off;
     pl.total_dyn = dyn_off;
