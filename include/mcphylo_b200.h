@@ -285,6 +285,10 @@ int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
  * row in global memory with RED.ADD.F64 beyond that), 0 always shared memory (fails if the tree does
  * not fit), 1 always global memory. */
 int mcp_set_accumulator_mode(mcp_ctx *ctx, int mode);
+/* State counts 6 < K <= 32 (e.g. 20-state protein alphabets): -1 / 1 the tile-cooperative kernel that runs the
+ * K x K by K x columns products of every node on the FP64 tensor path (mma.sync.m8n8k4.f64; 8 warps x 16 columns
+ * per CTA, bit-reproducible gradient), 0 the runtime-K fallback kernel (one thread per column, CUDA cores). */
+int mcp_set_large_alphabet_mode(mcp_ctx *ctx, int mode);
 /* Gradient pass, K <= 6: an internal node whose two children are leaves (a "cherry") is recomputed from the
  * two leaf codes instead of being stored by the post pass and re-read (bit-identical; a third of the stored
  * partials of a random binary tree).  -1 automatic (on), 0 off (every partial stored), 1 on. */

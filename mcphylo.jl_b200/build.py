@@ -26,7 +26,7 @@ UNITS = {
     "mcphylo_b200.cu": _COMMON + ["host_state.hpp", "planner.hpp", "nccl_dyn.hpp", "kernel_tables.cuh",
                                   "epilogue_prior.cuh", "kernel_finalize.cuh", HEADER],
     "walk_k2.cu": _KERNEL, "walk_k3.cu": _KERNEL, "walk_k4.cu": _KERNEL, "walk_k5.cu": _KERNEL, "walk_k6.cu": _KERNEL,
-    "walk_generic.cu": _COMMON + ["model_const.cuh", "device_math.cuh", "kernel_generic.cuh"],
+    "walk_generic.cu": _COMMON + ["model_const.cuh", "device_math.cuh", "kernel_generic.cuh", "kernel_mma.cuh"],
 }
 SOURCES = list(UNITS)
 

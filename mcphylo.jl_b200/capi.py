@@ -25,7 +25,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
-    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode",
+    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode",
     "mcp_schedule_dump", "mcp_model_reorder",
 ]
 
@@ -77,6 +77,7 @@ def load():
     lib.mcp_set_level_mode.argtypes = [_vp, C.c_int]
     lib.mcp_set_tile_order.argtypes = [_vp, C.c_int]
     lib.mcp_set_cherry_mode.argtypes = [_vp, C.c_int]
+    lib.mcp_set_large_alphabet_mode.argtypes = [_vp, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
@@ -238,6 +239,9 @@ class Context:
 
     def set_level_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_level_mode(self.handle, int(mode)))
+
+    def set_large_alphabet_mode(self, mode: int = -1):
+        self._check(self.lib.mcp_set_large_alphabet_mode(self.handle, int(mode)))
 
     def set_cherry_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_cherry_mode(self.handle, int(mode)))

@@ -325,6 +325,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     lc.stream = st;
     lc.smem_scratch = pl.smem_scratch;
     lc.acc_global = pl.acc_global;
+    lc.mma = pl.mma;
     {
         cudaError_t ce = pl.level_mode ? kt->launch_levels(lc, wp, dyn_model) : kt->launch_walk(lc, wp, dyn_model, all_null_last);
         if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(ce));
@@ -693,6 +694,12 @@ int wave_columns_impl(mcp_ctx* ctx, int K, int n_nodes, int want_grad, int64_t* 
         if (acc_global) cpt = 1;
         const size_t smem = walk_smem_bytes(K, std::max(n_nodes, 1), want_grad && !acc_global ? 1 : 0, block, cpt);
         if ((e = walk_occupancy(ctx, kt, K, block, cpt, smem, false, acc_global, false, &occ))) return e;
+    } else if (ctx->opt_mma != 0) {
+        if ((e = walk_occupancy(ctx, kt, K, MMA_WARPS * 32, 1, mma_smem_bytes(K, std::max(n_nodes, 1), want_grad), false, false, false, &occ, true))) return e;
+        if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM");
+        if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
+        *columns = (int64_t)occ * ctx->sm_count * MMA_TILE;
+        return 0;
     } else {
         cpt = 1;
         block = std::min(block, 128);
@@ -1250,6 +1257,16 @@ int mcp_set_accumulator_mode(mcp_ctx* ctx, int mode) {
     if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "accumulator mode must be -1 (automatic), 0 (shared memory) or 1 (global memory)");
     return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
         m->opt_acc_mode = mode;
+        invalidate_plans(m);
+        return 0;
+    });
+}
+
+int mcp_set_large_alphabet_mode(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "large-alphabet mode must be -1 (automatic), 0 (runtime-K kernel) or 1 (tensor-core kernel)");
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        m->opt_mma = mode;
         invalidate_plans(m);
         return 0;
     });

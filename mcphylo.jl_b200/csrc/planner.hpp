@@ -35,6 +35,15 @@ size_t walk_smem_bytes(int K, int max_br, int shared_acc, int block, int cpt) {
            (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * 2 * block * cpt;   // = WalkSmem<K>::total
 }
 size_t generic_smem_bytes(int max_br, int want_grad) { return want_grad ? (size_t)max_br * sizeof(double) : 0; }
+int mma_kp(int K) { return (K + 7) & ~7; }   // state count padded to the 8-wide MMA blocks
+size_t mma_smem_bytes(int K, int max_br, int want_grad) {
+    switch (mma_kp(K)) {
+        case 8: return MmaSmem<8>::total(max_br, want_grad);
+        case 16: return MmaSmem<16>::total(max_br, want_grad);
+        case 24: return MmaSmem<24>::total(max_br, want_grad);
+        default: return MmaSmem<32>::total(max_br, want_grad);
+    }
+}
 
 struct BatchArgs {
     int T;
@@ -59,15 +68,15 @@ struct BatchArgs {
 // Resident CTAs per SM of the walk kernel for a launch shape.  The occupancy calculator costs a few
 // microseconds per query and the planner asks for several shapes, so answers are remembered per process.
 int walk_occupancy(mcp_ctx* ctx, const KernelTable* kt, int K, int block, int cpt, size_t smem, bool sscr, bool accg,
-                   bool levels, int* out) {
-    struct Key { int device, K, block, cpt; size_t smem; bool sscr, accg, levels; int occ; };
+                   bool levels, int* out, bool mma = false) {
+    struct Key { int device, K, block, cpt; size_t smem; bool sscr, accg, levels, mma; int occ; };
     static std::mutex mu;
     static std::vector<Key> memo;
     {
         std::lock_guard<std::mutex> lock(mu);
         for (const Key& k : memo)
             if (k.device == ctx->device && k.K == K && k.block == block && k.cpt == cpt && k.smem == smem && k.sscr == sscr &&
-                k.accg == accg && k.levels == levels) {
+                k.accg == accg && k.levels == levels && k.mma == mma) {
                 *out = k.occ;
                 return 0;
             }
@@ -80,6 +89,7 @@ int walk_occupancy(mcp_ctx* ctx, const KernelTable* kt, int K, int block, int cp
     c.smem = smem;
     c.smem_scratch = sscr;
     c.acc_global = accg;
+    c.mma = mma;
     int occ = 0;
     cudaError_t e = levels ? kt->occupancy_levels(c, &occ) : kt->occupancy_walk(c, &occ);
     if (e != cudaSuccess) {
@@ -89,7 +99,7 @@ int walk_occupancy(mcp_ctx* ctx, const KernelTable* kt, int K, int block, int cp
         else return fail(ctx, MCP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
     }
     std::lock_guard<std::mutex> lock(mu);
-    memo.push_back({ctx->device, K, block, cpt, smem, sscr, accg, levels, occ});
+    memo.push_back({ctx->device, K, block, cpt, smem, sscr, accg, levels, mma, occ});
     *out = occ;
     return 0;
 }
@@ -129,6 +139,12 @@ int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, i
     }
     const bool templated = k_templated(K);
     const int shared_acc = a.want_grad && !acc_global ? 1 : 0;
+    if (!templated && ctx->opt_mma != 0) {   // large alphabets: fixed shape, 8 warps x 16 columns (kernel_mma.cuh)
+        int e0, o = 0;
+        if ((e0 = walk_occupancy(ctx, kt, K, MMA_WARPS * 32, 1, mma_smem_bytes(K, max_br, a.want_grad), false, false, false, &o, true))) return e0;
+        *out = {MMA_WARPS * 32, 1, o};
+        return 0;
+    }
     int block = ctx->opt_block;
     if (block <= 0) {
         block = templated ? 256 : 128;      // runtime-K kernel: at most 128 threads per CTA
@@ -255,6 +271,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     if (!level_mode && (e = build_all(false))) return e;
 
     // launch shape
+    const bool mma = !level_mode && !k_templated(K) && ctx->opt_mma != 0;
     int block, cpt, occ = 0;
     size_t smem;
     if (level_mode) {
@@ -269,9 +286,11 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
         cpt = ws.cpt;
         occ = ws.occ;
         smem = k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad && !acc_global ? 1 : 0, block, cpt)
-                              : generic_smem_bytes(max_br, a.want_grad);
+               : mma        ? mma_smem_bytes(K, max_br, a.want_grad)
+                            : generic_smem_bytes(max_br, a.want_grad);
     }
-    const int tile_w = level_mode ? 32 : block * cpt;
+    const int tile_w = level_mode ? 32 : mma ? MMA_TILE : block * cpt;
+    const int kdim = mma ? mma_kp(K) : K;       // doubles per column of a stored partial
     int tile_cursor = 0;
     for (int t = 0; t < T; ++t) {
         TreeDev& td = pl.trees[t];
@@ -282,6 +301,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
         tile_cursor += (int)nt;
     }
     pl.level_mode = level_mode;
+    pl.mma = mma;
     pl.max_rows = max_rows;
     pl.want_grad = a.want_grad;
     pl.cpt = cpt;
@@ -302,7 +322,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     // buffers.
     pl.smem_scratch = false;
     {
-        const size_t scr_bytes = (size_t)(pl.n_slots + pl.n_stack) * block * cpt * K * 8;
+        const size_t scr_bytes = (size_t)(pl.n_slots + pl.n_stack) * tile_w * kdim * 8;
         const bool fits = !level_mode && !acc_global && k_templated(K) && cpt == 1 && pl.smem_bytes + scr_bytes <= 96 * 1024;
         pl.smem_scratch = fits && (ctx->opt_smem_scratch == 1 || (ctx->opt_smem_scratch < 0 && pl.n_tiles <= 4 * ctx->sm_count));
         if (pl.smem_scratch) {
@@ -318,7 +338,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     if (pl.grid < 1) pl.grid = 1;
     {   // very large trees: fewer persistent CTAs rather than a scratch allocation that cannot succeed
         size_t free_b = 0, total_b = 0;
-        const double per_cta = level_mode ? 0.0 : (double)(pl.n_slots + pl.n_stack) * block * cpt * K * 8.0;
+        const double per_cta = level_mode ? 0.0 : (double)(pl.n_slots + pl.n_stack) * tile_w * kdim * 8.0;
         if (per_cta * pl.grid <= (double)ctx->d_scratch.cap) {
             // fits the scratch already held: nothing to allocate, no need to ask the driver
             // (cudaMemGetInfo costs milliseconds on a GPU with many live allocations)
@@ -355,9 +375,9 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
         pl.n_rows = row;
     }
     pl.row_stride = (max_br + 3) & ~3;
-    if ((!level_mode && (double)(pl.n_slots + n_stack + 1) * block * cpt * K * 8.0 >= 4.0e9) || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
+    if ((!level_mode && (double)(pl.n_slots + n_stack + 1) * tile_w * kdim * 8.0 >= 4.0e9) || (double)max_br * R * bt_size(K) * 8.0 >= 4.0e9)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree too large for 32-bit scratch offsets (%d nodes)", max_br);
-    pl.scratch_per_cta = level_mode ? 4 : (long long)(pl.n_slots + pl.n_stack) * block * cpt * K;
+    pl.scratch_per_cta = level_mode ? 4 : (long long)(pl.n_slots + pl.n_stack) * tile_w * kdim;
 
     // topology block: [TreeDev x T][ops][row_base][level offsets]
     pl.off_trees = 0;

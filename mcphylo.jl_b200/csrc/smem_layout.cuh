@@ -67,5 +67,22 @@ struct LevelSmem {
     }
 };
 
+// Tile-cooperative walk for large alphabets (kernel_mma.cuh): 8 warps x 16 columns per CTA.
+constexpr int MMA_WARPS = 8, MMA_MB = 2, MMA_WCOLS = 8 * MMA_MB, MMA_TILE = MMA_WARPS * MMA_WCOLS;   // 128 columns per CTA
+
+template <int KP>
+struct MmaSmem {
+    static constexpr int STRIDE = KP + 2;
+    static constexpr int TAB = (KP + 1) * STRIDE;                   // doubles of one staged table
+    static __host__ __device__ size_t acc_bytes(int n_br, int want_grad) { return want_grad ? (((size_t)n_br * 8 + 15) & ~(size_t)15) : 0; }
+    static __host__ __device__ size_t part_bytes() { return 2 * 2 * MMA_WARPS * 8 + 2 * 2 * 4; }    // parked sums + branch ids, 2 buffers
+    static __host__ __device__ size_t desc_bytes() { return 3 * 32; }
+    static __host__ __device__ size_t code_bytes() { return 2 * 2 * MMA_TILE; }
+    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * 4 * TAB * 8; }
+    static __host__ __device__ size_t total(int n_br, int want_grad) {
+        return acc_bytes(n_br, want_grad) + ((part_bytes() + 15) & ~(size_t)15) + desc_bytes() + code_bytes() + tab_bytes();
+    }
+};
+
 }  // namespace mcpdev
 using namespace mcpdev;

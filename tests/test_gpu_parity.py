@@ -127,6 +127,70 @@ def test_large_alphabets_generic_kernel(oracle, K, R, n_taxa, S):
     _check(mcp.logpdf(pd, aln), None, ll_o, None)
 
 
+@pytest.mark.parametrize("K,R,n_taxa,S,multi", [(7, 2, 30, 300, True), (8, 1, 17, 129, False), (13, 1, 40, 500, False),
+                                                (16, 2, 12, 77, True), (20, 4, 60, 400, False), (21, 1, 25, 130, True),
+                                                (24, 1, 9, 2000, False), (29, 1, 33, 260, False), (32, 2, 20, 140, True)])
+@pytest.mark.parametrize("mode", [1, 0])
+def test_large_alphabets_tensor_core_kernel(oracle, K, R, n_taxa, S, multi, mode):
+    """6 < K <= 32 on the tile-cooperative FP64 tensor-core walk (mode 1: K padded to 8 / 16 / 24 / 32, ragged
+    tiles, several rate categories, multifurcations and unary nodes) and on the runtime-K fallback (mode 0),
+    both against the oracle; the tensor-core kernel's gradient is bit-reproducible."""
+    rng = np.random.default_rng(1000 + K)
+    tree = random_tree(n_taxa, rng, multifurcate=multi, unary=(K % 5 == 0))
+    pi = rng.dirichlet(np.ones(K) * 5)
+    srates = rng.uniform(0.2, 3.0, size=K * (K - 1) // 2)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, srates), pi, rates, S, rng, gap_frac=0.05)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, mcp.GTR)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ctx = mcp.get_context()
+    ctx.set_large_alphabet_mode(mode)
+    try:
+        ll, g = mcp.gradlogpdf(pd, aln)
+        st = ctx.stats()
+        assert st["block"] == (256 if mode else min(128, st["block"]))
+        ll2, g2 = mcp.gradlogpdf(pd, aln)
+        ll_only = mcp.logpdf(pd, aln)
+    finally:
+        ctx.set_large_alphabet_mode(-1)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, mcp.GTR, pi, srates, rates)
+    _check(ll, g, ll_o, g_o)
+    _check(ll_only, None, ll_o, None)
+    if mode:
+        assert ll2 == ll and np.array_equal(g, g2)
+
+
+def test_large_alphabet_batch_and_posterior(oracle):
+    """The tensor-core kernel under mcp_eval_batch (trees of different sizes in one launch) and with the
+    branch-length prior epilogue."""
+    from mcphylo_jl_b200 import capi
+    from mcphylo_jl_b200.phylodist import _tree_args
+    K = 20
+    ctx = capi.Context(0)
+    try:
+        alns, targs, want = [], [], []
+        for i, (n_taxa, S) in enumerate([(11, 200), (40, 333), (5, 64)]):
+            rng = np.random.default_rng(4000 + i)
+            tree = random_tree(n_taxa, rng)
+            pi = rng.dirichlet(np.ones(K) * 5)
+            srates = rng.uniform(0.2, 3.0, size=K * (K - 1) // 2)
+            codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, srates), pi, np.ones(1), S, rng, gap_frac=0.02)
+            alns.append(ctx.alignment_from_codes(codes, K, leaf_nums))
+            targs.append(_tree_args(mcp.PhyloDist(tree, pi, srates, [1.0], mcp.GTR))[1])
+            want.append(_oracle_eval(oracle, tree, codes, leaf_nums, K, mcp.GTR, pi, srates, [1.0]))
+        ll, grads = ctx.eval_batch(alns, targs, want_grad=True)
+        for t in range(3):
+            _check(ll[t], grads[t], *want[t])
+        lp, gp = ctx.eval_posterior(alns[1], *targs[1], prior_kind=1, prior_params=[0.1])
+        blv = np.asarray(targs[1][2])
+        assert abs(lp - (want[1][0] + np.sum(-np.log(0.1) - blv / 0.1))) <= 1e-10 * abs(lp)
+        assert np.allclose(gp, want[1][1] - 10.0, rtol=1e-8, atol=1e-8 * np.max(np.abs(want[1][1])))
+        for a in alns:
+            a.close()
+    finally:
+        ctx.close()
+
+
 def test_every_launch_shape_agrees(oracle):
     rng = np.random.default_rng(3)
     tree = random_tree(40, rng)
