@@ -187,6 +187,21 @@ int mcp_eval_posterior(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int
                        int prior_kind, const double *prior_params, double *lp_out, double *grad_out);
 
 /*
+ * logL, the branch-length gradient AND the gradient with respect to the rate-category multipliers
+ * (rate_grad_out, R doubles: d logL / d rates[r]) in one call.  The reference has no such derivative -- it samples
+ * the Gamma shape behind `rates` gradient-free (/root/reference/src/Likelihood/Rates.jl:11-38) -- but it falls
+ * out of the quantities this path already computes: categories are not mixed and category r sees branch b as
+ * t_b * rates[r], hence d logL / d rates[r] = (1 / rates[r]) * sum_b t_b * d logL_r / d t_b.  Evaluated as R
+ * single-category evaluations on one cached plan, i.e. the same columns as one mcp_eval.  A host that wants
+ * d logL / d alpha for rates = discrete_gamma_rates(alpha, alpha, R) applies the chain rule with
+ * d rates / d alpha (mcphylo.jl_b200/rates.py: discrete_gamma_rates_jacobian).
+ */
+int mcp_eval_rate_gradient(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_t *postorder_num,
+                           const int32_t *parent_num, const double *blv, const double *U, const double *D,
+                           const double *Uinv, double mu, const double *rates, int R, const double *pi,
+                           double *ll_out, double *grad_out, double *rate_grad_out);
+
+/*
  * Same evaluation, result left on the device: d_out (DEVICE pointer, NN doubles) receives
  * [logL, grad[1..NN-1]] (grad part zero if !want_grad).  The work is enqueued on the context's
  * stream and NOT synchronised, so a site-sharded caller can all-reduce d_out across GPUs

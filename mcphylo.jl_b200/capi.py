@@ -24,7 +24,7 @@ SYMBOLS = [
     "mcp_get_stats_member", "mcp_timer_start", "mcp_timer_stop",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
-    "mcp_eval", "mcp_eval_posterior", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
+    "mcp_eval", "mcp_eval_posterior", "mcp_eval_rate_gradient", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
     "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode",
     "mcp_schedule_dump", "mcp_model_reorder",
 ]
@@ -85,6 +85,7 @@ def load():
     eval_args = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_double, _vp, C.c_int, _vp, C.c_int]
     lib.mcp_eval.argtypes = eval_args + [_dp, _vp]
     lib.mcp_eval_device.argtypes = eval_args + [_vp]
+    lib.mcp_eval_rate_gradient.argtypes = eval_args[:-1] + [_dp, _vp, _vp]
     lib.mcp_eval_posterior.argtypes = eval_args[:-1] + [C.c_int, _vp, _dp, _vp]
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
@@ -330,6 +331,19 @@ class Context:
                                       rates.ctypes.data, rates.size, pi.ctypes.data, int(want_grad),
                                       C.byref(ll), grad.ctypes.data if want_grad else None))
         return ll.value, (grad[:NN - 1] if want_grad else None)
+
+    def eval_rate_gradient(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi):
+        """(logL, d logL / d blv, d logL / d rates) in one call (mcp_eval_rate_gradient)."""
+        po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
+        NN = po.size
+        ll = C.c_double()
+        grad = np.zeros(max(NN - 1, 1), dtype=np.float64)
+        rgrad = np.zeros(rates.size, dtype=np.float64)
+        self._check(self.lib.mcp_eval_rate_gradient(self.handle, aln.handle, NN, po.ctypes.data, pa.ctypes.data,
+                                                    blv.ctypes.data, U.ctypes.data, D.ctypes.data, Uinv.ctypes.data,
+                                                    float(mu), rates.ctypes.data, rates.size, pi.ctypes.data,
+                                                    C.byref(ll), grad.ctypes.data, rgrad.ctypes.data))
+        return ll.value, grad[:NN - 1], rgrad
 
     def eval_posterior(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
                        prior_kind: int, prior_params, want_grad: bool = True):

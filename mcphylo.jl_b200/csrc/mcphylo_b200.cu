@@ -1402,6 +1402,38 @@ int mcp_eval_posterior(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int
     return eval_any(ctx, a, lp_out, &g);
 }
 
+int mcp_eval_rate_gradient(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
+                           const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
+                           double mu, const double* rates, int R, const double* pi, double* ll_out, double* grad_out,
+                           double* rate_grad_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!rates || !blv || !rate_grad_out || R < 1 || NN < 2) return fail(ctx, MCP_ERR_ARG, "mcp_eval_rate_gradient: bad argument");
+    // Rate categories are not mixed (logL = sum_r logL_r, VectorizedFunctions.jl:76-87) and category r sees every
+    // branch as t_b * rate_r, so  d logL / d rate_r = (1 / rate_r) * sum_b t_b * d logL_r / d t_b:  one evaluation
+    // per category with R = 1 -- the same columns as one R-category evaluation, on one cached plan -- gives
+    // logL, the branch gradient and the rate gradient together.
+    std::vector<double> g((size_t)NN - 1), gsum((size_t)NN - 1, 0.0);
+    double ll_total = 0.0;
+    for (int r = 0; r < R; ++r) {
+        const double* rate_r = rates + r;
+        double ll_r = 0.0;
+        double* gp = g.data();
+        BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rate_r, 1, &pi, 1};
+        int e = eval_any(ctx, a, &ll_r, &gp);
+        if (e) return e;
+        ll_total += ll_r;
+        double dot = 0.0;
+        for (int b = 0; b < NN - 1; ++b) {
+            gsum[b] += g[b];
+            dot += blv[b] * g[b];
+        }
+        rate_grad_out[r] = dot / rates[r];
+    }
+    if (ll_out) *ll_out = ll_total;
+    if (grad_out) std::memcpy(grad_out, gsum.data(), sizeof(double) * (NN - 1));
+    return 0;
+}
+
 int mcp_eval_device(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
                     const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
                     double mu, const double* rates, int R, const double* pi, int want_grad, double* d_out) {

@@ -203,6 +203,16 @@ def gradlogpdf(d: PhyloDist, x, device: Optional[int] = None) -> Tuple[float, np
     return ctx.eval(aln, *targs, want_grad=True)
 
 
+def gradlogpdf_rates(d: PhyloDist, x, device: Optional[int] = None) -> Tuple[float, np.ndarray, np.ndarray]:
+    """(logL, d logL / d branch length, d logL / d d.rates[r]) -- the rate-category gradient falls out of the
+    per-category branch gradients (mcp_eval_rate_gradient); with `rates.discrete_gamma_rates_dalpha` it gives
+    the Gamma-shape gradient  d logL / d alpha = rate_grad . d rates / d alpha."""
+    ctx = get_context(device)
+    ft, targs = _tree_args(d)
+    aln = _device_alignment(x, ft.leaf_nums, d.nbase, ctx)
+    return ctx.eval_rate_gradient(aln, *targs)
+
+
 class MultiplePhyloDist:
     """A collection of independent PhyloDists evaluated in one batched launch."""
 

@@ -41,3 +41,11 @@ def discrete_gamma_rates(alpha: float, beta: float, k: int, method: str = "mean"
         m[i] *= factor
     m[0] *= factor
     return m
+
+
+def discrete_gamma_rates_dalpha(alpha: float, k: int, method: str = "mean", rel_step: float = 1e-6) -> np.ndarray:
+    """d discrete_gamma_rates(alpha, alpha, k) / d alpha (the usual one-parameter Gamma: shape = rate, mean 1),
+    by a central difference -- the chain-rule factor that turns the library's d logL / d rates
+    (mcp_eval_rate_gradient) into d logL / d alpha.  Not in the reference, which samples alpha gradient-free."""
+    h = rel_step * max(abs(alpha), 1e-3)
+    return (discrete_gamma_rates(alpha + h, alpha + h, k, method) - discrete_gamma_rates(alpha - h, alpha - h, k, method)) / (2.0 * h)

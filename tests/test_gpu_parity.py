@@ -191,6 +191,40 @@ def test_large_alphabet_batch_and_posterior(oracle):
         ctx.close()
 
 
+def test_rate_category_and_gamma_shape_gradient(oracle):
+    """d logL / d rates[r] from mcp_eval_rate_gradient against central differences of the
+    ORACLE's logL, and the Gamma-shape gradient through the chain rule; logL and the branch gradient of the
+    same call equal the plain evaluation's."""
+    rng = np.random.default_rng(99)
+    tree = random_tree(30, rng, multifurcate=True)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    alpha = 0.7
+    rates = mcp.discrete_gamma_rates(alpha, alpha, 4)
+    codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 800, rng, gap_frac=0.02)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, 4)
+    pd = mcp.PhyloDist(tree, pi, sr, rates, mcp.GTR)
+    ll, g, rg = mcp.gradlogpdf_rates(pd, aln)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates)
+    _check(ll, g, ll_o, g_o)
+    assert rg.shape == (4,)
+
+    def oracle_ll(r):
+        return _oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, r, want_grad=False)[0]
+    for r in range(4):
+        h = 1e-5 * rates[r]
+        up, dn = rates.copy(), rates.copy()
+        up[r] += h
+        dn[r] -= h
+        fd = (oracle_ll(up) - oracle_ll(dn)) / (2 * h)
+        assert abs(rg[r] - fd) <= 2e-6 * max(1.0, abs(fd)), (r, rg[r], fd)
+    # Gamma shape: rates = discrete_gamma_rates(alpha, alpha, 4)
+    dalpha = float(rg @ mcp.discrete_gamma_rates_dalpha(alpha, 4))
+    ha = 1e-5
+    fd = (oracle_ll(mcp.discrete_gamma_rates(alpha + ha, alpha + ha, 4)) - oracle_ll(mcp.discrete_gamma_rates(alpha - ha, alpha - ha, 4))) / (2 * ha)
+    assert abs(dalpha - fd) <= 1e-5 * max(1.0, abs(fd)), (dalpha, fd)
+
+
 def test_every_launch_shape_agrees(oracle):
     rng = np.random.default_rng(3)
     tree = random_tree(40, rng)
