@@ -266,7 +266,7 @@ typedef struct mcp_stats {
     int32_t schedule_rebuilt;  /* 1 if the topology differed from the cached one */
     int64_t scratch_bytes;     /* device scratch currently held for partials */
     int32_t columns_per_thread;/* walk kernel: alignment columns per thread (1 or 2) */
-    int32_t reserved;
+    int32_t operand_ring;      /* walk kernel: depth of the gradient pass's operand ring (0 = not used by the last evaluation) */
 } mcp_stats;
 int mcp_get_stats(const mcp_ctx *ctx, mcp_stats *out);
 int mcp_get_stats_member(const mcp_ctx *ctx, int member, mcp_stats *out);
@@ -300,6 +300,10 @@ int mcp_set_scratch_mode(mcp_ctx *ctx, int mode);
  * row in global memory with RED.ADD.F64 beyond that), 0 always shared memory (fails if the tree does
  * not fit), 1 always global memory. */
 int mcp_set_accumulator_mode(mcp_ctx *ctx, int mode);
+/* Gradient pass of the depth-first walk (K = 2, 4; one substitution model per call; trees of up to 4096 nodes):
+ * -1 / 1 the stored child partials are fetched ahead of their use through a per-warp operand ring in shared memory
+ * (cp.async.bulk + mbarrier), 0 every thread loads its own partials when it needs them.  Results are identical. */
+int mcp_set_ring_mode(mcp_ctx *ctx, int mode);
 /* State counts 6 < K <= 32 (e.g. 20-state protein alphabets): -1 / 1 the tile-cooperative kernel that runs the
  * K x K by K x columns products of every node on the FP64 tensor path (mma.sync.m8n8k4.f64; 8 warps x 16 columns
  * per CTA, bit-reproducible gradient), 0 the runtime-K fallback kernel (one thread per column, CUDA cores). */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_rate_gradient", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
-    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode",
+    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode", "mcp_set_ring_mode",
     "mcp_schedule_dump", "mcp_model_reorder",
 ]
 
@@ -40,7 +40,7 @@ class Stats(C.Structure):
     _fields_ = [("walk_ms", C.c_double), ("device_ms", C.c_double), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("kernel_launches", C.c_int32), ("grid", C.c_int32),
                 ("block", C.c_int32), ("tiles", C.c_int32), ("schedule_rebuilt", C.c_int32),
-                ("scratch_bytes", C.c_int64), ("columns_per_thread", C.c_int32), ("reserved", C.c_int32)]
+                ("scratch_bytes", C.c_int64), ("columns_per_thread", C.c_int32), ("operand_ring", C.c_int32)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -78,6 +78,7 @@ def load():
     lib.mcp_set_tile_order.argtypes = [_vp, C.c_int]
     lib.mcp_set_cherry_mode.argtypes = [_vp, C.c_int]
     lib.mcp_set_large_alphabet_mode.argtypes = [_vp, C.c_int]
+    lib.mcp_set_ring_mode.argtypes = [_vp, C.c_int]
     lib.mcp_alignment_from_codes.argtypes = [_vp, _vp, C.c_int, C.c_int64, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_from_dense.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
     lib.mcp_alignment_destroy.argtypes = [_vp, _vp]
@@ -240,6 +241,9 @@ class Context:
 
     def set_level_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_level_mode(self.handle, int(mode)))
+
+    def set_ring_mode(self, mode: int = -1):
+        self._check(self.lib.mcp_set_ring_mode(self.handle, int(mode)))
 
     def set_large_alphabet_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_large_alphabet_mode(self.handle, int(mode)))

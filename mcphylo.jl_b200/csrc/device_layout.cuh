@@ -27,6 +27,7 @@ struct TreeDev {
     int row_lo, row_hi;      // accumulator rows [lo, hi) holding this tree's partial sums
     int lvl_off, n_post_lvl, n_pre_lvl;   // level-ordered program: offsets into WalkParams::levels
     int n_rows;              // leaf rows of the alignment
+    int fetch_off, n_fetch;  // operand ring of the gradient pass: this tree's fetch list, WalkParams::fetch[fetch_off .. + n_fetch)
 };
 
 struct LLRow {
@@ -45,6 +46,7 @@ struct WalkParams {
     LLRow* rows_ll;
     const int* cta_row_base;
     const int* levels;          // level offsets of the level-ordered programs (small-tree kernel)
+    const unsigned short* fetch; // fetch lists of the operand ring (post slots in the order the gradient pass reads them)
     double* out;                // small-tree kernel: [logL, grad] per tree, device or pinned host memory
     unsigned int* done_counter; // small-tree kernel: CTAs finished (the last one reduces the rows)
     long long row_stride;

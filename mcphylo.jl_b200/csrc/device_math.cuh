@@ -67,6 +67,10 @@ __device__ __forceinline__ unsigned char* keep_ptr(unsigned char* p) {
     asm volatile("mov.u64 %0, %0;" : "+l"(p));
     return p;
 }
+__device__ __forceinline__ unsigned keep_u32(unsigned v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
 __device__ __forceinline__ double keep_f64(double v) {
     asm volatile("mov.f64 %0, %0;" : "+d"(v));
     return v;
@@ -78,6 +82,45 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// ---- operand ring primitives (kernel_walk.cuh, RD > 0): mbarrier + bulk asynchronous copy, shared-window addresses ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// orders this thread's generic-proxy accesses (here: its st.global of partials) before later async-proxy accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// All 32 lanes wait together.  The loop is written in C with a warp vote as its condition: a branch loop inside the
+// asm block hid the control flow from the compiler, which then gave up keeping U / Uinv in uniform registers anywhere
+// in the kernel (+35 % instructions in the post pass); a per-lane condition still made it reload them after every wait.
+__device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    while (!__all_sync(0xffffffffu, mbar_try(bar, parity))) {}
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+template <int K>
+__device__ __forceinline__ void lds_partial(unsigned addr, double (&v)[K]) {
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2)
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[k]), "=d"(v[k + 1]) : "r"(addr + k * 8) : "memory");
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[k]) : "r"(addr + k * 8) : "memory");
+    }
+}
 
 // Model view: MOFS is the slot offset into c_model; with a compile-time 0 the constant operands
 // fold into the DFMA encodings.

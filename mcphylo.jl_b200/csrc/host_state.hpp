@@ -76,7 +76,12 @@ struct Plan {
     bool level_mode = false, smem_scratch = false, acc_global = false, mma = false;
     int n_tiles = 0, grid = 0, n_rows = 0, n_slots = 0, n_stack = 0, max_br = 0, max_rows = 1;
     long long total_out = 0, total_dyn = 0, total_btab = 0, scratch_per_cta = 0, row_stride = 0;
-    size_t smem_bytes = 0, topo_bytes = 0, off_trees = 0, off_ops = 0, off_rowbase = 0, off_levels = 0;
+    size_t smem_bytes = 0, topo_bytes = 0, off_trees = 0, off_ops = 0, off_rowbase = 0, off_levels = 0, off_fetch = 0;
+    // operand ring of the gradient pass (smem_layout.cuh): usable for this plan (the launch still falls back to the
+    // plain kernel for decompositions without a null eigenvalue or batches with several models) and the shared
+    // memory that variant needs
+    bool ring = false;
+    size_t smem_ring = 0;
     DevBuf d_topo;
     PinBuf h_topo;
 };
@@ -186,6 +191,7 @@ struct mcp_ctx {
     int opt_levels = -1;         // -1 automatic, 0 never, 1 whenever it fits
     int opt_smem_scratch = -1;   // -1 automatic, 0 off, 1 on when it fits
     int opt_acc_mode = -1;       // gradient accumulator of the walk: -1 automatic, 0 shared memory, 1 global memory (RED)
+    int opt_ring = -1;           // gradient pass: operand ring (-1 automatic = on where supported, 0 off, 1 on)
     int opt_mma = -1;            // K > 6: FP64 tensor-core walk (-1 / 1) or the runtime-K fallback kernel (0)
     int opt_cherry = -1;         // gradient pass recomputes cherries from their leaves (-1 / 1) or re-reads stored copies (0)
     int opt_dynamic = -1;        // resident single-tree walk: tiles by atomic ticket in site order (1) or static ranges (0)

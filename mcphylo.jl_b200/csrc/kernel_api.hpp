@@ -20,6 +20,7 @@ struct LaunchCfg {
     cudaStream_t stream = nullptr;
     bool smem_scratch = false; // partials scratch in shared memory (small inputs)
     bool acc_global = false;   // gradient accumulator in global memory (very large trees)
+    bool ring = false;         // gradient pass fetches its stored operands through the per-warp operand ring (cp.async.bulk)
     bool mma = false;          // K > 6: tile-cooperative FP64 tensor-core kernel instead of the runtime-K fallback
 };
 

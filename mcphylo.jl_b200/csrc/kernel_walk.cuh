@@ -48,7 +48,11 @@ static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 // every partial it has just written.
 // NE = active eigen-components (device_math.cuh): K - 1 when the host found (and moved last) a null
 // eigenvalue, the case for every rate matrix; K otherwise.
-template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE, bool ACCG>
+// RD = depth of the per-warp OPERAND RING of the gradient pass (0 = none): the stored child partials of the
+// families ahead are fetched by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier, issued by one
+// elected lane per warp) into shared memory RD entries before their use, in the order of the tree's fetch list
+// (schedule.hpp: pre_fetch), so that the warp never waits a DRAM round trip on its own partials.
+template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE, bool ACCG, int RD = 0>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
 #endif
@@ -57,6 +61,8 @@ template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE, bool ACCG>
 #endif
 __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLOCKS : MCP_WALK_MIN_BLOCKS2) felsenstein_walk(const __grid_constant__ WalkParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CHN = RD ? WALK_RING_CH : CH;       // ops staged per chunk
+    static_assert(RD == 0 || (!SSCR && !ACCG && !DYN_MODEL), "the operand ring exists for the HBM-scratch, shared-accumulator, single-model kernels");
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
 
@@ -87,34 +93,61 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
     constexpr bool GL2 = ACCG;
-    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K>::acc_bytes(p.max_br, p.want_grad && !ACCG));
-    // parked per-warp branch sums + their branch ids sit right below the descriptors (see WALK_PART_BYTES)
-    double* const s_part = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) - WALK_PART_BYTES);
-    int* const s_pbr = reinterpret_cast<int*>(s_part + WALK_PART_DOUBLES);
+    int4* const sdesc = reinterpret_cast<int4*>(smem_raw + WalkSmem<K, CHN>::acc_bytes(p.max_br, p.want_grad && !ACCG));
+    // parked per-warp branch sums + their branch ids sit right below the descriptors (see walk_part_bytes(CHN))
+    double* const s_part = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) - walk_part_bytes(CHN));
+    int* const s_pbr = reinterpret_cast<int*>(s_part + walk_part_doubles(CHN));
     // folds the parked sums of one chunk (buffer `buf`, `n` ops) into s_acc; call after the barrier that
     // follows the chunk, by all threads (2 * n of them do the work; each term has its own branch)
     auto fold_parked = [&](int buf, int n) {
         if (tid < 2 * n) {
-            const double* pp = s_part + (buf * CH * 2 + tid) * 8;
+            const double* pp = s_part + (buf * CHN * 2 + tid) * 8;
             double sum = pp[0];
             for (int w = 1; w < (TW >> 5); ++w) sum += pp[w];
-            s_acc[s_pbr[buf * CH * 2 + tid]] += sum;
+            s_acc[s_pbr[buf * CHN * 2 + tid]] += sum;
         }
     };
-    double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K>::desc_bytes());
-    OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K>::e_bytes());
-    double* const stab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srec) + WalkSmem<K>::rec_bytes());
-    unsigned char* const scode = reinterpret_cast<unsigned char*>(stab) + WalkSmem<K>::tab_bytes();
+    double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K, CHN>::desc_bytes());
+    OpRec* const srec = reinterpret_cast<OpRec*>(reinterpret_cast<unsigned char*>(se) + WalkSmem<K, CHN>::e_bytes());
+    double* const stab = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(srec) + WalkSmem<K, CHN>::rec_bytes());
+    unsigned char* const scode = reinterpret_cast<unsigned char*>(stab) + WalkSmem<K, CHN>::tab_bytes();
     constexpr int KK1 = K * (K + 1);                  // doubles of one leaf table (P or dP columns)
 
-    // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state]; all
-    // slot / LIFO offsets in the records are byte offsets from here
+    // per-thread base of the CTA-private scratch, laid out [slot][column c][thread][state] -- with an operand ring
+    // [slot][warp][column c][lane][state], so that a warp's share of a slot is ONE contiguous run, fetched by one
+    // bulk copy; all slot / LIFO offsets in the records are byte offsets from here
+    constexpr unsigned WB = 32 * K * 8;               // bytes of one warp's share of one column vector of a slot
     unsigned char* const scr = SSCR
-        ? scode + WalkSmem<K>::code_bytes(TS, 2) + (size_t)tid * K * 8
-        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta + (long long)tid * K));
-    const unsigned col_bytes = (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
-    const unsigned slot_bytes = col_bytes * CPT;
+        ? scode + WalkSmem<K, CHN>::code_bytes(TS, 2) + (size_t)tid * K * 8
+        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta +
+                                                    (RD > 0 ? (long long)(warp * (CPT * 32) + lane) * K : (long long)tid * K)));
+    const unsigned col_bytes = RD > 0 ? WB : (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
+    const unsigned slot_bytes = (unsigned)TW * K * 8 * CPT;
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
+    // ---- operand ring (RD > 0): this warp's stages and their mbarriers, as shared-window addresses ----
+    constexpr unsigned RBAR = RD * CPT * WB;          // this warp's block: RD stages of CPT vectors, then RD mbarriers
+    // Ring state is kept in ordinary (per-lane) registers on purpose -- it is warp-uniform, but the uniform register
+    // file is needed for U / Uinv (48 of its 63 registers at K = 4); `lane0` is a zero the compiler cannot see through
+    // and takes for lane-dependent.
+    //   ring_l   this LANE's vector in stage 0, column 0 (lane 0: the warp's block itself); stage s, column c at
+    //            + (s * CPT + c) * WB
+    //   rbar_w   the warp's mbarrier of stage 0; stage s at + 8 s
+    //   r_cnt    entries consumed since the kernel started: stage = r_cnt % RD, mbarrier parity = (r_cnt / RD) & 1
+    unsigned ring_l = 0, rbar_w = 0, r_cnt = 0, lane0 = 0;
+    if constexpr (RD > 0) {
+        static_assert((RD & (RD - 1)) == 0, "ring depth must be a power of two");
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(lane0) : "r"(tid));
+        const size_t roff = WalkSmem<K, CHN>::ring_offset(p.max_br, 1, TS);
+        const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + roff) + (unsigned)warp * (RBAR + RD * 8);
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < RD; ++st) mbar_init(base + RBAR + st * 8, 1);
+        }
+        fence_mbar_init();                            // ordered before the first use by the barriers of the first prologue
+        ring_l = keep_u32(base + lane * (K * 8));
+        rbar_w = keep_u32(base + RBAR + lane0);
+        r_cnt = lane0;
+    }
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
     constexpr int BT = 2 * K + 2 * K * (K + 1);
@@ -170,8 +203,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 
             // ---- chunk staging (all threads of the CTA) ----
             auto stage_desc = [&](const int4* ops, int n_ops, int c) {
-                const int base = c * CH, cnt = min(CH, n_ops - base);
-                int4* dst = sdesc + (c % 3) * (CH * 2);
+                const int base = c * CHN, cnt = min(CHN, n_ops - base);
+                int4* dst = sdesc + (c % 3) * (CHN * 2);
                 for (int i = tid; i < cnt * 2; i += TW) cp_async16(dst + i, ops + 2 * base + i);
             };
             // Copies e vectors / leaf codes / leaf tables of chunk c and derives the per-op records (byte
@@ -182,13 +215,13 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             //   CHERRY  (gradient pass) the code rows and P columns of BOTH leaves below it + its own (em1, de)
             //   REG/MEM (em1, de) of the branch
             auto stage_data = [&](int n_ops, int c, bool pre) {
-                const int base = c * CH, cnt = min(CH, n_ops - base);
-                const int4* d = sdesc + (c % 3) * (CH * 2);
-                double* eb = se + (c & 1) * (CH * 2 * 2 * K);
+                const int base = c * CHN, cnt = min(CHN, n_ops - base);
+                const int4* d = sdesc + (c % 3) * (CHN * 2);
+                double* eb = se + (c & 1) * (CHN * 2 * 2 * K);
                 const int crows = pre ? 2 : 1;               // code rows per child slot
-                unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * 2 * TS);
-                OpRec* rb = srec + (c & 1) * CH;
-                double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
+                unsigned char* cb = scode + (size_t)(c & 1) * (CHN * 2 * 2 * TS);
+                OpRec* rb = srec + (c & 1) * CHN;
+                double* tb = stab + (size_t)(c & 1) * (CHN * 2 * 2 * KK1);
                 const int pieces = TS / 16;                  // 16-byte pieces of one code row segment
                 const int tpieces = KK1 / 2;                 // 16-byte pieces of one leaf table (K (K + 1) is even)
                 auto copy_codes = [&](unsigned char* dstrow, int row) {
@@ -258,7 +291,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
             auto prologue = [&](const int4* ops, int n_ops, bool pre) {
                 __syncthreads();                              // previous pass / tile done with the buffers
                 stage_desc(ops, n_ops, 0);
-                if (n_ops > CH) stage_desc(ops, n_ops, 1);
+                if (n_ops > CHN) stage_desc(ops, n_ops, 1);
                 cp_async_commit();
                 cp_async_wait_all();
                 __syncthreads();
@@ -322,15 +355,15 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 #pragma unroll
             for (int c = 0; c < CPT; ++c) e_col[c] = 0;
             {
-                const int n_post = tr.n_post, n_chunks = (n_post + CH - 1) / CH;
+                const int n_post = tr.n_post, n_chunks = (n_post + CHN - 1) / CHN;
                 prologue(post_ops, n_post, false);
                 for (int c = 0; c < n_chunks; ++c) {
                     chunk_boundary(post_ops, n_post, c, n_chunks, false);
-                    const OpRec* rb = srec + (c & 1) * CH;
-                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * 2 * TS) + tid;
-                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
-                    const int cnt = min(CH, n_post - c * CH);
+                    const OpRec* rb = srec + (c & 1) * CHN;
+                    const double* eb = se + (c & 1) * (CHN * 2 * 2 * K);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CHN * 2 * 2 * TS) + tid;
+                    const double* tb = stab + (size_t)(c & 1) * (CHN * 2 * 2 * KK1);
+                    const int cnt = min(CHN, n_post - c * CHN);
                     double Lm[CPT][K];                                              // the op's stored operand
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
@@ -404,8 +437,46 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 
             // ------------------------------ gradient pass ------------------------------
             if (p.want_grad) {
-                const int n_pre = tr.n_pre, n_chunks = (n_pre + CH - 1) / CH;
+                const int n_pre = tr.n_pre, n_chunks = (n_pre + CHN - 1) / CHN;
+                // Operand ring: the post pass wrote its partials through the generic proxy, the ring reads them
+                // through the async proxy -- every thread fences its own stores, the barriers of the prologue
+                // order the fences before the first bulk copy.
+                if constexpr (RD > 0) fence_proxy_async();
                 prologue(pre_ops, n_pre, true);
+                // ring state of this pass: r_fi indexes the fetch-list entry the next refill requests (RD entries
+                // ahead of the one consumed next; the list ends with 0xffff entries), r_nxt holds that entry
+                unsigned r_fi = 0, r_nxt = 0;
+                // lane 0 (its scratch base and ring address are the warp's): request post slot `slot` into stage `st`
+                auto ring_issue = [&](unsigned st, unsigned slot) {
+                    const unsigned bar = rbar_w + st * 8;
+                    mbar_expect_tx(bar, CPT * WB);
+                    bulk_g2s(ring_l + st * (CPT * WB), scr + slot * slot_bytes, CPT * WB, bar);
+                };
+                // all lanes: wait for the entry at the head of the ring and read this thread's vectors
+                auto ring_consume = [&](double (&v)[CPT][K]) {
+                    const unsigned st = r_cnt & (RD - 1);
+                    mbar_wait(rbar_w + st * 8, (r_cnt / RD) & 1u);
+#pragma unroll
+                    for (int cc = 0; cc < CPT; ++cc) lds_partial<K>(ring_l + (st * CPT + cc) * WB, v[cc]);
+                };
+                // all lanes, once the vectors just consumed have been used: the freed stage takes the entry RD ahead
+                auto ring_refill = [&]() {
+                    __syncwarp();
+                    if (lane == 0 && r_nxt != 0xffffu) ring_issue(r_cnt & (RD - 1), r_nxt);
+                    ++r_cnt;
+                    r_nxt = __ldg(p.fetch + ++r_fi) + lane0;   // (+ lane0: stays in a vector register until lane 0 uses it)
+                };
+                if constexpr (RD > 0) {
+                    r_fi = (unsigned)tr.fetch_off + lane0;
+                    if (lane == 0) {
+                        for (int i = 0; i < RD; ++i) {
+                            const unsigned slot = __ldg(p.fetch + r_fi + i);
+                            if (slot != 0xffffu) ring_issue((r_cnt + i) & (RD - 1), slot);
+                        }
+                    }
+                    r_fi += RD;
+                    r_nxt = __ldg(p.fetch + r_fi) + lane0;
+                }
                 // the first family is the root's (PREM_ROOT, and only that one): its pre vector is pi
 #pragma unroll
                 for (int cc = 0; cc < CPT; ++cc)
@@ -414,13 +485,13 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 for (int c = 0; c < n_chunks; ++c) {
                     chunk_boundary(pre_ops, n_pre, c, n_chunks, true);
                     if constexpr (!GL2) {
-                        if (c > 0) fold_parked((c - 1) & 1, CH);   // the chunk before: complete since the barrier above
+                        if (c > 0) fold_parked((c - 1) & 1, CHN);   // the chunk before: complete since the barrier above
                     }
-                    const OpRec* rb = srec + (c & 1) * CH;
-                    const double* eb = se + (c & 1) * (CH * 2 * 2 * K);
-                    const unsigned char* cb = scode + (size_t)(c & 1) * (CH * 2 * 2 * TS) + tid;
-                    const double* tb = stab + (size_t)(c & 1) * (CH * 2 * 2 * KK1);
-                    const int cnt = min(CH, n_pre - c * CH);
+                    const OpRec* rb = srec + (c & 1) * CHN;
+                    const double* eb = se + (c & 1) * (CHN * 2 * 2 * K);
+                    const unsigned char* cb = scode + (size_t)(c & 1) * (CHN * 2 * 2 * TS) + tid;
+                    const double* tb = stab + (size_t)(c & 1) * (CHN * 2 * 2 * KK1);
+                    const int cnt = min(CHN, n_pre - c * CHN);
                     double La[CPT][K], Lb[CPT][K];                                  // the family's stored child partials
                     // All stored operands of a family -- pre[mother] popped from the LIFO (into `cur`), the
                     // internal children's partials -- are requested together: by the first op of a chunk for
@@ -433,7 +504,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         ld_cols_if(on && (fl & 3) == mcp::OPK_MEM, r.y, La, std::false_type{});
                         ld_cols_if(on && ((fl >> 2) & 3) == mcp::OPK_MEM, r.z, Lb, std::false_type{});
                     };
-                    if (MCP_EARLY_LOADS) request(*reinterpret_cast<const uint4*>(rb), true);
+                    if (MCP_EARLY_LOADS && RD == 0) request(*reinterpret_cast<const uint4*>(rb), true);
                     for (int j = 0; j < cnt; ++j) {
                         const uint4 rh = *reinterpret_cast<const uint4*>(rb + j);   // flags, xa, xb, y0
                         const int flags = (int)rh.x;
@@ -443,7 +514,13 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         // leaf; b internal implies a internal.  pre[mother] lives in `cur`: it is either
                         // already there (PREM_REG: kept by the op just before; PREM_ROOT: pi, set before the
                         // pass) or popped from the LIFO.
-                        if (!MCP_EARLY_LOADS) request(rh, true);
+                        if constexpr (RD > 0) {
+                            // ring kernels: only pre[mother] is loaded directly (a recent push, served by L2) -- by the
+                            // op before this one as soon as its own pre[mother] was dead, by the first op of a chunk itself
+                            if (j == 0) ld_cols_if(((flags >> 8) & 3) == mcp::PREM_STACK, rh.w, cur, std::true_type{});
+                        } else {
+                            if (!MCP_EARLY_LOADS) request(rh, true);
+                        }
                         // D = P L and Y: leaf child Y = dP L (table column); internal child Y = de * (Uinv L),
                         // the eigen-coordinates of dP L (the numerator is then formed in eigen-space)
                         double Da[CPT][K], Ya[CPT][K], Db[CPT][K], Yb[CPT][K];
@@ -477,8 +554,22 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 rescale_pow2<K>(La[cc]);
                             }
                         }
-                        if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
-                        if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
+                        if constexpr (RD > 0) {
+                            const bool am = (flags & 3) == mcp::OPK_MEM;
+                            if (am) ring_consume(La);
+                            if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
+                            if (am) ring_refill();
+                            if (bi) {
+                                ring_consume(Lb);
+                                internal_cols(1, Lb, Db, Yb);
+                                ring_refill();
+                            } else {
+                                leaf_cols(1, Db, Yb);
+                            }
+                        } else {
+                            if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
+                            if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
+                        }
                         double qa[CPT][K], qb[CPT][K];
                         double na[CPT], nb[CPT], inv[CPT];
 #pragma unroll
@@ -493,6 +584,14 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 den = fma(qa[cc][k], Da[cc][k], den);
                             }
                             inv[cc] = fast_rcp(den) * vmask[cc];
+                        }
+                        if constexpr (RD > 0) {
+                            // a is a leaf: nothing is kept, pre[mother] is dead from here on and the next family's
+                            // mother comes off the LIFO -- request it now, a whole op half ahead of its use
+                            if (!ai && j + 1 < cnt) {
+                                const uint4 rn = *reinterpret_cast<const uint4*>(rb + j + 1);
+                                ld_cols_if((((int)rn.x >> 8) & 3) == mcp::PREM_STACK, rn.w, cur, std::true_type{});
+                            }
                         }
                         // numerators q . (dP L) and the children's pre vectors P^T q (internal children only)
                         auto num_direct = [&](const double (&q)[CPT][K], const double (&Y)[CPT][K], double (&n)[CPT]) {
@@ -519,7 +618,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         }
                         if (ai) pre_child(0, qa, Ya, na, cur);   // cur (pre[mother]) is dead: qa, qb hold all that is left of it
                         else num_direct(qa, Ya, na);
-                        if (MCP_EARLY_LOADS) request(*reinterpret_cast<const uint4*>(rb + (j + 1 < cnt ? j + 1 : j)), j + 1 < cnt);
+                        if (MCP_EARLY_LOADS && RD == 0) request(*reinterpret_cast<const uint4*>(rb + (j + 1 < cnt ? j + 1 : j)), j + 1 < cnt);
                         double ga = 0.0, gb = 0.0;
 #pragma unroll
                         for (int cc = 0; cc < CPT; ++cc) {
@@ -531,7 +630,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                             if ((lane & 15) == 0) atomicAdd(grow + ((lane >> 4) ? rb[j].b_br : rb[j].a_br), red);
                         } else {
                             if ((lane & 15) == 0) {
-                                const int term = ((c & 1) * CH + j) * 2 + (lane >> 4);
+                                const int term = ((c & 1) * CHN + j) * 2 + (lane >> 4);
                                 s_part[term * 8 + warp] = red;
                                 if (warp == 0) s_pbr[term] = (lane >> 4) ? rb[j].b_br : rb[j].a_br;
                             }
@@ -540,7 +639,7 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 }
                 if constexpr (!GL2) {
                     __syncthreads();                                   // the last chunk's sums are parked
-                    fold_parked((n_chunks - 1) & 1, n_pre - (n_chunks - 1) * CH);
+                    fold_parked((n_chunks - 1) & 1, n_pre - (n_chunks - 1) * CHN);
                 }
             }
         }  // tiles of this tree

@@ -293,6 +293,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     wp.rows_ll = (LLRow*)ctx->d_rows_ll.p;
     wp.cta_row_base = (const int*)((char*)pl.d_topo.p + pl.off_rowbase);
     wp.levels = (const int*)((char*)pl.d_topo.p + pl.off_levels);
+    wp.fetch = (const unsigned short*)((char*)pl.d_topo.p + pl.off_fetch);
     // pinned host memory is device-addressable (unified addressing): the fused kernel writes results there
     wp.out = d_out_user ? d_out_user : via_comm ? d_out : (double*)ctx->h_out.p;
     wp.done_counter = (unsigned int*)ctx->d_counter.p;
@@ -321,7 +322,8 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     lc.grid = pl.grid;
     lc.block = pl.block;
     lc.cpt = pl.cpt;
-    lc.smem = pl.smem_bytes;
+    lc.ring = pl.ring && !dyn_model && all_null_last;
+    lc.smem = lc.ring ? pl.smem_ring : pl.smem_bytes;
     lc.stream = st;
     lc.smem_scratch = pl.smem_scratch;
     lc.acc_global = pl.acc_global;
@@ -363,6 +365,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     s.block = pl.block;
     s.tiles = pl.n_tiles;
     s.columns_per_thread = pl.cpt;
+    s.operand_ring = lc.ring ? WALK_RING_DEPTH : 0;
     s.schedule_rebuilt = rebuilt ? 1 : 0;
     s.scratch_bytes = (int64_t)ctx->d_scratch.cap;
     guard.ok = true;
@@ -1258,6 +1261,16 @@ int mcp_set_accumulator_mode(mcp_ctx* ctx, int mode) {
     return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
         m->opt_acc_mode = mode;
         invalidate_plans(m);
+        return 0;
+    });
+}
+
+int mcp_set_ring_mode(mcp_ctx* ctx, int mode) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (mode < -1 || mode > 1) return fail(ctx, MCP_ERR_ARG, "ring mode must be -1 (automatic), 0 (off) or 1 (on where supported)");
+    return for_members_or_self(ctx, [&](mcp_ctx* m) -> int {
+        if (m->opt_ring != mode) invalidate_plans(m);
+        m->opt_ring = mode;
         return 0;
     });
 }

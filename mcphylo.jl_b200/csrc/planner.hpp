@@ -30,9 +30,18 @@ const KernelTable* kernels_for(int K) {
 }
 
 size_t walk_smem_bytes(int K, int max_br, int shared_acc, int block, int cpt) {
-    const size_t acc = shared_acc ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
+    const size_t acc = shared_acc ? (((size_t)max_br * 8 + 15) & ~(size_t)15) + walk_part_bytes(CH) : 0;
     return acc + (size_t)3 * CH * 32 + (size_t)2 * CH * 2 * 2 * K * 8 + (size_t)2 * CH * 32 +
            (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8 + (size_t)2 * CH * 2 * 2 * block * cpt;   // = WalkSmem<K>::total
+}
+// the same kernel with the operand ring (shared accumulator, chunks of WALK_RING_CH ops, ring behind the staging buffers)
+size_t walk_smem_bytes_ring(int K, int max_br, int block, int cpt) {
+    const int TS = block * cpt, warps = block / 32;
+    switch (K) {
+        case 2: return WalkSmem<2, WALK_RING_CH>::ring_offset(max_br, 1, TS) + WalkSmem<2, WALK_RING_CH>::ring_bytes(warps, WALK_RING_DEPTH, cpt);
+        case 4: return WalkSmem<4, WALK_RING_CH>::ring_offset(max_br, 1, TS) + WalkSmem<4, WALK_RING_CH>::ring_bytes(warps, WALK_RING_DEPTH, cpt);
+        default: return 0;
+    }
 }
 size_t generic_smem_bytes(int max_br, int want_grad) { return want_grad ? (size_t)max_br * sizeof(double) : 0; }
 int mma_kp(int K) { return (K + 7) & ~7; }   // state count padded to the 8-wide MMA blocks
@@ -68,15 +77,15 @@ struct BatchArgs {
 // Resident CTAs per SM of the walk kernel for a launch shape.  The occupancy calculator costs a few
 // microseconds per query and the planner asks for several shapes, so answers are remembered per process.
 int walk_occupancy(mcp_ctx* ctx, const KernelTable* kt, int K, int block, int cpt, size_t smem, bool sscr, bool accg,
-                   bool levels, int* out, bool mma = false) {
-    struct Key { int device, K, block, cpt; size_t smem; bool sscr, accg, levels, mma; int occ; };
+                   bool levels, int* out, bool mma = false, bool ring = false) {
+    struct Key { int device, K, block, cpt; size_t smem; bool sscr, accg, levels, mma, ring; int occ; };
     static std::mutex mu;
     static std::vector<Key> memo;
     {
         std::lock_guard<std::mutex> lock(mu);
         for (const Key& k : memo)
             if (k.device == ctx->device && k.K == K && k.block == block && k.cpt == cpt && k.smem == smem && k.sscr == sscr &&
-                k.accg == accg && k.levels == levels && k.mma == mma) {
+                k.accg == accg && k.levels == levels && k.mma == mma && k.ring == ring) {
                 *out = k.occ;
                 return 0;
             }
@@ -90,6 +99,7 @@ int walk_occupancy(mcp_ctx* ctx, const KernelTable* kt, int K, int block, int cp
     c.smem_scratch = sscr;
     c.acc_global = accg;
     c.mma = mma;
+    c.ring = ring;
     int occ = 0;
     cudaError_t e = levels ? kt->occupancy_levels(c, &occ) : kt->occupancy_walk(c, &occ);
     if (e != cudaSuccess) {
@@ -99,7 +109,7 @@ int walk_occupancy(mcp_ctx* ctx, const KernelTable* kt, int K, int block, int cp
         else return fail(ctx, MCP_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
     }
     std::lock_guard<std::mutex> lock(mu);
-    memo.push_back({ctx->device, K, block, cpt, smem, sscr, accg, levels, mma, occ});
+    memo.push_back({ctx->device, K, block, cpt, smem, sscr, accg, levels, mma, ring, occ});
     *out = occ;
     return 0;
 }
@@ -333,6 +343,26 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     if (pl.smem_bytes > 200 * 1024)
         return fail(ctx, MCP_ERR_UNSUPPORTED, "tree with %d nodes exceeds the shared-memory gradient accumulator", max_br);
     if (occ < 1) return fail(ctx, MCP_ERR_CUDA, "walk kernel does not fit on an SM (block %d, smem %zu)", block, pl.smem_bytes);
+    // Operand ring for the gradient pass: taken when that variant keeps as many CTAs per SM as the plain
+    // kernel (the persistent grid and the accumulator rows below are shared by both).
+    pl.ring = false;
+    pl.smem_ring = 0;
+    // Automatic: K = 4 (cfg4 -14 % at 1 M sites, -22 % on a 125 k-site shard, cfg3 -3 %); at K = 2 the ops are too
+    // short for the ring's bookkeeping to pay (50-taxon tree, 4 M sites: +8 %), there only on request.
+    const bool ring_wanted = ctx->opt_ring == 1 || (ctx->opt_ring < 0 && K == 4);
+    if (a.want_grad && ring_wanted && !level_mode && !acc_global && !pl.smem_scratch && walk_ring_supported(K)) {
+        bool lists = true;
+        for (int t = 0; t < T; ++t) lists = lists && pl.scheds[t].n_slots < 65535;
+        const size_t sr = walk_smem_bytes_ring(K, max_br, block, cpt);
+        int occ_r = 0;
+        if (lists && sr <= 220 * 1024) {
+            if ((e = walk_occupancy(ctx, kt, K, block, cpt, sr, false, false, false, &occ_r, false, true))) return e;
+            if (occ_r >= occ) {
+                pl.ring = true;
+                pl.smem_ring = sr;
+            }
+        }
+    }
     if (ctx->opt_ctas_per_sm > 0) occ = std::min(occ, ctx->opt_ctas_per_sm);
     pl.grid = (int)std::min<long long>((long long)pl.n_tiles, (long long)occ * ctx->sm_count);
     if (pl.grid < 1) pl.grid = 1;
@@ -384,7 +414,15 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     pl.off_ops = (sizeof(TreeDev) * T + 31) & ~(size_t)31;
     pl.off_rowbase = pl.off_ops + (size_t)n_ops * 32;
     pl.off_levels = pl.off_rowbase + sizeof(int32_t) * pl.grid;
-    pl.topo_bytes = pl.off_levels + sizeof(int32_t) * (size_t)std::max<long long>(n_lvl_ints, 1);
+    pl.off_fetch = (pl.off_levels + sizeof(int32_t) * (size_t)std::max<long long>(n_lvl_ints, 1) + 15) & ~(size_t)15;
+    // fetch lists of the operand ring: per tree its entries + WALK_RING_DEPTH + 2 end marks 0xffff (the ring reads ahead)
+    size_t n_fetch_total = 0;
+    for (int t = 0; t < T; ++t) {
+        pl.trees[t].fetch_off = (int)n_fetch_total;
+        pl.trees[t].n_fetch = pl.ring ? (int)pl.scheds[t].pre_fetch.size() : 0;
+        n_fetch_total += (size_t)pl.trees[t].n_fetch + WALK_RING_DEPTH + 2;
+    }
+    pl.topo_bytes = pl.off_fetch + sizeof(uint16_t) * n_fetch_total;
     if ((e = ensure_pin(ctx, pl.h_topo, pl.topo_bytes))) return e;
     if ((e = ensure_dev(ctx, pl.d_topo, pl.topo_bytes))) return e;
     char* h = (char*)pl.h_topo.p;
@@ -405,6 +443,12 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
             for (int32_t v : sc.post_levels) *hl++ = v;
             for (int32_t v : sc.pre_levels) *hl++ = v;
         }
+    }
+    {
+        uint16_t* hf = (uint16_t*)(h + pl.off_fetch);
+        std::memset(hf, 0xff, sizeof(uint16_t) * n_fetch_total);
+        for (int t = 0; t < T; ++t)
+            if (pl.trees[t].n_fetch) std::memcpy(hf + pl.trees[t].fetch_off, pl.scheds[t].pre_fetch.data(), sizeof(uint16_t) * pl.trees[t].n_fetch);
     }
     for (int t = 0; t < T; ++t) {
         Plan::TreeSig sg;

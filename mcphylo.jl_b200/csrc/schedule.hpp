@@ -84,6 +84,11 @@ struct Schedule {
     int n_stack = 0;    // pre LIFO depth needed per column
     int n_real_branches = 0;  // NN-1
     int n_cherries = 0;       // pre-program children recomputed from their two leaves instead of re-read
+    // Depth-first gradient program only: the post slots of the stored child partials the pre program reads,
+    // in the order it reads them (per op: child a if MEM, then child b if MEM) -- the fetch list of the walk
+    // kernel's operand ring, which requests them a few entries ahead of their use.  Empty when a slot index
+    // does not fit 16 bits.
+    std::vector<uint16_t> pre_fetch;
     // level-ordered variant only: ops [levels[l], levels[l+1]) are mutually independent
     std::vector<int32_t> post_levels, pre_levels;
 };
@@ -357,6 +362,12 @@ inline std::string build_schedule(int NN, const int32_t* postorder_num, const in
             } else break;
         }
         out.n_stack = max_level < 1 ? 1 : max_level;
+        if (out.n_slots < 65535) {
+            for (const PreOp& op : out.pre) {
+                if ((op.flags & 3) == OPK_MEM) out.pre_fetch.push_back((uint16_t)op.a_src);
+                if (((op.flags >> 2) & 3) == OPK_MEM) out.pre_fetch.push_back((uint16_t)op.b_src);
+            }
+        }
     }
     return "";
 }

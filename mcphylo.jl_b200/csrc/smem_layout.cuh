@@ -23,27 +23,50 @@ inline bool walk_acc_global(int n_nodes, int mode /* -1 auto, 0 shared, 1 global
 // -- no atomics (a shared fp64 atomic add is a compare-and-swap loop, ~10 instructions, 38 % retries
 // with 8 warps on one address) and a run-to-run reproducible gradient.
 //   [2 buffers][CH ops][2 children][8 warps] doubles, then [2][CH][2] branch ids
-constexpr int WALK_PART_DOUBLES = 2 * CH * 2 * 8;
-constexpr int WALK_PART_BYTES = WALK_PART_DOUBLES * 8 + 2 * CH * 2 * 4;
+__host__ __device__ constexpr int walk_part_doubles(int chn) { return 2 * chn * 2 * 8; }
+__host__ __device__ constexpr int walk_part_bytes(int chn) { return walk_part_doubles(chn) * 8 + 2 * chn * 2 * 4; }
 
-template <int K>
+// Operand ring of the gradient pass (template parameter RD of the walk, 0 = none): the stored child partials a
+// warp will need are fetched RD entries ahead of their use by bulk asynchronous copies (one elected lane,
+// cp.async.bulk + mbarrier) into a per-warp ring, so their DRAM latency never reaches the scoreboard.
+//   [warps] x { [RD stages][columns per thread][32 lanes][K doubles], [RD] mbarriers }
+// Kernels with a ring stage their per-op inputs WALK_RING_CH ops at a time instead of CH, which pays for the
+// ring's shared memory.
+#ifndef MCP_RING_DEPTH
+#define MCP_RING_DEPTH 2
+#endif
+#ifndef MCP_RING_CH
+#define MCP_RING_CH 8
+#endif
+constexpr int WALK_RING_DEPTH = MCP_RING_DEPTH;
+constexpr int WALK_RING_CH = MCP_RING_CH;
+__host__ __device__ constexpr bool walk_ring_supported(int K) { return K == 2 || K == 4; }
+
+template <int K, int CHN = CH>
 struct WalkSmem {
     // dynamic shared memory carve-up (offsets in bytes)
     // branch-gradient accumulator of the CTA + parked per-warp sums (shared-accumulator kernels only:
     // callers pass want_grad && !ACCG)
     static __host__ __device__ size_t acc_bytes(int n_br, int shared_acc) {
-        return shared_acc ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + WALK_PART_BYTES : 0;
+        return shared_acc ? (((size_t)n_br * 8 + 15) & ~(size_t)15) + walk_part_bytes(CHN) : 0;
     }
-    static __host__ __device__ size_t desc_bytes() { return 3 * CH * 32; }
-    static __host__ __device__ size_t e_bytes() { return 2 * CH * 2 * 2 * K * 8; }   // (em1, de) per internal child
-    // state codes of leaf children: [2 buffers][CH ops][2 children][rows][tile sites]; a child slot holds two
+    static __host__ __device__ size_t desc_bytes() { return 3 * CHN * 32; }
+    static __host__ __device__ size_t e_bytes() { return 2 * CHN * 2 * 2 * K * 8; }   // (em1, de) per internal child
+    // state codes of leaf children: [2 buffers][CHN ops][2 children][rows][tile sites]; a child slot holds two
     // rows (a cherry child of the gradient pass stages the rows of both leaves below it)
-    static __host__ __device__ size_t code_bytes(int TS, int rows) { return (size_t)2 * CH * 2 * rows * TS; }
-    static __host__ __device__ size_t rec_bytes() { return 2 * CH * 32; }
+    static __host__ __device__ size_t code_bytes(int TS, int rows) { return (size_t)2 * CHN * 2 * rows * TS; }
+    static __host__ __device__ size_t rec_bytes() { return 2 * CHN * 32; }
     // leaf children: P (and, in the gradient pass, dP) columns [(K+1)][K] of the child's branch
-    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CH * 2 * 2 * K * (K + 1) * 8; }
+    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * CHN * 2 * 2 * K * (K + 1) * 8; }
     static __host__ __device__ size_t total(int n_br, int shared_acc, int TS) {
         return acc_bytes(n_br, shared_acc) + desc_bytes() + e_bytes() + rec_bytes() + tab_bytes() + code_bytes(TS, 2);
+    }
+    // operand ring behind everything else (128-byte aligned offset from the start of dynamic shared memory)
+    static __host__ __device__ size_t ring_offset(int n_br, int shared_acc, int TS) {
+        return (total(n_br, shared_acc, TS) + 127) & ~(size_t)127;
+    }
+    static __host__ __device__ size_t ring_bytes(int warps, int depth, int cpt) {
+        return (size_t)warps * depth * cpt * 32 * K * 8 + (size_t)warps * depth * 8;
     }
 };
 

@@ -47,10 +47,10 @@ cudaError_t ensure_smem_attr(int device, Kern kern, size_t smem) {
     return cudaSuccess;
 }
 
-template <int K, int CPT, bool DYN, bool SSCR, int NE, bool ACCG>
+template <int K, int CPT, bool DYN, bool SSCR, int NE, bool ACCG, int RD = 0>
 cudaError_t launch_walk_inst(const LaunchCfg& c, const WalkParams& wp) {
-    MCP_CU(ensure_smem_attr(c.device, felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG>, c.smem));
-    felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG><<<c.grid, c.block, c.smem, c.stream>>>(wp);
+    MCP_CU(ensure_smem_attr(c.device, felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG, RD>, c.smem));
+    felsenstein_walk<K, CPT, DYN, SSCR, NE, ACCG, RD><<<c.grid, c.block, c.smem, c.stream>>>(wp);
     return cudaGetLastError();
 }
 // null_last: every model of the batch has a null eigenvalue, moved to the last position by the host
@@ -61,6 +61,13 @@ cudaError_t launch_walk_inst(const LaunchCfg& c, const WalkParams& wp) {
 template <int K>
 cudaError_t launch_walk_k(const LaunchCfg& c, const WalkParams& wp, bool dyn_model, bool null_last) {
     constexpr int NE = K - 1;
+    if constexpr (walk_ring_supported(K)) {
+        // operand ring (host: only for one shared model with a null eigenvalue, shared-memory accumulator, scratch in HBM)
+        if (c.ring && !c.acc_global && !c.smem_scratch && null_last && !dyn_model)
+            return c.cpt == 2 ? launch_walk_inst<K, 2, false, false, NE, false, WALK_RING_DEPTH>(c, wp)
+                              : launch_walk_inst<K, 1, false, false, NE, false, WALK_RING_DEPTH>(c, wp);
+    }
+    if (c.ring) return cudaErrorInvalidValue;
     if (c.acc_global)
         return null_last ? launch_walk_inst<K, 1, true, false, NE, true>(c, wp) : launch_walk_inst<K, 1, true, false, K, true>(c, wp);
     if (!null_last)
@@ -78,6 +85,10 @@ cudaError_t occ_of(const LaunchCfg& c, Kern kern, int* out) {
 template <int K, int CPT>
 cudaError_t occupancy_inst(const LaunchCfg& c, int* out) {
     constexpr int NE = K - 1;
+    if (c.ring) {
+        if constexpr (walk_ring_supported(K)) return occ_of(c, felsenstein_walk<K, CPT, false, false, NE, false, WALK_RING_DEPTH>, out);
+        else return cudaErrorInvalidValue;
+    }
     if (c.acc_global) {
         int o1 = 0, o2 = 0;
         MCP_CU(occ_of(c, felsenstein_walk<K, 1, true, false, K, true>, &o1));
