@@ -357,9 +357,13 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
         int occ_r = 0;
         if (lists && sr <= 220 * 1024) {
             if ((e = walk_occupancy(ctx, kt, K, block, cpt, sr, false, false, false, &occ_r, false, true))) return e;
+            // The persistent grid is sized for the ring kernel; the plain kernel -- the launch-time fallback for
+            // a decomposition without a null eigenvalue or a batch with several models -- runs the same grid
+            // (and the same accumulator rows) even where it would fit fewer or more CTAs per SM itself.
             if (occ_r >= occ) {
                 pl.ring = true;
                 pl.smem_ring = sr;
+                occ = occ_r;
             }
         }
     }

@@ -249,6 +249,73 @@ def test_every_launch_shape_agrees(oracle):
         ctx.set_columns_per_thread(0)
 
 
+@pytest.mark.parametrize("K,R,S,n_taxa", [(4, 4, 3000, 40), (2, 1, 2100, 33), (4, 2, 700, 150), (2, 2, 96, 7)])
+def test_operand_ring_is_bit_identical(oracle, K, R, S, n_taxa):
+    """Gradient pass with the operand ring (stored child partials fetched ahead by cp.async.bulk into shared
+    memory, mcp_set_ring_mode) against the oracle and, bit for bit, against the same launch without the ring:
+    one and two columns per thread, several tile widths incl. ragged last tiles and widths of one warp, trees
+    with multifurcations and unary nodes (virtual leaves), rings shallower than the fetch list and empty ones."""
+    rng = np.random.default_rng(500 + K + R)
+    tree = random_tree(n_taxa, rng, multifurcate=True)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, S, rng, gap_frac=0.03)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_scratch_mode(0)          # partials in HBM (the small-input shared-memory scratch has no ring)
+        for block, cpt in [(256, 2), (256, 1), (32, 2), (96, 1), (128, 2)]:
+            ctx.set_launch(block, 0)
+            ctx.set_columns_per_thread(cpt)
+            ctx.set_ring_mode(0)
+            ll0, g0 = mcp.gradlogpdf(pd, aln)
+            assert ctx.stats()["operand_ring"] == 0
+            ctx.set_ring_mode(1)
+            ll1, g1 = mcp.gradlogpdf(pd, aln)
+            assert ctx.stats()["operand_ring"] > 0, "the ring kernel did not run"
+            _check(ll1, g1, ll_o, g_o)
+            assert ll1 == ll0 and np.array_equal(g1, g0), (block, cpt)
+            ll2, g2 = mcp.gradlogpdf(pd, aln)            # ring phase carried over from the call before
+            assert ll2 == ll1 and np.array_equal(g2, g1)
+    finally:
+        ctx.set_launch(0, 0)
+        ctx.set_columns_per_thread(0)
+        ctx.set_ring_mode(-1)
+        ctx.set_scratch_mode(-1)
+
+
+def test_operand_ring_batch_of_trees(oracle):
+    """Several trees of different sizes in one batched launch through the ring kernel: each tree has its own
+    fetch list and the ring's phase carries over from tree to tree inside a CTA."""
+    rng = np.random.default_rng(77)
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    sr = np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 2)
+    trees, alns, want = [], [], []
+    for n in (5, 23, 64, 3, 31):
+        tree = random_tree(n, rng, multifurcate=True)
+        codes, leaf_nums = simulate_codes(tree, mcp.GTR(pi, sr), pi, rates, 400 + 37 * n, rng, gap_frac=0.02)
+        trees.append(tree)
+        alns.append(mcp.DeviceAlignment(codes, leaf_nums, 4))
+        want.append(_oracle_eval(oracle, tree, codes, leaf_nums, 4, mcp.GTR, pi, sr, rates))
+    ctx = mcp.get_context()
+    try:
+        ctx.set_ring_mode(1)
+        ctx.set_level_mode(0)
+        ctx.set_scratch_mode(0)
+        res = mcp.multi_gradlogpdf(mcp.MultiplePhyloDist(trees, pi, sr, rates, mcp.GTR), alns)
+        assert ctx.stats()["operand_ring"] > 0
+        for (ll, g), (ll_o, g_o) in zip(res, want):
+            _check(ll, g, ll_o, g_o)
+    finally:
+        ctx.set_ring_mode(-1)
+        ctx.set_level_mode(-1)
+        ctx.set_scratch_mode(-1)
+
+
 @pytest.mark.parametrize("K,R,S", [(2, 1, 1500), (3, 2, 700), (5, 1, 300)])
 def test_two_columns_per_thread(oracle, K, R, S):
     """The two-columns-per-thread instantiation (automatic only for large K <= 3 problems) against
