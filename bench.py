@@ -316,6 +316,7 @@ def oracle_window(ctx, w, codes, leaf_nums, stats, sites=256):
         ctx.set_scratch_mode(-1)
     scale = np.max(np.abs(g_o))
     return {"sites": int(s), "block": int(shape["block"]), "columns_per_thread": int(shape["columns_per_thread"]),
+            "operand_ring": int(shape.get("operand_ring", 0)),
             "ll_rel_err": float(abs(ll - ll_o) / abs(ll_o)),
             "grad_max_rel_err": float(np.max(np.abs(g - g_o) / np.maximum(np.abs(g_o), 1e-3 * scale))),
             "logL_cuda": float(ll), "logL_oracle": float(ll_o),
@@ -432,7 +433,8 @@ def leg_single(name, local_rank, steps, warmup, with_cpu=True):
            "ms_per_call_device": float(np.median(ms)), "ms_per_call_device_l2_warm": float(np.median(ms_nf)),
            "ms_per_call_host_wall_l2_warm": wall_ms, "api_overhead_ms": wall_ms - float(np.median(ms_nf)),
            "kernel_ms": wk, "kernel_launches_per_call": st["kernel_launches"],
-           "launch": {"grid": st["grid"], "block": st["block"], "columns_per_thread": st["columns_per_thread"], "tiles": st["tiles"]},
+           "launch": {"grid": st["grid"], "block": st["block"], "columns_per_thread": st["columns_per_thread"], "tiles": st["tiles"],
+                      "operand_ring": st.get("operand_ring", 0)},
            "roofline": roofline_block(w, w["S"], wk, w["tree"]),
            "oracle_window": oracle_window(ctx, w, codes, leaf_nums, st, sites=256),
            "steps": steps, "warmup": warmup}
@@ -501,7 +503,8 @@ def leg_batch(local_rank, steps, warmup, n_trees=CFG5_TREES, sites=None, with_cp
                       "l2": "inputs larger than L2 (256 alignments, 1.3 GB of codes, 30 GB of partial traffic per step)"},
            "value": n_trees * 1e3 / float(np.median(ms)), "unit": "tree-evals/s", "ms_per_step": float(np.median(ms)),
            "kernel_ms": wk, "kernel_launches_per_call": st["kernel_launches"],
-           "launch": {"grid": st["grid"], "block": st["block"], "columns_per_thread": st["columns_per_thread"], "tiles": st["tiles"]},
+           "launch": {"grid": st["grid"], "block": st["block"], "columns_per_thread": st["columns_per_thread"], "tiles": st["tiles"],
+                      "operand_ring": st.get("operand_ring", 0)},
            "roofline": rl, "steps": steps, "warmup": warmup, "setup": {"alignment_generate_s": t_gen},
            "result_check": {"sum_logL": float(np.sum(ll)), "finite": bool(all(np.all(np.isfinite(g)) for g in grads))}}
     w1 = dict(w)
@@ -701,6 +704,7 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "launch": {"grid": stats["grid"], "block": stats["block"], "columns_per_thread": stats["columns_per_thread"],
                        "tiles": stats["tiles"], "scratch_bytes": stats["scratch_bytes"],
+                       "operand_ring": stats.get("operand_ring", 0),
                        "walk_ms_per_gpu": [s["walk_ms"] for s in member_stats],
                        "reduce": capi.REDUCE_NAMES.get(ctx.reduce_mode, "none") if n_gpus > 1 else "none"},
             "setup": {"alignment_generate_s": t_gen, "upload_and_first_eval_s": t_up,

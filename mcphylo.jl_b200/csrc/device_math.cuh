@@ -59,6 +59,46 @@ __device__ __forceinline__ void ld_partial_if(bool pred, const double* p, double
     }
 }
 
+// ---- piece layout (cp.async flavour of the operand ring): a K-vector is split into 16-byte pieces, piece h of lane l
+// at + h * 512 + l * 16 inside the warp's share of a column, so that every warp access (global: 512 contiguous bytes,
+// shared: 32 x 16 bytes) is dense and conflict-free and a thread can move its own vector with 16-byte cp.async copies ----
+constexpr unsigned PIECE_STRIDE = 32 * 16;
+template <int K>
+__device__ __forceinline__ void ld_partial_pc(const unsigned char* p, double (&v)[K]) {
+    static_assert(K % 2 == 0, "piece layout needs an even state count");
+#pragma unroll
+    for (int h = 0; h < K / 2; ++h)
+        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v[2 * h]), "=d"(v[2 * h + 1]) : "l"(p + h * PIECE_STRIDE) : "memory");
+}
+template <int K>
+__device__ __forceinline__ void st_partial_pc(unsigned char* p, const double (&v)[K]) {
+#pragma unroll
+    for (int h = 0; h < K / 2; ++h)
+        asm volatile("st.global.cg.v2.f64 [%0], {%1,%2};" :: "l"(p + h * PIECE_STRIDE), "d"(v[2 * h]), "d"(v[2 * h + 1]) : "memory");
+}
+template <int K, bool KEEP_OLD>
+__device__ __forceinline__ void ld_partial_pc_if(bool pred, const unsigned char* p, double (&v)[K]) {
+    if constexpr (!KEEP_OLD) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) asm volatile("" : "=d"(v[k]));
+    }
+#pragma unroll
+    for (int h = 0; h < K / 2; ++h)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q ld.global.cg.v2.f64 {%0,%1}, [%2];\n\t}"
+                     : "+d"(v[2 * h]), "+d"(v[2 * h + 1]) : "l"(p + h * PIECE_STRIDE), "r"((unsigned)pred) : "memory");
+}
+template <int K>
+__device__ __forceinline__ void lds_partial_pc(unsigned addr, double (&v)[K]) {
+#pragma unroll
+    for (int h = 0; h < K / 2; ++h)
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2 * h]), "=d"(v[2 * h + 1]) : "r"(addr + h * PIECE_STRIDE) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
 // Identity moves the compiler cannot see through: a value passed through them is kept in a register
 // (or spilled as one word) instead of being RE-COMPUTED at every use.  ptxas otherwise rematerialises
 // the per-thread scratch base (blockIdx * scratch_per_cta + tid * K * 8, ~13 instructions) in front of

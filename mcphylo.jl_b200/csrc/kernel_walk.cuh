@@ -117,10 +117,14 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     // [slot][warp][column c][lane][state], so that a warp's share of a slot is ONE contiguous run, fetched by one
     // bulk copy; all slot / LIFO offsets in the records are byte offsets from here
     constexpr unsigned WB = 32 * K * 8;               // bytes of one warp's share of one column vector of a slot
+    // RLS: cp.async flavour of the ring -- a warp's share of a column is split into 16-byte pieces [piece][lane]
+    // (device_math.cuh: piece layout), every thread copies its own pieces
+    constexpr bool RLS = RD > 0 && WALK_RING_LDGSTS;
     unsigned char* const scr = SSCR
         ? scode + WalkSmem<K, CHN>::code_bytes(TS, 2) + (size_t)tid * K * 8
-        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta +
-                                                    (RD > 0 ? (long long)(warp * (CPT * 32) + lane) * K : (long long)tid * K)));
+        : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta) +
+                   (RLS ? (long long)warp * (CPT * WB) + lane * 16
+                        : RD > 0 ? ((long long)(warp * (CPT * 32) + lane) * K) * 8 : ((long long)tid * K) * 8));
     const unsigned col_bytes = RD > 0 ? WB : (unsigned)TW * K * 8;  // distance between a thread's columns within a slot
     const unsigned slot_bytes = (unsigned)TW * K * 8 * CPT;
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
@@ -139,14 +143,16 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
         asm volatile("and.b32 %0, %1, 0;" : "=r"(lane0) : "r"(tid));
         const size_t roff = WalkSmem<K, CHN>::ring_offset(p.max_br, 1, TS);
         const unsigned base = (unsigned)__cvta_generic_to_shared(smem_raw + roff) + (unsigned)warp * (RBAR + RD * 8);
-        if (lane == 0) {
+        if constexpr (!RLS) {
+            if (lane == 0) {
 #pragma unroll
-            for (int st = 0; st < RD; ++st) mbar_init(base + RBAR + st * 8, 1);
+                for (int st = 0; st < RD; ++st) mbar_init(base + RBAR + st * 8, 1);
+            }
+            fence_mbar_init();                        // ordered before the first use by the barriers of the first prologue
         }
-        fence_mbar_init();                            // ordered before the first use by the barriers of the first prologue
-        ring_l = keep_u32(base + lane * (K * 8));
+        ring_l = keep_u32(base + lane * (RLS ? 16 : K * 8));
         rbar_w = keep_u32(base + RBAR + lane0);
-        r_cnt = lane0;
+        r_cnt = RLS ? 0u : lane0;
     }
     int row = p.cta_row_base[blockIdx.x];
     const int R = p.R;
@@ -298,12 +304,25 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 stage_data(n_ops, 0, pre);
                 cp_async_commit();
             };
+            // cp.async flavour of the ring: its refills are cp.async groups of their own, committed between the staging
+            // groups.  ring_k counts the refill groups committed since the last staging group: the staging group (and
+            // everything older) is complete once at most min(ring_k, RD) of the newest groups are pending -- the chunk
+            // boundary does not wait for operands that were requested for the ops to come.
+            int ring_k = 0;
             auto chunk_boundary = [&](const int4* ops, int n_ops, int c, int n_chunks, bool pre) {
-                cp_async_wait_all();
+                if constexpr (RLS) {
+                    static_assert(!RLS || RD == 2, "the boundary wait below is written out for a ring of depth 2");
+                    if (ring_k >= 2) cp_async_wait_group<2>();
+                    else if (ring_k == 1) cp_async_wait_group<1>();
+                    else cp_async_wait_group<0>();
+                } else {
+                    cp_async_wait_all();
+                }
                 __syncthreads();                              // chunk c data + descriptors c, c+1 visible
                 if (c + 1 < n_chunks) stage_data(n_ops, c + 1, pre);
                 if (c + 2 < n_chunks) stage_desc(ops, n_ops, c + 2);
                 cp_async_commit();
+                ring_k = 0;
             };
             auto ld_cols = [&](unsigned off, double (&v)[CPT][K]) {
 #pragma unroll
@@ -312,6 +331,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         const double* src = reinterpret_cast<const double*>(scr + off + c * col_bytes);
 #pragma unroll
                         for (int k = 0; k < K; ++k) v[c][k] = src[k];
+                    } else if constexpr (RLS) {
+                        ld_partial_pc<K>(scr + off + c * col_bytes, v[c]);
                     } else {
                         ld_partial<K>(reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
                     }
@@ -327,6 +348,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
 #pragma unroll
                             for (int k = 0; k < K; ++k) v[c][k] = src[k];
                         }
+                    } else if constexpr (RLS) {
+                        ld_partial_pc_if<K, decltype(keep_old)::value>(pred, scr + off + c * col_bytes, v[c]);
                     } else {
                         ld_partial_if<K, decltype(keep_old)::value>(pred, reinterpret_cast<const double*>(scr + off + c * col_bytes), v[c]);
                     }
@@ -339,6 +362,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                         double* dst = reinterpret_cast<double*>(scr + off + c * col_bytes);
 #pragma unroll
                         for (int k = 0; k < K; ++k) dst[k] = v[c][k];
+                    } else if constexpr (RLS) {
+                        st_partial_pc<K>(scr + off + c * col_bytes, v[c]);
                     } else {
                         st_partial<K>(reinterpret_cast<double*>(scr + off + c * col_bytes), v[c]);
                     }
@@ -441,37 +466,62 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                 // Operand ring: the post pass wrote its partials through the generic proxy, the ring reads them
                 // through the async proxy -- every thread fences its own stores, the barriers of the prologue
                 // order the fences before the first bulk copy.
-                if constexpr (RD > 0) fence_proxy_async();
+                if constexpr (RD > 0 && !RLS) fence_proxy_async();
                 prologue(pre_ops, n_pre, true);
                 // ring state of this pass: r_fi indexes the fetch-list entry the next refill requests (RD entries
                 // ahead of the one consumed next; the list ends with 0xffff entries), r_nxt holds that entry
                 unsigned r_fi = 0, r_nxt = 0;
-                // lane 0 (its scratch base and ring address are the warp's): request post slot `slot` into stage `st`
+                // bulk flavour: lane 0 (its scratch base and ring address are the warp's) requests post slot `slot` into
+                // stage `st`; cp.async flavour: every thread copies its own pieces of the slot
                 auto ring_issue = [&](unsigned st, unsigned slot) {
-                    const unsigned bar = rbar_w + st * 8;
-                    mbar_expect_tx(bar, CPT * WB);
-                    bulk_g2s(ring_l + st * (CPT * WB), scr + slot * slot_bytes, CPT * WB, bar);
+                    if constexpr (RLS) {
+#pragma unroll
+                        for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                            for (int h = 0; h < K / 2; ++h)
+                                cp_async16_s(ring_l + (st * CPT + cc) * WB + h * PIECE_STRIDE,
+                                             scr + slot * slot_bytes + cc * col_bytes + h * PIECE_STRIDE);
+                    } else {
+                        const unsigned bar = rbar_w + st * 8;
+                        mbar_expect_tx(bar, CPT * WB);
+                        bulk_g2s(ring_l + st * (CPT * WB), scr + slot * slot_bytes, CPT * WB, bar);
+                    }
                 };
                 // all lanes: wait for the entry at the head of the ring and read this thread's vectors
                 auto ring_consume = [&](double (&v)[CPT][K]) {
                     const unsigned st = r_cnt & (RD - 1);
-                    mbar_wait(rbar_w + st * 8, (r_cnt / RD) & 1u);
+                    if constexpr (RLS) {
+                        cp_async_wait_group<RD - 1>();   // at most the RD - 1 newer refills (or a staging group) stay pending
 #pragma unroll
-                    for (int cc = 0; cc < CPT; ++cc) lds_partial<K>(ring_l + (st * CPT + cc) * WB, v[cc]);
+                        for (int cc = 0; cc < CPT; ++cc) lds_partial_pc<K>(ring_l + (st * CPT + cc) * WB, v[cc]);
+                    } else {
+                        mbar_wait(rbar_w + st * 8, (r_cnt / RD) & 1u);
+#pragma unroll
+                        for (int cc = 0; cc < CPT; ++cc) lds_partial<K>(ring_l + (st * CPT + cc) * WB, v[cc]);
+                    }
                 };
                 // all lanes, once the vectors just consumed have been used: the freed stage takes the entry RD ahead
                 auto ring_refill = [&]() {
-                    __syncwarp();
-                    if (lane == 0 && r_nxt != 0xffffu) ring_issue(r_cnt & (RD - 1), r_nxt);
-                    ++r_cnt;
-                    r_nxt = __ldg(p.fetch + ++r_fi) + lane0;   // (+ lane0: stays in a vector register until lane 0 uses it)
+                    if constexpr (RLS) {
+                        if (r_nxt != 0xffffu) ring_issue(r_cnt & (RD - 1), r_nxt);
+                        cp_async_commit();               // a group per refill, empty or not: the waits count groups
+                        ++ring_k;
+                        ++r_cnt;
+                        r_nxt = __ldg(p.fetch + ++r_fi) + lane0;   // (+ lane0: no move to a uniform register right behind the load)
+                    } else {
+                        __syncwarp();
+                        if (lane == 0 && r_nxt != 0xffffu) ring_issue(r_cnt & (RD - 1), r_nxt);
+                        ++r_cnt;
+                        r_nxt = __ldg(p.fetch + ++r_fi) + lane0;   // (+ lane0: stays in a vector register until lane 0 uses it)
+                    }
                 };
                 if constexpr (RD > 0) {
-                    r_fi = (unsigned)tr.fetch_off + lane0;
-                    if (lane == 0) {
+                    r_fi = (unsigned)tr.fetch_off + (RLS ? 0u : lane0);
+                    if (RLS || lane == 0) {
                         for (int i = 0; i < RD; ++i) {
                             const unsigned slot = __ldg(p.fetch + r_fi + i);
                             if (slot != 0xffffu) ring_issue((r_cnt + i) & (RD - 1), slot);
+                            if constexpr (RLS) { cp_async_commit(); ++ring_k; }
                         }
                     }
                     r_fi += RD;

@@ -38,6 +38,12 @@ __host__ __device__ constexpr int walk_part_bytes(int chn) { return walk_part_do
 #ifndef MCP_RING_CH
 #define MCP_RING_CH 8
 #endif
+// Flavour of the ring: 0 = bulk copies (cp.async.bulk + mbarrier, one lane per warp issues), 1 = every thread moves its
+// own vectors with 16-byte cp.async copies (completion by cp.async.wait_group; no mbarrier, no elected lane).
+#ifndef MCP_RING_LDGSTS
+#define MCP_RING_LDGSTS 0
+#endif
+constexpr bool WALK_RING_LDGSTS = MCP_RING_LDGSTS != 0;
 constexpr int WALK_RING_DEPTH = MCP_RING_DEPTH;
 constexpr int WALK_RING_CH = MCP_RING_CH;
 __host__ __device__ constexpr bool walk_ring_supported(int K) { return K == 2 || K == 4; }
