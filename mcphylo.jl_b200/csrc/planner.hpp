@@ -347,9 +347,10 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     // kernel (the persistent grid and the accumulator rows below are shared by both).
     pl.ring = false;
     pl.smem_ring = 0;
-    // Automatic: K = 4 (cfg4 -14 % at 1 M sites, -22 % on a 125 k-site shard, cfg3 -3 %); at K = 2 the ops are too
-    // short for the ring's bookkeeping to pay (50-taxon tree, 4 M sites: +8 %), there only on request.
-    const bool ring_wanted = ctx->opt_ring == 1 || (ctx->opt_ring < 0 && K == 4);
+    // Automatic wherever the kernel exists (K = 2, 4): cfg4 -14 % at 1 M sites, -22 % on a 125 k-site shard, cfg3 -4 %;
+    // K = 2 (cfg2's 50-taxon and cfg5's 100-taxon tree on millions of sites) -14 % / -19 %, where the shorter chunks
+    // also make room for a third CTA per SM.
+    const bool ring_wanted = ctx->opt_ring != 0;
     if (a.want_grad && ring_wanted && !level_mode && !acc_global && !pl.smem_scratch && walk_ring_supported(K)) {
         bool lists = true;
         for (int t = 0; t < T; ++t) lists = lists && pl.scheds[t].n_slots < 65535;

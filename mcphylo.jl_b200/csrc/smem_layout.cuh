@@ -40,8 +40,11 @@ __host__ __device__ constexpr int walk_part_bytes(int chn) { return walk_part_do
 #endif
 // Flavour of the ring: 0 = bulk copies (cp.async.bulk + mbarrier, one lane per warp issues), 1 = every thread moves its
 // own vectors with 16-byte cp.async copies (completion by cp.async.wait_group; no mbarrier, no elected lane).
+// Measured (profiles/r2_ab_ring_flavour_*.json, r2_ab_ring_k2_*.json): equal at cfg4 / 1 M sites, the cp.async flavour
+// 1.5 % faster on a 125 k-site shard and on cfg3, 3-4 % faster at K = 2 (no elected-lane issue path through uniform
+// registers, no reloads of U / Uinv around the try_wait branch) -- it is the default.
 #ifndef MCP_RING_LDGSTS
-#define MCP_RING_LDGSTS 0
+#define MCP_RING_LDGSTS 1
 #endif
 constexpr bool WALK_RING_LDGSTS = MCP_RING_LDGSTS != 0;
 constexpr int WALK_RING_DEPTH = MCP_RING_DEPTH;
