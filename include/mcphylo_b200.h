@@ -335,6 +335,11 @@ int mcp_set_level_mode(mcp_ctx *ctx, int mode);
 int mcp_schedule_dump(int NN, const int32_t *postorder_num, const int32_t *parent_num,
                       const int32_t *leaf_row, int want_grad, int32_t *post_ops, int cap_post,
                       int32_t *pre_ops, int cap_pre, int32_t *info);
+/* Host only: the fetch list of the gradient pass's operand ring for the same tree -- the post slots of the stored child
+ * partials in the order the gradient program reads them (per family: child a if stored, then child b if stored).
+ * slots: cap uint16; *n_out receives the number of entries. */
+int mcp_schedule_fetch_list(int NN, const int32_t *postorder_num, const int32_t *parent_num, const int32_t *leaf_row,
+                            int cherries, uint16_t *slots, int cap, int32_t *n_out);
 
 /*
  * Host-only: the reordering every evaluation applies to the caller's eigen-decomposition before it

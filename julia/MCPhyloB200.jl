@@ -124,6 +124,25 @@ function evaluate(d::PhyloDist, x::Array{Float64,3}, want_grad::Bool)
     ll[], grad
 end
 
+# (logL, d logL / d branch length, d logL / d rates[r]) in one call (mcp_eval_rate_gradient).  The reference samples the
+# Gamma shape behind `rates` gradient-free (src/Likelihood/Rates.jl:11-38); with this a gradient-based sampler can take
+# alpha along:  d logL / d alpha = dot(rate_grad, d discrete_gamma_rates(alpha, alpha, k) / d alpha).
+function rate_gradient(d::PhyloDist, x::Array{Float64,3})
+    NN, po, pa, blv, leaf_nums = flatten(d.tree)
+    U, D, Uinv, mu = d.substitution_model(d.base_freq, d.substitution_rates)
+    ll = Ref{Float64}(0.0)
+    grad = Vector{Float64}(undef, NN - 1)
+    rgrad = Vector{Float64}(undef, length(d.rates))
+    check(ccall((:mcp_eval_rate_gradient, LIB[]), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Cint, Ptr{Float64},
+                 Ref{Float64}, Ptr{Float64}, Ptr{Float64}),
+                context(), alignment(x, leaf_nums), NN, po, pa, Vector{Float64}(blv),
+                Matrix{Float64}(U), Vector{Float64}(D), Matrix{Float64}(Uinv), Float64(mu),
+                d.rates, length(d.rates), d.base_freq, ll, grad, rgrad))
+    ll[], grad, rgrad
+end
+
 # Likelihood + branch-length prior in one device call: what logpdfgrad!(::Type{provided}, ...)
 # (src/samplers/sampler.jl:172-190) assembles from gradlogpdf(m, target) and the Zygote-differentiated
 # prior (src/Likelihood/Prior.jl:39-57).  Topology priors contribute (0, zeros) (Prior.jl:59-66).

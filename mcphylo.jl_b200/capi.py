@@ -26,7 +26,7 @@ SYMBOLS = [
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_rate_gradient", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
     "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode", "mcp_set_ring_mode",
-    "mcp_schedule_dump", "mcp_model_reorder",
+    "mcp_schedule_dump", "mcp_schedule_fetch_list", "mcp_model_reorder",
 ]
 
 
@@ -466,6 +466,21 @@ def model_reorder(U, D, Uinv):
     if rc:
         raise McpError(rc, lib.mcp_last_error(None).decode())
     return Uo, Do, Uio, bool(flag.value)
+
+
+def schedule_fetch_list(postorder_num, parent_num, leaf_row, cherries: bool = True) -> np.ndarray:
+    """Host-only: fetch list of the gradient pass's operand ring (post slots in the order they are read)."""
+    lib = load()
+    po, pa, lr = _i32(postorder_num), _i32(parent_num), _i32(leaf_row)
+    NN = po.size
+    out = np.zeros(2 * NN + 8, dtype=np.uint16)
+    n = C.c_int32()
+    lib.mcp_schedule_fetch_list.argtypes = [C.c_int, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int32)]
+    rc = lib.mcp_schedule_fetch_list(NN, po.ctypes.data, pa.ctypes.data, lr.ctypes.data, int(bool(cherries)), out.ctypes.data,
+                                     out.size, C.byref(n))
+    if rc:
+        raise McpError(rc, lib.mcp_last_error(None).decode())
+    return out[:n.value].copy()
 
 
 def schedule_dump(postorder_num, parent_num, leaf_row, want_grad: bool, by_levels: bool = False, cherries: bool = False):

@@ -1655,4 +1655,16 @@ int mcp_schedule_dump(int NN, const int32_t* postorder_num, const int32_t* paren
     return 0;
 }
 
+int mcp_schedule_fetch_list(int NN, const int32_t* postorder_num, const int32_t* parent_num, const int32_t* leaf_row,
+                            int cherries, uint16_t* slots, int cap, int32_t* n_out) {
+    if (!postorder_num || !parent_num || !leaf_row || !n_out) return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_fetch_list: null argument");
+    mcp::Schedule sc;
+    std::string err = mcp::build_schedule(NN, postorder_num, parent_num, leaf_row, true, sc, false, cherries != 0);
+    if (!err.empty()) return fail(nullptr, MCP_ERR_ARG, "%s", err.c_str());
+    *n_out = (int32_t)sc.pre_fetch.size();
+    if ((int)sc.pre_fetch.size() > cap) return fail(nullptr, MCP_ERR_ARG, "mcp_schedule_fetch_list: output array too small");
+    if (slots && !sc.pre_fetch.empty()) std::memcpy(slots, sc.pre_fetch.data(), sc.pre_fetch.size() * sizeof(uint16_t));
+    return 0;
+}
+
 }  // extern "C"

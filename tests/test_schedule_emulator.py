@@ -112,6 +112,32 @@ def test_structure_of_the_program():
     assert progc0["n_slots"] == 1
 
 
+@pytest.mark.parametrize("n_taxa,seed,cherries", [(2, 0, True), (3, 1, True), (40, 2, True), (200, 3, False), (200, 4, True)])
+def test_fetch_list_of_the_operand_ring(n_taxa, seed, cherries):
+    """The fetch list the walk kernel's operand ring follows (mcp_schedule_fetch_list) is exactly the sequence of
+    stored child partials the gradient program reads -- per family child a, then child b -- and every entry is a
+    slot the post program really stores (a recomputed cherry has none and is never fetched)."""
+    rng = np.random.default_rng(seed)
+    tree = random_tree(n_taxa, rng, multifurcate=(seed % 2 == 1), unary=(seed == 3))
+    ft = mcp.flatten(tree)
+    lr = _leaf_row(ft, ft.leaf_nums)
+    prog = capi.schedule_dump(ft.postorder_num, ft.parent_num, lr, True, cherries=cherries)
+    fetch = capi.schedule_fetch_list(ft.postorder_num, ft.parent_num, lr, cherries=cherries)
+    want = []
+    for op in prog["pre"]:
+        if (op[5] & 3) == 2:
+            want.append(op[0])
+        if ((op[5] >> 2) & 3) == 2:
+            want.append(op[2])
+    assert fetch.tolist() == want
+    stored = {int(op[4]) for op in prog["post"] if op[5] & 16}
+    assert set(want) <= stored
+    # every stored post result is read exactly once by the gradient pass (the post pass may read it as well)
+    assert sorted(want) == sorted(stored)
+    if cherries and n_taxa >= 40:
+        assert prog["n_cherries"] > 0 and len(want) == len(prog["post"]) - 1 - prog["n_cherries"]
+
+
 def test_bad_trees_are_rejected():
     po = np.array([1, 2, 3], dtype=np.int32)
     with pytest.raises(capi.McpError):   # leaf without alignment row
