@@ -70,6 +70,16 @@ struct WalkParams {
     double model[176];
 };
 
+// Kernel parameters of the level-parallel small-tree kernel: the walk parameters plus, for MCMC-sized inputs, the
+// whole per-evaluation parameter block (branch lengths, priors: two doubles per node) INLINE -- kernel arguments are
+// delivered with the launch (CUDA 12.1+: up to 32 KB), so such an evaluation is one launch with no staging kernel and
+// no read of pinned host memory in front of it.  w.dyn == nullptr selects the inline copy.
+constexpr int LEVEL_DYN_INLINE = 448;           // doubles (3.5 KB): a tree of up to ~210 nodes, or the NNI pair of cfg2's 99-node tree
+struct LevelParams {
+    WalkParams w;
+    double dyn_inline[LEVEL_DYN_INLINE];
+};
+
 // per-tree layout of the per-evaluation parameter block (offsets in doubles from dyn_off)
 __host__ __device__ inline long long dyn_blv(int) { return 0; }
 __host__ __device__ inline long long dyn_U(int NN) { return NN - 1; }

@@ -30,7 +30,8 @@ struct KernelTable {
     cudaError_t (*launch_walk)(const LaunchCfg&, const WalkParams&, bool dyn_model, bool null_last);
     cudaError_t (*occupancy_walk)(const LaunchCfg&, int* ctas_per_sm);
     // level-parallel small-tree kernel (kernel_levels.cuh); null for the runtime-K unit
-    cudaError_t (*launch_levels)(const LaunchCfg&, const WalkParams&, bool dyn_model);
+    // dyn_inline != nullptr: the per-evaluation parameter block (n_inline doubles) travels in the kernel arguments
+    cudaError_t (*launch_levels)(const LaunchCfg&, const WalkParams&, bool dyn_model, const double* dyn_inline, size_t n_inline);
     cudaError_t (*occupancy_levels)(const LaunchCfg&, int* ctas_per_sm);
     // fills this unit's constant-memory model slots (batches with several models, full-K kernels);
     // null for the runtime-K unit, which reads its tables from global memory

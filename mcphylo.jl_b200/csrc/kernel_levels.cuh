@@ -14,7 +14,10 @@ namespace {
 // --------------------------------------------------------------------------------------------
 template <int K, bool DYN_MODEL>
 // 3 CTAs per SM (<= 85 registers): an MCMC-sized input is one tile per CTA, and all of them should be resident at once
-__global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_constant__ WalkParams p) {
+__global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_constant__ LevelParams lp) {
+    const WalkParams& p = lp.w;
+    // per-evaluation parameters: in device memory, or inline in the kernel arguments (device_layout.cuh: LevelParams)
+    const double* const dynp = p.dyn != nullptr ? p.dyn : lp.dyn_inline;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
         }
         long long e_total = 0;
         double logsum = 0.0;
-        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)__ldg(p.dyn + tr.dyn_off + dyn_slot(tr.NN, K, R)) * MODEL_SLOT : 0};
+        const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)dynp[tr.dyn_off + dyn_slot(tr.NN, K, R)] * MODEL_SLOT : 0};
         // post program, then pre program (contiguous in the topology block); likewise the level offsets
         __syncthreads();                                       // the previous tree's program is no longer in use
         for (int i = tid; i < 2 * (tr.n_post + tr.n_pre); i += NT) s_ops[i] = __ldg(p.ops + 2 * tr.post_off + i);
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
                 // branch table of (tree, rate r), built here instead of by a separate kernel:
                 // e = exp(t * D mu rate), P = U diag(e) Uinv, dP = U diag(D mu rate e) Uinv, plus the
                 // row-sum columns (same operation order as build_branch_tables)
-                const double* const blv = p.dyn + tr.dyn_off;
+                const double* const blv = dynp + tr.dyn_off;
                 for (int br = tid; br < tr.n_br; br += NT) {
                     double* ev = s_tab + (size_t)br * BT;
                     double* P = ev + 2 * K;
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
                             for (int m = 0; m < K; ++m) { P[n * K + m] = (n == K || n == m) ? 1.0 : 0.0; dP[n * K + m] = 0.0; }
                         continue;
                     }
-                    const double t = __ldg(blv + br);
+                    const double t = blv[br];
                     double em1[K], de[K];
 #pragma unroll
                     for (int i = 0; i < K; ++i) {
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
         for (int t = 0; t < p.T; ++t) {
             const TreeDev tr = p.trees[t];
             double* o = p.out + tr.out_off;
-            const double* d = p.dyn + tr.dyn_off;
+            const double* d = dynp + tr.dyn_off;
             const double* hdr = d + dyn_prior(tr.NN, K, R);
             const bool prior = hdr[0] != 0.0;
             PriorSums ps{0.0, 0.0};

@@ -255,10 +255,16 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         s.h2d_bytes += (int64_t)pl.topo_bytes;
         pl.uploaded = true;
     }
-    CUDA_TRY(ctx, stage(hd, ctx->d_dyn.p, sizeof(double) * pl.total_dyn));
+    // MCMC-sized inputs on the fused small-tree kernel: the parameter block rides in the kernel arguments -- one
+    // launch per evaluation, nothing read from pinned host memory in front of it (LevelParams, device_layout.cuh)
+    static const bool inline_allowed = []() { const char* v = std::getenv("MCPHYLO_B200_INLINE_PARAMS"); return !(v && v[0] == '0'); }();
+    const bool inline_dyn = fused && pl.total_dyn <= (long long)LEVEL_DYN_INLINE && inline_allowed;
+    if (!inline_dyn) {
+        CUDA_TRY(ctx, stage(hd, ctx->d_dyn.p, sizeof(double) * pl.total_dyn));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged[slot], st));
+        ctx->staged_pending[slot] = true;
+    }
     s.h2d_bytes += (int64_t)(sizeof(double) * pl.total_dyn);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_staged[slot], st));
-    ctx->staged_pending[slot] = true;
     // resident alignment, one tree: tiles by atomic ticket (site-major order) instead of static ranges
     const bool dyn_tiles = !ctx->sf && ctx->opt_dynamic == 1 && !pl.level_mode && !pl.acc_global && k_templated(K) && T == 1;
     if (dyn_tiles) {
@@ -329,7 +335,8 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     lc.acc_global = pl.acc_global;
     lc.mma = pl.mma;
     {
-        cudaError_t ce = pl.level_mode ? kt->launch_levels(lc, wp, dyn_model) : kt->launch_walk(lc, wp, dyn_model, all_null_last);
+        cudaError_t ce = pl.level_mode ? kt->launch_levels(lc, wp, dyn_model, inline_dyn ? hd : nullptr, (size_t)pl.total_dyn)
+                                       : kt->launch_walk(lc, wp, dyn_model, all_null_last);
         if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(ce));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -360,7 +367,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
                                                (const double*)ctx->d_dyn.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    s.kernel_launches = (fused ? 1 : 3) + 1 + (rebuilt ? 1 : 0);   // + parameter staging (+ topology staging)
+    s.kernel_launches = (fused ? 1 : 3) + (inline_dyn ? 0 : 1) + (rebuilt ? 1 : 0);   // + parameter staging (+ topology staging)
     s.grid = pl.grid;
     s.block = pl.block;
     s.tiles = pl.n_tiles;

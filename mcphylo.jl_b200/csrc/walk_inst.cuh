@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -123,9 +124,16 @@ cudaError_t occupancy_levels_k(const LaunchCfg& c, int* out) {
     return cudaSuccess;
 }
 template <int K>
-cudaError_t launch_levels_k(const LaunchCfg& c, const WalkParams& wp, bool dyn_model) {
-    if (dyn_model) felsenstein_walk_levels<K, true><<<c.grid, c.block, c.smem, c.stream>>>(wp);
-    else felsenstein_walk_levels<K, false><<<c.grid, c.block, c.smem, c.stream>>>(wp);
+cudaError_t launch_levels_k(const LaunchCfg& c, const WalkParams& wp, bool dyn_model, const double* dyn_inline, size_t n_inline) {
+    static thread_local LevelParams lp;            // 5 KB: not on the stack of whatever thread calls in
+    lp.w = wp;
+    if (dyn_inline) {
+        if (n_inline > (size_t)LEVEL_DYN_INLINE) return cudaErrorInvalidValue;
+        std::memcpy(lp.dyn_inline, dyn_inline, n_inline * sizeof(double));
+        lp.w.dyn = nullptr;
+    }
+    if (dyn_model) felsenstein_walk_levels<K, true><<<c.grid, c.block, c.smem, c.stream>>>(lp);
+    else felsenstein_walk_levels<K, false><<<c.grid, c.block, c.smem, c.stream>>>(lp);
     return cudaGetLastError();
 }
 cudaError_t upload_model_slots(const double* h_slots, size_t bytes, cudaStream_t stream) {
