@@ -99,12 +99,16 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     int* const s_pbr = reinterpret_cast<int*>(s_part + walk_part_doubles(CHN));
     // folds the parked sums of one chunk (buffer `buf`, `n` ops) into s_acc; call after the barrier that
     // follows the chunk, by all threads (2 * n of them do the work; each term has its own branch)
+    // The once-per-chunk jobs of a few threads -- this fold, the derivation of the op records -- are given to
+    // DIFFERENT warps (the last one, the one before it): every warp waits at the chunk barrier for the slowest.
+    const int fold_t = tid - ((TW >> 5) - 1) * 32;                       // lane of the folding warp, negative elsewhere
+    const int rec_t = tid - ((TW >> 5) > 1 ? (TW >> 5) - 2 : 0) * 32;    // lane of the record-deriving warp
     auto fold_parked = [&](int buf, int n) {
-        if (tid < 2 * n) {
-            const double* pp = s_part + (buf * CHN * 2 + tid) * 8;
+        if (fold_t >= 0 && fold_t < 2 * n) {
+            const double* pp = s_part + (buf * CHN * 2 + fold_t) * 8;
             double sum = pp[0];
             for (int w = 1; w < (TW >> 5); ++w) sum += pp[w];
-            s_acc[s_pbr[buf * CHN * 2 + tid]] += sum;
+            s_acc[s_pbr[buf * CHN * 2 + fold_t]] += sum;
         }
     };
     double* const se = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(sdesc) + WalkSmem<K, CHN>::desc_bytes());
@@ -273,7 +277,8 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                        reinterpret_cast<const unsigned char*>(bsrc) + lane * 16);
                     }
                 }
-                for (int j = tid; j < cnt; j += TW) {
+                if (rec_t >= 0 && rec_t < cnt) {
+                    const int j = rec_t;
                     const int4 o0 = d[2 * j], o1 = d[2 * j + 1];
                     const int fl = o1.y, ka = fl & 3, kb = (fl >> 2) & 3;
                     OpRec rec;
