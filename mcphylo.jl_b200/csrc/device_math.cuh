@@ -213,6 +213,24 @@ __device__ __forceinline__ void eig_project(const M& m, const double (&L)[C][K],
         }
     }
 }
+// yd[c] = c_r * (Uinv D[c]),  c_r = D mu rate_r:  the eigen-coordinates of dP L when D = P L is what is at hand
+// (dP = U diag(c_r) Uinv P); rate category `r` is uniform over the tile
+template <int K, int C, int NE = K, class M>
+__device__ __forceinline__ void eig_project_rate(const M& m, const double (&D)[C][K], int r, double (&yd)[C][K]) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+        double w[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = m.Ui(i, 0) * D[c][0];
+#pragma unroll
+        for (int j = 1; j < K; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) w[c] = fma(m.Ui(i, j), D[c][j], w[c]);
+        const double cr = m.c(r, i);
+#pragma unroll
+        for (int c = 0; c < C; ++c) yd[c][i] = cr * w[c];
+    }
+}
 // out[c] = base[c] + U z[c]
 template <int K, int C, int NE = K, class M>
 __device__ __forceinline__ void eig_expand(const M& m, const double (&z)[C][K], const double (&base)[C][K], double (&out)[C][K]) {

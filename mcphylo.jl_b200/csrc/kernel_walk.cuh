@@ -124,6 +124,13 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     // RLS: cp.async flavour of the ring -- a warp's share of a column is split into 16-byte pieces [piece][lane]
     // (device_math.cuh: piece layout), every thread copies its own pieces
     constexpr bool RLS = RD > 0 && WALK_RING_LDGSTS;
+    // DST: what a stored (or register-carried) post result is.  false: the node's partial L, and every op applies the
+    // children's branches (P L in the mother's post op and AGAIN in the family's gradient op).  true (K >= 3): D = P L --
+    // a post op ends by applying the branch above its node, so the product is formed once; the gradient pass uses the
+    // stored D as it is and takes the numerator's eigen-coordinates from it (dP = U diag(c) Uinv P).  Same bits in the
+    // post pass either way; 15 of ~130 FP64 operations per node and column less at K = 4 (cfg4 -1.4 %, cfg3 -3.8 %).
+    // At K = 2 the products are too small to matter and the longer dependency chain of the post op costs 2.6 %.
+    constexpr bool DST = K >= 3;
     unsigned char* const scr = SSCR
         ? scode + WalkSmem<K, CHN>::code_bytes(TS, 2) + (size_t)tid * K * 8
         : keep_ptr(reinterpret_cast<unsigned char*>(p.scratch + (long long)blockIdx.x * p.scratch_per_cta) +
@@ -263,7 +270,15 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                     if (kind == mcp::OPK_LEAF) {
                         copy_codes(crow, src);
                         copy_table(tdst, bsrc + 2 * K, pre ? 2 : 1);
-                    } else {
+                    }
+                    if (DST && !pre) {
+                        // post pass: internal children arrive with their own branch already applied (see the post op);
+                        // what an op needs is the (em1, de) vector of ITS OWN branch (word 6 of the op: its device
+                        // node), staged in the slot of child a -- the root has no branch
+                        if (ch == 0 && !(fl & mcp::POST_ROOT) && lane < K)
+                            cp_async16(reinterpret_cast<unsigned char*>(eb + (j * 2) * 2 * K) + lane * 16,
+                                       btab_b + (unsigned)o1.z * br_bytes + lane * 16);
+                    } else if (kind != mcp::OPK_LEAF) {
                         if (pre && kind == mcp::OPK_CHERRY) {    // child a only: leaves in a_src, their branches in a_dst
                             const int bx = o1.z & 0xffff, by = (o1.z >> 16) & 0xffff;
                             copy_codes(crow, src & 0xffff);
@@ -407,7 +422,10 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 ld_cols_if(j + 1 < cnt && ((int)rn.x & 3) == mcp::OPK_MEM, rn.y, Lm, std::false_type{});
                             }
                         };
-                        // Canonical operand kinds (schedule.hpp): (LEAF, LEAF), (REG, LEAF), (MEM, REG).
+                        // Canonical operand kinds (schedule.hpp): (LEAF, LEAF), (REG, LEAF), (MEM, REG).  An internal
+                        // child's vector -- carried in `cur` (REG) or stored (MEM) -- is D = P L, the child's partial with
+                        // its own branch already applied (below), so the op itself is a product and one
+                        // matrix-vector product for the branch above this node.
                         double Da[CPT][K], Db[CPT][K];
                         auto leaf_cols = [&](int ch, double (&D)[CPT][K]) {
 #pragma unroll
@@ -418,37 +436,75 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 for (int k = 0; k < K; ++k) D[cc][k] = t[k];
                             }
                         };
-                        auto internal_cols = [&](int ch, const double (&L)[CPT][K], double (&D)[CPT][K]) {
-                            double e[K], z[CPT][K];
+                        if constexpr (DST) {
+                            if (ka == mcp::OPK_MEM) {
+                                ld_cols_if(!MCP_EARLY_LOADS || j == 0, rh.y, Lm, std::true_type{});
 #pragma unroll
-                            for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
-                            eig_project<K, CPT, false, NE>(mdl, L, e, nullptr, z, z);
-                            eig_expand<K, CPT, NE>(mdl, z, L, D);
-                        };
-                        if (ka == mcp::OPK_MEM) {
-                            ld_cols_if(!MCP_EARLY_LOADS || j == 0, rh.y, Lm, std::true_type{});
-                            if (MCP_EARLY_LOADS) {
-                                internal_cols(0, Lm, Da);
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = Lm[cc][k] * cur[cc][k];
                                 request_next();
-                                internal_cols(1, cur, Db);
-                            } else {   // latency of the stored operand overlaps the product on the register operand
-                                internal_cols(1, cur, Db);
-                                internal_cols(0, Lm, Da);
+                            } else if (ka == mcp::OPK_REG) {
+                                request_next();
+                                leaf_cols(1, Db);
+#pragma unroll
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = cur[cc][k] * Db[cc][k];
+                            } else {
+                                request_next();
+                                leaf_cols(0, Da);
+                                leaf_cols(1, Db);
+#pragma unroll
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) cur[cc][k] = Da[cc][k] * Db[cc][k];
                             }
-                        } else if (ka == mcp::OPK_REG) {
-                            request_next();
-                            leaf_cols(1, Db);
-                            internal_cols(0, cur, Da);
+#pragma unroll
+                            for (int cc = 0; cc < CPT; ++cc) e_col[cc] += rescale_pow2<K>(cur[cc]);
+                            // The branch above this node is applied HERE, D = P L = L + U (em1 * (Uinv L)) (same operands,
+                            // same order, hence the same bits as applying it in the mother's op): the mother's op and the
+                            // gradient pass read D and never repeat this product.  The root has no branch.
+                            if (!(flags & mcp::POST_ROOT)) {
+                                double e[K], z[CPT][K];
+#pragma unroll
+                                for (int k = 0; k < K; ++k) e[k] = eb[(j * 2) * 2 * K + k];
+                                eig_project<K, CPT, false, NE>(mdl, cur, e, nullptr, z, z);
+                                eig_expand<K, CPT, NE>(mdl, z, cur, cur);
+                            }
                         } else {
-                            request_next();
-                            leaf_cols(0, Da);
-                            leaf_cols(1, Db);
-                        }
+                            auto internal_cols = [&](int ch, const double (&L)[CPT][K], double (&D)[CPT][K]) {
+                                double e[K], z[CPT][K];
 #pragma unroll
-                        for (int cc = 0; cc < CPT; ++cc) {
+                                for (int k = 0; k < K; ++k) e[k] = eb[(j * 2 + ch) * 2 * K + k];
+                                eig_project<K, CPT, false, NE>(mdl, L, e, nullptr, z, z);
+                                eig_expand<K, CPT, NE>(mdl, z, L, D);
+                            };
+                            if (ka == mcp::OPK_MEM) {
+                                ld_cols_if(!MCP_EARLY_LOADS || j == 0, rh.y, Lm, std::true_type{});
+                                if (MCP_EARLY_LOADS) {
+                                    internal_cols(0, Lm, Da);
+                                    request_next();
+                                    internal_cols(1, cur, Db);
+                                } else {   // latency of the stored operand overlaps the product on the register operand
+                                    internal_cols(1, cur, Db);
+                                    internal_cols(0, Lm, Da);
+                                }
+                            } else if (ka == mcp::OPK_REG) {
+                                request_next();
+                                leaf_cols(1, Db);
+                                internal_cols(0, cur, Da);
+                            } else {
+                                request_next();
+                                leaf_cols(0, Da);
+                                leaf_cols(1, Db);
+                            }
 #pragma unroll
-                            for (int k = 0; k < K; ++k) cur[cc][k] = Da[cc][k] * Db[cc][k];
-                            e_col[cc] += rescale_pow2<K>(cur[cc]);
+                            for (int cc = 0; cc < CPT; ++cc) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) cur[cc][k] = Da[cc][k] * Db[cc][k];
+                                e_col[cc] += rescale_pow2<K>(cur[cc]);
+                            }
                         }
                         if (flags & mcp::POST_STORE) st_cols(rh.w, cur);
                     }
@@ -609,21 +665,67 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
                                 rescale_pow2<K>(La[cc]);
                             }
                         }
-                        if constexpr (RD > 0) {
-                            const bool am = (flags & 3) == mcp::OPK_MEM;
-                            if (am) ring_consume(La);
-                            if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
-                            if (am) ring_refill();
+                        // A STORED child arrives as D = P L (the post pass applied the child's branch before storing),
+                        // nothing is recomputed; the eigen-coordinates of dP L follow from dP = U diag(c) Uinv P,
+                        // c = D mu rate:  Y = c * (Uinv D).
+                        auto stored_cols = [&](const double (&D)[CPT][K], double (&Y)[CPT][K]) {
+                            eig_project_rate<K, CPT, NE>(mdl, D, r, Y);
+                        };
+                        const bool am = (flags & 3) == mcp::OPK_MEM;
+                        if constexpr (!DST) {            // stored children are partials L: apply their branches again
+                            if constexpr (RD > 0) {
+                                if (am) ring_consume(La);
+                                if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
+                                if (am) ring_refill();
+                                if (bi) {
+                                    ring_consume(Lb);
+                                    internal_cols(1, Lb, Db, Yb);
+                                    ring_refill();
+                                } else {
+                                    leaf_cols(1, Db, Yb);
+                                }
+                            } else {
+                                if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
+                                if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
+                            }
+                        } else if constexpr (RD > 0) {
+                            if (am) {
+                                ring_consume(Da);
+                                stored_cols(Da, Ya);
+                                ring_refill();
+                            } else if (ai) {
+                                internal_cols(0, La, Da, Ya);          // cherry, rebuilt above
+                            } else {
+                                leaf_cols(0, Da, Ya);
+                            }
                             if (bi) {
-                                ring_consume(Lb);
-                                internal_cols(1, Lb, Db, Yb);
+                                ring_consume(Db);
+                                stored_cols(Db, Yb);
                                 ring_refill();
                             } else {
                                 leaf_cols(1, Db, Yb);
                             }
                         } else {
-                            if (ai) internal_cols(0, La, Da, Ya); else leaf_cols(0, Da, Ya);
-                            if (bi) internal_cols(1, Lb, Db, Yb); else leaf_cols(1, Db, Yb);
+                            if (am) {
+#pragma unroll
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) Da[cc][k] = La[cc][k];
+                                stored_cols(Da, Ya);
+                            } else if (ai) {
+                                internal_cols(0, La, Da, Ya);          // cherry, rebuilt above
+                            } else {
+                                leaf_cols(0, Da, Ya);
+                            }
+                            if (bi) {
+#pragma unroll
+                                for (int cc = 0; cc < CPT; ++cc)
+#pragma unroll
+                                    for (int k = 0; k < K; ++k) Db[cc][k] = Lb[cc][k];
+                                stored_cols(Db, Yb);
+                            } else {
+                                leaf_cols(1, Db, Yb);
+                            }
                         }
                         double qa[CPT][K], qb[CPT][K];
                         double na[CPT], nb[CPT], inv[CPT];

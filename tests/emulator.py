@@ -23,7 +23,10 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
     eigen = dict(U, D, Uinv, mu, blv, rates, NE) switches INTERNAL children to the walk kernel's own
     arithmetic (csrc/device_math.cuh): P L = L + U (em1 * (Uinv L)) and P^T q = q + Uinv^T (em1 * (U^T q))
     over the first NE eigen-components only (the host has moved the null eigenvalue last,
-    capi.model_reorder), and the gradient numerator in eigen-space, sum_i (U^T q)_i de_i (Uinv L)_i.
+    capi.model_reorder), and the gradient numerator in eigen-space.  As in the kernel, a post op applies
+    the branch ABOVE its node before the result is carried on or stored (slots and `reg` hold D = P L), a
+    stored child of the gradient pass is used as it is and its numerator is sum_i (U^T q)_i c_i (Uinv D)_i
+    with c = D mu rate (dP = U diag(c) Uinv P); a recomputed cherry goes the old way, sum_i (U^T q)_i de_i (Uinv L)_i.
     Leaf children keep using the P / dP table columns, as on the device."""
     R = P.shape[2]
     S = codes.shape[1]
@@ -40,6 +43,7 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
         c = np.full(S, K) if row < 0 else np.minimum(codes[row].astype(int), K)
         return ext[:, c]
 
+    dstore = eigen is not None and K >= 3          # kernel_walk.cuh: DST (slots hold D = P L) for K >= 3 only
     if eigen is not None:
         NE = eigen["NE"]
         Ue, Uie = np.asarray(eigen["U"])[:, :NE], np.asarray(eigen["Uinv"])[:NE, :]
@@ -57,13 +61,15 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
         reg = np.ones((K, S))
         esum = np.zeros(S, dtype=np.int64)
         for op in prog["post"]:
-            a_src, a_br, b_src, b_br, dst, flags = (int(v) for v in op[:6])
+            a_src, a_br, b_src, b_br, dst, flags, node = (int(v) for v in op[:7])
 
             def down(kind, src, br):
                 Pm, _ = tables(br, r)
                 if kind == OPK_LEAF:
                     return leaf_down(Pm, src)
                 L = reg if kind == OPK_REG else slots[src]
+                if dstore:
+                    return L                     # already D = P L: the child's op applied its branch
                 if eigen is not None:
                     em1, _ = eig_vecs(br, r)
                     return L + Ue @ (em1[:, None] * (Uie @ L))
@@ -72,6 +78,9 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
             Db = down((flags >> 2) & 3, b_src, b_br)
             reg, e = _rescale(Da * Db)
             esum += e
+            if dstore and not (flags & 32):                     # the branch above this node (the root has none)
+                em1, _ = eig_vecs(node, r)
+                reg = reg + Ue @ (em1[:, None] * (Uie @ reg))
             if flags & 16:
                 slots[dst] = reg
         ll += (esum * np.log(2.0) + np.log(pi @ reg)).sum()
@@ -93,9 +102,12 @@ def run_program(prog, codes, K, P, dP, pi, n_real_branches, eigen=None):
                     else:
                         L = slots[src]
                     if eigen is not None:    # Y = eigen-coordinates of dP L
-                        em1, de = eig_vecs(br, r)
-                        w = Uie @ L
-                        return L + Ue @ (em1[:, None] * w), de[:, None] * w, Pm
+                        if kind == OPK_CHERRY or not dstore:
+                            em1, de = eig_vecs(br, r)
+                            w = Uie @ L
+                            return L + Ue @ (em1[:, None] * w), de[:, None] * w, Pm
+                        crate = np.zeros(NE) if br >= n_real_branches else np.asarray(eigen["D"])[:NE] * eigen["mu"] * eigen["rates"][r]
+                        return L, crate[:, None] * (Uie @ L), Pm          # the slot holds D = P L
                     return Pm @ L, dPm @ L, Pm
                 return leaf_down(Pm, src), leaf_down(dPm, src), Pm
             Da, Ya, Pa = child(flags & 3, a_src, a_br, a_dst)
