@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--cases", default="cfg4:1000000,cfg4:125000")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cpt", type=int, default=0, help="force columns per thread (0 = automatic)")
+    ap.add_argument("--block", type=int, default=0, help="force the tile width in threads (0 = automatic)")
     ap.add_argument("--tag", default="")
     args = ap.parse_args()
     import mcphylo_jl_b200 as mcp
@@ -32,6 +33,8 @@ def main():
     ctx = capi.Context(0)
     if args.cpt:
         ctx.set_columns_per_thread(args.cpt)
+    if args.block:
+        ctx.set_launch(args.block, 0)
     for case in args.cases.split(","):
         name, S = case.split(":")
         S = int(S)
@@ -51,7 +54,7 @@ def main():
                 if ref is None:
                     ref = res
                 row = {"case": case, "round": rnd, "ring_mode": ring, "operand_ring": st["operand_ring"],
-                       "columns_per_thread": st["columns_per_thread"], "grid": st["grid"],
+                       "columns_per_thread": st["columns_per_thread"], "grid": st["grid"], "block": st["block"],
                        "walk_ms_median": float(np.median(ms[1:])), "walk_ms_min": float(np.min(ms[1:])),
                        "ll": res[0], "ll_equal_to_first": bool(res[0] == ref[0]),
                        "grad_equal_to_first": bool(np.array_equal(res[1], ref[1])),
