@@ -141,9 +141,9 @@ __global__ void __launch_bounds__(MCP_WALK_MAXT, K * CPT <= 4 ? MCP_WALK_MIN_BLO
     const unsigned stack_base = (unsigned)p.n_slots * slot_bytes;
     // ---- operand ring (RD > 0): this warp's stages and their mbarriers, as shared-window addresses ----
     constexpr unsigned RBAR = RD * CPT * WB;          // this warp's block: RD stages of CPT vectors, then RD mbarriers
-    // Ring state is kept in ordinary (per-lane) registers on purpose -- it is warp-uniform, but the uniform register
-    // file is needed for U / Uinv (48 of its 63 registers at K = 4); `lane0` is a zero the compiler cannot see through
-    // and takes for lane-dependent.
+    // Ring state is kept in ordinary (per-lane) registers on purpose -- it is warp-uniform, but values ptxas takes for
+    // uniform are moved to uniform registers right behind their loads (a stall on the load) and compete with U / Uinv
+    // there; `lane0` is a zero the compiler cannot see through and takes for lane-dependent.
     //   ring_l   this LANE's vector in stage 0, column 0 (lane 0: the warp's block itself); stage s, column c at
     //            + (s * CPT + c) * WB
     //   rbar_w   the warp's mbarrier of stage 0; stage s at + 8 s
