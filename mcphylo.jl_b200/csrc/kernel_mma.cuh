@@ -20,6 +20,12 @@
 // permutation of a contraction index, applied to A and B alike.
 // Shared-memory table T (per child and per P / dP): rows = child state j (KP rows, zero beyond K) plus one
 // row for the all-ones leaf (row KP = row sums), columns = parent state s (zero beyond K), row stride KP + 2.
+// Gradient evaluations form each product P L ONCE: a post op ends by applying the branch above its node, so what is
+// carried in registers and what is stored is D = P L (same table, same operand, hence the same bits as applying it in
+// the mother's op); the gradient pass uses a stored child as it is and gets dP L = Q' (P L) from one more product with
+// Q' = mu * rate * Q, a table built once per tile -- 2 instead of 3 tensor-core products per internal child there
+// (K = 20: 3.70 -> 3.42 ms, K = 12: 1.54 -> 1.39 ms).  logL-only evaluations keep the products in the mother's op,
+// where the two children's products are independent of each other (the chained form cost them 9-19 %).
 // Partials in HBM scratch are stored fragment-major, [slot][warp][m][n][h][lane]: every access of a warp is a
 // run of 32 consecutive doubles.  Gradient sums: one fixed-order butterfly per op, per-warp sums parked in
 // shared memory and folded by one thread per branch after the next barrier -- no atomics, bit-reproducible.
@@ -57,7 +63,9 @@ __device__ __forceinline__ void mma_product(const double* T, const double (&in)[
         }
 }
 
-template <int KP>
+// DST: stored / carried post results are D = P L (gradient evaluations) or the partials L themselves (logL only); two
+// instantiations, because with both post ops in one kernel the logL-only path lost 5-17 % to the other's registers.
+template <int KP, bool DST>
 __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_walk_mma(const __grid_constant__ WalkParams p, const int K) {
     constexpr int NB = KP / 8, KB = KP / 4, MB = MMA_MB, STRIDE = MmaSmem<KP>::STRIDE, TAB = MmaSmem<KP>::TAB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -80,9 +88,11 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
     unsigned char* const scode = sp;                                            // [2 buffers][2 children][128]
     sp += MmaSmem<KP>::code_bytes();
     double* const stab = reinterpret_cast<double*>(sp);                         // [2 buffers][4 tables][TAB]
+    double* const stq = stab + 2 * 4 * TAB;                                     // Q' of the tile's (tree, rate)
+    constexpr bool dst = DST;                                                   // stored / carried vectors are D = P L
 
     // zero the tables once: the padding (states >= K) is never written again
-    for (int i = tid; i < 2 * 4 * TAB; i += blockDim.x) stab[i] = 0.0;
+    for (int i = tid; i < (2 * 4 + 1) * TAB; i += blockDim.x) stab[i] = 0.0;
 
     const int R = p.R;
     const int BT = bt_size(K), KK1 = K * (K + 1);
@@ -165,6 +175,21 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
             const double* const btab_r = p.btab + tr.btab_off + (long long)r * BT;      // (branch 0, rate r)
             const long long br_stride = (long long)R * BT;
 
+            if (p.want_grad) {
+                // Q' = mu rate U diag(D) Uinv in table layout (row = child state j, column = parent state s): dP = Q' P
+                __syncthreads();                                    // the previous tile is done with the table
+                const double* const dd = p.dyn + tr.dyn_off;
+                const double* const U = dd + dyn_U(tr.NN);
+                const double* const Dg = dd + dyn_D(tr.NN, K);
+                const double* const Ui = dd + dyn_Uinv(tr.NN, K);
+                const double scale = __ldg(dd + dyn_mu(tr.NN, K)) * __ldg(dd + dyn_rates(tr.NN, K) + r);
+                for (int i = tid; i < K * K; i += blockDim.x) {
+                    const int jj = i / K, s = i - jj * K;
+                    double acc = 0.0;
+                    for (int k = 0; k < K; ++k) acc += (__ldg(U + s + K * k) * __ldg(Dg + k)) * __ldg(Ui + k + K * jj);
+                    stq[jj * STRIDE + s] = acc * scale;
+                }
+            }                                                       // (visible after the barriers of the prologues)
             // ---- staging, one op ahead: descriptor of op j + 2, tables and codes of op j + 1 ----
             auto stage_desc = [&](const int4* ops, int n_ops, int j) {
                 if (j < n_ops && tid < 2) cp_async16(sdesc + (j % 3) * 2 + tid, ops + 2 * j + tid);
@@ -176,11 +201,21 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
                 double* tb = stab + (size_t)(j & 1) * 4 * TAB;
                 unsigned char* cb = scode + (size_t)(j & 1) * 2 * MMA_TILE;
                 const int per = (K + 1) * K;                        // doubles of one global table (P or dP columns)
+                if (dst && !pre && !(fl & mcp::POST_ROOT)) {
+                    // post pass: the P table of the op's OWN branch (word 6 of the op: its device node), table slot 1
+                    const double* gt = btab_r + o1.z * br_stride + 2 * K;
+                    for (int i = tid; i < per; i += blockDim.x) {
+                        const int jj = i / K, s = i - jj * K;
+                        cp_async8(tb + (size_t)TAB + (jj == K ? KP : jj) * STRIDE + s, gt + i);
+                    }
+                }
                 for (int ch = 0; ch < 2; ++ch) {
                     const int kind = ch ? ((fl >> 2) & 3) : (fl & 3);
                     const int src = ch ? o0.z : o0.x, br = ch ? o0.w : o0.y;
                     const double* gt = btab_r + br * br_stride + 2 * K;         // P columns, then dP columns
-                    const int n_tab = pre ? 2 : 1;
+                    // a leaf child needs its table rows (P; gradient pass: and dP), an internal child only P, and
+                    // only in the gradient pass (for P^T q): in the post pass it arrives with its branch applied
+                    const int n_tab = kind == mcp::OPK_LEAF ? (pre ? 2 : 1) : (pre || !dst ? 1 : 0);
                     for (int i = tid; i < n_tab * per; i += blockDim.x) {
                         const int which = i >= per, e = i - which * per, jj = e / K, s = e - jj * K;
                         cp_async8(tb + (size_t)(ch * 2 + which) * TAB + (jj == K ? KP : jj) * STRIDE + s, gt + which * KK1 + e);
@@ -239,26 +274,53 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
                     const double* tb = stab + (size_t)(j & 1) * 4 * TAB;
                     const unsigned char* cb = scode + (size_t)(j & 1) * 2 * MMA_TILE;
                     double Da[MB][NB][2], Db[MB][NB][2];
-                    // canonical operand kinds (schedule.hpp): (LEAF, LEAF), (REG, LEAF), (MEM, REG)
-                    if (ka == mcp::OPK_LEAF) {
-                        leaf_vec(tb, cb, Da);
-                    } else if (ka == mcp::OPK_REG) {
-                        mma_product<KP, false>(tb, cur, Da, g, t);
-                    } else {
-                        double L[MB][NB][2];
-                        ld_vec(scr + (long long)o0.x * slot_stride, L);
-                        mma_product<KP, false>(tb, L, Da, g, t);
+                    // canonical operand kinds (schedule.hpp): (LEAF, LEAF), (REG, LEAF), (MEM, REG); an internal child's
+                    // vector -- `cur` (REG) or stored (MEM) -- already is D = P L
+                    if constexpr (dst) {
+                        if (ka == mcp::OPK_LEAF) {
+                            leaf_vec(tb, cb, Da);
+                        } else if (ka == mcp::OPK_MEM) {
+                            ld_vec(scr + (long long)o0.x * slot_stride, Da);
+                        }
+                        if (kb_ == mcp::OPK_LEAF) leaf_vec(tb + 2 * TAB, cb + MMA_TILE, Db);
+#pragma unroll
+                        for (int m = 0; m < MB; ++m)
+#pragma unroll
+                            for (int n = 0; n < NB; ++n)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const double a = ka == mcp::OPK_REG ? cur[m][n][h] : Da[m][n][h];
+                                    const double b = kb_ == mcp::OPK_LEAF ? Db[m][n][h] : cur[m][n][h];
+                                    cur[m][n][h] = a * b;
+                                }
+                    } else {                                                        // logL only: L stored, products here
+                        if (ka == mcp::OPK_LEAF) {
+                            leaf_vec(tb, cb, Da);
+                        } else if (ka == mcp::OPK_REG) {
+                            mma_product<KP, false>(tb, cur, Da, g, t);
+                        } else {
+                            double L[MB][NB][2];
+                            ld_vec(scr + (long long)o0.x * slot_stride, L);
+                            mma_product<KP, false>(tb, L, Da, g, t);
+                        }
+                        if (kb_ == mcp::OPK_LEAF) leaf_vec(tb + 2 * TAB, cb + MMA_TILE, Db);
+                        else mma_product<KP, false>(tb + 2 * TAB, cur, Db, g, t);   // REG
+#pragma unroll
+                        for (int m = 0; m < MB; ++m)
+#pragma unroll
+                            for (int n = 0; n < NB; ++n) { cur[m][n][0] = Da[m][n][0] * Db[m][n][0]; cur[m][n][1] = Da[m][n][1] * Db[m][n][1]; }
                     }
-                    if (kb_ == mcp::OPK_LEAF) leaf_vec(tb + 2 * TAB, cb + MMA_TILE, Db);
-                    else mma_product<KP, false>(tb + 2 * TAB, cur, Db, g, t);       // REG
-#pragma unroll
-                    for (int m = 0; m < MB; ++m)
-#pragma unroll
-                        for (int n = 0; n < NB; ++n) { cur[m][n][0] = Da[m][n][0] * Db[m][n][0]; cur[m][n][1] = Da[m][n][1] * Db[m][n][1]; }
                     int ex[MB];
                     rescale(cur, ex);
 #pragma unroll
                     for (int m = 0; m < MB; ++m) e_col[m] += ex[m];
+                    if (dst && !(flags & mcp::POST_ROOT)) {                         // the branch above this node
+                        mma_product<KP, false>(tb + TAB, cur, Da, g, t);
+#pragma unroll
+                        for (int m = 0; m < MB; ++m)
+#pragma unroll
+                            for (int n = 0; n < NB; ++n) { cur[m][n][0] = Da[m][n][0]; cur[m][n][1] = Da[m][n][1]; }
+                    }
                     if (flags & mcp::POST_STORE) st_vec(scr + (long long)o1.x * slot_stride, cur);
                 }
             }
@@ -301,20 +363,16 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
                     if (((flags >> 8) & 3) == mcp::PREM_STACK) ld_vec(stk + (long long)o1.x * slot_stride, cur);
                     // family {mother; a, b}: D = P L, Y = dP L
                     double Da[MB][NB][2], Ya[MB][NB][2], Db[MB][NB][2], Yb[MB][NB][2];
-                    if (ai) {
-                        double L[MB][NB][2];
-                        ld_vec(scr + (long long)o0.x * slot_stride, L);
-                        mma_product<KP, false>(tb, L, Da, g, t);
-                        mma_product<KP, false>(tb + TAB, L, Ya, g, t);
+                    if (ai) {                                                   // stored D = P L; dP L = Q' D
+                        ld_vec(scr + (long long)o0.x * slot_stride, Da);
+                        mma_product<KP, false>(stq, Da, Ya, g, t);
                     } else {
                         leaf_vec(tb, cb, Da);
                         leaf_vec(tb + TAB, cb, Ya);
                     }
                     if (bi) {
-                        double L[MB][NB][2];
-                        ld_vec(scr + (long long)o0.z * slot_stride, L);
-                        mma_product<KP, false>(tb + 2 * TAB, L, Db, g, t);
-                        mma_product<KP, false>(tb + 3 * TAB, L, Yb, g, t);
+                        ld_vec(scr + (long long)o0.z * slot_stride, Db);
+                        mma_product<KP, false>(stq, Db, Yb, g, t);
                     } else {
                         leaf_vec(tb + 2 * TAB, cb + MMA_TILE, Db);
                         leaf_vec(tb + 3 * TAB, cb + MMA_TILE, Yb);

@@ -110,7 +110,8 @@ struct MmaSmem {
     static __host__ __device__ size_t part_bytes() { return 2 * 2 * MMA_WARPS * 8 + 2 * 2 * 4; }    // parked sums + branch ids, 2 buffers
     static __host__ __device__ size_t desc_bytes() { return 3 * 32; }
     static __host__ __device__ size_t code_bytes() { return 2 * 2 * MMA_TILE; }
-    static __host__ __device__ size_t tab_bytes() { return (size_t)2 * 4 * TAB * 8; }
+    // [2 buffers][4 tables] staged per op + one table per tile: Q' = mu * rate * Q (dP = Q' P), kernel_mma.cuh
+    static __host__ __device__ size_t tab_bytes() { return (size_t)(2 * 4 + 1) * TAB * 8; }
     static __host__ __device__ size_t total(int n_br, int want_grad) {
         return acc_bytes(n_br, want_grad) + ((part_bytes() + 15) & ~(size_t)15) + desc_bytes() + code_bytes() + tab_bytes();
     }

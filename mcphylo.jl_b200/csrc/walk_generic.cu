@@ -20,18 +20,26 @@ template <class Kern>
 cudaError_t raise_smem(Kern kern, size_t smem) {
     return smem > 48 * 1024 ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) : cudaSuccess;
 }
-template <int KP>
-cudaError_t launch_mma(const LaunchCfg& c, const WalkParams& wp) {
-    cudaError_t e = raise_smem(felsenstein_walk_mma<KP>, c.smem);
+template <int KP, bool DST>
+cudaError_t launch_mma_inst(const LaunchCfg& c, const WalkParams& wp) {
+    cudaError_t e = raise_smem(felsenstein_walk_mma<KP, DST>, c.smem);
     if (e != cudaSuccess) return e;
-    felsenstein_walk_mma<KP><<<c.grid, MMA_WARPS * 32, c.smem, c.stream>>>(wp, c.K);
+    felsenstein_walk_mma<KP, DST><<<c.grid, MMA_WARPS * 32, c.smem, c.stream>>>(wp, c.K);
     return cudaGetLastError();
 }
 template <int KP>
-cudaError_t occupancy_mma(const LaunchCfg& c, int* out) {
-    cudaError_t e = raise_smem(felsenstein_walk_mma<KP>, c.smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk_mma<KP>, MMA_WARPS * 32, c.smem);
+cudaError_t launch_mma(const LaunchCfg& c, const WalkParams& wp) {
+    return wp.want_grad ? launch_mma_inst<KP, true>(c, wp) : launch_mma_inst<KP, false>(c, wp);
+}
+template <int KP>
+cudaError_t occupancy_mma(const LaunchCfg& c, int* out) {   // the persistent grid is sized for the more demanding of the two
+    int o1 = 0, o2 = 0;
+    cudaError_t e = raise_smem(felsenstein_walk_mma<KP, true>, c.smem);
+    if (e == cudaSuccess) e = raise_smem(felsenstein_walk_mma<KP, false>, c.smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, felsenstein_walk_mma<KP, true>, MMA_WARPS * 32, c.smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, felsenstein_walk_mma<KP, false>, MMA_WARPS * 32, c.smem);
+    *out = o1 < o2 ? o1 : o2;
+    return e;
 }
 cudaError_t launch_generic(const LaunchCfg& c, const WalkParams& wp, bool, bool) {
     if (c.mma) {
