@@ -9,13 +9,16 @@ namespace {
 // tiles; a tile = blockDim.x columns of one rate category of one tree.
 //
 // Per-op inputs that are uniform over the tile or byte-sized per column are staged in shared
-// memory CH ops at a time with cp.async, one chunk ahead of the compute:
-//   sdesc  3 x CH op descriptors (ring of 3: descriptors must be resident one chunk before the
+// memory CHN ops at a time with cp.async (16, ring kernels 8), one chunk ahead of the compute:
+//   sdesc  3 x CHN op descriptors (ring of 3: descriptors must be resident one chunk before the
 //          data they describe can be requested)
-//   se     2 x CH x 2 x 2K doubles: (em1, de) eigen-coefficient vectors of INTERNAL children
-//   scode  2 x CH x 2 x TW bytes: the state codes of LEAF children for the tile's columns
-// so the only global accesses on the per-op critical path are the thread's own partials and the
-// leaf-table gathers.  One __syncthreads per chunk.
+//   se     2 x CHN x 2 x 2K doubles: (em1, de) eigen-coefficient vectors (gradient pass: of the internal
+//          children; post pass with DST: of the op's own branch)
+//   stab   2 x CHN x 2 x 2 leaf tables: P (and dP) columns of LEAF children
+//   scode  2 x CHN x 2 x 2 x TS bytes: the state codes of LEAF children for the tile's columns
+// so the only global accesses on the per-op critical path are the thread's own partials -- and with an
+// operand ring (RD > 0) those of the gradient pass arrive through shared memory as well.  One
+// __syncthreads per chunk.
 // --------------------------------------------------------------------------------------------
 // Per-op record derived by the staging threads from the raw descriptor (schedule.hpp): everything the
 // compute threads need as ready-to-add byte offsets, so no warp repeats the uniform address math.
@@ -49,9 +52,11 @@ static_assert(sizeof(OpRec) == 32, "OpRec is two 16-byte words");
 // NE = active eigen-components (device_math.cuh): K - 1 when the host found (and moved last) a null
 // eigenvalue, the case for every rate matrix; K otherwise.
 // RD = depth of the per-warp OPERAND RING of the gradient pass (0 = none): the stored child partials of the
-// families ahead are fetched by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier, issued by one
-// elected lane per warp) into shared memory RD entries before their use, in the order of the tree's fetch list
-// (schedule.hpp: pre_fetch), so that the warp never waits a DRAM round trip on its own partials.
+// families ahead are fetched into shared memory RD entries before their use, in the order of the tree's fetch
+// list (schedule.hpp: pre_fetch), so that the warp never waits a DRAM round trip on its own partials.  Two
+// flavours (smem_layout.cuh: MCP_RING_LDGSTS): every thread copies its own 16-byte pieces with cp.async
+// (completion by cp.async.wait_group; the default), or one elected lane per warp issues a bulk copy
+// (cp.async.bulk, completion on an mbarrier).  profiles/r2_walk_notes.md has the measurements.
 template <int K, int CPT, bool DYN_MODEL, bool SSCR, int NE, bool ACCG, int RD = 0>
 #ifndef MCP_WALK_MAXT
 #define MCP_WALK_MAXT 256
