@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
     sp += MmaSmem<KP>::code_bytes();
     double* const stab = reinterpret_cast<double*>(sp);                         // [2 buffers][4 tables][TAB]
     double* const stq = stab + 2 * 4 * TAB;                                     // Q' of the tile's (tree, rate)
+    // this lane's element 0 of the warp's two prefetched child vectors (gradient pass), laid out like the scratch
+    double* const spf = stab + (2 * 4 + 1) * TAB + (size_t)warp * 2 * (MMA_WCOLS * KP) + lane;
     constexpr bool dst = DST;                                                   // stored / carried vectors are D = P L
 
     // zero the tables once: the padding (states >= K) is never written again
@@ -108,6 +110,19 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
             for (int n = 0; n < NB; ++n)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) v[m][n][h] = __ldcg(base + ((m * NB + n) * 2 + h) * 32);
+    };
+    // the same vector from / into the warp's prefetch buffer in shared memory
+    auto lds_vec = [&](const double* base, double (&v)[MB][NB][2]) {
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+#pragma unroll
+            for (int n = 0; n < NB; ++n)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) v[m][n][h] = base[((m * NB + n) * 2 + h) * 32];
+    };
+    auto prefetch_vec = [&](double* dst, const double* src) {
+#pragma unroll
+        for (int i = 0; i < MB * NB * 2; ++i) cp_async8(dst + i * 32, src + i * 32);
     };
     auto st_vec = [&](double* base, const double (&v)[MB][NB][2]) {
 #pragma unroll
@@ -363,19 +378,29 @@ __global__ void __launch_bounds__(MMA_WARPS * 32, KP <= 16 ? 2 : 1) felsenstein_
                     if (((flags >> 8) & 3) == mcp::PREM_STACK) ld_vec(stk + (long long)o1.x * slot_stride, cur);
                     // family {mother; a, b}: D = P L, Y = dP L
                     double Da[MB][NB][2], Ya[MB][NB][2], Db[MB][NB][2], Yb[MB][NB][2];
+                    // The stored child vectors of family j were requested during family j - 1 (below) and are complete
+                    // since the cp.async wait of the op boundary; the first family reads its own.
                     if (ai) {                                                   // stored D = P L; dP L = Q' D
-                        ld_vec(scr + (long long)o0.x * slot_stride, Da);
+                        if (j > 0) lds_vec(spf, Da); else ld_vec(scr + (long long)o0.x * slot_stride, Da);
                         mma_product<KP, false>(stq, Da, Ya, g, t);
                     } else {
                         leaf_vec(tb, cb, Da);
                         leaf_vec(tb + TAB, cb, Ya);
                     }
                     if (bi) {
-                        ld_vec(scr + (long long)o0.z * slot_stride, Db);
+                        if (j > 0) lds_vec(spf + MMA_WCOLS * KP, Db); else ld_vec(scr + (long long)o0.z * slot_stride, Db);
                         mma_product<KP, false>(stq, Db, Yb, g, t);
                     } else {
                         leaf_vec(tb + 2 * TAB, cb + MMA_TILE, Db);
                         leaf_vec(tb + 3 * TAB, cb + MMA_TILE, Yb);
+                    }
+                    if (j + 1 < n_pre) {
+                        // request the stored children of the NEXT family (its descriptor is resident): post results, written
+                        // a whole pass ago.  pre[mother] is not requested ahead -- this very op may be the one that pushes it.
+                        const int4 n0 = sdesc[((j + 1) % 3) * 2], n1 = sdesc[((j + 1) % 3) * 2 + 1];
+                        __syncwarp();                                            // every lane has read its part of the buffer
+                        if ((n1.y & 3) == mcp::OPK_MEM) prefetch_vec(spf, scr + (long long)n0.x * slot_stride);
+                        if (((n1.y >> 2) & 3) == mcp::OPK_MEM) prefetch_vec(spf + MMA_WCOLS * KP, scr + (long long)n0.z * slot_stride);
                     }
                     // qa = pre_m * Db, qb = pre_m * Da (kept in Db / Da), den = sum pre_m Da Db, numerators q . Y
                     double ga = 0.0, gb = 0.0;

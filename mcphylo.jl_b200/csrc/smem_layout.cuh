@@ -112,8 +112,12 @@ struct MmaSmem {
     static __host__ __device__ size_t code_bytes() { return 2 * 2 * MMA_TILE; }
     // [2 buffers][4 tables] staged per op + one table per tile: Q' = mu * rate * Q (dP = Q' P), kernel_mma.cuh
     static __host__ __device__ size_t tab_bytes() { return (size_t)(2 * 4 + 1) * TAB * 8; }
+    // gradient evaluations: the two stored child vectors of the NEXT family, fetched one op ahead with cp.async:
+    // [8 warps][2 children][vector of 16 columns x KP states, fragment-major like the scratch]
+    static __host__ __device__ size_t pref_bytes(int want_grad) { return want_grad ? (size_t)MMA_WARPS * 2 * MMA_WCOLS * KP * 8 : 0; }
     static __host__ __device__ size_t total(int n_br, int want_grad) {
-        return acc_bytes(n_br, want_grad) + ((part_bytes() + 15) & ~(size_t)15) + desc_bytes() + code_bytes() + tab_bytes();
+        return acc_bytes(n_br, want_grad) + ((part_bytes() + 15) & ~(size_t)15) + desc_bytes() + code_bytes() + tab_bytes() +
+               pref_bytes(want_grad);
     }
 };
 
