@@ -304,6 +304,12 @@ int mcp_set_accumulator_mode(mcp_ctx *ctx, int mode);
  * -1 / 1 the stored child partials are fetched ahead of their use through a per-warp operand ring in shared memory
  * (cp.async.bulk + mbarrier), 0 every thread loads its own partials when it needs them.  Results are identical. */
 int mcp_set_ring_mode(mcp_ctx *ctx, int mode);
+/* Environment switches read once per process (measurement / fall-back aids, never needed for correct results):
+ *   MCPHYLO_B200_INLINE_PARAMS=0   MCMC-sized evaluations stage their parameter block through device memory (a second
+ *                                  launch) instead of carrying it in the arguments of the fused small-tree kernel
+ *   MCPHYLO_B200_STREAM_BLOCKS=1   mcp_eval_streamed uses the block-per-launch pipeline instead of one fused launch
+ *   MCPHYLO_B200_SERIAL_GROUP=1    a multi-device context enqueues its devices from the calling thread
+ *   MCPHYLO_B200_NCCL=<path>       NCCL library to dlopen instead of libnccl.so.2 */
 /* State counts 6 < K <= 32 (e.g. 20-state protein alphabets): -1 / 1 the tile-cooperative kernel that runs the
  * K x K by K x columns products of every node on the FP64 tensor path (mma.sync.m8n8k4.f64; 8 warps x 16 columns
  * per CTA, bit-reproducible gradient), 0 the runtime-K fallback kernel (one thread per column, CUDA cores). */

@@ -1428,6 +1428,8 @@ int mcp_eval_rate_gradient(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const
                            double* rate_grad_out) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!rates || !blv || !rate_grad_out || R < 1 || NN < 2) return fail(ctx, MCP_ERR_ARG, "mcp_eval_rate_gradient: bad argument");
+    for (int r = 0; r < R; ++r)
+        if (!(rates[r] > 0.0)) return fail(ctx, MCP_ERR_ARG, "mcp_eval_rate_gradient: rate category %d is not positive", r);
     // Rate categories are not mixed (logL = sum_r logL_r, VectorizedFunctions.jl:76-87) and category r sees every
     // branch as t_b * rate_r, so  d logL / d rate_r = (1 / rate_r) * sum_b t_b * d logL_r / d t_b:  one evaluation
     // per category with R = 1 -- the same columns as one R-category evaluation, on one cached plan -- gives
