@@ -165,7 +165,15 @@ int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, i
     const bool cpt2_ok = templated && K <= 4 && !acc_global;
     int max_nn = 0;
     for (int t = 0; t < a.T; ++t) max_nn = std::max(max_nn, (int)a.NN[t]);
-    if (cpt <= 0) cpt = cpt2_ok && tiles_for(a, block) > 2LL * ctx->sm_count && (K == 2 || max_nn >= 1000) ? 2 : 1;
+    // Round 2, kernels with the operand ring and D = P L stored (K = 4, gradient evaluations): two columns per thread
+    // win for EVERY tree size once the input is more than ~5 tiles of 256 columns per SM (20 .. 500 taxa: -5 .. -13 %,
+    // cfg3 1.40 -> 1.33 ms); below that the 444 resident one-column CTAs cover the input in fewer rounds
+    // (profiles/r2_ab_columns_per_thread.json).
+    const bool ring_k4 = K == 4 && a.want_grad && ctx->opt_ring != 0 && !acc_global;
+    if (cpt <= 0) {
+        const long long tiles = tiles_for(a, block);
+        cpt = cpt2_ok && ((tiles > 2LL * ctx->sm_count && (K == 2 || max_nn >= 1000)) || (ring_k4 && tiles > 5LL * ctx->sm_count)) ? 2 : 1;
+    }
     if (!cpt2_ok) cpt = 1;
     const size_t smem = templated ? walk_smem_bytes(K, max_br, shared_acc, block, cpt) : generic_smem_bytes(max_br, a.want_grad);
     int e, occ = 0;

@@ -8,6 +8,7 @@ compared bit for bit with the ring off.
 import argparse
 import json
 import os
+import re
 import sys
 
 import numpy as np
@@ -38,6 +39,9 @@ def main():
     for case in args.cases.split(","):
         name, S = case.split(":")
         S = int(S)
+        m = re.match(r"^t(\d+)k(\d+)r(\d+)$", name)     # ad-hoc shape: t<taxa>k<states>r<rate categories>
+        if m and name not in bench.WORKLOADS:
+            bench.WORKLOADS[name] = (int(m.group(1)), S, int(m.group(2)), int(m.group(3)), 31000 + int(m.group(1)), 32000 + int(m.group(1)))
         w = bench.make_workload(name, S)
         codes, leaf_nums = bench.make_codes(w, 0, S)
         aln = ctx.alignment_from_codes(codes, w["K"], leaf_nums)
