@@ -202,6 +202,42 @@ int mcp_eval_rate_gradient(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const
                            double *ll_out, double *grad_out, double *rate_grad_out);
 
 /*
+ * logL, the branch-length gradient AND the gradient with respect to the parameters of the substitution model
+ * (base frequencies, exchangeabilities / free rates) in one evaluation.  The reference has no such derivative --
+ * pi and the substitution rates are sampled gradient-free (e.g. SliceSimplex(:mypi),
+ * /root/reference/src/samplers/tree_samplers.jl:49; the models are /root/reference/src/Likelihood/SubstitutionModels.jl:13-102)
+ * -- it is the adjacent capability SURVEY.md 8f names: the partials the gradient pass already holds are reused.
+ * Per branch b and rate category r the gradient pass accumulates the K x K moment matrix
+ *     M[b][r][s][k] = sum over the columns of category r of  q_b[s] L_b[k] / den          (= d logL / d P_{b,r}[s][k])
+ * (q_b: outer partial at the top of the branch, L_b: partial below it, den: the column likelihood) and the root vector
+ *     W[s] = sum over all columns of  L_root[s] / (pi . L_root)                         (= d logL / d pi[s] at the root);
+ * the host contracts them with d P_{b,r} / d theta_p, which follows from the eigen-decomposition the caller passes anyway:
+ * with A = mu U diag(D) Uinv (so that P_{b,r} = exp(A t_b rates[r])) the caller supplies
+ *   dA   K x K x n_par, column-major per parameter: d A / d theta_p  (derivative of the NORMALISED rate matrix, i.e. including
+ *        the dependence of mu on the parameter)
+ *   dpi  K x n_par column-major: d pi / d theta_p as seen by the ROOT term (1 in row s for "base frequency s", 0 for
+ *        rates); NULL if no parameter enters the root distribution
+ * and receives par_grad_out[p] = d logL / d theta_p (n_par doubles).  mcphylo.jl_b200/substitution_models.py
+ * (model_derivatives) and julia/MCPhyloB200.jl hold dA / dpi for Restriction, JC, GTR and freeK, and a Richardson-extrapolated
+ * difference quotient for user-supplied model functions.
+ * moments_out (optional, may be NULL): (NN-1) * R * K * K doubles M[b][r][s * K + k] followed by W[K].
+ * Runs on the runtime-K kernel for every K (one thread per column; per op and child a warp forms its 32-column sum of
+ * outer products cooperatively in shared memory and adds it to M with one atomic per entry), so it costs several
+ * plain evaluations; on a multi-device context every device evaluates its site shard and the host adds the parts.
+ * mcp_model_gradient_contract is the host-only second half (no GPU needed): moments -> parameter gradient, and optionally
+ * the branch gradient re-derived from the same moments (grad_check_out, n_branches doubles) as a consistency check.
+ */
+int mcp_eval_model_gradient(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const int32_t *postorder_num,
+                            const int32_t *parent_num, const double *blv, const double *U, const double *D,
+                            const double *Uinv, double mu, const double *rates, int R, const double *pi,
+                            int n_par, const double *dA, const double *dpi, double *ll_out, double *grad_out,
+                            double *par_grad_out, double *moments_out);
+int mcp_model_gradient_contract(int K, int R, int n_branches, const double *blv, const double *U, const double *D,
+                                const double *Uinv, double mu, const double *rates, const double *moments,
+                                const double *root_w, int n_par, const double *dA, const double *dpi,
+                                double *par_grad_out, double *grad_check_out);
+
+/*
  * Same evaluation, result left on the device: d_out (DEVICE pointer, NN doubles) receives
  * [logL, grad[1..NN-1]] (grad part zero if !want_grad).  The work is enqueued on the context's
  * stream and NOT synchronised, so a site-sharded caller can all-reduce d_out across GPUs

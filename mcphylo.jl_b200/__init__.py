@@ -9,12 +9,13 @@ without a GPU raises.
 from .tree import (GeneralNode, Node, ParseNewick, newick, post_order, pre_order, get_leaves,  # noqa: F401
                    get_mother, find_by_name, find_num, number_nodes, get_branchlength_vector,
                    set_branchlength_vector, tree_length, NNI, flatten, FlatTree)
-from .substitution_models import Restriction, JC, GTR, freeK, setmatrix, freeK_equilibrium  # noqa: F401
+from .substitution_models import (Restriction, JC, GTR, freeK, setmatrix, freeK_equilibrium,  # noqa: F401
+                                  model_derivatives, normalised_rate_matrix)
 from .rates import discrete_gamma_rates, discrete_gamma_rates_dalpha, mean_boundaries, median_boundaries  # noqa: F401
 from .parser import (ParseNexus, ParseCSV, datafortree, codesfortree, dense_to_codes,  # noqa: F401
                      get_alphabet, FileSyntaxError)
 from .phylodist import (PhyloDist, MultiplePhyloDist, DeviceAlignment, DimensionMismatch, logpdf,  # noqa: F401
-                        gradlogpdf, gradlogpdf_rates, multi_gradlogpdf, minimum, maximum, size, get_context,
+                        gradlogpdf, gradlogpdf_rates, gradlogpdf_model, multi_gradlogpdf, minimum, maximum, size, get_context,
                         set_default_device, release_device_cache)
 from . import phylodist as _phylodist
 globals()["__logpdf"] = getattr(_phylodist, "__logpdf")

@@ -24,7 +24,7 @@ SYMBOLS = [
     "mcp_get_stats_member", "mcp_timer_start", "mcp_timer_stop",
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
-    "mcp_eval", "mcp_eval_posterior", "mcp_eval_rate_gradient", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
+    "mcp_eval", "mcp_eval_posterior", "mcp_eval_rate_gradient", "mcp_eval_model_gradient", "mcp_model_gradient_contract", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
     "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode", "mcp_set_ring_mode",
     "mcp_schedule_dump", "mcp_schedule_fetch_list", "mcp_model_reorder",
 ]
@@ -88,6 +88,9 @@ def load():
     lib.mcp_eval_device.argtypes = eval_args + [_vp]
     lib.mcp_eval_rate_gradient.argtypes = eval_args[:-1] + [_dp, _vp, _vp]
     lib.mcp_eval_posterior.argtypes = eval_args[:-1] + [C.c_int, _vp, _dp, _vp]
+    lib.mcp_eval_model_gradient.argtypes = eval_args[:-1] + [C.c_int, _vp, _vp, _dp, _vp, _vp, _vp]
+    lib.mcp_model_gradient_contract.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp,
+                                                C.c_int, _vp, _vp, _vp, _vp]
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     lib.mcp_get_stats_member.argtypes = [_vp, C.c_int, C.POINTER(Stats)]
@@ -114,6 +117,35 @@ def load():
         raise ImportError("libmcphylo_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+def model_gradient_contract(blv, U, D, Uinv, mu, rates, moments, root_w, dA, dpi=None, want_grad_check=False):
+    """Host-only second half of mcp_eval_model_gradient (no GPU): moments M[b, r, s, k] and root vector W[s] ->
+    d logL / d theta_p; optionally the branch gradient re-derived from the same moments."""
+    lib = load()
+    blv = np.ascontiguousarray(blv, dtype=np.float64)
+    rates = np.ascontiguousarray(rates, dtype=np.float64)
+    D = np.ascontiguousarray(D, dtype=np.float64)
+    K, R, NB = D.size, rates.size, blv.size
+    Uf = np.ascontiguousarray(np.asarray(U, dtype=np.float64).ravel(order="F"))
+    Uif = np.ascontiguousarray(np.asarray(Uinv, dtype=np.float64).ravel(order="F"))
+    M = np.ascontiguousarray(moments, dtype=np.float64).reshape(NB, R, K, K)
+    W = np.ascontiguousarray(root_w, dtype=np.float64) if root_w is not None else None
+    dA = np.asarray(dA, dtype=np.float64)
+    if dA.ndim == 2:
+        dA = dA[:, :, None]
+    n_par = dA.shape[2]
+    dA_f = np.ascontiguousarray(np.stack([dA[:, :, p].ravel(order="F") for p in range(n_par)]).ravel()) if n_par else np.zeros(1)
+    dpi_f = np.ascontiguousarray(np.asarray(dpi, dtype=np.float64).reshape(K, n_par).ravel(order="F")) if dpi is not None else None
+    pg = np.zeros(max(n_par, 1))
+    gc = np.zeros(max(NB, 1)) if want_grad_check else None
+    rc = lib.mcp_model_gradient_contract(K, R, NB, blv.ctypes.data, Uf.ctypes.data, D.ctypes.data, Uif.ctypes.data, float(mu),
+                                         rates.ctypes.data, M.ctypes.data, W.ctypes.data if W is not None else None, n_par,
+                                         dA_f.ctypes.data, dpi_f.ctypes.data if dpi_f is not None else None, pg.ctypes.data,
+                                         gc.ctypes.data if want_grad_check else None)
+    if rc:
+        raise McpError(rc, lib.mcp_last_error(None).decode())
+    return (pg[:n_par], gc[:NB]) if want_grad_check else pg[:n_par]
 
 
 def _f64(a, order="C"):
@@ -348,6 +380,39 @@ class Context:
                                                     float(mu), rates.ctypes.data, rates.size, pi.ctypes.data,
                                                     C.byref(ll), grad.ctypes.data, rgrad.ctypes.data))
         return ll.value, grad[:NN - 1], rgrad
+
+    def eval_model_gradient(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi, dA, dpi=None,
+                            want_moments: bool = False):
+        """(logL, d logL / d blv, d logL / d theta) for the substitution-model parameters whose normalised-rate-matrix
+        derivatives are dA[:, :, p] (and root-frequency derivatives dpi[:, p]); with want_moments also the moment
+        matrices M[b, r, s, k] and the root vector W[s] (mcp_eval_model_gradient)."""
+        po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
+        NN, K, R = po.size, aln.K, rates.size
+        dA = np.asarray(dA, dtype=np.float64)
+        if dA.ndim == 2:
+            dA = dA[:, :, None]
+        n_par = dA.shape[2]
+        assert dA.shape[:2] == (K, K)
+        dA_f = np.ascontiguousarray(np.stack([dA[:, :, p].ravel(order="F") for p in range(n_par)]).ravel()) if n_par else np.zeros(1)
+        dpi_f = None
+        if dpi is not None:
+            dpi = np.asarray(dpi, dtype=np.float64).reshape(K, n_par)
+            dpi_f = np.ascontiguousarray(dpi.ravel(order="F"))
+        ll = C.c_double()
+        grad = np.zeros(max(NN - 1, 1), dtype=np.float64)
+        pgrad = np.zeros(max(n_par, 1), dtype=np.float64)
+        mom = np.zeros((NN - 1) * R * K * K + K, dtype=np.float64) if want_moments else None
+        self._check(self.lib.mcp_eval_model_gradient(self.handle, aln.handle, NN, po.ctypes.data, pa.ctypes.data,
+                                                     blv.ctypes.data, U.ctypes.data, D.ctypes.data, Uinv.ctypes.data,
+                                                     float(mu), rates.ctypes.data, R, pi.ctypes.data, n_par,
+                                                     dA_f.ctypes.data, dpi_f.ctypes.data if dpi_f is not None else None,
+                                                     C.byref(ll), grad.ctypes.data, pgrad.ctypes.data,
+                                                     mom.ctypes.data if want_moments else None))
+        out = (ll.value, grad[:NN - 1], pgrad[:n_par])
+        if want_moments:
+            n_m = (NN - 1) * R * K * K
+            out += (mom[:n_m].reshape(NN - 1, R, K, K), mom[n_m:])
+        return out
 
     def eval_posterior(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi,
                        prior_kind: int, prior_params, want_grad: bool = True):

@@ -74,6 +74,7 @@ struct Plan {
     std::vector<mcp::Schedule> scheds;
     int block = 0, cpt = 1;
     bool level_mode = false, smem_scratch = false, acc_global = false, mma = false;
+    bool model_grad = false;        // planned for the runtime-K kernel with the model-gradient moments (any K)
     int n_tiles = 0, grid = 0, n_rows = 0, n_slots = 0, n_stack = 0, max_br = 0, max_rows = 1;
     long long total_out = 0, total_dyn = 0, total_btab = 0, scratch_per_cta = 0, row_stride = 0;
     size_t smem_bytes = 0, topo_bytes = 0, off_trees = 0, off_ops = 0, off_rowbase = 0, off_levels = 0, off_fetch = 0;
@@ -198,7 +199,8 @@ struct mcp_ctx {
     unsigned long long next_aln_id = 1, clock = 0;
 
     DevBuf d_dyn, d_btab, d_scratch, d_rows, d_rows_ll, d_out, d_counter, d_part, d_ticket;
-    PinBuf h_out;
+    DevBuf d_mg;                            // model-gradient moments of the last mcp_eval_model_gradient
+    PinBuf h_out, h_mg;
     // parameter staging ring: an evaluation fills slot `stage_next`, the copy to the device is
     // asynchronous, and the slot is reused only after its event has passed
     PinBuf h_dyn[MCP_STAGE_SLOTS], h_model[MCP_STAGE_SLOTS];

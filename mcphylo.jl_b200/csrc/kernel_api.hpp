@@ -22,6 +22,7 @@ struct LaunchCfg {
     bool acc_global = false;   // gradient accumulator in global memory (very large trees)
     bool ring = false;         // gradient pass fetches its stored operands through the per-warp operand ring (cp.async.bulk)
     bool mma = false;          // K > 6: tile-cooperative FP64 tensor-core kernel instead of the runtime-K fallback
+    double* mg = nullptr;      // runtime-K kernel only: per-(branch, rate) moment matrices of a model-gradient evaluation
 };
 
 // Every entry returns cudaSuccess or the error of the CUDA call that failed.

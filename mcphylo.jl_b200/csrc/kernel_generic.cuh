@@ -9,12 +9,28 @@ namespace {
 // layout and accumulator rows as the templated kernel, but dense-table arithmetic straight from the
 // branch table (P / dP columns are stored for every branch) and per-thread vectors in local memory.
 // Correctness path for large alphabets (e.g. 20-state protein models); not tuned.
+//
+// Model-gradient evaluations (mcp_eval_model_gradient, any K; mg != nullptr, one tree): next to logL and the
+// branch gradient the gradient pass accumulates, for every branch b and rate category r, the K x K moment matrix
+//     M[b][r][s][k] = sum over the columns of category r of  q_b[s] * L_b[k] / den,
+// q_b = outer partial at the top of branch b (pre[mother] times the siblings' Down), L_b = the stored partial
+// below it, den = the column likelihood -- i.e. d logL / d P_{b,r}[s][k] -- and the root vector
+//     W[s] = sum over all columns of  L_root[s] / (pi . L_root)                 = d logL / d pi[s] at the root.
+// Every derivative of logL with respect to a parameter of the substitution model is a contraction of these
+// with d P_{b,r} / d theta (host side, model_gradient_contract in mcphylo_b200.cu).  Per op and child a warp
+// leaves its 32 columns' q / den and L in shared memory and forms the 32-column sum of outer products
+// cooperatively (K * K outputs spread over the lanes, no shuffles), then adds it to M with one atomic per output.
+// mg layout: [device branch][rate][s * K + k], then W[K].
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams p, const int K) {
+__global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams p, const int K, double* __restrict__ const mg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
     double* const s_acc = reinterpret_cast<double*>(smem_raw);
+    // model gradient: per warp [32 lanes][K] q / den and [32 lanes][K] L, behind the gradient accumulator
+    double* const s_mq = reinterpret_cast<double*>(smem_raw + (((size_t)p.max_br * 8 + 15) & ~(size_t)15)) +
+                         (size_t)(threadIdx.x >> 5) * 64 * K;
+    double* const s_ml = s_mq + 32 * K;
 
     const int tid = threadIdx.x, TW = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int q = p.n_tiles / gridDim.x, rem = p.n_tiles - q * gridDim.x;
@@ -115,10 +131,36 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     logsum += log(rootv);
                     e_total += e_col;
                 }
+                if (mg) {   // W[s] += L_root[s] / (pi . L_root)
+                    double* const w_dst = mg + (long long)tr.n_br * R * K * K;
+                    const double w = valid ? 1.0 / rootv : 0.0;
+                    for (int k = 0; k < K; ++k) {
+                        double v = valid ? cur[k] * w : 0.0;
+                        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                        if (lane == 0) atomicAdd(w_dst + k, v);
+                    }
+                }
             }
 
             if (p.want_grad) {
                 double pm[KMAX_GENERIC], Ya[KMAX_GENERIC], Yb[KMAX_GENERIC];
+                // M[br][r] += sum over this warp's 32 columns of (qv * w) (x) Lv; Lv == nullptr: leaf with state `code`
+                auto moments = [&](const double* qv, const double* Lv, int code, double w, int br) {
+                    for (int k = 0; k < K; ++k) {
+                        s_mq[lane * K + k] = valid ? qv[k] * w : 0.0;
+                        s_ml[lane * K + k] = Lv ? Lv[k] : ((code >= K || code == k) ? 1.0 : 0.0);
+                    }
+                    __syncwarp();
+                    double* const dst = mg + ((long long)br * R + r) * K * K;
+                    for (int idx = lane; idx < K * K; idx += 32) {
+                        const int s = idx / K, k = idx - s * K;
+                        double acc = 0.0;
+                        for (int l = 0; l < 32; ++l) acc = fma(s_mq[l * K + s], s_ml[l * K + k], acc);
+                        atomicAdd(dst + idx, acc);
+                    }
+                    __syncwarp();
+                };
+                double La[KMAX_GENERIC], Lb[KMAX_GENERIC];
                 for (int i = 0; i < tr.n_pre; ++i) {
                     const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
                     const int flags = o1.y;
@@ -132,6 +174,7 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     const double* tb = tab_r + b_br * br_stride;
                     if (ai) {
                         for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.x * slot_stride + k);
+                        if (mg) { for (int k = 0; k < K; ++k) La[k] = L[k]; }
                         down(ta, L, Da);
                         down(ta + KK1, L, Ya);
                     } else {
@@ -140,6 +183,7 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     }
                     if (bi) {
                         for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.z * slot_stride + k);
+                        if (mg) { for (int k = 0; k < K; ++k) Lb[k] = L[k]; }
                         down(tb, L, Db);
                         down(tb + KK1, L, Yb);
                     } else {
@@ -159,6 +203,10 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     const double red = warp_pair_reduce(valid ? na * inv : 0.0, valid ? nb * inv : 0.0, lane);
                     if (lane == 0) atomicAdd(&s_acc[a_br], red);
                     else if (lane == 16) atomicAdd(&s_acc[b_br], red);
+                    if (mg) {   // Ya / Yb hold qa / qb here
+                        moments(Ya, ai ? La : nullptr, ai ? 0 : leaf_code(o0.x), inv, a_br);
+                        moments(Yb, bi ? Lb : nullptr, bi ? 0 : leaf_code(o0.z), inv, b_br);
+                    }
 
                     const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
                     // pre[child][j] = sum_s P[s][j] q[s] = column j of the table dotted with q

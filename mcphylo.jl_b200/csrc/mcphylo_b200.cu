@@ -133,6 +133,8 @@ int validate_batch(mcp_ctx* ctx, const BatchArgs& a, int* K_out) {
                 return fail(ctx, MCP_ERR_ARG, a.prior_kind == MCP_PRIOR_EXPONENTIAL ? "exponentialBL: scale must be positive"
                                                                                     : "CompoundDirichlet: alpha, a, beta, c must be positive");
     }
+    if (a.model_grad && (a.T != 1 || !a.want_grad))
+        return fail(ctx, MCP_ERR_ARG, "a model-gradient evaluation takes one tree and computes the branch gradient with it");
     *K_out = K;
     return 0;
 }
@@ -151,7 +153,15 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     if ((e = get_plan(ctx, a, K, &plp, &rebuilt))) return e;
     Plan& pl = *plp;
     ctx->last_plan = plp;
-    const KernelTable* kt = kernels_for(K);
+    const bool templ = k_templated(K) && !a.model_grad;     // model-gradient evaluations run the runtime-K kernel
+    const KernelTable* kt = a.model_grad ? mcpdev::kernels_generic() : kernels_for(K);
+    if (a.model_grad && (d_out_user || ctx->sf)) return fail(ctx, MCP_ERR_ARG, "internal: model-gradient evaluation must be synchronous and resident");
+    // model-gradient moments: [device branch][rate][K x K] and the root vector W[K] (kernel_generic.cuh)
+    const size_t mg_doubles = a.model_grad ? (size_t)pl.trees[0].n_br * R * K * K + K : 0;
+    if (a.model_grad) {
+        if ((e = ensure_dev(ctx, ctx->d_mg, sizeof(double) * mg_doubles))) return e;
+        if ((e = ensure_pin(ctx, ctx->h_mg, sizeof(double) * mg_doubles))) return e;
+    }
 
     // buffers
     const int slot = ctx->stage_next;
@@ -198,10 +208,10 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     }
 
     // substitution-model constants: one slot per distinct model of the batch
-    const int model_doubles = k_templated(K) ? 2 * K * K + K + R * K : 0;
+    const int model_doubles = templ ? 2 * K * K + K + R * K : 0;
     double* hm = (double*)ctx->h_model[slot].p;
     int n_models = 0;
-    for (int t = 0; t < T && k_templated(K); ++t) {
+    for (int t = 0; t < T && templ; ++t) {
         double cand[MODEL_SLOT];
         const double* dt = hd + pl.trees[t].dyn_off;       // the permuted decomposition stored above
         std::memcpy(cand, dt + dyn_U(a.NN[t]), sizeof(double) * K * K);
@@ -221,7 +231,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         hd[pl.trees[t].dyn_off + dyn_slot(a.NN[t], K, R)] = (double)ms;
     }
     // the walk kernels with all K eigen-components read their model from constant memory only
-    const bool dyn_model = n_models > 1 || (k_templated(K) && (!all_null_last || pl.acc_global));
+    const bool dyn_model = n_models > 1 || (templ && (!all_null_last || pl.acc_global));
 
     // ---- everything below only enqueues; from the first enqueue on, an error leaves the plan marked
     // "not uploaded" so that a retry re-sends the topology block instead of trusting a half-done one ----
@@ -266,7 +276,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     }
     s.h2d_bytes += (int64_t)(sizeof(double) * pl.total_dyn);
     // resident alignment, one tree: tiles by atomic ticket (site-major order) instead of static ranges
-    const bool dyn_tiles = !ctx->sf && ctx->opt_dynamic == 1 && !pl.level_mode && !pl.acc_global && k_templated(K) && T == 1;
+    const bool dyn_tiles = !ctx->sf && ctx->opt_dynamic == 1 && !pl.level_mode && !pl.acc_global && templ && T == 1;
     if (dyn_tiles) {
         if ((e = ensure_dev(ctx, ctx->d_ticket, sizeof(unsigned) * STREAM_CTL_WORDS))) return e;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_ticket.p, 0, sizeof(unsigned) * STREAM_CTL_WORDS, st));
@@ -334,6 +344,10 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     lc.smem_scratch = pl.smem_scratch;
     lc.acc_global = pl.acc_global;
     lc.mma = pl.mma;
+    if (a.model_grad) {
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_mg.p, 0, sizeof(double) * mg_doubles, st));
+        lc.mg = (double*)ctx->d_mg.p;
+    }
     {
         cudaError_t ce = pl.level_mode ? kt->launch_levels(lc, wp, dyn_model, inline_dyn ? hd : nullptr, (size_t)pl.total_dyn)
                                        : kt->launch_walk(lc, wp, dyn_model, all_null_last);
@@ -385,9 +399,17 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         const mcpnccl::Api& nc = mcpnccl::api();
         mcpnccl::result_t nr = nc.AllReduce(d_out, d_out, (size_t)pl.total_out, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, st);
         if (nr) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce failed: %s", nc.GetErrorString(nr));
+        if (a.model_grad) {
+            nr = nc.AllReduce(ctx->d_mg.p, ctx->d_mg.p, mg_doubles, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, st);
+            if (nr) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce (model-gradient moments) failed: %s", nc.GetErrorString(nr));
+        }
     }
     if (!fused || via_comm) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * pl.total_out, cudaMemcpyDeviceToHost, st));
     s.d2h_bytes = (int64_t)(sizeof(double) * pl.total_out);
+    if (a.model_grad) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_mg.p, ctx->d_mg.p, sizeof(double) * mg_doubles, cudaMemcpyDeviceToHost, st));
+        s.d2h_bytes += (int64_t)(sizeof(double) * mg_doubles);
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     for (bool& p : ctx->staged_pending) p = false;
@@ -1000,9 +1022,10 @@ void destroy_single(mcp_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     drop_stream_set(ctx);
     if (ctx->rank_comm) mcpnccl::api().CommDestroy(ctx->rank_comm);
-    for (DevBuf* b : {&ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter, &ctx->d_part, &ctx->d_ticket})
+    for (DevBuf* b : {&ctx->d_dyn, &ctx->d_btab, &ctx->d_scratch, &ctx->d_rows, &ctx->d_rows_ll, &ctx->d_out, &ctx->d_counter, &ctx->d_part, &ctx->d_ticket, &ctx->d_mg})
         free_dev(*b);
     free_pin(ctx->h_out);
+    free_pin(ctx->h_mg);
     for (int i = 0; i < MCP_STAGE_SLOTS; ++i) {
         free_pin(ctx->h_dyn[i]);
         free_pin(ctx->h_model[i]);
@@ -1453,6 +1476,145 @@ int mcp_eval_rate_gradient(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const
     }
     if (ll_out) *ll_out = ll_total;
     if (grad_out) std::memcpy(grad_out, gsum.data(), sizeof(double) * (NN - 1));
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// gradient with respect to the parameters of the substitution model
+// --------------------------------------------------------------------------------------------
+namespace {
+
+// Contraction of the moment matrices with d P_{b,r} / d theta.  With A = mu U diag(D) Uinv, x_i = mu D_i t_b rate_r,
+//   P_{b,r} = exp(A t_b rate_r) = U diag(exp x) Uinv,
+//   d P_{b,r} / d theta = U (Phi o (Uinv (dA/dtheta) U)) Uinv * t_b rate_r,     Phi_ij = (e^{x_i} - e^{x_j}) / (x_i - x_j), Phi_ii = e^{x_i}
+// (Daleckii-Krein), hence   sum_{s,k} M[s][k] dP[s][k] = t rate sum_ij Phi_ij G_ij Mt_ij   with   Mt = U^T M Uinv^T,  G = Uinv dA U,
+// and the sum over branches and categories needs one K x K matrix  H = sum_{b,r} t_b rate_r Phi^{b,r} o Mt^{b,r}  whatever the
+// number of parameters:  d logL / d theta_p = sum_ij G^p_ij H_ij + sum_s (d pi_s / d theta_p) W[s].
+// The same Mt gives the branch gradient (grad_check[b] = sum_r rate_r sum_i mu D_i e^{x_i} Mt_ii), returned for cross-checks.
+void model_gradient_contract(int K, int R, int NB, const double* blv, const double* U, const double* D, const double* Uinv, double mu,
+                             const double* rates, const double* M, const double* W, int n_par, const double* dA, const double* dpi,
+                             double* par_grad, double* grad_check) {
+    std::vector<double> H((size_t)K * K, 0.0), T1((size_t)K * K), Mt((size_t)K * K), x(K), ex(K);
+    for (int b = 0; b < NB; ++b) {
+        double gb = 0.0;
+        for (int r = 0; r < R; ++r) {
+            const double* Mb = M + ((size_t)b * R + r) * K * K;     // Mb[s * K + k]
+            // T1[i][k] = sum_s U[s][i] Mb[s][k];   Mt[i][j] = sum_k T1[i][k] Uinv[j][k]     (col-major: U[s + K i], Uinv[j + K k])
+            for (int i = 0; i < K; ++i)
+                for (int k = 0; k < K; ++k) {
+                    double acc = 0.0;
+                    for (int s = 0; s < K; ++s) acc += U[s + (size_t)K * i] * Mb[(size_t)s * K + k];
+                    T1[(size_t)i * K + k] = acc;
+                }
+            for (int i = 0; i < K; ++i)
+                for (int j = 0; j < K; ++j) {
+                    double acc = 0.0;
+                    for (int k = 0; k < K; ++k) acc += T1[(size_t)i * K + k] * Uinv[j + (size_t)K * k];
+                    Mt[(size_t)i * K + j] = acc;
+                }
+            const double tau = blv[b] * rates[r];
+            for (int i = 0; i < K; ++i) {
+                x[i] = mu * D[i] * tau;
+                ex[i] = std::exp(x[i]);
+                gb += rates[r] * mu * D[i] * ex[i] * Mt[(size_t)i * K + i];
+            }
+            for (int i = 0; i < K; ++i)
+                for (int j = 0; j < K; ++j) {
+                    const double d = x[i] - x[j];
+                    // the larger exponent is the base, so the divided difference never overflows or cancels
+                    const double phi = d == 0.0 ? ex[i] : d > 0.0 ? ex[i] * (-std::expm1(-d) / d) : ex[j] * (std::expm1(d) / d);
+                    H[(size_t)i * K + j] += tau * phi * Mt[(size_t)i * K + j];
+                }
+        }
+        if (grad_check) grad_check[b] = gb;
+    }
+    for (int p = 0; p < n_par; ++p) {
+        const double* dAp = dA + (size_t)p * K * K;     // col-major K x K
+        double g = 0.0;
+        // G[i][j] = sum_{a,c} Uinv[i][a] dA[a][c] U[c][j]
+        for (int i = 0; i < K; ++i)
+            for (int c = 0; c < K; ++c) {
+                double acc = 0.0;
+                for (int a = 0; a < K; ++a) acc += Uinv[i + (size_t)K * a] * dAp[a + (size_t)K * c];
+                T1[(size_t)i * K + c] = acc;
+            }
+        for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) {
+                double acc = 0.0;
+                for (int c = 0; c < K; ++c) acc += T1[(size_t)i * K + c] * U[c + (size_t)K * j];
+                g += acc * H[(size_t)i * K + j];
+            }
+        if (dpi && W)
+            for (int s = 0; s < K; ++s) g += dpi[(size_t)p * K + s] * W[s];
+        par_grad[p] = g;
+    }
+}
+
+}  // namespace
+
+int mcp_model_gradient_contract(int K, int R, int n_branches, const double* blv, const double* U, const double* D,
+                                const double* Uinv, double mu, const double* rates, const double* moments,
+                                const double* root_w, int n_par, const double* dA, const double* dpi, double* par_grad_out,
+                                double* grad_check_out) {
+    if (K < 1 || R < 1 || n_branches < 0 || n_par < 0 || !blv || !U || !D || !Uinv || !rates || !moments || (n_par > 0 && (!dA || !par_grad_out)))
+        return fail(nullptr, MCP_ERR_ARG, "mcp_model_gradient_contract: bad argument");
+    model_gradient_contract(K, R, n_branches, blv, U, D, Uinv, mu, rates, moments, root_w, n_par, dA, dpi, par_grad_out, grad_check_out);
+    return 0;
+}
+
+int mcp_eval_model_gradient(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
+                            const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
+                            double mu, const double* rates, int R, const double* pi, int n_par, const double* dA,
+                            const double* dpi, double* ll_out, double* grad_out, double* par_grad_out, double* moments_out) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    if (!aln || NN < 2 || n_par < 0 || (n_par > 0 && (!dA || !par_grad_out)))
+        return fail(ctx, MCP_ERR_ARG, "mcp_eval_model_gradient: bad argument");
+    const int K = aln->K;
+    const size_t n_m = (size_t)(NN - 1) * R * K * K;      // moments of the real branches; the root vector follows
+    std::vector<double> msum(n_m + K, 0.0), grad((size_t)NN - 1, 0.0);
+    double ll = 0.0;
+    BatchArgs a{1, &aln, &NN, &postorder_num, &parent_num, &blv, &U, &D, &Uinv, &mu, &rates, R, &pi, 1};
+    a.model_grad = 1;
+    // rows of the device array beyond NN-1 belong to the root and to virtual branches (binarisation): dropped here
+    auto take = [&](const mcp_ctx* m, double* dst, bool add) {
+        const double* h = (const double*)m->h_mg.p;
+        const size_t n_br = (size_t)m->last_plan->trees[0].n_br;
+        for (size_t i = 0; i < n_m; ++i) dst[i] = add ? dst[i] + h[i] : h[i];
+        for (int k = 0; k < K; ++k) dst[n_m + k] = add ? dst[n_m + k] + h[n_br * R * K * K + k] : h[n_br * R * K * K + k];
+    };
+    if (ctx->members.empty()) {
+        double* gp = grad.data();
+        int e = eval_impl(ctx, a, nullptr, &ll, &gp);
+        if (e) return e;
+        take(ctx, msum.data(), false);
+    } else {
+        // every device evaluates its site shard (one host thread per device); logL, the branch gradient and the moments
+        // are sums over sites, added on the host in device order
+        const int G = (int)ctx->members.size();
+        int K0 = 0, e;
+        if ((e = validate_batch(ctx, a, &K0))) return e;
+        if ((int)aln->shards.size() != G) return fail(ctx, MCP_ERR_ARG, "the alignment was not created on this multi-device context");
+        std::vector<double> lls(G, 0.0);
+        std::vector<std::vector<double>> grads(G, std::vector<double>((size_t)NN - 1, 0.0));
+        e = for_each_member(ctx, [&](int g) -> int {
+            const mcp_alignment* sh = aln->shards[g];
+            BatchArgs ag = a;
+            ag.alns = &sh;
+            double* gp = grads[g].data();
+            return eval_impl(ctx->members[g], ag, nullptr, &lls[g], &gp);
+        });
+        if (e) return e;
+        for (int g = 0; g < G; ++g) {
+            ll += lls[g];
+            for (int b = 0; b < NN - 1; ++b) grad[b] += grads[g][b];
+            take(ctx->members[g], msum.data(), g > 0);
+        }
+    }
+    if (ll_out) *ll_out = ll;
+    if (grad_out) std::memcpy(grad_out, grad.data(), sizeof(double) * (NN - 1));
+    if (moments_out) std::memcpy(moments_out, msum.data(), sizeof(double) * (n_m + K));
+    if (n_par > 0)
+        model_gradient_contract(K, R, NN - 1, blv, U, D, Uinv, mu, rates, msum.data(), msum.data() + n_m, n_par, dA, dpi, par_grad_out, nullptr);
     return 0;
 }
 

@@ -43,7 +43,12 @@ size_t walk_smem_bytes_ring(int K, int max_br, int block, int cpt) {
         default: return 0;
     }
 }
-size_t generic_smem_bytes(int max_br, int want_grad) { return want_grad ? (size_t)max_br * sizeof(double) : 0; }
+// runtime-K kernel: the per-branch gradient accumulator and, for a model-gradient evaluation (mg_K = state count),
+// per warp 2 x 32 x K doubles behind it (kernel_generic.cuh: s_mq / s_ml, offset by the accumulator of max_br doubles)
+size_t generic_smem_bytes(int max_br, int want_grad, int mg_K = 0, int block = 0) {
+    if (mg_K > 0) return (((size_t)max_br * sizeof(double) + 15) & ~(size_t)15) + (size_t)(block / 32) * 64 * mg_K * sizeof(double);
+    return want_grad ? (size_t)max_br * sizeof(double) : 0;
+}
 int mma_kp(int K) { return (K + 7) & ~7; }   // state count padded to the 8-wide MMA blocks
 size_t mma_smem_bytes(int K, int max_br, int want_grad) {
     switch (mma_kp(K)) {
@@ -72,6 +77,9 @@ struct BatchArgs {
     // optional branch-length prior (mcp_eval_posterior); applies to every tree of the batch
     int prior_kind = MCP_PRIOR_NONE;
     const double* prior_params = nullptr;
+    // model-gradient evaluation (mcp_eval_model_gradient): one tree, runtime-K kernel for every K, moment matrices
+    // accumulated next to the branch gradient
+    int model_grad = 0;
 };
 
 // Resident CTAs per SM of the walk kernel for a launch shape.  The occupancy calculator costs a few
@@ -147,9 +155,9 @@ int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, i
         total_cols += a.alns[t]->S * R;
         widest = std::max<long long>(widest, a.alns[t]->S);
     }
-    const bool templated = k_templated(K);
+    const bool templated = k_templated(K) && !a.model_grad;
     const int shared_acc = a.want_grad && !acc_global ? 1 : 0;
-    if (!templated && ctx->opt_mma != 0) {   // large alphabets: fixed shape, 8 warps x 16 columns (kernel_mma.cuh)
+    if (!templated && ctx->opt_mma != 0 && !a.model_grad) {   // large alphabets: fixed shape, 8 warps x 16 columns (kernel_mma.cuh)
         int e0, o = 0;
         if ((e0 = walk_occupancy(ctx, kt, K, MMA_WARPS * 32, 1, mma_smem_bytes(K, max_br, a.want_grad), false, false, false, &o, true))) return e0;
         *out = {MMA_WARPS * 32, 1, o};
@@ -175,7 +183,8 @@ int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, i
         cpt = cpt2_ok && ((tiles > 2LL * ctx->sm_count && (K == 2 || max_nn >= 1000)) || (ring_k4 && tiles > 5LL * ctx->sm_count)) ? 2 : 1;
     }
     if (!cpt2_ok) cpt = 1;
-    const size_t smem = templated ? walk_smem_bytes(K, max_br, shared_acc, block, cpt) : generic_smem_bytes(max_br, a.want_grad);
+    const size_t smem = templated ? walk_smem_bytes(K, max_br, shared_acc, block, cpt)
+                                  : generic_smem_bytes(max_br, a.want_grad, a.model_grad ? K : 0, block);
     int e, occ = 0;
     if ((e = walk_occupancy(ctx, kt, K, block, cpt, smem, false, acc_global, false, &occ))) return e;
     *out = {block, cpt, occ};
@@ -183,7 +192,9 @@ int choose_walk_shape(mcp_ctx* ctx, const KernelTable* kt, const BatchArgs& a, i
 }
 
 bool plan_matches(const Plan& pl, const BatchArgs& a, int K) {
-    if (!pl.valid || (int)pl.sig.size() != a.T || pl.want_grad != a.want_grad || pl.K != K || pl.R != a.R) return false;
+    if (!pl.valid || (int)pl.sig.size() != a.T || pl.want_grad != a.want_grad || pl.K != K || pl.R != a.R ||
+        pl.model_grad != (a.model_grad != 0))
+        return false;
     for (int t = 0; t < a.T; ++t) {
         const auto& s = pl.sig[t];
         if (s.aln_id != a.alns[t]->id || s.NN != a.NN[t] ||
@@ -213,7 +224,9 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     pl.valid = false;
     pl.uploaded = false;
     pl.sig.clear();
-    const KernelTable* kt = kernels_for(K);
+    // model-gradient evaluations run the runtime-K kernel whatever K is
+    const bool templ = k_templated(K) && !a.model_grad;
+    const KernelTable* kt = a.model_grad ? mcpdev::kernels_generic() : kernels_for(K);
     if (!kt) return fail(ctx, MCP_ERR_UNSUPPORTED, "no kernel compiled for K = %d states", K);
     long long total_cols = 0;
     int max_nn = 0;
@@ -223,10 +236,10 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     }
     // Very large trees: the per-branch accumulator no longer fits in shared memory next to the staging
     // buffers; those kernels exist with one column per thread only.
-    const bool acc_global = a.want_grad && k_templated(K) && walk_acc_global(max_nn, ctx->opt_acc_mode);
+    const bool acc_global = a.want_grad && templ && walk_acc_global(max_nn, ctx->opt_acc_mode);
     // Small inputs (a few one-warp tiles per SM): level-parallel kernel, a tile is 32 columns wide
     // and is worked on by all 8 warps of a 256-thread CTA.
-    bool level_mode = k_templated(K) && ctx->opt_levels != 0 &&
+    bool level_mode = templ && ctx->opt_levels != 0 &&
                       (ctx->opt_levels == 1 || (ctx->opt_block == 0 && total_cols <= 32LL * 4 * ctx->sm_count));
 
     long long n_ops = 0, out_off = 0, dyn_off = 0, btab_off = 0, n_lvl_ints = 0;
@@ -247,7 +260,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
                 if (num >= 1 && num <= NN) leaf_row[num - 1] = i;
             }
             std::string err = mcp::build_schedule(NN, a.po[t], a.pa[t], leaf_row.data(), a.want_grad != 0, pl.scheds[t], by_levels,
-                                                  !by_levels && k_templated(K) && ctx->opt_cherry != 0);
+                                                  !by_levels && templ && ctx->opt_cherry != 0);
             if (!err.empty()) return fail(ctx, MCP_ERR_ARG, "tree %d: %s", t, err.c_str());
             const mcp::Schedule& sc = pl.scheds[t];
             TreeDev& td = pl.trees[t];
@@ -289,7 +302,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     if (!level_mode && (e = build_all(false))) return e;
 
     // launch shape
-    const bool mma = !level_mode && !k_templated(K) && ctx->opt_mma != 0;
+    const bool mma = !level_mode && !k_templated(K) && ctx->opt_mma != 0 && !a.model_grad;
     int block, cpt, occ = 0;
     size_t smem;
     if (level_mode) {
@@ -303,9 +316,9 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
         block = ws.block;
         cpt = ws.cpt;
         occ = ws.occ;
-        smem = k_templated(K) ? walk_smem_bytes(K, max_br, a.want_grad && !acc_global ? 1 : 0, block, cpt)
-               : mma        ? mma_smem_bytes(K, max_br, a.want_grad)
-                            : generic_smem_bytes(max_br, a.want_grad);
+        smem = templ ? walk_smem_bytes(K, max_br, a.want_grad && !acc_global ? 1 : 0, block, cpt)
+               : mma ? mma_smem_bytes(K, max_br, a.want_grad)
+                     : generic_smem_bytes(max_br, a.want_grad, a.model_grad ? K : 0, block);
     }
     const int tile_w = level_mode ? 32 : mma ? MMA_TILE : block * cpt;
     const int kdim = mma ? mma_kp(K) : K;       // doubles per column of a stored partial
@@ -320,6 +333,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     }
     pl.level_mode = level_mode;
     pl.mma = mma;
+    pl.model_grad = a.model_grad != 0;
     pl.max_rows = max_rows;
     pl.want_grad = a.want_grad;
     pl.cpt = cpt;
@@ -341,7 +355,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     pl.smem_scratch = false;
     {
         const size_t scr_bytes = (size_t)(pl.n_slots + pl.n_stack) * tile_w * kdim * 8;
-        const bool fits = !level_mode && !acc_global && k_templated(K) && cpt == 1 && pl.smem_bytes + scr_bytes <= 96 * 1024;
+        const bool fits = !level_mode && !acc_global && templ && cpt == 1 && pl.smem_bytes + scr_bytes <= 96 * 1024;
         pl.smem_scratch = fits && (ctx->opt_smem_scratch == 1 || (ctx->opt_smem_scratch < 0 && pl.n_tiles <= 4 * ctx->sm_count));
         if (pl.smem_scratch) {
             pl.smem_bytes += scr_bytes;
@@ -359,7 +373,7 @@ int build_plan(mcp_ctx* ctx, const BatchArgs& a, int K, Plan& pl) {
     // K = 2 (cfg2's 50-taxon and cfg5's 100-taxon tree on millions of sites) -14 % / -19 %, where the shorter chunks
     // also make room for a third CTA per SM.
     const bool ring_wanted = ctx->opt_ring != 0;
-    if (a.want_grad && ring_wanted && !level_mode && !acc_global && !pl.smem_scratch && walk_ring_supported(K)) {
+    if (a.want_grad && ring_wanted && templ && !level_mode && !acc_global && !pl.smem_scratch && walk_ring_supported(K)) {
         bool lists = true;
         for (int t = 0; t < T; ++t) lists = lists && pl.scheds[t].n_slots < 65535;
         const size_t sr = walk_smem_bytes_ring(K, max_br, block, cpt);

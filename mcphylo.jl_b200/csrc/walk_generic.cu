@@ -48,7 +48,7 @@ cudaError_t launch_generic(const LaunchCfg& c, const WalkParams& wp, bool, bool)
     }
     cudaError_t e = raise_smem(felsenstein_walk_generic, c.smem);
     if (e != cudaSuccess) return e;
-    felsenstein_walk_generic<<<c.grid, c.block, c.smem, c.stream>>>(wp, c.K);
+    felsenstein_walk_generic<<<c.grid, c.block, c.smem, c.stream>>>(wp, c.K, c.mg);
     return cudaGetLastError();
 }
 cudaError_t occupancy_generic(const LaunchCfg& c, int* out) {

@@ -123,3 +123,104 @@ def transition_matrix(model_out: ModelOut, t: float, rate: float = 1.0) -> np.nd
     used by tests and by the synthetic-alignment simulator, never by the product path."""
     U, D, Uinv, mu = model_out
     return (U * np.exp(mu * t * D * rate)[None, :]) @ Uinv
+
+
+# ---------------------------------------------------------------------------------------------
+# Derivatives of the NORMALISED rate matrix A = mu * U diag(D) Uinv (so that P(t) = exp(A t rate))
+# with respect to the model's own parameters -- what mcp_eval_model_gradient takes as `dA` / `dpi`
+# (include/mcphylo_b200.h).  The reference has no such derivative (SURVEY.md 8f row 3); these follow
+# the functional forms above literally, base frequencies treated as independent coordinates (a
+# caller on the simplex projects afterwards).
+# ---------------------------------------------------------------------------------------------
+def normalised_rate_matrix(model_out: ModelOut) -> np.ndarray:
+    U, D, Uinv, mu = model_out
+    return mu * ((U * np.asarray(D)[None, :]) @ Uinv)
+
+
+def _gtr_A(pi: np.ndarray, sr: np.ndarray):
+    S = setmatrix(sr)
+    Q = S * pi[None, :]
+    dia = Q.sum(axis=1)
+    Q[np.arange(pi.size), np.arange(pi.size)] = -dia
+    return S, Q, 1.0 / dia.sum()
+
+
+def model_derivatives(model, base_freq: Sequence[float], SubstitutionRates: Sequence[float] = ()):
+    """(names, dA, dpi): dA[:, :, p] = d A / d theta_p (K x K), dpi[:, p] = d pi / d theta_p as seen by the root term,
+    for theta = (base_freq[0..K-1], SubstitutionRates[0..]) -- analytic for Restriction, JC, GTR and freeK, a
+    Richardson-extrapolated central difference of the model function otherwise."""
+    pi = np.atleast_1d(np.asarray(base_freq, dtype=np.float64))
+    sr = np.atleast_1d(np.asarray(SubstitutionRates, dtype=np.float64)).ravel()
+    K = pi.size
+    names = [f"base_freq[{i}]" for i in range(K)] + [f"substitution_rates[{i}]" for i in range(sr.size)]
+    n_par = K + sr.size
+    dA = np.zeros((K, K, n_par))
+    dpi = np.zeros((K, n_par))
+    dpi[np.arange(K), np.arange(K)] = 1.0
+    if model is JC:
+        pass                                            # Q has no parameters
+    elif model is Restriction:
+        # the closed form above gives Q = [[-pi2, pi2], [1 - pi2, -(1 - pi2)]] (a function of pi2 only) and mu = 1 / (2 pi1 pi2)
+        p1, p2 = pi
+        Q = np.array([[-p2, p2], [1.0 - p2, -(1.0 - p2)]])
+        mu = 1.0 / (2.0 * p1 * p2)
+        dA[:, :, 0] = -(mu / p1) * Q
+        dA[:, :, 1] = -(mu / p2) * Q + mu * np.array([[-1.0, 1.0], [-1.0, 1.0]])
+    elif model is GTR:
+        S, Q, mu = _gtr_A(pi, sr)
+        for m in range(K):                              # d / d pi_m: column m of Q is S[:, m] pi_m, the diagonal carries -row sums
+            dQ = np.zeros((K, K))
+            dQ[:, m] = S[:, m]
+            dQ[np.arange(K), np.arange(K)] -= S[:, m]
+            dmu = -mu * mu * S[:, m].sum()
+            dA[:, :, m] = mu * dQ + dmu * Q
+        k = 0
+        for j in range(K):                              # setmatrix order: column by column, i < j
+            for i in range(j):
+                dQ = np.zeros((K, K))
+                dQ[i, j] = pi[j]
+                dQ[j, i] = pi[i]
+                dQ[i, i] = -pi[j]
+                dQ[j, j] = -pi[i]
+                dmu = -mu * mu * (pi[i] + pi[j])
+                dA[:, :, K + k] = mu * dQ + dmu * Q
+                k += 1
+    elif model is freeK:
+        Kq = int(np.ceil(np.sqrt(sr.size)))
+        assert Kq == K, "freeK: number of rates and of base frequencies disagree"
+        Q = np.zeros((K, K))
+        c = 0
+        where = []
+        for i in range(K):
+            for j in range(K):
+                if i != j:
+                    Q[j, i] = sr[c]
+                    where.append((j, i))
+                    c += 1
+        dia = Q.sum(axis=1)
+        Q[np.arange(K), np.arange(K)] = -dia
+        mu = 1.0 / dia.sum()
+        for c, (j, i) in enumerate(where):
+            dQ = np.zeros((K, K))
+            dQ[j, i] = 1.0
+            dQ[j, j] = -1.0
+            dA[:, :, K + c] = mu * dQ - mu * mu * Q
+    else:
+        theta = np.concatenate([pi, sr])
+
+        def A_of(th):
+            return normalised_rate_matrix(model(th[:K].copy(), th[K:].copy()))
+
+        for p in range(n_par):
+            h = 1e-3 * max(abs(theta[p]), 1e-2)
+
+            def cd(step):
+                tp, tm = theta.copy(), theta.copy()
+                tp[p] += step
+                tm[p] -= step
+                return (A_of(tp) - A_of(tm)) / (2.0 * step)
+
+            d1, d2, d3 = cd(h), cd(h / 2.0), cd(h / 4.0)
+            r1, r2 = (4.0 * d2 - d1) / 3.0, (4.0 * d3 - d2) / 3.0      # O(h^4), then O(h^6)
+            dA[:, :, p] = (16.0 * r2 - r1) / 15.0
+    return names, dA, dpi
