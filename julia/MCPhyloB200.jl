@@ -14,6 +14,7 @@
 module MCPhyloB200
 
 using MCPhylo
+using LinearAlgebra: Diagonal
 import MCPhylo: PhyloDist, MultiplePhyloDist, logpdf, gradlogpdf, __logpdf,
                 post_order, get_leaves, get_branchlength_vector, get_mother
 
@@ -141,6 +142,56 @@ function rate_gradient(d::PhyloDist, x::Array{Float64,3})
                 Matrix{Float64}(U), Vector{Float64}(D), Matrix{Float64}(Uinv), Float64(mu),
                 d.rates, length(d.rates), d.base_freq, ll, grad, rgrad))
     ll[], grad, rgrad
+end
+
+# Derivatives of the normalised rate matrix A = mu * U * Diagonal(D) * Uinv with respect to theta =
+# (base_freq..., substitution_rates...), as a K x K x n_par array, for ANY substitution_model function: central
+# differences of the K x K matrix, Richardson-extrapolated twice (O(h^6); mcphylo.jl_b200/substitution_models.py holds
+# the closed forms for Restriction / JC / GTR / freeK and checks them against exactly this quotient).
+function rate_matrix_derivatives(model, base_freq::Vector{Float64}, subst::Vector{Float64})
+    K = length(base_freq)
+    theta = vcat(base_freq, subst)
+    A(th) = begin
+        U, D, Uinv, mu = model(th[1:K], th[K+1:end])
+        mu .* (Matrix{Float64}(U) * Diagonal(Vector{Float64}(D)) * Matrix{Float64}(Uinv))
+    end
+    dA = zeros(K, K, length(theta))
+    for p in eachindex(theta)
+        h = 1e-3 * max(abs(theta[p]), 1e-2)
+        cd(s) = begin
+            tp = copy(theta); tm = copy(theta); tp[p] += s; tm[p] -= s
+            (A(tp) .- A(tm)) ./ (2s)
+        end
+        d1, d2, d3 = cd(h), cd(h / 2), cd(h / 4)
+        r1 = (4 .* d2 .- d1) ./ 3; r2 = (4 .* d3 .- d2) ./ 3
+        dA[:, :, p] = (16 .* r2 .- r1) ./ 15
+    end
+    dA
+end
+
+# (logL, d logL / d branch length, d logL / d base_freq, d logL / d substitution_rates) in one call
+# (mcp_eval_model_gradient): the gradient pass accumulates per-branch moment matrices, the library contracts them
+# with d P / d theta.  The reference samples these parameters gradient-free (SliceSimplex(:mypi),
+# src/samplers/tree_samplers.jl:49); base_freq entries are independent coordinates here (root term + rate matrix).
+function model_gradient(d::PhyloDist, x::Array{Float64,3})
+    NN, po, pa, blv, leaf_nums = flatten(d.tree)
+    U, D, Uinv, mu = d.substitution_model(d.base_freq, d.substitution_rates)
+    K = length(d.base_freq)
+    subst = Vector{Float64}(vec(d.substitution_rates))
+    dA = rate_matrix_derivatives(d.substitution_model, Vector{Float64}(d.base_freq), subst)
+    n_par = size(dA, 3)
+    dpi = zeros(K, n_par); for s in 1:K; dpi[s, s] = 1.0; end
+    ll = Ref{Float64}(0.0)
+    grad = Vector{Float64}(undef, NN - 1)
+    pgrad = Vector{Float64}(undef, n_par)
+    check(ccall((:mcp_eval_model_gradient, LIB[]), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Cint, Ptr{Float64},
+                 Cint, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                context(), alignment(x, leaf_nums), NN, po, pa, Vector{Float64}(blv),
+                Matrix{Float64}(U), Vector{Float64}(D), Matrix{Float64}(Uinv), Float64(mu),
+                d.rates, length(d.rates), d.base_freq, n_par, dA, dpi, ll, grad, pgrad, C_NULL))
+    ll[], grad, pgrad[1:K], pgrad[K+1:end]
 end
 
 # Likelihood + branch-length prior in one device call: what logpdfgrad!(::Type{provided}, ...)
