@@ -12,6 +12,10 @@ namespace {
 // The critical path is the tree height instead of the node count; used when the whole input is only
 // a few tiles per SM (MCMC-sized problems), where the depth-first walk runs at single-warp latency.
 // --------------------------------------------------------------------------------------------
+constexpr int LEVEL_FIN_GROUP = 8;          // CTAs per group of the two-level final reduction
+constexpr int LEVEL_FIN_MIN_GRID = 192;     // fewer CTAs: the single last CTA walks the rows (at most 6 round trips)
+constexpr int LEVEL_FIN_MAX_GROUPS = 62;    // group counters behind done_counter[0] (64 words); also the extra rows the host allocates
+
 template <int K, bool DYN_MODEL>
 // 3 CTAs per SM (<= 85 registers): an MCMC-sized input is one tile per CTA, and all of them should be resident at once
 __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_constant__ LevelParams lp) {
@@ -289,11 +293,71 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
     // ---- fused final reduction: the last CTA to finish sums the accumulator rows in fixed order
     // and writes [logL, grad] per tree to p.out (device memory, or pinned host memory for the
     // synchronous entry points: no separate kernel, no device-to-host copy) ----
+    //
+    // One tree and a few hundred CTAs (an MCMC-sized evaluation: one tile and one row per CTA): the walk of the row
+    // list by a single CTA is 10 dependent L2 round trips at cfg2 (313 rows), so there the reduction is a two-level tree -- the last CTA to finish in each group of LEVEL_FIN_GROUP consecutive CTAs
+    // adds the group's rows (all of them requested at once: one round trip) into a group row behind the CTA rows,
+    // and the last GROUP to finish adds the group rows.  Fixed grouping and fixed order of additions: reproducible.
+    // Measured (profiles/r2e_ab_small_tree.jsonl): cfg2 kernel 39.6 -> 37.6 us L2-warm, 46.7 -> 43.2 us L2-cold; the second
+    // counter round trip costs ~3 us, so a 32-CTA launch (cfg1) LOSES 3 us -- hence only above LEVEL_FIN_MIN_GRID CTAs.
+    // done_counter[0] counts CTAs (one level) or finished groups (two levels), done_counter[1 + g] the CTAs of group g.
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
-    __syncthreads();
-    if (s_ticket == gridDim.x - 1) {
+    const int n_groups = ((int)gridDim.x + LEVEL_FIN_GROUP - 1) / LEVEL_FIN_GROUP;
+#ifdef MCP_LEVEL_FIN_SINGLE     // A/B builds (tools/build_variant.py): the one-level reduction of round 2's first half
+    const bool two_level = false;
+#else
+    const bool two_level = p.T == 1 && gridDim.x > LEVEL_FIN_MIN_GRID && n_groups <= LEVEL_FIN_MAX_GROUPS;
+#endif
+    bool last;
+    if (two_level) {
+        const int g = (int)blockIdx.x / LEVEL_FIN_GROUP, g_lo = g * LEVEL_FIN_GROUP, g_hi = min(g_lo + LEVEL_FIN_GROUP, (int)gridDim.x);
+        if (tid == 0) s_ticket = atomicAdd(p.done_counter + 1 + g, 1u);
+        __syncthreads();
+        if (s_ticket != (unsigned)(g_hi - g_lo - 1)) return;
+        __threadfence();
+        const int nb = p.trees[0].NN - 1;
+        if (p.want_grad) {
+            for (int j = tid; j < nb; j += NT) {
+                double v[LEVEL_FIN_GROUP];
+#pragma unroll
+                for (int b = 0; b < LEVEL_FIN_GROUP; ++b)
+                    v[b] = g_lo + b < g_hi ? __ldcg(p.rows + (long long)(g_lo + b) * p.row_stride + j) : 0.0;
+                double acc = v[0];
+#pragma unroll
+                for (int b = 1; b < LEVEL_FIN_GROUP; ++b)
+                    if (g_lo + b < g_hi) acc += v[b];
+                p.rows[(long long)((int)gridDim.x + g) * p.row_stride + j] = acc;
+            }
+        }
+        if (warp == 0) {
+            static_assert(LEVEL_FIN_GROUP == 8, "the shuffle tree below adds groups of 8 lanes");
+            long long es = 0;
+            double ls = 0.0;
+            if (lane < LEVEL_FIN_GROUP && g_lo + lane < g_hi) {
+                es = __ldcg(&p.rows_ll[g_lo + lane].esum);
+                ls = __ldcg(&p.rows_ll[g_lo + lane].logsum);
+            }
+            for (int off = 4; off > 0; off >>= 1) {
+                es += __shfl_xor_sync(0xffffffffu, es, off);
+                ls += __shfl_xor_sync(0xffffffffu, ls, off);
+            }
+            if (lane == 0) {
+                p.rows_ll[(int)gridDim.x + g].esum = es;
+                p.rows_ll[(int)gridDim.x + g].logsum = ls;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
+        __syncthreads();
+        last = s_ticket == (unsigned)(n_groups - 1);
+    } else {
+        if (tid == 0) s_ticket = atomicAdd(p.done_counter, 1u);
+        __syncthreads();
+        last = s_ticket == gridDim.x - 1;
+    }
+    if (last) {
         __threadfence();
         // All 8 warps take part: warp w sums rows row_lo + w, row_lo + w + W, ... (lanes across the
         // branches, so a warp reads one contiguous run per row), the per-warp partial sums meet in
@@ -304,6 +368,8 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
         double* const s_prior = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(s_tab) + LevelSmem::tab_bytes(p.max_br, K));
         for (int t = 0; t < p.T; ++t) {
             const TreeDev tr = p.trees[t];
+            // rows to add: the tree's own CTA rows, or the group rows behind them
+            const int fin_lo = two_level ? (int)gridDim.x : tr.row_lo, fin_hi = two_level ? (int)gridDim.x + n_groups : tr.row_hi;
             double* o = p.out + tr.out_off;
             const double* d = dynp + tr.dyn_off;
             const double* hdr = d + dyn_prior(tr.NN, K, R);
@@ -313,7 +379,7 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
             {
                 long long es = 0;
                 double ls = 0.0;
-                for (int rw = tr.row_lo + tid; rw < tr.row_hi; rw += NT) {
+                for (int rw = fin_lo + tid; rw < fin_hi; rw += NT) {
                     es += __ldcg(&p.rows_ll[rw].esum);
                     ls += __ldcg(&p.rows_ll[rw].logsum);
                 }
@@ -330,20 +396,20 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
                     // 4 rows are requested before the first is added (same order of additions): one L2 round
                     // trip per 4 rows instead of one per row -- the walk of the row list used to be 40 % of a
                     // cfg2 evaluation
-                    for (int rw0 = tr.row_lo + warp; rw0 < tr.row_hi; rw0 += 4 * W) {
+                    for (int rw0 = fin_lo + warp; rw0 < fin_hi; rw0 += 4 * W) {
                         double v[4][4];
 #pragma unroll
                         for (int b = 0; b < 4; ++b) {
                             const int rw = rw0 + b * W;
                             const double* rp = p.rows + (long long)rw * p.row_stride + j0;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) v[b][u] = (rw < tr.row_hi && j0 + 32 * u < nb) ? __ldcg(rp + 32 * u) : 0.0;
+                            for (int u = 0; u < 4; ++u) v[b][u] = (rw < fin_hi && j0 + 32 * u < nb) ? __ldcg(rp + 32 * u) : 0.0;
                         }
 #pragma unroll
                         for (int b = 0; b < 4; ++b)
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
-                                if (rw0 + b * W < tr.row_hi) acc[u] += v[b][u];
+                                if (rw0 + b * W < fin_hi) acc[u] += v[b][u];
                     }
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
@@ -366,7 +432,9 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
             }
             __syncthreads();                       // before the next tree reuses s_fin / s_e / s_l
         }
-        if (tid == 0) *p.done_counter = 0;   // ready for the next launch
+        // ready for the next launch
+        if (tid == 0) *p.done_counter = 0;
+        if (two_level && tid < n_groups) p.done_counter[1 + tid] = 0;
     }
 }
 

@@ -175,8 +175,9 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     if ((e = ensure_dev(ctx, ctx->d_dyn, sizeof(double) * pl.total_dyn))) return e;
     if ((e = ensure_dev(ctx, ctx->d_btab, sizeof(double) * pl.total_btab))) return e;
     if ((e = ensure_dev(ctx, ctx->d_scratch, sizeof(double) * pl.scratch_per_cta * pl.grid))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_rows, sizeof(double) * pl.row_stride * pl.n_rows))) return e;
-    if ((e = ensure_dev(ctx, ctx->d_rows_ll, sizeof(LLRow) * pl.n_rows))) return e;
+    // + 64 rows: the group rows of the small-tree kernel's two-level final reduction (kernel_levels.cuh)
+    if ((e = ensure_dev(ctx, ctx->d_rows, sizeof(double) * pl.row_stride * (pl.n_rows + 64)))) return e;
+    if ((e = ensure_dev(ctx, ctx->d_rows_ll, sizeof(LLRow) * (pl.n_rows + 64)))) return e;
     const bool fused = pl.level_mode;   // small-tree kernel: tables, walk and final reduction in ONE launch
     const bool via_comm = !d_out_user && ctx->rank_comm != nullptr;
     double* d_out = d_out_user;
