@@ -23,6 +23,8 @@ struct LaunchCfg {
     bool ring = false;         // gradient pass fetches its stored operands through the per-warp operand ring (cp.async.bulk)
     bool mma = false;          // K > 6: tile-cooperative FP64 tensor-core kernel instead of the runtime-K fallback
     double* mg = nullptr;      // runtime-K kernel only: per-(branch, rate) moment matrices of a model-gradient evaluation
+    int mg_rep = 1;            // ... kept in mg_rep replicas mg_stride doubles apart (CTA c adds to replica c % mg_rep), folded afterwards
+    long long mg_stride = 0;
 };
 
 // Every entry returns cudaSuccess or the error of the CUDA call that failed.

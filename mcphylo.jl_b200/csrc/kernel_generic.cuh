@@ -22,7 +22,17 @@ namespace {
 // cooperatively (K * K outputs spread over the lanes, no shuffles), then adds it to M with one atomic per output.
 // mg layout: [device branch][rate][s * K + k], then W[K].
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams p, const int K, double* __restrict__ const mg) {
+// Every CTA of the launch adds to the same few addresses at about the same time (all walk the ops in the same order), so
+// the matrices are kept in mg_rep replicas (CTA c uses replica c % mg_rep) that the host folds with one small kernel.
+// KT > 0 fixes the state count at compile time (model-gradient evaluations of K <= 6: the per-thread vectors then live
+// in registers and every loop over states unrolls -- the runtime-K instantiation keeps them in local memory and is
+// 4x slower at K = 4); KT == 0 is the runtime-K kernel for 6 < K <= KMAX_GENERIC.
+template <int KT>
+__global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams p, const int K_rt, double* __restrict__ const mg_base,
+                                                                const int mg_rep, const long long mg_stride) {
+    constexpr int KA = KT > 0 ? KT : KMAX_GENERIC;      // capacity of the per-thread vectors
+    const int K = KT > 0 ? KT : K_rt;
+    double* const mg = mg_base ? mg_base + (long long)(blockIdx.x % (unsigned)mg_rep) * mg_stride : nullptr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long s_e[8];
     __shared__ double s_l[8];
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                 return min(code, K);
             };
 
-            double cur[KMAX_GENERIC], Da[KMAX_GENERIC], Db[KMAX_GENERIC], L[KMAX_GENERIC];
+            double cur[KA], Da[KA], Db[KA], L[KA];
             for (int k = 0; k < K; ++k) cur[k] = 1.0;
             int e_col = 0;
             for (int i = 0; i < tr.n_post; ++i) {
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
             }
 
             if (p.want_grad) {
-                double pm[KMAX_GENERIC], Ya[KMAX_GENERIC], Yb[KMAX_GENERIC];
+                double pm[KA], Ya[KA], Yb[KA];
                 // M[br][r] += sum over this warp's 32 columns of (qv * w) (x) Lv; Lv == nullptr: leaf with state `code`
                 auto moments = [&](const double* qv, const double* Lv, int code, double w, int br) {
                     for (int k = 0; k < K; ++k) {
@@ -156,11 +166,15 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                         const int s = idx / K, k = idx - s * K;
                         double acc = 0.0;
                         for (int l = 0; l < 32; ++l) acc = fma(s_mq[l * K + s], s_ml[l * K + k], acc);
+#ifdef MCP_MG_NO_ATOMIC      // measurement builds only: the cost of the atomics (results are wrong)
+                        if (acc == 123.456) atomicAdd(dst + idx, acc);
+#else
                         atomicAdd(dst + idx, acc);
+#endif
                     }
                     __syncwarp();
                 };
-                double La[KMAX_GENERIC], Lb[KMAX_GENERIC];
+                double La[KA], Lb[KA];
                 for (int i = 0; i < tr.n_pre; ++i) {
                     const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
                     const int flags = o1.y;

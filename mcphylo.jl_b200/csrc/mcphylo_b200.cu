@@ -157,9 +157,15 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     const KernelTable* kt = a.model_grad ? mcpdev::kernels_generic() : kernels_for(K);
     if (a.model_grad && (d_out_user || ctx->sf)) return fail(ctx, MCP_ERR_ARG, "internal: model-gradient evaluation must be synchronous and resident");
     // model-gradient moments: [device branch][rate][K x K] and the root vector W[K] (kernel_generic.cuh)
-    const size_t mg_doubles = a.model_grad ? (size_t)pl.trees[0].n_br * R * K * K + K : 0;
+    const size_t mg_doubles = a.model_grad ? (((size_t)pl.trees[0].n_br * R * K * K + K + 3) & ~(size_t)3) : 0;
+    // replicas against same-address atomics (kernel_generic.cuh): as many as 64 MB hold, at most 32 and at most one per CTA
+    static const int mg_rep_env = []() { const char* v = std::getenv("MCPHYLO_B200_MG_REPLICAS"); return v ? std::atoi(v) : 0; }();
+    int mg_rep = 1;
     if (a.model_grad) {
-        if ((e = ensure_dev(ctx, ctx->d_mg, sizeof(double) * mg_doubles))) return e;
+        mg_rep = (int)std::min<size_t>(32, std::max<size_t>(1, ((size_t)64 << 20) / (sizeof(double) * mg_doubles)));
+        if (mg_rep_env > 0) mg_rep = mg_rep_env;
+        mg_rep = std::max(1, std::min(mg_rep, pl.grid));
+        if ((e = ensure_dev(ctx, ctx->d_mg, sizeof(double) * mg_doubles * (mg_rep + 1)))) return e;   // + the folded result
         if ((e = ensure_pin(ctx, ctx->h_mg, sizeof(double) * mg_doubles))) return e;
     }
 
@@ -346,8 +352,10 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     lc.acc_global = pl.acc_global;
     lc.mma = pl.mma;
     if (a.model_grad) {
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_mg.p, 0, sizeof(double) * mg_doubles, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_mg.p, 0, sizeof(double) * mg_doubles * mg_rep, st));
         lc.mg = (double*)ctx->d_mg.p;
+        lc.mg_rep = mg_rep;
+        lc.mg_stride = (long long)mg_doubles;
     }
     {
         cudaError_t ce = pl.level_mode ? kt->launch_levels(lc, wp, dyn_model, inline_dyn ? hd : nullptr, (size_t)pl.total_dyn)
@@ -368,6 +376,12 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         CUDA_TRY(ctx, cudaEventRecord(en->ev, st));
         en->last = ctx;
     }
+    double* const d_mg_result = a.model_grad ? (double*)ctx->d_mg.p + (mg_rep > 1 ? (size_t)mg_rep * mg_doubles : 0) : nullptr;
+    if (a.model_grad && mg_rep > 1) {   // fold the replicas, in replica order, into the slot behind them
+        sum_rows<<<(unsigned)((mg_doubles + 255) / 256), 256, 0, st>>>((const double*)ctx->d_mg.p, (long long)mg_doubles, mg_rep,
+                                                                        (long long)mg_doubles, d_mg_result);
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_done, st));
     for (int t = 0; t < T; ++t) {
         a.alns[t]->read_since_upload = true;
@@ -382,7 +396,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
                                                (const double*)ctx->d_dyn.p, K, R);
         CUDA_TRY(ctx, cudaGetLastError());
     }
-    s.kernel_launches = (fused ? 1 : 3) + (inline_dyn ? 0 : 1) + (rebuilt ? 1 : 0);   // + parameter staging (+ topology staging)
+    s.kernel_launches = (fused ? 1 : 3) + (inline_dyn ? 0 : 1) + (rebuilt ? 1 : 0) + (a.model_grad && mg_rep > 1 ? 1 : 0);   // + parameter staging (+ topology staging) (+ fold of the moment replicas)
     s.grid = pl.grid;
     s.block = pl.block;
     s.tiles = pl.n_tiles;
@@ -401,14 +415,14 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         mcpnccl::result_t nr = nc.AllReduce(d_out, d_out, (size_t)pl.total_out, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, st);
         if (nr) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce failed: %s", nc.GetErrorString(nr));
         if (a.model_grad) {
-            nr = nc.AllReduce(ctx->d_mg.p, ctx->d_mg.p, mg_doubles, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, st);
+            nr = nc.AllReduce(d_mg_result, d_mg_result, mg_doubles, mcpnccl::kFloat64, mcpnccl::kSum, ctx->rank_comm, st);
             if (nr) return fail(ctx, MCP_ERR_CUDA, "ncclAllReduce (model-gradient moments) failed: %s", nc.GetErrorString(nr));
         }
     }
     if (!fused || via_comm) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_out.p, d_out, sizeof(double) * pl.total_out, cudaMemcpyDeviceToHost, st));
     s.d2h_bytes = (int64_t)(sizeof(double) * pl.total_out);
     if (a.model_grad) {
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_mg.p, ctx->d_mg.p, sizeof(double) * mg_doubles, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_mg.p, d_mg_result, sizeof(double) * mg_doubles, cudaMemcpyDeviceToHost, st));
         s.d2h_bytes += (int64_t)(sizeof(double) * mg_doubles);
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));

@@ -41,24 +41,47 @@ cudaError_t occupancy_mma(const LaunchCfg& c, int* out) {   // the persistent gr
     *out = o1 < o2 ? o1 : o2;
     return e;
 }
+// state counts 2 .. 6 reach this unit only for model-gradient evaluations: compile-time K (kernel_generic.cuh)
+template <int KT>
+cudaError_t launch_generic_inst(const LaunchCfg& c, const WalkParams& wp) {
+    cudaError_t e = raise_smem(felsenstein_walk_generic<KT>, c.smem);
+    if (e != cudaSuccess) return e;
+    felsenstein_walk_generic<KT><<<c.grid, c.block, c.smem, c.stream>>>(wp, c.K, c.mg, c.mg_rep, c.mg_stride);
+    return cudaGetLastError();
+}
+template <int KT>
+cudaError_t occupancy_generic_inst(const LaunchCfg& c, int* out) {
+    cudaError_t e = raise_smem(felsenstein_walk_generic<KT>, c.smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk_generic<KT>, c.block, c.smem);
+}
 cudaError_t launch_generic(const LaunchCfg& c, const WalkParams& wp, bool, bool) {
     if (c.mma) {
         const int KP = (c.K + 7) & ~7;
         return KP == 8 ? launch_mma<8>(c, wp) : KP == 16 ? launch_mma<16>(c, wp) : KP == 24 ? launch_mma<24>(c, wp) : launch_mma<32>(c, wp);
     }
-    cudaError_t e = raise_smem(felsenstein_walk_generic, c.smem);
-    if (e != cudaSuccess) return e;
-    felsenstein_walk_generic<<<c.grid, c.block, c.smem, c.stream>>>(wp, c.K, c.mg);
-    return cudaGetLastError();
+    switch (c.K) {
+        case 2: return launch_generic_inst<2>(c, wp);
+        case 3: return launch_generic_inst<3>(c, wp);
+        case 4: return launch_generic_inst<4>(c, wp);
+        case 5: return launch_generic_inst<5>(c, wp);
+        case 6: return launch_generic_inst<6>(c, wp);
+        default: return launch_generic_inst<0>(c, wp);
+    }
 }
 cudaError_t occupancy_generic(const LaunchCfg& c, int* out) {
     if (c.mma) {
         const int KP = (c.K + 7) & ~7;
         return KP == 8 ? occupancy_mma<8>(c, out) : KP == 16 ? occupancy_mma<16>(c, out) : KP == 24 ? occupancy_mma<24>(c, out) : occupancy_mma<32>(c, out);
     }
-    cudaError_t e = raise_smem(felsenstein_walk_generic, c.smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, felsenstein_walk_generic, c.block, c.smem);
+    switch (c.K) {
+        case 2: return occupancy_generic_inst<2>(c, out);
+        case 3: return occupancy_generic_inst<3>(c, out);
+        case 4: return occupancy_generic_inst<4>(c, out);
+        case 5: return occupancy_generic_inst<5>(c, out);
+        case 6: return occupancy_generic_inst<6>(c, out);
+        default: return occupancy_generic_inst<0>(c, out);
+    }
 }
 
 }  // namespace
