@@ -445,6 +445,21 @@ def leg_single(name, local_rank, steps, warmup, with_cpu=True):
         rate, sec, threads, s = cpu_oracle_rate(w, codes, leaf_nums, sample, 2, 1)
         out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": threads, "kind": "port",
                                "sample": f"first {s} of {w['S']} sites; {sec:.3f} s per evaluation on the sample"}
+    try:    # logL + branch gradient + gradient w.r.t. the substitution-model parameters in one call
+        from mcphylo_jl_b200.substitution_models import model_derivatives
+        _, dA, dpi = model_derivatives(w["model"], w["pi"], w["srates"])
+        mg_ms, res = [], None
+        for i in range(4):
+            ctx.timer_start()
+            res = ctx.eval_model_gradient(aln, *targs, dA=dA, dpi=dpi)
+            mg_ms.append(ctx.timer_stop())
+        ll_p, g_p = ctx.eval(aln, *targs, want_grad=True)
+        out["model_gradient"] = {"ms_per_call_device": float(np.median(mg_ms[1:])), "n_parameters": int(dA.shape[2]),
+                                 "ll_rel_diff_to_plain": abs(res[0] - ll_p) / abs(ll_p),
+                                 "grad_max_rel_diff_to_plain": float(np.max(np.abs(res[1] - g_p)) / np.max(np.abs(g_p))),
+                                 "what": "mcp_eval_model_gradient: d logL / d (base_freq, substitution_rates) next to the branch gradient"}
+    except Exception as ex:
+        out["model_gradient"] = {"error": repr(ex)}
     aln.close()
     ctx.close()
     return out

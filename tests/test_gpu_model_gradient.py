@@ -145,3 +145,65 @@ def test_model_gradient_argument_errors():
         assert np.isfinite(ll) and np.all(np.isfinite(g))
     finally:
         aln.close()
+
+
+def _rank_worker(rank, n_ranks, uid, q, payload):
+    """One process per GPU (mcp_create_rank): evaluates its site shard; mcp_eval_model_gradient all-reduces logL, the
+    branch gradient and the moment matrices over the ranks, so every rank returns the full-alignment result."""
+    import numpy as np
+
+    from mcphylo_jl_b200 import capi as _capi
+
+    codes, leaf_nums, targs, dA, dpi, K = payload
+    try:
+        ctx = _capi.Context(rank, rank=(n_ranks, rank, uid))
+        lo, hi = _capi.shard_bounds(codes.shape[1], n_ranks, rank)
+        aln = ctx.alignment_from_codes(np.ascontiguousarray(codes[:, lo:hi]), K, leaf_nums)
+        ll, g, pg = ctx.eval_model_gradient(aln, *targs, dA=dA, dpi=dpi)
+        ll2, g2 = ctx.eval(aln, *targs, want_grad=True)          # the plain all-reduced evaluation still works afterwards
+        aln.close()
+        ctx.close()
+        q.put((rank, ll, g, pg, ll2, g2, None))
+    except Exception as ex:      # noqa: BLE001 - reported to the parent
+        q.put((rank, None, None, None, None, None, repr(ex)))
+
+
+def test_one_process_per_gpu_allreduces_the_moments(oracle):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import multiprocessing as mp_
+
+    rng = np.random.default_rng(314)
+    pi, sr = np.array([0.1, 0.2, 0.3, 0.4]), np.array([1.0, 2.0, 1.5, 0.8, 2.5, 1.2])
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, 4)
+    tree = random_tree(25, rng)
+    model_out = sm.GTR(pi, sr)
+    codes, leaf_nums = simulate_codes(tree, model_out, pi, rates, 3001, rng, gap_frac=0.02)
+    ft = mcp.flatten(tree)
+    U, D, Uinv, mu = model_out
+    targs = (ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, rates, pi)
+    _, dA, dpi = sm.model_derivatives(sm.GTR, pi, sr)
+    single = mcp.get_context()
+    aln = single.alignment_from_codes(codes, 4, leaf_nums)
+    try:
+        ll1, g1, pg1 = single.eval_model_gradient(aln, *targs, dA=dA, dpi=dpi)
+    finally:
+        aln.close()
+    mpc = mp_.get_context("spawn")
+    q = mpc.Queue()
+    uid = capi.nccl_unique_id()
+    procs = [mpc.Process(target=_rank_worker, args=(r, 2, uid, q, (codes, leaf_nums, targs, dA, dpi, 4))) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ll, g, pg, ll2, g2, err in results:
+        assert err is None, err
+        assert abs(ll - ll1) <= 1e-12 * abs(ll1)
+        assert np.max(np.abs(g - g1)) <= 1e-10 * np.max(np.abs(g1))
+        assert np.max(np.abs(pg - pg1)) <= 1e-10 * np.max(np.abs(pg1))
+        assert abs(ll2 - ll1) <= 1e-12 * abs(ll1)
+        assert np.max(np.abs(g2 - g1)) <= 1e-10 * np.max(np.abs(g1))
