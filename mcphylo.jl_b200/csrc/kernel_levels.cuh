@@ -63,8 +63,14 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
         double logsum = 0.0;
         const ModelT<K, DYN_MODEL> mdl{p, DYN_MODEL ? (int)dynp[tr.dyn_off + dyn_slot(tr.NN, K, R)] * MODEL_SLOT : 0};
         // post program, then pre program (contiguous in the topology block); likewise the level offsets
+        cp_async_wait_all();                                   // (a tree without a tile for this CTA leaves its program copy pending)
         __syncthreads();                                       // the previous tree's program is no longer in use
+#ifdef MCP_LEVEL_SYNC_STAGING    // A/B builds: every thread loads and stores its own words (round 2's first half)
         for (int i = tid; i < 2 * (tr.n_post + tr.n_pre); i += NT) s_ops[i] = __ldg(p.ops + 2 * tr.post_off + i);
+#else                            // asynchronous copies, completed together with the first tile's codes below
+        for (int i = tid; i < 2 * (tr.n_post + tr.n_pre); i += NT) cp_async16(s_ops + i, p.ops + 2 * tr.post_off + i);
+        cp_async_commit();
+#endif
         for (int i = tid; i < tr.n_post_lvl + tr.n_pre_lvl + 2; i += NT) s_lvl[i] = __ldg(p.levels + tr.lvl_off + i);
         const int4* const post_ops = s_ops;
         const int4* const pre_ops = s_ops + 2 * tr.n_post;
@@ -81,6 +87,15 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
             constexpr long long br_stride = BT;
 
             __syncthreads();                                   // previous tile done with the shared buffers
+#ifndef MCP_LEVEL_SYNC_STAGING
+            // This tile's state codes, all leaves: one 16-byte asynchronous copy per (leaf row, half tile), requested BEFORE
+            // the branch table is built so that the one memory round trip runs under that arithmetic.  (Byte loads by
+            // every thread were 6-7 dependent round trips at cfg2's 50 leaves: 12 % of the kernel's stall samples.)
+            // Rows are 1024-byte-padded and tiles start at multiples of 32 sites: 16-byte aligned, never past the row.
+            for (int i = tid; i < tr.n_rows * 2; i += NT)
+                cp_async16(s_code + i * 16, tr.codes + (long long)(i >> 1) * tr.code_stride + site0 + (i & 1) * 16);
+            cp_async_commit();
+#endif
             if (r != built_rate) {
                 // branch table of (tree, rate r), built here instead of by a separate kernel:
                 // e = exp(t * D mu rate), P = U diag(e) Uinv, dP = U diag(D mu rate e) Uinv, plus the
@@ -131,14 +146,18 @@ __global__ void __launch_bounds__(256, 3) felsenstein_walk_levels(const __grid_c
                 }
                 built_rate = r;
             }
+#ifdef MCP_LEVEL_SYNC_STAGING
             for (int i = tid; i < tr.n_rows * 32; i += NT) {   // this tile's state codes, all leaves
                 const int rw = i >> 5, l = i & 31;
                 s_code[i] = (site0 + l < tr.S) ? __ldg(tr.codes + (long long)rw * tr.code_stride + site0 + l) : (unsigned char)K;
             }
+#endif
             if (tid < 32) s_exp[tid] = 0;
+            cp_async_wait_all();
             __syncthreads();
 
-            auto leaf_code = [&](int src) -> int { return src >= 0 ? min((int)s_code[src * 32 + lane], K) : K; };
+            // columns behind the last site read whatever the row holds there (inside its padded stride): masked here
+            auto leaf_code = [&](int src) -> int { return (src >= 0 && valid) ? min((int)s_code[src * 32 + lane], K) : K; };
             auto ld_slot = [&](const double* base, int slot, double (&v)[1][K]) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) v[0][k] = base[(size_t)slot * SLOT + k];
