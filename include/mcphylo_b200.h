@@ -327,6 +327,10 @@ int mcp_wave_columns(mcp_ctx *ctx, int K, int n_nodes, int want_grad, int64_t *c
  * alignment columns wide; 0 = automatic: 256, the measured optimum at every input size, narrowed only for
  * alignments of fewer than 256 sites), ctas_per_sm = persistent CTAs per SM (0 = occupancy maximum). */
 int mcp_set_launch(mcp_ctx *ctx, int block, int ctas_per_sm);
+/* The four CUDA timing events every evaluation records for mcp_get_stats (walk_ms, device_ms): 1 = recorded (default),
+ * 0 = not recorded, the two times then read 0.  A latency-bound caller (one MCMC-sized evaluation per leapfrog, cfg2:
+ * a 38 us kernel) saves the events' share of the call; MCPHYLO_B200_TIMING=0 sets the same default per process. */
+int mcp_set_timing(mcp_ctx *ctx, int on);
 /* Alignment columns walked by one thread: 1, 2, or 0 = automatic (2 once the GPU is full). */
 int mcp_set_columns_per_thread(mcp_ctx *ctx, int cpt);
 /* Where a CTA keeps its partial-likelihood scratch: -1 automatic (shared memory for small inputs

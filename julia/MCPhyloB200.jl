@@ -56,6 +56,8 @@ function context()
         end
         rc == 0 || error("libmcphylo_b200 ($rc): " * last_error(C_NULL))   # no CPU fallback
         CTX[] = out[]
+        # no per-evaluation timing events (they only feed mcp_get_stats): 5-13 us of a 36-58 us MCMC-sized call
+        get(ENV, "MCPHYLO_B200_TIMING", "0") == "1" || ccall((:mcp_set_timing, LIB[]), Cint, (Ptr{Cvoid}, Cint), CTX[], 0)
     end
     CTX[]
 end

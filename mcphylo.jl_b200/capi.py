@@ -25,7 +25,7 @@ SYMBOLS = [
     "mcp_alignment_from_codes", "mcp_alignment_from_dense", "mcp_alignment_update_codes",
     "mcp_alignment_destroy",
     "mcp_eval", "mcp_eval_posterior", "mcp_eval_rate_gradient", "mcp_eval_model_gradient", "mcp_model_gradient_contract", "mcp_eval_device", "mcp_eval_batch", "mcp_get_stats", "mcp_wave_columns", "mcp_set_launch",
-    "mcp_set_columns_per_thread", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode", "mcp_set_ring_mode",
+    "mcp_set_columns_per_thread", "mcp_set_timing", "mcp_set_scratch_mode", "mcp_set_accumulator_mode", "mcp_set_level_mode", "mcp_set_tile_order", "mcp_set_cherry_mode", "mcp_set_large_alphabet_mode", "mcp_set_ring_mode",
     "mcp_schedule_dump", "mcp_schedule_fetch_list", "mcp_model_reorder",
 ]
 
@@ -270,6 +270,10 @@ class Context:
 
     def set_columns_per_thread(self, cpt: int = 0):
         self._check(self.lib.mcp_set_columns_per_thread(self.handle, int(cpt)))
+
+    def set_timing(self, on: bool = True):
+        """Per-evaluation CUDA timing events behind stats() on / off (mcp_set_timing)."""
+        self._check(self.lib.mcp_set_timing(self.handle, int(bool(on))))
 
     def set_level_mode(self, mode: int = -1):
         self._check(self.lib.mcp_set_level_mode(self.handle, int(mode)))

@@ -195,6 +195,7 @@ struct mcp_ctx {
     int opt_ring = -1;           // gradient pass: operand ring (-1 automatic = on where supported, 0 off, 1 on)
     int opt_mma = -1;            // K > 6: FP64 tensor-core walk (-1 / 1) or the runtime-K fallback kernel (0)
     int opt_cherry = -1;         // gradient pass recomputes cherries from their leaves (-1 / 1) or re-reads stored copies (0)
+    int opt_timing = 1;          // per-evaluation CUDA timing events behind mcp_get_stats (0: not recorded, times read 0)
     int opt_dynamic = -1;        // resident single-tree walk: tiles by atomic ticket in site order (1) or static ranges (0)
     unsigned long long next_aln_id = 1, clock = 0;
 

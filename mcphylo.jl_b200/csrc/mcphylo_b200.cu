@@ -250,7 +250,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         explicit UploadGuard(Plan& p) : pl(p), was(p.uploaded) {}
         ~UploadGuard() { if (!ok) pl.uploaded = false; }
     } guard(pl);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (ctx->opt_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
     if (dyn_model) {   // several models: slots in constant memory; one model travels as a kernel parameter
         std::lock_guard<std::mutex> lock(g_slots.mu);
         ModelSlotGuard::Entry* en = g_slots.find(ctx->device, kt);
@@ -337,7 +337,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     static_assert(sizeof(wp.model) / sizeof(double) >= 2 * 6 * 6 + 6 + MAX_RATES * 6, "model parameter block too small");
     std::memset(wp.model, 0, sizeof wp.model);
     if (n_models == 1) std::memcpy(wp.model, hm, sizeof(double) * model_doubles);
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (ctx->opt_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
     if (ctx->ev_walk_begin) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_begin, st));
     LaunchCfg lc;
     lc.device = ctx->device;
@@ -362,7 +362,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
                                        : kt->launch_walk(lc, wp, dyn_model, all_null_last);
         if (ce != cudaSuccess) return fail(ctx, MCP_ERR_CUDA, "walk kernel launch failed: %s", cudaGetErrorString(ce));
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+    if (ctx->opt_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
     if (ctx->ev_walk_end) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_walk_end, st));
     if (dyn_model) {   // the next writer of this unit's model slots on this device waits for this kernel
         std::lock_guard<std::mutex> lock(g_slots.mu);
@@ -406,7 +406,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
     s.scratch_bytes = (int64_t)ctx->d_scratch.cap;
     guard.ok = true;
     if (d_out_user) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+        if (ctx->opt_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
         ctx->pending_async = true;
         return 0;
     }
@@ -425,7 +425,7 @@ int eval_impl(mcp_ctx* ctx, const BatchArgs& a, double* d_out_user, double* ll_o
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_mg.p, d_mg_result, sizeof(double) * mg_doubles, cudaMemcpyDeviceToHost, st));
         s.d2h_bytes += (int64_t)(sizeof(double) * mg_doubles);
     }
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (ctx->opt_timing) CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
     for (bool& p : ctx->staged_pending) p = false;
     ctx->pending_async = false;
@@ -1027,6 +1027,10 @@ int create_single(mcp_ctx** out, int device) {
         return fail(nullptr, MCP_ERR_CUDA, "stream/event creation failed: %s", msg.c_str());
     }
     ctx->stream = ctx->own_stream;
+    {
+        const char* v = std::getenv("MCPHYLO_B200_TIMING");
+        if (v && v[0] == '0') ctx->opt_timing = 0;
+    }
     *out = ctx;
     return 0;
 }
@@ -1357,6 +1361,11 @@ int mcp_set_level_mode(mcp_ctx* ctx, int mode) {
         invalidate_plans(m);
         return 0;
     });
+}
+
+int mcp_set_timing(mcp_ctx* ctx, int on) {
+    if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
+    return for_members_or_self(ctx, [&](mcp_ctx* m) { m->opt_timing = on ? 1 : 0; return 0; });
 }
 
 int mcp_set_columns_per_thread(mcp_ctx* ctx, int cpt) {
@@ -1727,6 +1736,7 @@ static void read_stats(const mcp_ctx* ctx, mcp_stats* out) {
     *out = ctx->stats;
     // event times are read lazily: they exist once the stream has passed the last event
     float ms = 0.f;
+    if (!ctx->opt_timing) return;
     if (ctx->ev[3] && cudaEventQuery(ctx->ev[3]) == cudaSuccess) {
         if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) out->walk_ms = ms;
         if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3]) == cudaSuccess) out->device_ms = ms;

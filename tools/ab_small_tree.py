@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default="cfg2,cfg1")
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--no-timing", action="store_true", help="mcp_set_timing(0): no per-evaluation timing events (kernel_us reads 0)")
     ap.add_argument("--tag", default=os.environ.get("MCPHYLO_B200_LIB", "lib"))
     args = ap.parse_args()
     import mcphylo_jl_b200 as mcp
@@ -28,6 +29,8 @@ def main():
     from mcphylo_jl_b200.phylodist import _tree_args
 
     ctx = capi.Context(0)
+    if args.no_timing:
+        ctx.set_timing(False)
     flush = bench.L2Flusher(0)
     rows = []
     for case in args.cases.split(","):
