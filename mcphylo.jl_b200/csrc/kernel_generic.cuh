@@ -98,21 +98,35 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
             const unsigned char* const codes = tr.codes + (valid ? site : 0);
             const double* const tab_r = p.btab + tr.btab_off + (long long)r * BT + 2 * K;   // P columns of (branch 0, rate r)
             const long long br_stride = (long long)R * BT;
-            auto leaf_code = [&](int src) -> int {
-                int code = (valid && src >= 0) ? (int)__ldg(codes + (long long)src * tr.code_stride) : K;
-                return min(code, K);
+            // Op descriptors and the state codes of leaf children are requested ONE OP AHEAD: a leaf child costs two dependent
+            // loads (code, then the table column it selects) and the code comes from DRAM -- ncu on the first version
+            // showed the warps waiting on exactly these (long scoreboard 5.9 per issue, a third of it on min(code, K)).
+            // raw_code returns the byte as loaded; min(., K) is applied where the code is used, one op later.
+            auto raw_code = [&](int src) -> int {
+                return (valid && src >= 0) ? (int)__ldg(codes + (long long)src * tr.code_stride) : K;
+            };
+            int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+            int ca_n = K, cb_n = K;
+            auto request = [&](const int4* ops, int i) {
+                n0 = __ldg(ops + 2 * i);
+                n1 = __ldg(ops + 2 * i + 1);
+                ca_n = (n1.y & 3) == mcp::OPK_LEAF ? raw_code(n0.x) : K;
+                cb_n = ((n1.y >> 2) & 3) == mcp::OPK_LEAF ? raw_code(n0.z) : K;
             };
 
             double cur[KA], Da[KA], Db[KA], L[KA];
             for (int k = 0; k < K; ++k) cur[k] = 1.0;
             int e_col = 0;
+            if (tr.n_post > 0) request(post_ops, 0);
             for (int i = 0; i < tr.n_post; ++i) {
-                const int4 o0 = __ldg(post_ops + 2 * i), o1 = __ldg(post_ops + 2 * i + 1);
+                const int4 o0 = n0, o1 = n1;
+                const int ca = min(ca_n, K), cb = min(cb_n, K);
+                if (i + 1 < tr.n_post) request(post_ops, i + 1);
                 const int flags = o1.y, ka = flags & 3, kb = (flags >> 2) & 3;
                 const double* ta = tab_r + o0.y * br_stride;
                 const double* tb = tab_r + o0.w * br_stride;
                 if (ka == mcp::OPK_LEAF) {
-                    const double* col = ta + leaf_code(o0.x) * K;
+                    const double* col = ta + ca * K;
                     for (int s = 0; s < K; ++s) Da[s] = __ldg(col + s);
                 } else if (ka == mcp::OPK_REG) {
                     down(ta, cur, Da);
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     down(ta, L, Da);
                 }
                 if (kb == mcp::OPK_LEAF) {
-                    const double* col = tb + leaf_code(o0.z) * K;
+                    const double* col = tb + cb * K;
                     for (int s = 0; s < K; ++s) Db[s] = __ldg(col + s);
                 } else if (kb == mcp::OPK_REG) {
                     down(tb, cur, Db);
@@ -175,8 +189,11 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     __syncwarp();
                 };
                 double La[KA], Lb[KA];
+                if (tr.n_pre > 0) request(pre_ops, 0);
                 for (int i = 0; i < tr.n_pre; ++i) {
-                    const int4 o0 = __ldg(pre_ops + 2 * i), o1 = __ldg(pre_ops + 2 * i + 1);
+                    const int4 o0 = n0, o1 = n1;
+                    const int ca = min(ca_n, K), cb = min(cb_n, K);
+                    if (i + 1 < tr.n_pre) request(pre_ops, i + 1);
                     const int flags = o1.y;
                     const int a_br = o0.y, b_br = o0.w;
                     const bool ai = (flags & 3) == mcp::OPK_MEM, bi = ((flags >> 2) & 3) == mcp::OPK_MEM;
@@ -187,21 +204,19 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     const double* ta = tab_r + a_br * br_stride;
                     const double* tb = tab_r + b_br * br_stride;
                     if (ai) {
-                        for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.x * slot_stride + k);
-                        if (mg) { for (int k = 0; k < K; ++k) La[k] = L[k]; }
-                        down(ta, L, Da);
-                        down(ta + KK1, L, Ya);
+                        for (int k = 0; k < K; ++k) La[k] = __ldcg(slots + o0.x * slot_stride + k);
+                        down(ta, La, Da);
+                        down(ta + KK1, La, Ya);
                     } else {
-                        const double* col = ta + leaf_code(o0.x) * K;
+                        const double* col = ta + ca * K;
                         for (int s = 0; s < K; ++s) { Da[s] = __ldg(col + s); Ya[s] = __ldg(col + KK1 + s); }
                     }
                     if (bi) {
-                        for (int k = 0; k < K; ++k) L[k] = __ldcg(slots + o0.z * slot_stride + k);
-                        if (mg) { for (int k = 0; k < K; ++k) Lb[k] = L[k]; }
-                        down(tb, L, Db);
-                        down(tb + KK1, L, Yb);
+                        for (int k = 0; k < K; ++k) Lb[k] = __ldcg(slots + o0.z * slot_stride + k);
+                        down(tb, Lb, Db);
+                        down(tb + KK1, Lb, Yb);
                     } else {
-                        const double* col = tb + leaf_code(o0.z) * K;
+                        const double* col = tb + cb * K;
                         for (int s = 0; s < K; ++s) { Db[s] = __ldg(col + s); Yb[s] = __ldg(col + KK1 + s); }
                     }
                     double den = 0.0, na = 0.0, nb = 0.0;
@@ -218,8 +233,8 @@ __global__ void __launch_bounds__(128) felsenstein_walk_generic(const WalkParams
                     if (lane == 0) atomicAdd(&s_acc[a_br], red);
                     else if (lane == 16) atomicAdd(&s_acc[b_br], red);
                     if (mg) {   // Ya / Yb hold qa / qb here
-                        moments(Ya, ai ? La : nullptr, ai ? 0 : leaf_code(o0.x), inv, a_br);
-                        moments(Yb, bi ? Lb : nullptr, bi ? 0 : leaf_code(o0.z), inv, b_br);
+                        moments(Ya, ai ? La : nullptr, ca, inv, a_br);
+                        moments(Yb, bi ? Lb : nullptr, cb, inv, b_br);
                     }
 
                     const int a_out = (flags >> 10) & 3, b_out = (flags >> 12) & 3;
