@@ -835,6 +835,41 @@ def test_level_parallel_kernel(oracle, n_taxa, K, R, S, multi):
     _check(ll0, g0, ll_o, g_o)
 
 
+@pytest.mark.parametrize("n_taxa,K,R,S", [(50, 2, 1, 10000),      # cfg2's shape: 313 CTAs -> 40 groups, the last one of 1 CTA
+                                          (30, 4, 2, 3300),       # 208 CTAs -> 26 groups, two rate categories
+                                          (20, 2, 1, 6176)])      # 193 CTAs: the smallest launch that takes two levels
+def test_level_kernel_two_level_final_reduction(oracle, n_taxa, K, R, S):
+    """Launches of more than 192 CTAs of the fused small-tree kernel reduce their accumulator rows in two levels (groups
+    of 8 CTAs, then the group rows): logL, gradient and the prior epilogue against the oracle, bit-reproducible."""
+    rng = np.random.default_rng(900 + n_taxa + K)
+    tree = random_tree(n_taxa, rng)
+    pi = rng.dirichlet(np.ones(K) * 5)
+    model, pi, srates = _model(K, pi, rng)
+    rates = mcp.discrete_gamma_rates(0.5, 0.5, R) if R > 1 else np.ones(1)
+    codes, leaf_nums = simulate_codes(tree, model(pi, srates), pi, rates, S, rng, gap_frac=0.02)
+    pd = mcp.PhyloDist(tree, pi, srates, rates, model)
+    aln = mcp.DeviceAlignment(codes, leaf_nums, K)
+    ll_o, g_o = _oracle_eval(oracle, tree, codes, leaf_nums, K, model, pi, srates, rates)
+    prior = mcp.CompoundDirichlet(1.3, 0.9, 0.2, 1.4)
+    vp, gp = _oracle_prior(oracle, prior, tree)
+    ctx = mcp.get_context()
+    try:
+        ctx.set_level_mode(1)
+        ll1, g1 = mcp.gradlogpdf(pd, aln)
+        st = ctx.stats()
+        assert st["block"] == 256 and st["grid"] > 192 and st["kernel_launches"] == 1 + st["schedule_rebuilt"]
+        ll2, g2 = mcp.gradlogpdf(pd, aln)
+        l1 = mcp.logpdf(pd, aln)
+        lp, gl = mcp.logpdfgrad(pd, aln, prior)
+        ll3, g3 = mcp.gradlogpdf(pd, aln)                  # the group counters were left at zero by every launch
+    finally:
+        ctx.set_level_mode(-1)
+    _check(ll1, g1, ll_o, g_o)
+    assert ll2 == ll1 and np.array_equal(g1, g2) and ll3 == ll1 and np.array_equal(g1, g3)
+    _check(l1, None, ll_o, None)
+    _check(lp, gl, ll_o + vp, g_o + gp)
+
+
 # ---------------------------------------------------------------------------------------------
 # likelihood + branch-length prior in one device call (mcp_eval_posterior; SURVEY.md §8f row 4,
 # the body of logpdfgrad!(::Type{provided}), /root/reference/src/samplers/sampler.jl:172-190)
