@@ -217,7 +217,9 @@ int mcp_eval_rate_gradient(mcp_ctx *ctx, const mcp_alignment *aln, int NN, const
  *        the dependence of mu on the parameter)
  *   dpi  K x n_par column-major: d pi / d theta_p as seen by the ROOT term (1 in row s for "base frequency s", 0 for
  *        rates); NULL if no parameter enters the root distribution
- * and receives par_grad_out[p] = d logL / d theta_p (n_par doubles).  mcphylo.jl_b200/substitution_models.py
+ * and receives par_grad_out[p] = d logL / d theta_p (n_par doubles) and, if rate_grad_out != NULL, d logL / d rates[r]
+ * (R doubles: the same quantity mcp_eval_rate_gradient returns, here from the moments of the one evaluation -- with
+ * d rates / d alpha the Gamma-shape gradient; n_par may be 0 for a caller that only wants this).  mcphylo.jl_b200/substitution_models.py
  * (model_derivatives) and julia/MCPhyloB200.jl hold dA / dpi for Restriction, JC, GTR and freeK, and a Richardson-extrapolated
  * difference quotient for user-supplied model functions.
  * moments_out (optional, may be NULL): (NN-1) * R * K * K doubles M[b][r][s * K + k] followed by W[K].
@@ -232,11 +234,11 @@ int mcp_eval_model_gradient(mcp_ctx *ctx, const mcp_alignment *aln, int NN, cons
                             const int32_t *parent_num, const double *blv, const double *U, const double *D,
                             const double *Uinv, double mu, const double *rates, int R, const double *pi,
                             int n_par, const double *dA, const double *dpi, double *ll_out, double *grad_out,
-                            double *par_grad_out, double *moments_out);
+                            double *par_grad_out, double *rate_grad_out, double *moments_out);
 int mcp_model_gradient_contract(int K, int R, int n_branches, const double *blv, const double *U, const double *D,
                                 const double *Uinv, double mu, const double *rates, const double *moments,
                                 const double *root_w, int n_par, const double *dA, const double *dpi,
-                                double *par_grad_out, double *grad_check_out);
+                                double *par_grad_out, double *grad_check_out, double *rate_grad_out);
 
 /*
  * Same evaluation, result left on the device: d_out (DEVICE pointer, NN doubles) receives

@@ -171,7 +171,7 @@ function rate_matrix_derivatives(model, base_freq::Vector{Float64}, subst::Vecto
     dA
 end
 
-# (logL, d logL / d branch length, d logL / d base_freq, d logL / d substitution_rates) in one call
+# (logL, d logL / d branch length, d logL / d base_freq, d logL / d substitution_rates, d logL / d rates) in one call
 # (mcp_eval_model_gradient): the gradient pass accumulates per-branch moment matrices, the library contracts them
 # with d P / d theta.  The reference samples these parameters gradient-free (SliceSimplex(:mypi),
 # src/samplers/tree_samplers.jl:49); base_freq entries are independent coordinates here (root term + rate matrix).
@@ -186,14 +186,15 @@ function model_gradient(d::PhyloDist, x::Array{Float64,3})
     ll = Ref{Float64}(0.0)
     grad = Vector{Float64}(undef, NN - 1)
     pgrad = Vector{Float64}(undef, n_par)
+    rgrad = Vector{Float64}(undef, length(d.rates))          # d logL / d rates[r], from the same moments
     check(ccall((:mcp_eval_model_gradient, LIB[]), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Float64},
                  Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Cint, Ptr{Float64},
-                 Cint, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                 Cint, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 context(), alignment(x, leaf_nums), NN, po, pa, Vector{Float64}(blv),
                 Matrix{Float64}(U), Vector{Float64}(D), Matrix{Float64}(Uinv), Float64(mu),
-                d.rates, length(d.rates), d.base_freq, n_par, dA, dpi, ll, grad, pgrad, C_NULL))
-    ll[], grad, pgrad[1:K], pgrad[K+1:end]
+                d.rates, length(d.rates), d.base_freq, n_par, dA, dpi, ll, grad, pgrad, rgrad, C_NULL))
+    ll[], grad, pgrad[1:K], pgrad[K+1:end], rgrad
 end
 
 # Likelihood + branch-length prior in one device call: what logpdfgrad!(::Type{provided}, ...)

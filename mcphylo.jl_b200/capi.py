@@ -88,9 +88,9 @@ def load():
     lib.mcp_eval_device.argtypes = eval_args + [_vp]
     lib.mcp_eval_rate_gradient.argtypes = eval_args[:-1] + [_dp, _vp, _vp]
     lib.mcp_eval_posterior.argtypes = eval_args[:-1] + [C.c_int, _vp, _dp, _vp]
-    lib.mcp_eval_model_gradient.argtypes = eval_args[:-1] + [C.c_int, _vp, _vp, _dp, _vp, _vp, _vp]
+    lib.mcp_eval_model_gradient.argtypes = eval_args[:-1] + [C.c_int, _vp, _vp, _dp, _vp, _vp, _vp, _vp]
     lib.mcp_model_gradient_contract.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp,
-                                                C.c_int, _vp, _vp, _vp, _vp]
+                                                C.c_int, _vp, _vp, _vp, _vp, _vp]
     lib.mcp_eval_batch.argtypes = [_vp, C.c_int] + [_vp] * 10 + [C.c_int, _vp, C.c_int, _vp, _vp]
     lib.mcp_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     lib.mcp_get_stats_member.argtypes = [_vp, C.c_int, C.POINTER(Stats)]
@@ -119,7 +119,8 @@ def load():
     return lib
 
 
-def model_gradient_contract(blv, U, D, Uinv, mu, rates, moments, root_w, dA, dpi=None, want_grad_check=False):
+def model_gradient_contract(blv, U, D, Uinv, mu, rates, moments, root_w, dA, dpi=None, want_grad_check=False,
+                            want_rate_grad=False):
     """Host-only second half of mcp_eval_model_gradient (no GPU): moments M[b, r, s, k] and root vector W[s] ->
     d logL / d theta_p; optionally the branch gradient re-derived from the same moments."""
     lib = load()
@@ -139,13 +140,19 @@ def model_gradient_contract(blv, U, D, Uinv, mu, rates, moments, root_w, dA, dpi
     dpi_f = np.ascontiguousarray(np.asarray(dpi, dtype=np.float64).reshape(K, n_par).ravel(order="F")) if dpi is not None else None
     pg = np.zeros(max(n_par, 1))
     gc = np.zeros(max(NB, 1)) if want_grad_check else None
+    rg = np.zeros(R) if want_rate_grad else None
     rc = lib.mcp_model_gradient_contract(K, R, NB, blv.ctypes.data, Uf.ctypes.data, D.ctypes.data, Uif.ctypes.data, float(mu),
                                          rates.ctypes.data, M.ctypes.data, W.ctypes.data if W is not None else None, n_par,
                                          dA_f.ctypes.data, dpi_f.ctypes.data if dpi_f is not None else None, pg.ctypes.data,
-                                         gc.ctypes.data if want_grad_check else None)
+                                         gc.ctypes.data if want_grad_check else None, rg.ctypes.data if want_rate_grad else None)
     if rc:
         raise McpError(rc, lib.mcp_last_error(None).decode())
-    return (pg[:n_par], gc[:NB]) if want_grad_check else pg[:n_par]
+    out = (pg[:n_par],)
+    if want_grad_check:
+        out += (gc[:NB],)
+    if want_rate_grad:
+        out += (rg,)
+    return out if len(out) > 1 else out[0]
 
 
 def _f64(a, order="C"):
@@ -386,10 +393,11 @@ class Context:
         return ll.value, grad[:NN - 1], rgrad
 
     def eval_model_gradient(self, aln: Alignment, postorder_num, parent_num, blv, U, D, Uinv, mu, rates, pi, dA, dpi=None,
-                            want_moments: bool = False):
+                            want_moments: bool = False, want_rate_grad: bool = False):
         """(logL, d logL / d blv, d logL / d theta) for the substitution-model parameters whose normalised-rate-matrix
-        derivatives are dA[:, :, p] (and root-frequency derivatives dpi[:, p]); with want_moments also the moment
-        matrices M[b, r, s, k] and the root vector W[s] (mcp_eval_model_gradient)."""
+        derivatives are dA[:, :, p] (and root-frequency derivatives dpi[:, p]); with want_rate_grad also d logL / d rates[r]
+        (appended 4th), with want_moments also the moment matrices M[b, r, s, k] and the root vector W[s] (appended
+        last) (mcp_eval_model_gradient)."""
         po, pa, blv, U, D, Uinv, rates, pi = self._pack(postorder_num, parent_num, blv, U, D, Uinv, rates, pi)
         NN, K, R = po.size, aln.K, rates.size
         dA = np.asarray(dA, dtype=np.float64)
@@ -406,13 +414,17 @@ class Context:
         grad = np.zeros(max(NN - 1, 1), dtype=np.float64)
         pgrad = np.zeros(max(n_par, 1), dtype=np.float64)
         mom = np.zeros((NN - 1) * R * K * K + K, dtype=np.float64) if want_moments else None
+        rgrad = np.zeros(R, dtype=np.float64) if want_rate_grad else None
         self._check(self.lib.mcp_eval_model_gradient(self.handle, aln.handle, NN, po.ctypes.data, pa.ctypes.data,
                                                      blv.ctypes.data, U.ctypes.data, D.ctypes.data, Uinv.ctypes.data,
                                                      float(mu), rates.ctypes.data, R, pi.ctypes.data, n_par,
                                                      dA_f.ctypes.data, dpi_f.ctypes.data if dpi_f is not None else None,
                                                      C.byref(ll), grad.ctypes.data, pgrad.ctypes.data,
+                                                     rgrad.ctypes.data if want_rate_grad else None,
                                                      mom.ctypes.data if want_moments else None))
         out = (ll.value, grad[:NN - 1], pgrad[:n_par])
+        if want_rate_grad:
+            out += (rgrad,)
         if want_moments:
             n_m = (NN - 1) * R * K * K
             out += (mom[:n_m].reshape(NN - 1, R, K, K), mom[n_m:])

@@ -1514,11 +1514,14 @@ namespace {
 // (Daleckii-Krein), hence   sum_{s,k} M[s][k] dP[s][k] = t rate sum_ij Phi_ij G_ij Mt_ij   with   Mt = U^T M Uinv^T,  G = Uinv dA U,
 // and the sum over branches and categories needs one K x K matrix  H = sum_{b,r} t_b rate_r Phi^{b,r} o Mt^{b,r}  whatever the
 // number of parameters:  d logL / d theta_p = sum_ij G^p_ij H_ij + sum_s (d pi_s / d theta_p) W[s].
-// The same Mt gives the branch gradient (grad_check[b] = sum_r rate_r sum_i mu D_i e^{x_i} Mt_ii), returned for cross-checks.
+// The same Mt gives the branch gradient (grad_check[b] = sum_r rate_r sum_i mu D_i e^{x_i} Mt_ii), returned for cross-checks,
+// and the gradient with respect to the rate-category multipliers (rate_grad[r] = sum_b t_b sum_i mu D_i e^{x_i} Mt^{b,r}_ii).
 void model_gradient_contract(int K, int R, int NB, const double* blv, const double* U, const double* D, const double* Uinv, double mu,
                              const double* rates, const double* M, const double* W, int n_par, const double* dA, const double* dpi,
-                             double* par_grad, double* grad_check) {
+                             double* par_grad, double* grad_check, double* rate_grad) {
     std::vector<double> H((size_t)K * K, 0.0), T1((size_t)K * K), Mt((size_t)K * K), x(K), ex(K);
+    if (rate_grad)
+        for (int r = 0; r < R; ++r) rate_grad[r] = 0.0;
     for (int b = 0; b < NB; ++b) {
         double gb = 0.0;
         for (int r = 0; r < R; ++r) {
@@ -1541,6 +1544,8 @@ void model_gradient_contract(int K, int R, int NB, const double* blv, const doub
                 x[i] = mu * D[i] * tau;
                 ex[i] = std::exp(x[i]);
                 gb += rates[r] * mu * D[i] * ex[i] * Mt[(size_t)i * K + i];
+                // category r sees the branch as t_b * rate_r: the same diagonal term, weighted by t_b instead of rate_r
+                if (rate_grad) rate_grad[r] += blv[b] * mu * D[i] * ex[i] * Mt[(size_t)i * K + i];
             }
             for (int i = 0; i < K; ++i)
                 for (int j = 0; j < K; ++j) {
@@ -1579,17 +1584,19 @@ void model_gradient_contract(int K, int R, int NB, const double* blv, const doub
 int mcp_model_gradient_contract(int K, int R, int n_branches, const double* blv, const double* U, const double* D,
                                 const double* Uinv, double mu, const double* rates, const double* moments,
                                 const double* root_w, int n_par, const double* dA, const double* dpi, double* par_grad_out,
-                                double* grad_check_out) {
+                                double* grad_check_out, double* rate_grad_out) {
     if (K < 1 || R < 1 || n_branches < 0 || n_par < 0 || !blv || !U || !D || !Uinv || !rates || !moments || (n_par > 0 && (!dA || !par_grad_out)))
         return fail(nullptr, MCP_ERR_ARG, "mcp_model_gradient_contract: bad argument");
-    model_gradient_contract(K, R, n_branches, blv, U, D, Uinv, mu, rates, moments, root_w, n_par, dA, dpi, par_grad_out, grad_check_out);
+    model_gradient_contract(K, R, n_branches, blv, U, D, Uinv, mu, rates, moments, root_w, n_par, dA, dpi, par_grad_out, grad_check_out,
+                            rate_grad_out);
     return 0;
 }
 
 int mcp_eval_model_gradient(mcp_ctx* ctx, const mcp_alignment* aln, int NN, const int32_t* postorder_num,
                             const int32_t* parent_num, const double* blv, const double* U, const double* D, const double* Uinv,
                             double mu, const double* rates, int R, const double* pi, int n_par, const double* dA,
-                            const double* dpi, double* ll_out, double* grad_out, double* par_grad_out, double* moments_out) {
+                            const double* dpi, double* ll_out, double* grad_out, double* par_grad_out, double* rate_grad_out,
+                            double* moments_out) {
     if (!ctx) return fail(nullptr, MCP_ERR_ARG, "null context");
     if (!aln || NN < 2 || n_par < 0 || (n_par > 0 && (!dA || !par_grad_out)))
         return fail(ctx, MCP_ERR_ARG, "mcp_eval_model_gradient: bad argument");
@@ -1637,8 +1644,9 @@ int mcp_eval_model_gradient(mcp_ctx* ctx, const mcp_alignment* aln, int NN, cons
     if (ll_out) *ll_out = ll;
     if (grad_out) std::memcpy(grad_out, grad.data(), sizeof(double) * (NN - 1));
     if (moments_out) std::memcpy(moments_out, msum.data(), sizeof(double) * (n_m + K));
-    if (n_par > 0)
-        model_gradient_contract(K, R, NN - 1, blv, U, D, Uinv, mu, rates, msum.data(), msum.data() + n_m, n_par, dA, dpi, par_grad_out, nullptr);
+    if (n_par > 0 || rate_grad_out)
+        model_gradient_contract(K, R, NN - 1, blv, U, D, Uinv, mu, rates, msum.data(), msum.data() + n_m, n_par, dA, dpi, par_grad_out, nullptr,
+                                rate_grad_out);
     return 0;
 }
 

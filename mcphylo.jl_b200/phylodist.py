@@ -213,21 +213,24 @@ def gradlogpdf_rates(d: PhyloDist, x, device: Optional[int] = None) -> Tuple[flo
     return ctx.eval_rate_gradient(aln, *targs)
 
 
-def gradlogpdf_model(d: PhyloDist, x, device: Optional[int] = None):
+def gradlogpdf_model(d: PhyloDist, x, device: Optional[int] = None, with_rates: bool = False):
     """(logL, d logL / d branch length, d logL / d base_freq, d logL / d substitution_rates): the gradient with respect
     to the substitution model's own parameters next to the branch gradient (mcp_eval_model_gradient; the reference
     samples these parameters gradient-free).  base_freq entries are independent coordinates --
     they enter through the root distribution and, for GTR / Restriction, through the rate matrix; project onto the
     simplex on the caller's side.  Works for any callable substitution_model (difference quotients of the K x K
-    normalised rate matrix for functions other than Restriction / JC / GTR / freeK)."""
+    normalised rate matrix for functions other than Restriction / JC / GTR / freeK).  with_rates appends
+    d logL / d d.rates[r], taken from the same moment matrices (what gradlogpdf_rates returns)."""
     from .substitution_models import model_derivatives
 
     ctx = get_context(device)
     ft, targs = _tree_args(d)
     aln = _device_alignment(x, ft.leaf_nums, d.nbase, ctx)
     _, dA, dpi = model_derivatives(d.substitution_model, d.base_freq, d.substitution_rates)
-    ll, grad, pg = ctx.eval_model_gradient(aln, *targs, dA=dA, dpi=dpi)
+    ll, grad, pg, rg = ctx.eval_model_gradient(aln, *targs, dA=dA, dpi=dpi, want_rate_grad=True)
     K = d.nbase
+    if with_rates:
+        return ll, grad, pg[:K], pg[K:], rg
     return ll, grad, pg[:K], pg[K:]
 
 

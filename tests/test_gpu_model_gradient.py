@@ -87,6 +87,14 @@ def test_phylodist_api_and_plan_cache_keep_apart(oracle):
     ll0, g0 = mcp.gradlogpdf(pd, x)
     ll1, g1, g_pi, g_sr = mcp.gradlogpdf_model(pd, x)
     ll2, g2 = mcp.gradlogpdf(pd, x)
+    # the rate-category gradient from the moments of ONE evaluation = the one from R single-category evaluations
+    ctx = mcp.get_context()
+    from mcphylo_jl_b200.phylodist import _device_alignment, _tree_args
+    ft_, targs_ = _tree_args(pd)
+    aln_ = _device_alignment(x, ft_.leaf_nums, 4, ctx)
+    rg_moments = ctx.eval_model_gradient(aln_, *targs_, dA=np.zeros((4, 4, 0)), want_rate_grad=True)[3]
+    _, _, rg_ref = mcp.gradlogpdf_rates(pd, x)
+    assert np.max(np.abs(rg_moments - rg_ref)) <= 1e-9 * np.max(np.abs(rg_ref)), (rg_moments, rg_ref)
     assert ll2 == ll0 and np.array_equal(g0, g2)
     assert abs(ll1 - ll0) <= 1e-10 * abs(ll0)
     assert np.max(np.abs(g1 - g0)) <= 1e-8 * np.max(np.abs(g0))
@@ -138,7 +146,7 @@ def test_model_gradient_argument_errors():
     U, D, Uinv, mu = sm.Restriction(pi)
     try:
         rc = ctx.lib.mcp_eval_model_gradient(ctx.handle, aln.handle, ft.NN, None, None, None, None, None, None, 1.0, None, 1, None,
-                                             0, None, None, None, None, None, None)
+                                             0, None, None, None, None, None, None, None)
         assert rc == capi.ERR_ARG if hasattr(capi, "ERR_ARG") else rc < 0
         # the context is still usable
         ll, g = ctx.eval(aln, ft.postorder_num, ft.parent_num, ft.blv, U, D, Uinv, mu, np.ones(1), pi, want_grad=True)

@@ -113,9 +113,18 @@ def test_contract_matches_finite_differences_of_the_oracle(oracle, name, model, 
     assert np.max(np.abs(grad - grad_o)) <= 1e-8 * np.max(np.abs(grad_o))
 
     names, dA, dpi = sm.model_derivatives(model, pi, sr)
-    pg, gc = capi.model_gradient_contract(ft.blv, U, D, Uinv, mu, rates, M, W, dA, dpi, want_grad_check=True)
+    pg, gc, rg = capi.model_gradient_contract(ft.blv, U, D, Uinv, mu, rates, M, W, dA, dpi, want_grad_check=True,
+                                              want_rate_grad=True)
     # the branch gradient re-derived from the moments is the oracle's
     assert np.max(np.abs(gc - grad_o)) <= 1e-9 * np.max(np.abs(grad_o))
+    # d logL / d rates[r] from the same moments against central differences of the oracle's logL
+    fd_r = np.zeros(rates.size)
+    for r in range(rates.size):
+        rp, rm = rates.copy(), rates.copy()
+        rp[r] += 1e-6
+        rm[r] -= 1e-6
+        fd_r[r] = (oracle_ll(oracle, ft, x, model, pi, sr, rp) - oracle_ll(oracle, ft, x, model, pi, sr, rm)) / 2e-6
+    assert np.max(np.abs(rg - fd_r)) <= 2e-6 * max(np.max(np.abs(fd_r)), 1.0), (rg, fd_r)
     fd = fd_param_gradient(oracle, ft, x, model, pi, sr, rates)
     assert pg.shape == fd.shape == (len(names),)
     assert np.max(np.abs(pg - fd)) <= 2e-6 * max(np.max(np.abs(fd)), 1.0), (pg, fd)
@@ -144,6 +153,6 @@ def test_user_supplied_model_function_uses_difference_quotients(oracle):
 def test_contract_rejects_bad_arguments():
     with pytest.raises(capi.McpError):
         capi.load()
-        rc = capi.load().mcp_model_gradient_contract(0, 1, 0, None, None, None, None, 1.0, None, None, None, 0, None, None, None, None)
+        rc = capi.load().mcp_model_gradient_contract(0, 1, 0, None, None, None, None, 1.0, None, None, None, 0, None, None, None, None, None)
         if rc:
             raise capi.McpError(rc, capi.load().mcp_last_error(None).decode())
