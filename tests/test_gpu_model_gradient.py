@@ -30,6 +30,9 @@ CASES = [
      mcp.discrete_gamma_rates(0.5, 0.5, 4), 23, 1031, True, False),
     ("jc_unary", sm.JC, np.full(4, 0.25), np.zeros(0), np.array([0.6, 1.4]), 12, 300, False, True),
     ("freek3", sm.freeK, np.array([0.2, 0.3, 0.5]), np.array([1.0, 2.0, 0.5, 0.7, 1.3, 0.9]), np.ones(1), 10, 129, False, False),
+    ("gtr5_gamma2", sm.GTR, np.array([0.1, 0.15, 0.2, 0.25, 0.3]), np.linspace(0.5, 2.3, 10), mcp.discrete_gamma_rates(0.8, 0.8, 2),
+     14, 333, True, False),
+    ("jc6", sm.JC, np.full(6, 1.0 / 6.0), np.zeros(0), np.ones(1), 9, 65, False, True),
     ("protein20", _protein_like, np.random.default_rng(9).dirichlet(np.ones(20) * 8), np.array([1.3]), np.array([0.5, 1.5]),
      8, 96, False, False),
 ]
@@ -66,7 +69,7 @@ def test_moments_and_parameter_gradient(oracle, case):
     pg_n, gc = capi.model_gradient_contract(ft.blv, U, D, Uinv, mu, rates, M, W, dA, dpi, want_grad_check=True)
     assert np.array_equal(pg, pg_n)
     assert np.max(np.abs(gc - grad_o)) <= 1e-8 * np.max(np.abs(grad_o))
-    if K <= 4:
+    if K <= 6:
         fd = fd_param_gradient(oracle, ft, x, model, pi, sr, rates)
         assert np.max(np.abs(pg - fd)) <= 2e-6 * max(np.max(np.abs(fd)), 1.0), (pg, fd)
     else:
