@@ -156,3 +156,19 @@ def test_contract_rejects_bad_arguments():
         rc = capi.load().mcp_model_gradient_contract(0, 1, 0, None, None, None, None, 1.0, None, None, None, 0, None, None, None, None, None)
         if rc:
             raise capi.McpError(rc, capi.load().mcp_last_error(None).decode())
+
+
+@pytest.mark.parametrize("name,model,pi,sr,rates", CASES, ids=[c[0] for c in CASES])
+def test_closed_form_rate_matrix_derivatives_match_difference_quotients(name, model, pi, sr, rates):
+    """model_derivatives: the closed forms for the four built-in models against the Richardson-extrapolated difference
+    quotient the same function applies to user-supplied models (and that julia/MCPhyloB200.jl applies to every model)."""
+    names, dA, dpi = sm.model_derivatives(model, pi, sr)
+    _, dA_num, dpi_num = sm.model_derivatives(lambda a, b: model(a, b), pi, sr)     # a lambda is "a model it has never seen"
+    K = len(pi)
+    assert dA.shape == dA_num.shape == (K, K, K + len(sr)) and len(names) == K + len(sr)
+    assert np.max(np.abs(dA - dA_num)) <= 1e-9 * max(np.max(np.abs(dA_num)), 1.0)
+    assert np.array_equal(dpi, dpi_num) and np.array_equal(dpi[:, :K], np.eye(K)) and not dpi[:, K:].any()
+    # rows of a rate matrix sum to zero, and so do the rows of its derivatives
+    assert np.max(np.abs(dA.sum(axis=1))) <= 1e-12 * max(np.max(np.abs(dA)), 1.0)
+    A = sm.normalised_rate_matrix(model(pi, sr))
+    assert np.max(np.abs(A.sum(axis=1))) <= 1e-12
