@@ -352,7 +352,9 @@ int mcp_set_ring_mode(mcp_ctx *ctx, int mode);
  *                                  launch) instead of carrying it in the arguments of the fused small-tree kernel
  *   MCPHYLO_B200_STREAM_BLOCKS=1   mcp_eval_streamed uses the block-per-launch pipeline instead of one fused launch
  *   MCPHYLO_B200_SERIAL_GROUP=1    a multi-device context enqueues its devices from the calling thread
- *   MCPHYLO_B200_NCCL=<path>       NCCL library to dlopen instead of libnccl.so.2 */
+ *   MCPHYLO_B200_NCCL=<path>       NCCL library to dlopen instead of libnccl.so.2
+ *   MCPHYLO_B200_TIMING=0          contexts start with mcp_set_timing(ctx, 0)
+ *   MCPHYLO_B200_MG_REPLICAS=<n>   replicas of the moment matrices of mcp_eval_model_gradient (default: as many as 64 MB hold, <= 32) */
 /* State counts 6 < K <= 32 (e.g. 20-state protein alphabets): -1 / 1 the tile-cooperative kernel that runs the
  * K x K by K x columns products of every node on the FP64 tensor path (mma.sync.m8n8k4.f64; 8 warps x 16 columns
  * per CTA, bit-reproducible gradient), 0 the runtime-K fallback kernel (one thread per column, CUDA cores). */
