@@ -162,6 +162,39 @@ def load_traffic(workload, sites_per_gpu):
     return None, None
 
 
+def load_traffic_entry(workload, sites_per_gpu):
+    try:
+        with open(os.path.join(ROOT, "profiles", "walk_traffic.json")) as fh:
+            tj = json.load(fh)
+        for e in tj.get("entries") or [tj]:
+            if e.get("workload") == workload and int(e.get("sites_per_gpu", -1)) == int(sites_per_gpu):
+                return e
+    except Exception:
+        pass
+    return None
+
+
+def issue_block(w, local_S, kernel_ms, clocks, sm_count=148):
+    """What the walk kernel is actually bound by: neither roof of the HBM model, but the instruction stream.  Warp
+    instructions per launch (ncu `smsp__inst_executed.sum` of the committed capture of this exact shape) over the issue
+    slots of the timed launch: SMs x 4 schedulers x measured SM clock x live kernel time."""
+    try:
+        e = load_traffic_entry(w["name"], local_S)
+        mhz = float((clocks or {}).get("sm_mhz") or 0.0)
+        if not e or not e.get("warp_instructions") or not kernel_ms or mhz <= 0:
+            return None
+        slots = sm_count * 4 * mhz * 1e6 * kernel_ms * 1e-3
+        return {"warp_instructions_per_launch": e["warp_instructions"], "issue_slots_per_launch": slots,
+                "frac": e["warp_instructions"] / slots, "sm_mhz": mhz,
+                "fp64_pipe_active_pct_under_ncu": e.get("fp64_pipe_active_pct"),
+                "issue_active_pct_under_ncu": e.get("issue_active_pct"),
+                "what": "share of the warp-instruction issue slots the launch used (instructions from the committed ncu capture "
+                        "of this shape, time and clock measured live): the walk is instruction-issue / FP64-latency bound, "
+                        "which is why frac_physical sits near 0.5"}
+    except Exception:
+        return None
+
+
 def roofline_block(w, local_S, kernel_ms, tree, want_grad=True):
     peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -695,6 +728,8 @@ def run_b200(args):
         local_S = -(-w["S"] // n_gpus)
         wk = float(np.mean(walk_ms)) if walk_ms and all(m > 0 for m in walk_ms) else None
         roofline = roofline_block(w, local_S, wk, tree)
+        clocks = sampler.summary()
+        roofline["issue"] = issue_block(w, local_S, wk, clocks)
         # parity stamp at the launch shape of the timed run (member 0's shape on a multi-device context)
         check_ctx = capi.Context(primary)
         window = oracle_window(check_ctx, w, codes, leaf_nums, member_stats[0], sites=256)
@@ -725,7 +760,7 @@ def run_b200(args):
             "ms_per_step_host_wall": t_wall / args.steps,
             "gpu_launches": int(launches + e2e_launches),
             "gpu_launches_timed": int(launches),
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "launch": {"grid": stats["grid"], "block": stats["block"], "columns_per_thread": stats["columns_per_thread"],
                        "tiles": stats["tiles"], "scratch_bytes": stats["scratch_bytes"],
                        "operand_ring": stats.get("operand_ring", 0),
