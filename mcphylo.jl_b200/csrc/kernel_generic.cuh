@@ -1,5 +1,6 @@
-// kernel_generic.cuh — kernel 2b: runtime-K walk for large alphabets.
-// Part of libmcphylo_b200.so; included by mcphylo_b200.cu only (one translation unit).
+// kernel_generic.cuh — kernel 2b: column-per-thread walk on dense branch tables -- the runtime-K fallback for large
+// alphabets and, with the moment matrices, the kernel of mcp_eval_model_gradient (compile-time K for K <= 6).
+// Part of libmcphylo_b200.so; included by walk_generic.cu only (one translation unit).
 #pragma once
 
 namespace {
